@@ -1,0 +1,368 @@
+// Epipolar geometry in float64: patch->image affine, two-view triangulation
+// (homogeneous DLT / linear LS / iterative LS) and projection to labels.
+// Reference arithmetic: lib/utils/triangulation.py, lib/utils/img_utils.py:63-111,
+// 141-155,193-243, lib/utils/prep_h36m.py:170-204, lib/core/integral_loss.py:170-205.
+// The SVDs the reference obtains from OpenCV (cv2.triangulatePoints,
+// cv2.solve(DECOMP_SVD)) are one-sided Jacobi SVDs on the un-squared matrix,
+// as in OpenCV's JacobiSVD (so the condition number is not squared).
+//
+// One thread per (pair, joint): the problem is a few hundred bytes per joint
+// and latency-bound at real sizes (64 pairs x 17 joints); no tensor cores.
+// Compiled with --fmad=false so that a*b+c rounds twice as on the CPU.
+#include "common.cuh"
+#include <float.h>
+
+namespace {
+
+// One-sided (Hestenes) Jacobi: rotate columns of A (R x C) until mutually
+// orthogonal; V (C x C) accumulates the right rotations.  On exit
+// A = U*diag(sigma) (columns), sigma_j = ||A[:,j]||.
+template <int R, int C>
+__device__ void jacobi_onesided(double (&A)[R][C], double (&V)[C][C]) {
+#pragma unroll
+  for (int i = 0; i < C; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool changed = false;
+#pragma unroll
+    for (int p = 0; p < C - 1; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < C; ++q) {
+        double a = 0, b = 0, g = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          a += A[i][p] * A[i][p];
+          b += A[i][q] * A[i][q];
+          g += A[i][p] * A[i][q];
+        }
+        if (fabs(g) <= DBL_EPSILON * sqrt(a * b) || g == 0.0) continue;
+        changed = true;
+        const double zeta = (b - a) / (2.0 * g);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const double x = A[i][p], y = A[i][q];
+          A[i][p] = c * x - s * y;
+          A[i][q] = s * x + c * y;
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+          const double x = V[i][p], y = V[i][q];
+          V[i][p] = c * x - s * y;
+          V[i][q] = s * x + c * y;
+        }
+      }
+    }
+    if (!changed) break;
+  }
+}
+
+// least-squares solve of A(4x3) x = b via SVD, as cv2.solve(.., DECOMP_SVD)
+__device__ void solve_ls_4x3(const double (&A0)[4][3], const double (&b)[4], double (&x)[3]) {
+  double A[4][3], V[3][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A[i][j] = A0[i][j];
+  jacobi_onesided<4, 3>(A, V);
+  double s2[3], y[3], ssum = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double n2 = 0, d = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { n2 += A[i][j] * A[i][j]; d += A[i][j] * b[i]; }
+    s2[j] = n2;
+    y[j] = d;
+    ssum += sqrt(n2);
+  }
+  const double thr = DBL_EPSILON * 2.0 * ssum;  // cv::SVD::backSubst threshold
+#pragma unroll
+  for (int j = 0; j < 3; ++j) y[j] = (sqrt(s2[j]) > thr) ? y[j] / s2[j] : 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) x[i] = V[i][0] * y[0] + V[i][1] * y[1] + V[i][2] * y[2];
+}
+
+// triangulation.py:139-150 / :80-92: rows C*P[:3,:3], b = -(C*P[:3,3]),
+// C = [[-1,0,u],[0,-1,v]]
+__device__ void build_Ab(const double* u1, const double* P1, const double* u2, const double* P2,
+                         double (&A)[4][3], double (&b)[4]) {
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const double* u = v ? u2 : u1;
+    const double* P = v ? P2 : P1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      A[2 * v + 0][k] = -P[0 * 4 + k] + u[0] * P[2 * 4 + k];
+      A[2 * v + 1][k] = -P[1 * 4 + k] + u[1] * P[2 * 4 + k];
+    }
+    b[2 * v + 0] = -(-P[0 * 4 + 3] + u[0] * P[2 * 4 + 3]);
+    b[2 * v + 1] = -(-P[1 * 4 + 3] + u[1] * P[2 * 4 + 3]);
+  }
+}
+
+__global__ void triangulate_kernel(const double* __restrict__ u1, const double* __restrict__ u2,
+                                   int stride_u, const double* __restrict__ P1,
+                                   const double* __restrict__ P2, int NP, int J, int method,
+                                   double tol, double* __restrict__ X,
+                                   int32_t* __restrict__ status) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NP * J) return;
+  const int pair = idx / J;
+  double p1[12], p2[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) { p1[k] = P1[pair * 12 + k]; p2[k] = P2[pair * 12 + k]; }
+  const double a1[2] = {u1[(int64_t)idx * stride_u], u1[(int64_t)idx * stride_u + 1]};
+  const double a2[2] = {u2[(int64_t)idx * stride_u], u2[(int64_t)idx * stride_u + 1]};
+  double x[3];
+  int st;
+  if (method == 0) {
+    // triangulation.py:22 cv2.triangulatePoints: A rows x*P[2]-P[0], y*P[2]-P[1]
+    double A[4][4], V[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      A[0][k] = a1[0] * p1[8 + k] - p1[0 + k];
+      A[1][k] = a1[1] * p1[8 + k] - p1[4 + k];
+      A[2][k] = a2[0] * p2[8 + k] - p2[0 + k];
+      A[3][k] = a2[1] * p2[8 + k] - p2[4 + k];
+    }
+    jacobi_onesided<4, 4>(A, V);
+    int best = 0;
+    double bn = DBL_MAX;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double n2 = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) n2 += A[i][j] * A[i][j];
+      if (n2 < bn) { bn = n2; best = j; }
+    }
+    double h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = V[i][0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j)
+        if (best == j) h[i] = V[i][j];
+    }
+    x[0] = h[0] / h[3]; x[1] = h[1] / h[3]; x[2] = h[2] / h[3];  // :24
+    const double mx = fmax(fabs(x[0]), fmax(fabs(x[1]), fabs(x[2])));
+    st = (mx <= 1.e16) ? 1 : 0;  // :25 (NaN compares false)
+  } else {
+    double A[4][3], b[4];
+    build_Ab(a1, p1, a2, p2, A, b);
+    if (method == 1) {
+      solve_ls_4x3(A, b, x);
+      st = 1;
+    } else {
+      double d1 = 1.0, d2 = 1.0, d1n = 1.0, d2n = 1.0;
+      for (int it = 0; it < 10; ++it) {   // :152
+        solve_ls_4x3(A, b, x);
+        d1n = ((p1[8] * x[0] + p1[9] * x[1]) + p1[10] * x[2]) + p1[11];   // :158
+        d2n = ((p2[8] * x[0] + p2[9] * x[1]) + p2[10] * x[2]) + p2[11];
+        if (fabs(d1n - d1) <= tol && fabs(d2n - d2) <= tol) break;  // :161-163
+        const double r1 = 1.0 / d1n, r2 = 1.0 / d2n;
+        // :165-169 CUMULATIVE re-weighting of the already weighted rows
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          A[0][k] *= r1; A[1][k] *= r1; A[2][k] *= r2; A[3][k] *= r2;
+        }
+        b[0] *= r1; b[1] *= r1; b[2] *= r2; b[3] *= r2;
+        d1 = d1n; d2 = d2n;
+      }
+      st = (d1n > 0 && d2n > 0) ? 1 : 0;  // :175-176 (i < 10 always holds)
+      if (d1n <= 0) st -= 1;
+      if (d2n <= 0) st -= 2;
+    }
+  }
+  X[(int64_t)idx * 3 + 0] = x[0];
+  X[(int64_t)idx * 3 + 1] = x[1];
+  X[(int64_t)idx * 3 + 2] = x[2];
+  if (status) status[idx] = st;
+}
+
+// img_utils.py:72-105 with its float32 roundings.  Returns the 2x3 transform
+// mapping src->dst (inv=0: image->patch) or dst->src (inv=1: patch->image).
+__device__ void patch_affine(const double* box, double patch_w, double patch_h, int inv,
+                             double (&M)[2][3]) {
+  const double c_x = box[0], c_y = box[1], scale = box[4], rot = box[5];
+  const double src_w = box[2] * scale, src_h = box[3] * scale;
+  const double rot_rad = 3.141592653589793 * rot / 180;
+  const double sn = sin(rot_rad), cs = cos(rot_rad);
+  // rotate_2d(np.array([0, src_h*0.5], f32), rot_rad) -> f32 (:63-69)
+  const double dy_ = (double)(float)(src_h * 0.5), rx_ = (double)(float)(src_w * 0.5);
+  const float down_x = (float)(0.0 * cs - dy_ * sn), down_y = (float)(0.0 * sn + dy_ * cs);
+  const float right_x = (float)(rx_ * cs - 0.0 * sn), right_y = (float)(rx_ * sn + 0.0 * cs);
+  float s[3][2], d[3][2];
+  s[0][0] = (float)c_x;                       s[0][1] = (float)c_y;
+  s[1][0] = (float)(c_x + (double)down_x);    s[1][1] = (float)(c_y + (double)down_y);
+  s[2][0] = (float)(c_x + (double)right_x);   s[2][1] = (float)(c_y + (double)right_y);
+  const float dcx = (float)(patch_w * 0.5), dcy = (float)(patch_h * 0.5);
+  d[0][0] = dcx;        d[0][1] = dcy;
+  d[1][0] = dcx + 0.f;  d[1][1] = dcy + (float)(patch_h * 0.5);
+  d[2][0] = dcx + (float)(patch_w * 0.5);  d[2][1] = dcy + 0.f;
+  const float (*from)[2] = inv ? d : s;
+  const float (*to)[2] = inv ? s : d;
+  // cv2.getAffineTransform: solve [x y 1] m = to, float64
+  const double e1x = (double)from[1][0] - from[0][0], e1y = (double)from[1][1] - from[0][1];
+  const double e2x = (double)from[2][0] - from[0][0], e2y = (double)from[2][1] - from[0][1];
+  const double det = e1x * e2y - e1y * e2x;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const double f1 = (double)to[1][r] - to[0][r], f2 = (double)to[2][r] - to[0][r];
+    const double a = (f1 * e2y - f2 * e1y) / det;
+    const double b = (e1x * f2 - e2x * f1) / det;
+    M[r][0] = a;
+    M[r][1] = b;
+    M[r][2] = (double)to[0][r] - a * from[0][0] - b * from[0][1];
+  }
+}
+
+__global__ void patch_to_image_kernel(const float* __restrict__ coords,
+                                      const double* __restrict__ box, int B, int J,
+                                      double patch_w, double patch_h, double rect3d_w,
+                                      double* __restrict__ kps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * J) return;
+  const int b = idx / J;
+  // integral_loss.py:196-201
+  const double px = ((double)coords[idx * 3 + 0] + 0.5) * patch_w;
+  const double py = ((double)coords[idx * 3 + 1] + 0.5) * patch_h;
+  const double pz = (double)coords[idx * 3 + 2] * patch_w;
+  double M[2][3];
+  patch_affine(box + b * 6, patch_w, patch_h, 1, M);
+  // img_utils.py:108-111 np.dot(trans, [x, y, 1])
+  kps[(int64_t)idx * 4 + 0] = (M[0][0] * px + M[0][1] * py) + M[0][2];
+  kps[(int64_t)idx * 4 + 1] = (M[1][0] * px + M[1][1] * py) + M[1][2];
+  kps[(int64_t)idx * 4 + 2] = pz / patch_w * rect3d_w;  // img_utils.py:154
+  kps[(int64_t)idx * 4 + 3] = 1.0;
+}
+
+__global__ void project_labels_kernel(const double* __restrict__ X, const double* __restrict__ cam,
+                                      const double* __restrict__ box, int B, int J,
+                                      double patch_w, double patch_h, double rect3d_w,
+                                      float* __restrict__ label, float* __restrict__ weight) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * J) return;
+  const int b = idx / J;
+  const double* c = cam + b * 16;   // R(9) T(3) f(2) c(2)
+  const double* x = X + (int64_t)idx * 3;
+  const double* x0 = X + (int64_t)b * J * 3;  // root joint 0 (prep_h36m.py:181)
+  // prep_h36m.py:186 np.dot(rot, keypoints - trans)
+  const double dx = x[0] - c[9], dy = x[1] - c[10], dz = x[2] - c[11];
+  const double cx = (c[0] * dx + c[1] * dy) + c[2] * dz;
+  const double cy = (c[3] * dx + c[4] * dy) + c[5] * dz;
+  const double cz = (c[6] * dx + c[7] * dy) + c[8] * dz;
+  const double rx = x0[0] - c[9], ry = x0[1] - c[10], rz = x0[2] - c[11];
+  const double pelvis_z = (c[6] * rx + c[7] * ry) + c[8] * rz;
+  // CamProj :170-175
+  double u = cx / cz * c[12] + c[14];
+  double v = cy / cz * c[13] + c[15];
+  double z = cz - pelvis_z;  // :199
+  double M[2][3];
+  patch_affine(box + b * 6, patch_w, patch_h, 0, M);
+  const double pu = (M[0][0] * u + M[0][1] * v) + M[0][2];   // img_utils.py:235
+  const double pv = (M[1][0] * u + M[1][1] * v) + M[1][2];
+  z = z / (rect3d_w * box[b * 6 + 4]) * patch_w;               // :236
+  // integral_loss.py:171-173
+  label[idx * 3 + 0] = (float)(pu / patch_w - 0.5);
+  label[idx * 3 + 1] = (float)(pv / patch_h - 0.5);
+  label[idx * 3 + 2] = (float)(z / patch_w);
+  weight[idx * 3 + 0] = 1.f;
+  weight[idx * 3 + 1] = 1.f;
+  weight[idx * 3 + 2] = 1.f;
+}
+
+// --------------------------------------------------------------- argmax
+// inference.py:24-39: one warp per (n,j) map; (value, index) reduction with
+// smallest-index tie-break == numpy argmax first-occurrence.  NaN: numpy
+// treats the first NaN as the maximum; reproduced by ordering NaN above all.
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+  const bool vn = (v != v), bn = (bv != bv);
+  if (vn || bn) return vn && (!bn || i < bi);
+  return v > bv || (v == bv && i < bi);
+}
+
+__global__ void argmax2d_kernel(const float* __restrict__ hm, int NJ, int HW, int W,
+                                int32_t* __restrict__ idx_out, float* __restrict__ maxval,
+                                float* __restrict__ preds) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= NJ) return;
+  const float* p = hm + (int64_t)warp * HW;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < HW; i += 32) {
+    const float v = p[i];
+    if (better(v, i, bv, bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) {
+    if (bi == 0x7fffffff) bi = 0;  // all -inf: numpy returns index 0
+    if (idx_out) idx_out[warp] = bi;
+    if (maxval) maxval[warp] = bv;
+    if (preds) {
+      const float mask = (bv > 0.f) ? 1.f : 0.f;   // :35-39
+      preds[warp * 2 + 0] = (float)(bi % W) * mask;
+      preds[warp * 2 + 1] = floorf((float)bi / (float)W) * mask;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int epb_triangulate(const double* u1, const double* u2, int stride_u, const double* P1,
+                               const double* P2, int NP, int J, int method, double tol, double* X,
+                               int32_t* status, epb_stream_t stream) {
+  EPB_CHECK_ARG(u1 && u2 && P1 && P2 && X);
+  EPB_CHECK_ARG(NP >= 0 && J >= 0 && stride_u >= 2);
+  EPB_CHECK_ARG(method >= 0 && method <= 2);
+  if (NP * J == 0) return EPB_OK;
+  const int n = NP * J;
+  triangulate_kernel<<<(n + 63) / 64, 64, 0, as_stream(stream)>>>(u1, u2, stride_u, P1, P2, NP, J,
+                                                                  method, tol, X, status);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_patch_to_image(const float* coords, const double* box, int B, int J,
+                                  double patch_w, double patch_h, double rect3d_w, double* kps,
+                                  epb_stream_t stream) {
+  EPB_CHECK_ARG(coords && box && kps);
+  EPB_CHECK_ARG(B >= 0 && J >= 0);
+  if (B * J == 0) return EPB_OK;
+  const int n = B * J;
+  patch_to_image_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(coords, box, B, J, patch_w,
+                                                                       patch_h, rect3d_w, kps);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_project_labels(const double* X, const double* cam, const double* box, int B,
+                                  int J, double patch_w, double patch_h, double rect3d_w,
+                                  float* label, float* weight, epb_stream_t stream) {
+  EPB_CHECK_ARG(X && cam && box && label && weight);
+  EPB_CHECK_ARG(B >= 0 && J >= 0);
+  if (B * J == 0) return EPB_OK;
+  const int n = B * J;
+  project_labels_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(
+      X, cam, box, B, J, patch_w, patch_h, rect3d_w, label, weight);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_argmax2d(const float* hm, int NJ, int H, int W, int32_t* idx, float* maxval,
+                            float* preds, epb_stream_t stream) {
+  EPB_CHECK_ARG(hm && NJ >= 0 && H > 0 && W > 0);
+  if (NJ == 0) return EPB_OK;
+  const int threads = 256;
+  const int blocks = (NJ * 32 + threads - 1) / threads;
+  argmax2d_kernel<<<blocks, threads, 0, as_stream(stream)>>>(hm, NJ, H * W, W, idx, maxval, preds);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}

@@ -1,0 +1,226 @@
+// Module-boundary layout conversion (NCHW <-> NHWC), weight packing between
+// the reference's state_dict layouts (Conv2d [O][I][kh][kw], ConvTranspose2d
+// [I][O][kh][kw]; lib/models/pose3d_resnet.py:99,116-122,171-178) and the
+// packed GEMM operand [X][T][Ypad], and the fused optimiser steps
+// (torch.optim.Adam / SGD call sites lib/utils/utils.py:45-61).
+#include "common.cuh"
+
+namespace {
+
+// [N][C][HW] -> [N][HW][Cpad] (zero padded) through a 32x32 smem tile
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
+                                    int HW, int Cpad) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[((int64_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < Cpad) dst[((int64_t)n * HW + p) * Cpad + c] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
+                                    int HW, int Cpad) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < Cpad) ? src[((int64_t)n * HW + p) * Cpad + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[((int64_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// src [A][B][T] (T = kh*kw), packed [X][T][Ypad]: swap=0 -> X=A,Y=B ; swap=1 -> X=B,Y=A
+__global__ void pack_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int A,
+                                   int B, int T, int swap, int Ypad, int unpack) {
+  const int X = swap ? B : A, Y = swap ? A : B;
+  const int64_t total = (int64_t)X * T * Ypad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i % Ypad);
+    const int t = (int)((i / Ypad) % T);
+    const int x = (int)(i / ((int64_t)Ypad * T));
+    const int a = swap ? y : x, b = swap ? x : y;
+    if (!unpack) {
+      dst[i] = (y < Y) ? src[((int64_t)a * B + b) * T + t] : 0.f;
+    } else if (y < Y) {
+      // inverse: `src` is the packed tensor, `dst` the state_dict layout
+      dst[((int64_t)a * B + b) * T + t] = src[i];
+    }
+  }
+}
+
+__global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                            float4* __restrict__ m, float4* __restrict__ v, int64_t n4, float lr,
+                            float b1, float b2, float eps, float wd, float bc1, float rsqrt_bc2,
+                            float gscale) {
+  const float step = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float* P = &pp.x; float* G = &gg.x; float* Mv = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr = G[k] * gscale;
+      if (wd != 0.f) gr += wd * P[k];
+      Mv[k] = b1 * Mv[k] + (1.f - b1) * gr;
+      V[k] = b2 * V[k] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(V[k]) * rsqrt_bc2 + eps;
+      P[k] -= step * (Mv[k] / denom);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
+__global__ void adam_kernel1(float* __restrict__ p, const float* __restrict__ g,
+                             float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                             float b1, float b2, float eps, float wd, float bc1, float rsqrt_bc2,
+                             float gscale) {
+  const float step = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gscale;
+    if (wd != 0.f) gr += wd * p[i];
+    const float mm = b1 * m[i] + (1.f - b1) * gr;
+    const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mm; v[i] = vv;
+    p[i] -= step * (mm / (sqrtf(vv) * rsqrt_bc2 + eps));
+  }
+}
+
+__global__ void sgd_kernel1(float* __restrict__ p, const float* __restrict__ g,
+                            float* __restrict__ buf, int64_t n, float lr, float mom, float wd,
+                            int nesterov, int first, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gscale;
+    if (wd != 0.f) gr += wd * p[i];
+    if (mom != 0.f) {
+      const float b = first ? gr : mom * buf[i] + gr;
+      buf[i] = b;
+      gr = nesterov ? gr + mom * b : b;
+    }
+    p[i] -= lr * gr;
+  }
+}
+
+__global__ void sgd_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                           float4* __restrict__ buf, int64_t n4, float lr, float mom, float wd,
+                           int nesterov, int first, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i];
+    float4 bb = buf ? buf[i] : make_float4(0, 0, 0, 0);
+    float* P = &pp.x; float* G = &gg.x; float* Bf = &bb.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr = G[k] * gscale;
+      if (wd != 0.f) gr += wd * P[k];
+      if (mom != 0.f) {
+        Bf[k] = first ? gr : mom * Bf[k] + gr;
+        gr = nesterov ? gr + mom * Bf[k] : Bf[k];
+      }
+      P[k] -= lr * gr;
+    }
+    p[i] = pp;
+    if (buf) buf[i] = bb;
+  }
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int epb_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int Cpad,
+                                epb_stream_t stream) {
+  EPB_CHECK_ARG(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C);
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (Cpad + 31) / 32, N);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, dst, C, HW, Cpad);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int Cpad,
+                                epb_stream_t stream) {
+  EPB_CHECK_ARG(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C);
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (Cpad + 31) / 32, N);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, dst, C, HW, Cpad);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_pack_weight(const float* src, float* dst, int A, int B, int kh, int kw, int swap,
+                               int Ypad, int unpack, epb_stream_t stream) {
+  EPB_CHECK_ARG(src && dst && A > 0 && B > 0 && kh > 0 && kw > 0);
+  EPB_CHECK_ARG(Ypad >= (swap ? A : B));
+  const int64_t total = (int64_t)(swap ? B : A) * kh * kw * Ypad;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  pack_weight_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, dst, A, B, kh * kw, swap,
+                                                                 Ypad, unpack);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                             int64_t n, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int step, float grad_scale, epb_stream_t stream) {
+  EPB_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1);
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  const bool vec = (n % 4 == 0) && (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg |
+                                     (uintptr_t)exp_avg_sq) % 16 == 0);
+  if (!vec) {
+    blocks = (n + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    adam_kernel1<<<(int)blocks, 256, 0, as_stream(stream)>>>(
+        param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+        (float)(1.0 / sqrt(bc2)), grad_scale);
+    EPB_LAUNCH_CHECK();
+    return EPB_OK;
+  }
+  adam_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad),
+      reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq), n / 4, lr, beta1,
+      beta2, eps, weight_decay, (float)bc1, (float)(1.0 / sqrt(bc2)), grad_scale);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n,
+                            float lr, float momentum, float weight_decay, int nesterov,
+                            int first_step, float grad_scale, epb_stream_t stream) {
+  EPB_CHECK_ARG(param && grad && n > 0);
+  EPB_CHECK_ARG(momentum == 0.f || momentum_buf);
+  const bool vec = (n % 4 == 0) &&
+                   (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)momentum_buf) % 16 == 0);
+  if (!vec) {
+    int64_t b1 = (n + 255) / 256;
+    if (b1 > kNumSMs * 8) b1 = kNumSMs * 8;
+    sgd_kernel1<<<(int)b1, 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, n, lr, momentum,
+                                                        weight_decay, nesterov, first_step,
+                                                        grad_scale);
+    EPB_LAUNCH_CHECK();
+    return EPB_OK;
+  }
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  sgd_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad),
+      reinterpret_cast<float4*>(momentum_buf), n / 4, lr, momentum, weight_decay, nesterov,
+      first_step, grad_scale);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}

@@ -1,0 +1,114 @@
+"""Train / validate / evaluate loops -- host-side mirror of the reference
+lib/core/function.py signatures: train_integral(config, train_loader, model,
+criterion, optimizer, epoch) (:14-63), validate_integral(val_loader, model)
+(:66-110), eval_integral(epoch, preds, val_loader, path, debug) (:113-135).
+
+Differences from the reference body (same observable behaviour):
+  * the loss value is kept on the device and read back only when a log line
+    is printed (the reference's per-step loss.item() sync, :48, is gone);
+  * when config.TRAIN.ONLINE_TRIANGULATION is set the labels are produced per
+    batch by the epipolar self-supervision path (lib/utils/img_utils.py
+    self_supervision: soft-argmax -> patch->image -> two-view triangulation ->
+    re-projection) entirely on the device -- the glue the released reference
+    leaves unwired;
+  * the gradient all-reduce for multi-GPU data parallelism happens inside the
+    model's backward (one NCCL call on the flat gradient buffer).
+"""
+import logging
+import time
+
+import numpy as np
+import torch
+
+from ..utils.img_utils import (self_supervision_device,
+                               trans_coords_from_patch_to_org_3d_batch)
+from .integral_loss import get_result_func
+from ..utils.utils import AverageMeter
+
+logger = logging.getLogger(__name__)
+
+
+def _online_tri(config):
+    train = getattr(config, 'TRAIN', None)
+    return bool(train is not None and getattr(train, 'ONLINE_TRIANGULATION', False))
+
+
+def train_integral(config, train_loader, model, criterion, optimizer, epoch):
+    batch_time = AverageMeter()
+    data_time = AverageMeter()
+    losses = AverageMeter()
+    model.train()
+    online = _online_tri(config)
+    method = getattr(config.TRAIN, 'TRIANGULATION_METHOD', 'iterative') if online else None
+    pending = []           # (device loss, batch size) not yet folded into `losses`
+    end = time.time()
+    for i, data in enumerate(train_loader):
+        data_time.update(time.time() - end)
+        batch_data, batch_label, batch_label_weight, meta = data
+        optimizer.zero_grad()
+        batch_data = batch_data.cuda(non_blocking=True)
+        batch_size = batch_data.size(0)
+        preds = model(batch_data)
+        if online:
+            batch_label, batch_label_weight = self_supervision_device(preds.detach(), meta, method)
+        else:
+            batch_label = batch_label.cuda(non_blocking=True)
+            batch_label_weight = batch_label_weight.cuda(non_blocking=True)
+        loss = criterion(preds, batch_label, batch_label_weight)
+        del batch_data, batch_label, batch_label_weight, preds
+        loss.backward()
+        optimizer.step()
+        pending.append((loss.detach(), batch_size))
+        del loss
+        if i % config.PRINT_FREQ == 0:
+            for lv, bs in pending:
+                losses.update(lv.item(), bs)      # the only device sync of the loop
+            pending = []
+            batch_time.update(time.time() - end)
+            msg = 'Epoch: [{0}][{1}/{2}]\t' \
+                  'Time {batch_time.val:.3f}s ({batch_time.avg:.3f}s)\t' \
+                  'Speed {speed:.1f} samples/s\t' \
+                  'Data {data_time.val:.3f}s ({data_time.avg:.3f}s)\t' \
+                  'Loss {loss.val:.5f} ({loss.avg:.5f})'.format(
+                      epoch, i, len(train_loader), batch_time=batch_time,
+                      speed=batch_size / max(batch_time.val, 1e-9),
+                      data_time=data_time, loss=losses)
+            logger.info(msg)
+        else:
+            batch_time.update(time.time() - end)
+        end = time.time()
+    for lv, bs in pending:
+        losses.update(lv.item(), bs)
+    return losses.avg
+
+
+def validate_integral(val_loader, model):
+    print("Validation stage")
+    result_func = get_result_func()
+    model.eval()
+    chunks = []
+    with torch.no_grad():
+        for i, data in enumerate(val_loader):
+            batch_data = data[0].cuda(non_blocking=True)
+            preds = model(batch_data)
+            chunks.append(result_func(256, 256, preds))     # hard-coded 256 as reference :87
+            del preds, batch_data
+    if not chunks:
+        return np.zeros((0, 0, 4))
+    out = np.concatenate(chunks, axis=0)                   # ragged last batch handled
+    return out[0:len(val_loader.dataset)]
+
+
+def eval_integral(epoch, preds_in_patch_with_score, val_loader, final_output_path, debug=False):
+    print("Evaluation stage")
+    imdb_list = val_loader.dataset.db
+    imdb = val_loader.dataset
+    n = len(val_loader.dataset)
+    get = lambda k: np.array([imdb_list[s][k] for s in range(n)], dtype=np.float64)
+    preds_in_img_with_score = trans_coords_from_patch_to_org_3d_batch(
+        np.asarray(preds_in_patch_with_score)[:n], get('center_x'), get('center_y'), get('width'),
+        get('height'), 256, 256, 2000)
+    name_value, perf = imdb.evaluate(preds_in_img_with_score.copy(), final_output_path, debug=debug)
+    for name, value in name_value:
+        logger.info('Epoch[%d] Validation-%s %f', epoch, name, value)
+    return perf

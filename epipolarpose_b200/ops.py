@@ -1,0 +1,200 @@
+"""Thin torch-tensor wrappers over the libepb.so C ABI (include/epb.h).
+
+torch is plumbing only here: it owns device memory and the current stream;
+every op below is one or more hand-written sm_100a kernels.  Each wrapper
+validates dtype / device / contiguity and raises on any failure -- there is no
+CPU or eager fallback.  `launches` counts kernel launches issued through this
+module (bench.py reports it as gpu_launches).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvGeom
+
+launches = 0
+
+# kernels launched per C-ABI call (for the gpu_launches accounting)
+_KERNELS_PER_CALL = {
+    "epb_softargmax_fwd": 2, "epb_bn_bwd_apply": 2, "epb_colsum": 3,
+}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.EpbError("tensor must live on a CUDA device (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.EpbError("expected dtype %s, got %s" % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _lib.EpbError("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _call(name, *args):
+    global launches
+    _lib.call(name, *args)
+    launches += _KERNELS_PER_CALL.get(name, 1)
+
+
+def device_check():
+    _lib.call("epb_device_check")
+
+
+# ------------------------------------------------------------------ conv family
+
+def make_geom(N, Hi, Wi, Cin, Ho, Wo, Cout, Hp, Wp, os, ph, pw, is_, taps, Tw,
+              in_relu=0, accumulate=0, precision=0):
+    """taps: list of (dh, dw, wt)."""
+    g = ConvGeom()
+    g.N, g.Hi, g.Wi, g.Cin = N, Hi, Wi, Cin
+    g.Ho, g.Wo, g.Cout = Ho, Wo, Cout
+    g.Hp, g.Wp, g.os, g.ph, g.pw, g.is_ = Hp, Wp, os, ph, pw, is_
+    g.T = len(taps)
+    if g.T > _lib.EPB_MAX_TAPS:
+        raise _lib.EpbError("too many taps")
+    for i, (dh, dw, wt) in enumerate(taps):
+        g.dh[i], g.dw[i], g.wt[i] = dh, dw, wt
+    g.Tw = Tw
+    g.in_relu, g.accumulate, g.precision = in_relu, accumulate, precision
+    return g
+
+
+def conv_fprop(g, x, w, out, in_scale=None, in_shift=None, bias=None, stats=None):
+    _call("epb_conv_fprop", ctypes.byref(g), _p(x), _p(w), _p(in_scale), _p(in_shift),
+          _p(bias), _p(out), _p(stats, torch.float64), _stream())
+
+
+def conv_wgrad(g, x, dout, dw, in_scale=None, in_shift=None):
+    _call("epb_conv_wgrad", ctypes.byref(g), _p(x), _p(dout), _p(in_scale), _p(in_shift),
+          _p(dw), _stream())
+
+
+def pack_weight(src, dst, A, B, kh, kw, swap, ypad, unpack=0):
+    _call("epb_pack_weight", _p(src), _p(dst), A, B, kh, kw, swap, ypad, unpack, _stream())
+
+
+def nchw_to_nhwc(src, dst, N, C, H, W, Cpad):
+    _call("epb_nchw_to_nhwc", _p(src), _p(dst), N, C, H, W, Cpad, _stream())
+
+
+def nhwc_to_nchw(src, dst, N, C, H, W, Cpad):
+    _call("epb_nhwc_to_nchw", _p(src), _p(dst), N, C, H, W, Cpad, _stream())
+
+
+# ------------------------------------------------------------------ BN family
+
+def channel_stats(x, M, C, stats):
+    _call("epb_channel_stats", _p(x), M, C, _p(stats, torch.float64), _stream())
+
+
+def bn_finalize(stats, M, C, gamma, beta, eps, momentum, running_mean, running_var,
+                scale, shift, mean, invstd):
+    _call("epb_bn_finalize", _p(stats, torch.float64), M, C, _p(gamma), _p(beta), eps, momentum,
+          _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd), _stream())
+
+
+def bn_eval_affine(C, gamma, beta, running_mean, running_var, eps, scale, shift):
+    _call("epb_bn_eval_affine", C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps,
+          _p(scale), _p(shift), _stream())
+
+
+def bn_act(x, scale, shift, r, rscale, rshift, relu, y, M, C):
+    _call("epb_bn_act", _p(x), _p(scale), _p(shift), _p(r), _p(rscale), _p(rshift), int(relu),
+          _p(y), M, C, _stream())
+
+
+def bn_relu_maxpool(x, scale, shift, y, argidx, N, H, W, C):
+    _call("epb_bn_relu_maxpool", _p(x), _p(scale), _p(shift), _p(y), _p(argidx, torch.uint8),
+          N, H, W, C, _stream())
+
+
+def maxpool_bwd(dy, argidx, dx, N, H, W, C):
+    _call("epb_maxpool_bwd", _p(dy), _p(argidx, torch.uint8), _p(dx), N, H, W, C, _stream())
+
+
+def bn_bwd_reduce(dy, x, y_out, scale, shift, mean, invstd, relu, M, C, sums):
+    _call("epb_bn_bwd_reduce", _p(dy), _p(x), _p(y_out), _p(scale), _p(shift), _p(mean),
+          _p(invstd), int(relu), M, C, _p(sums, torch.float64), _stream())
+
+
+def bn_bwd_apply(dy, x, y_out, scale, shift, mean, invstd, gamma, relu, sums, M, C, dx,
+                 dgamma, dbeta):
+    _call("epb_bn_bwd_apply", _p(dy), _p(x), _p(y_out), _p(scale), _p(shift), _p(mean),
+          _p(invstd), _p(gamma), int(relu), _p(sums, torch.float64), M, C, _p(dx), _p(dgamma),
+          _p(dbeta), _stream())
+
+
+def add_masked(a, b, mask_src, dx, n):
+    _call("epb_add_masked", _p(a), _p(b), _p(mask_src), _p(dx), n, _stream())
+
+
+def avgpool(x, y, N, HW, C):
+    _call("epb_avgpool", _p(x), _p(y), N, HW, C, _stream())
+
+
+def avgpool_bwd(dy, dx, N, HW, C, accumulate):
+    _call("epb_avgpool_bwd", _p(dy), _p(dx), N, HW, C, int(accumulate), _stream())
+
+
+def colsum(x, M, C, out):
+    _call("epb_colsum", _p(x), M, C, _p(out), _stream())
+
+
+# ------------------------------------------------------------------ decode / loss
+
+def softargmax_fwd(logits, layout, N, J, D, H, W, coords, lse):
+    _call("epb_softargmax_fwd", _p(logits), layout, N, J, D, H, W, _p(coords), _p(lse), _stream())
+
+
+def softargmax_bwd(logits, layout, N, J, D, H, W, coords, lse, dcoords, dlogits):
+    _call("epb_softargmax_bwd", _p(logits), layout, N, J, D, H, W, _p(coords), _p(lse),
+          _p(dcoords), _p(dlogits), _stream())
+
+
+def jointloss(x, t, w, n, kind, norm, div, loss, dx):
+    _call("epb_jointloss_fwd_bwd", _p(x), _p(t), _p(w), n, kind, int(norm), float(div),
+          _p(loss), _p(dx), _stream())
+
+
+def argmax2d(hm, NJ, H, W, idx, maxval, preds):
+    _call("epb_argmax2d", _p(hm), NJ, H, W, _p(idx, torch.int32), _p(maxval), _p(preds), _stream())
+
+
+# ------------------------------------------------------------------ geometry (fp64)
+
+def patch_to_image(coords, box, B, J, patch_w, patch_h, rect3d_w, kps):
+    _call("epb_patch_to_image", _p(coords), _p(box, torch.float64), B, J, float(patch_w),
+          float(patch_h), float(rect3d_w), _p(kps, torch.float64), _stream())
+
+
+def triangulate(u1, u2, stride_u, P1, P2, NP, J, method, tol, X, status):
+    _call("epb_triangulate", _p(u1, torch.float64), _p(u2, torch.float64), stride_u,
+          _p(P1, torch.float64), _p(P2, torch.float64), NP, J, method, float(tol),
+          _p(X, torch.float64), _p(status, torch.int32), _stream())
+
+
+def project_labels(X, cam, box, B, J, patch_w, patch_h, rect3d_w, label, weight):
+    _call("epb_project_labels", _p(X, torch.float64), _p(cam, torch.float64),
+          _p(box, torch.float64), B, J, float(patch_w), float(patch_h), float(rect3d_w),
+          _p(label), _p(weight), _stream())
+
+
+# ------------------------------------------------------------------ optimiser
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step,
+              grad_scale=1.0):
+    _call("epb_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, lr, beta1, beta2,
+          eps, weight_decay, step, grad_scale, _stream())
+
+
+def sgd_step(param, grad, buf, n, lr, momentum, weight_decay, nesterov, first_step,
+             grad_scale=1.0):
+    _call("epb_sgd_step", _p(param), _p(grad), _p(buf), n, lr, momentum, weight_decay,
+          int(nesterov), int(first_step), grad_scale, _stream())

@@ -1,0 +1,243 @@
+/*
+ * epb.h -- C ABI of libepb.so, the B200 (sm_100a) implementation of the
+ * EpipolarPose training-loop hot path.
+ *
+ * The reference (mkocabas/EpipolarPose) has no FFI layer: its extension points
+ * are Python call sites that reach cuDNN / ATen / numpy / OpenCV.  Each entry
+ * point below replaces one of those library call sites; the comment on each
+ * names the reference file:line whose arithmetic it reproduces.  The Python
+ * mirror of the reference interface (epipolarpose_b200/lib/...) binds these
+ * symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *     the caller owns all memory; the library never allocates caller-visible
+ *     memory and never synchronises the device;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - activations are NHWC float32 ("pixel rows"), row pitch == channel count;
+ *     packed weights are [Cout][T][Cin] float32 (T = taps);
+ *   - return value: 0 on success, negative EPB_E* otherwise; the message is
+ *     available from epb_last_error() (thread local);
+ *   - alignment: all float buffers 16-byte aligned, channel counts that feed
+ *     the tensor-core path are multiples of 32.
+ */
+#ifndef EPB_H_
+#define EPB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPB_OK 0
+#define EPB_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define EPB_ECUDA (-2)    /* a CUDA runtime / driver call failed          */
+#define EPB_ENOGPU (-3)   /* no sm_100 device present                     */
+
+#define EPB_MAX_TAPS 64
+
+typedef void* epb_stream_t;
+
+int epb_version(void);
+const char* epb_last_error(void);
+/* 0 if a compute-capability 10.x device is usable, EPB_ENOGPU otherwise */
+int epb_device_check(void);
+
+/* ------------------------------------------------------------------------
+ * Convolution family (cuDNN call sites behind nn.Conv2d / nn.ConvTranspose2d:
+ * lib/models/pose3d_resnet.py:12-15,55-60,99,116-122,132,171-178).
+ *
+ * One "tap-list implicit GEMM" geometry expresses forward convs, transposed
+ * convs (one call per output phase), and both of their data gradients:
+ *
+ *   out[n, i*os+ph, j*os+pw, co] (+)= sum_t sum_ci
+ *        f(in[n, i*is+dh[t], j*is+dw[t], ci]) * w[co][wt[t]][ci]   (+ bias[co])
+ *
+ * for i<Hp, j<Wp (the phase grid), out-of-range input pixels contribute 0.
+ * f is identity, or the fused BatchNorm+ReLU of the producing layer
+ * (relu(in*in_scale[ci] + in_shift[ci])) when in_scale != NULL.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int N, Hi, Wi, Cin;        /* input tensor  [N,Hi,Wi,Cin]                 */
+  int Ho, Wo, Cout;          /* output tensor [N,Ho,Wo,Cout]                */
+  int Hp, Wp;                /* phase grid (== Ho,Wo when os == 1)          */
+  int os, ph, pw;            /* output stride and phase offset              */
+  int is;                    /* input stride                                */
+  int T;                     /* number of taps                              */
+  int dh[EPB_MAX_TAPS];      /* input row offset per tap                    */
+  int dw[EPB_MAX_TAPS];      /* input col offset per tap                    */
+  int wt[EPB_MAX_TAPS];      /* index of the tap inside the packed weight   */
+  int Tw;                    /* taps in the packed weight (row = Tw*Cin)    */
+  int in_relu;               /* 1: relu after the input affine              */
+  int accumulate;            /* 1: out += result (beta = 1)                 */
+  int precision;             /* 0: fp32 SIMT, 1: tf32 (1 pass), 3: tf32x3   */
+} epb_conv_geom;
+
+/* out = conv(in) ; optional fused input BN+ReLU, bias, per-channel
+ * statistics of the output (stats[0..Cout) += sum, stats[Cout..2Cout) +=
+ * sum of squares, float64, caller zeroes).  Any of in_scale/in_shift/bias/
+ * stats may be NULL. */
+int epb_conv_fprop(const epb_conv_geom* g, const float* in, const float* w,
+                   const float* in_scale, const float* in_shift,
+                   const float* bias, float* out, double* stats,
+                   epb_stream_t stream);
+
+/* dw[co][wt[t]][ci] += sum_{n,i,j} dout[n,i*os+ph,j*os+pw,co] * f(in[...tap t...][ci])
+ * (cuDNN wgrad).  dw must be zeroed by the caller before the first phase. */
+int epb_conv_wgrad(const epb_conv_geom* g, const float* in, const float* dout,
+                   const float* in_scale, const float* in_shift, float* dw,
+                   epb_stream_t stream);
+
+/* Weight layout conversion between the reference's state_dict layouts
+ * (Conv2d [O][I][kh][kw], ConvTranspose2d [I][O][kh][kw]) and the packed GEMM
+ * operand.  src is [A][B][kh*kw]; packed is [X][kh*kw][Ypad] with
+ * (X,Y) = (A,B) when swap == 0 and (B,A) when swap == 1, zero padded to Ypad.
+ *   Conv2d fprop: swap 0 (X=O,Y=I)      Conv2d dgrad:   swap 1 (X=I,Y=O)
+ *   Deconv fprop: swap 1 (X=O,Y=I)      Deconv dgrad:   swap 0 (X=I,Y=O)
+ * No spatial flip: the tap tables in epb_conv_geom index taps by the original
+ * (r,s).  unpack != 0 runs the inverse map (packed gradient -> state_dict
+ * layout; `src` is then the packed tensor). */
+int epb_pack_weight(const float* src, float* dst, int A, int B, int kh, int kw,
+                    int swap, int Ypad, int unpack, epb_stream_t stream);
+
+/* NCHW <-> NHWC float32 with channel padding (module boundary only:
+ * pose3d_resnet.py:185 takes NCHW images, returns NCHW heatmaps). */
+int epb_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W,
+                     int Cpad, epb_stream_t stream);
+int epb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W,
+                     int Cpad, epb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * BatchNorm2d(momentum=0.1, eps=1e-5) training semantics (cuDNN BN call
+ * sites: pose3d_resnet.py:24,56-63,101,134,179), ReLU, residual add, MaxPool.
+ * ---------------------------------------------------------------------- */
+/* per-channel sum / sum-of-squares of x[M][C] into stats[2C] (float64, +=) */
+int epb_channel_stats(const float* x, int64_t M, int C, double* stats,
+                      epb_stream_t stream);
+/* stats -> (scale, shift, mean, invstd) and running-stat update (biased var
+ * for normalisation, unbiased for running_var; pose3d_resnet.py:8). */
+int epb_bn_finalize(const double* stats, int64_t M, int C, const float* gamma,
+                    const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var, float* scale,
+                    float* shift, float* mean, float* invstd,
+                    epb_stream_t stream);
+/* eval mode: scale/shift from running statistics */
+int epb_bn_eval_affine(int C, const float* gamma, const float* beta,
+                       const float* running_mean, const float* running_var,
+                       float eps, float* scale, float* shift,
+                       epb_stream_t stream);
+/* y = act(x*scale+shift [+ r*rscale+rshift | + r]) ; r may be NULL, rscale
+ * NULL means identity residual (pose3d_resnet.py:44-45,85-86). */
+int epb_bn_act(const float* x, const float* scale, const float* shift,
+               const float* r, const float* rscale, const float* rshift,
+               int relu, float* y, int64_t M, int C, epb_stream_t stream);
+/* stem: y = maxpool3x3s2p1(relu(x*scale+shift)) (pose3d_resnet.py:187-189);
+ * also records the argmax position (0..8) for the backward. */
+int epb_bn_relu_maxpool(const float* x, const float* scale, const float* shift,
+                        float* y, uint8_t* argidx, int N, int H, int W, int C,
+                        epb_stream_t stream);
+int epb_maxpool_bwd(const float* dy, const uint8_t* argidx, float* dx, int N,
+                    int H, int W, int C, epb_stream_t stream);
+/* BatchNorm(+ReLU) backward, two passes.
+ *   g = dy * [mask]   where mask = (y_out > 0) if y_out != NULL, else
+ *                     (x*scale+shift > 0) if relu, else 1
+ * reduce: sums[0..C) += sum g ; sums[C..2C) += sum g * xhat   (float64)
+ * apply : dx = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M); dgamma, dbeta out */
+int epb_bn_bwd_reduce(const float* dy, const float* x, const float* y_out,
+                      const float* scale, const float* shift, const float* mean,
+                      const float* invstd, int relu, int64_t M, int C,
+                      double* sums, epb_stream_t stream);
+int epb_bn_bwd_apply(const float* dy, const float* x, const float* y_out,
+                     const float* scale, const float* shift, const float* mean,
+                     const float* invstd, const float* gamma, int relu,
+                     const double* sums, int64_t M, int C, float* dx,
+                     float* dgamma, float* dbeta, epb_stream_t stream);
+/* dx = a + b * [mask_src > 0] (residual gradient merge); mask_src may be NULL */
+int epb_add_masked(const float* a, const float* b, const float* mask_src,
+                   float* dx, int64_t n, epb_stream_t stream);
+/* VOLUME=False head: y[n][c] = mean over HW (pose3d_resnet.py:125,208) */
+int epb_avgpool(const float* x, float* y, int N, int HW, int C,
+                epb_stream_t stream);
+int epb_avgpool_bwd(const float* dy, float* dx, int N, int HW, int C,
+                    int accumulate, epb_stream_t stream);
+/* column sums of x[M][C] (bias gradients): out[c] = sum_m x[m][c] */
+int epb_colsum(const float* x, int64_t M, int C, float* out,
+               epb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Soft-argmax (ATen softmax + 9 reductions: lib/core/integral_loss.py:49-86)
+ * logits: volume per (n,j) of D*H*W float32.  layout 0 = NCHW contiguous
+ * ([N][J*D][H][W]); layout 1 = NHWC ([N][H][W][J*D]).
+ * coords: [N][J*3] float32 (x,y,z interleaved, in [-0.5,0.5)).
+ * lse_ws: [N*J*2] float32 workspace written by fwd (max, sum) and consumed by
+ * bwd so the backward is a single pass.
+ * ---------------------------------------------------------------------- */
+int epb_softargmax_fwd(const float* logits, int layout, int N, int J, int D,
+                       int H, int W, float* coords, float* lse_ws,
+                       epb_stream_t stream);
+/* dlogits = p * (s - sum p s),  s = gx*x/W + gy*y/H + gz*z/D */
+int epb_softargmax_bwd(const float* logits, int layout, int N, int J, int D,
+                       int H, int W, const float* coords, const float* lse_ws,
+                       const float* dcoords, float* dlogits,
+                       epb_stream_t stream);
+
+/* Fused joint-location loss (integral_loss.py:7-47): kind 0 = weighted MSE,
+ * 1 = weighted L1, 2 = weighted SmoothL1(beta=1).  loss = sum(w*l(x-t))/div,
+ * dx = dloss/dx.  norm != 0: x,t divided by their global L1 norms first
+ * (integral_loss.py:9-11).  n = N*J*3 elements (single CTA; n is tiny). */
+int epb_jointloss_fwd_bwd(const float* x, const float* t, const float* w, int n,
+                          int kind, int norm, float div, float* loss, float* dx,
+                          epb_stream_t stream);
+
+/* Hard argmax (numpy call site lib/core/inference.py:24-39).  hm [NJ][HW]
+ * float32 contiguous.  idx: flat first-max index (int32), maxval float32,
+ * preds [NJ][2] float32 = (idx%W, idx/W) * (max > 0). */
+int epb_argmax2d(const float* hm, int NJ, int H, int W, int32_t* idx,
+                 float* maxval, float* preds, epb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Epipolar geometry in float64 (OpenCV/numpy call sites).
+ * ---------------------------------------------------------------------- */
+/* lib/core/integral_loss.py:196-205 + lib/utils/img_utils.py:141-155:
+ * coords [B][J*3] f32 (soft-argmax output) -> image-frame keypoints
+ * kps [B][J][4] f64 = (affine_inv(x,y), z*2000/.., 1).  box [B][6] f64 =
+ * (c_x, c_y, width, height, scale, rot). */
+int epb_patch_to_image(const float* coords, const double* box, int B, int J,
+                       double patch_w, double patch_h, double rect3d_w,
+                       double* kps, epb_stream_t stream);
+/* lib/utils/triangulation.py: u1,u2 [NP][J][stride_u] f64 (first two entries
+ * used), P1,P2 [NP][12] f64 row-major 3x4.  X [NP][J][3] f64, status [NP][J].
+ * method 0: linear-eigen homogeneous DLT (:8-27, cv2.triangulatePoints);
+ * method 1: linear LS (:34-97); method 2: iterative LS, 10 cumulative
+ * re-weighting rounds, tol 3e-5 (:104-181). */
+int epb_triangulate(const double* u1, const double* u2, int stride_u,
+                    const double* P1, const double* P2, int NP, int J,
+                    int method, double tol, double* X, int32_t* status,
+                    epb_stream_t stream);
+/* lib/utils/img_utils.py:212-243 + lib/utils/prep_h36m.py:170-204 +
+ * integral_loss.py:170-177: X [B][J][3] world -> label,weight [B][J*3] f32.
+ * cam [B][16] f64 = R(9) T(3) f(2) c(2); box as above. */
+int epb_project_labels(const double* X, const double* cam, const double* box,
+                       int B, int J, double patch_w, double patch_h,
+                       double rect3d_w, float* label, float* weight,
+                       epb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Optimiser (torch.optim.Adam call site lib/utils/utils.py:56-60; betas
+ * (0.9,0.999), eps 1e-8, no weight decay) over one flat parameter buffer.
+ * step is the 1-based step count.  grad_scale multiplies the gradient first
+ * (1/world_size after the NCCL sum).
+ * ---------------------------------------------------------------------- */
+int epb_adam_step(float* param, const float* grad, float* exp_avg,
+                  float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step,
+                  float grad_scale, epb_stream_t stream);
+int epb_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n,
+                 float lr, float momentum, float weight_decay, int nesterov,
+                 int first_step, float grad_scale, epb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPB_H_ */

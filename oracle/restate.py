@@ -1,0 +1,416 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy / torch-CPU fp32) of the
+EpipolarPose hot path.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module; the product path
+(epipolarpose_b200/*) never does and fails loudly without its CUDA library.
+
+Every function cites the reference file:line it restates (paths relative to
+the reference root).  Pinning: tests/golden/*.npz were produced by running the
+UNMODIFIED reference (oracle/refshim.py) in the build container with
+tests/golden/make_golden.py; tests/test_oracle_pinned.py checks each function
+below against those vectors, so the restatement is pinned to the reference's
+own outputs (the reference ships no tests / golden vectors of its own:
+SURVEY.md section 4).  Third-party arithmetic (OpenCV 4.x triangulatePoints /
+solve(DECOMP_SVD) / getAffineTransform; pinned opencv=4.1.0 in the reference's
+environment.yml:96, 4.13.0 executed here) is restated with numpy.linalg in
+float64 and pinned through the same golden vectors.
+"""
+import math
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# a7: soft-argmax  (lib/core/integral_loss.py:49-86)
+# --------------------------------------------------------------------------
+
+
+def softmax_integral(preds, num_joints, hm_width, hm_height, hm_depth):
+    """preds [N, J*D, H, W] float32 -> [N, J*3] float32 (x,y,z interleaved).
+
+    integral_loss.py:71-86: softmax over D*H*W per (n,j) (:73-74), marginal
+    expectations with channel order [j][z][y][x] (:52), index ranges 0..dim-1
+    (:61-63), then coord/dim - 0.5 (:81-83), cat on dim 2 (:84-85).
+    float32 arithmetic as in the reference (torch CPU); accumulation order
+    differs from ATen, so agreement is to ~1e-6 abs, not bit-exact."""
+    p = np.asarray(preds, dtype=np.float32)
+    n = p.shape[0]
+    v = p.reshape(n, num_joints, -1).astype(np.float64)
+    v = v - v.max(axis=2, keepdims=True)
+    e = np.exp(v)
+    sm = (e / e.sum(axis=2, keepdims=True))
+    sm = sm.reshape(n, num_joints, hm_depth, hm_height, hm_width)
+    ax = sm.sum(axis=(2, 3)) @ np.arange(hm_width, dtype=np.float64)
+    ay = sm.sum(axis=(2, 4)) @ np.arange(hm_height, dtype=np.float64)
+    az = sm.sum(axis=(3, 4)) @ np.arange(hm_depth, dtype=np.float64)
+    x = ax / float(hm_width) - 0.5
+    y = ay / float(hm_height) - 0.5
+    z = az / float(hm_depth) - 0.5
+    out = np.stack([x, y, z], axis=2).reshape(n, num_joints * 3)
+    return out.astype(np.float32)
+
+
+def softmax_integral_grad(preds, grad_out, num_joints, hm_width, hm_height, hm_depth):
+    """d(sum(out*grad_out))/d(preds): analytic backward of softmax_integral
+    (what autograd produces through integral_loss.py:71-86).
+    dL/dlogit_i = p_i * (g.c_i - sum_k p_k g.c_k) with c_i = (x/W, y/H, z/D)."""
+    p = np.asarray(preds, dtype=np.float32)
+    n = p.shape[0]
+    v = p.reshape(n, num_joints, -1).astype(np.float64)
+    v = v - v.max(axis=2, keepdims=True)
+    e = np.exp(v)
+    sm = (e / e.sum(axis=2, keepdims=True)).reshape(
+        n, num_joints, hm_depth, hm_height, hm_width)
+    g = np.asarray(grad_out, dtype=np.float64).reshape(n, num_joints, 3)
+    ix = np.arange(hm_width, dtype=np.float64) / hm_width
+    iy = np.arange(hm_height, dtype=np.float64) / hm_height
+    iz = np.arange(hm_depth, dtype=np.float64) / hm_depth
+    s = (g[:, :, 0, None, None, None] * ix[None, None, None, None, :]
+         + g[:, :, 1, None, None, None] * iy[None, None, None, :, None]
+         + g[:, :, 2, None, None, None] * iz[None, None, :, None, None])
+    mean = (sm * s).sum(axis=(2, 3, 4), keepdims=True)
+    return (sm * (s - mean)).reshape(p.shape).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# a9: weighted losses  (lib/core/integral_loss.py:7-47)
+# --------------------------------------------------------------------------
+
+def weighted_loss(kind, inp, target, weights, size_average=True, norm=False):
+    """kind in {'mse','l1','smoothl1'}; integral_loss.py:7-18 / 20-31 / 33-47.
+    Divisor is len(input) = batch size (:16,29,45).  Returns (loss, dL/dinput)
+    in float64 for checking (reference computes in float32)."""
+    x = np.asarray(inp, dtype=np.float64)
+    t = np.asarray(target, dtype=np.float64)
+    w = np.asarray(weights, dtype=np.float64)
+    sx = st = 1.0
+    if norm:  # :9-11 divide each by its global L1 norm
+        sx = np.abs(x).sum()
+        st = np.abs(t).sum()
+    xn, tn = x / sx, t / st
+    d = xn - tn
+    if kind == "mse":
+        out, dd = d * d, 2 * d
+    elif kind == "l1":
+        out, dd = np.abs(d), np.sign(d)
+    elif kind == "smoothl1":
+        a = np.abs(d)
+        out = np.where(a < 1.0, 0.5 * d * d, a - 0.5)
+        dd = np.where(a < 1.0, d, np.sign(d))
+    else:
+        raise ValueError(kind)
+    div = float(len(x)) if size_average else 1.0
+    loss = (out * w).sum() / div
+    gxn = dd * w / div
+    if norm:
+        # d(x/||x||_1)/dx = I/s - x sign(x)^T / s^2
+        gx = gxn / sx - np.sign(x) * (gxn * x).sum() / (sx * sx)
+    else:
+        gx = gxn
+    return loss, gx
+
+
+# --------------------------------------------------------------------------
+# a8: hard argmax  (lib/core/inference.py:12-40)
+# --------------------------------------------------------------------------
+
+def get_max_preds(batch_heatmaps):
+    """inference.py:12-40: flat argmax (first index on ties) -> (x=idx%W,
+    y=floor(idx/W)) float32, masked to 0 where max<=0 (:35-39)."""
+    hm = np.asarray(batch_heatmaps)
+    n, j, h, w = hm.shape
+    flat = hm.reshape(n, j, -1)
+    idx = np.argmax(flat, axis=2)
+    maxvals = np.max(flat, axis=2).reshape(n, j, 1)
+    preds = np.zeros((n, j, 2), dtype=np.float32)
+    preds[:, :, 0] = (idx % w).astype(np.float32)
+    preds[:, :, 1] = np.floor(idx.astype(np.float32) / w)
+    preds *= (maxvals > 0.0).astype(np.float32)
+    return preds, maxvals, idx
+
+
+def final_preds_refine(batch_heatmaps, coords):
+    """inference.py:49-61 (+-0.25 px toward the higher neighbour)."""
+    hm = np.asarray(batch_heatmaps)
+    n, j, h, w = hm.shape
+    c = np.array(coords, dtype=np.float32, copy=True)
+    for a in range(n):
+        for b in range(j):
+            px = int(math.floor(c[a, b, 0] + 0.5))
+            py = int(math.floor(c[a, b, 1] + 0.5))
+            if 1 < px < w - 1 and 1 < py < h - 1:
+                diff = np.array([hm[a, b, py, px + 1] - hm[a, b, py, px - 1],
+                                 hm[a, b, py + 1, px] - hm[a, b, py - 1, px]])
+                c[a, b] += np.sign(diff) * .25
+    return c
+
+
+# --------------------------------------------------------------------------
+# a10: decode  (lib/core/integral_loss.py:187-207)
+# --------------------------------------------------------------------------
+
+def joint_location_result(patch_width, patch_height, coords_norm):
+    """coords_norm [N, J*3] float32 (output of softmax_integral) ->
+    [N,J,4] float64: (x+.5)*pw, (y+.5)*ph, z*pw, score 1 (:196-205)."""
+    c = np.asarray(coords_norm).astype(float)
+    c = c.reshape(c.shape[0], c.shape[1] // 3, 3).copy()
+    c[:, :, 0] = (c[:, :, 0] + 0.5) * patch_width
+    c[:, :, 1] = (c[:, :, 1] + 0.5) * patch_height
+    c[:, :, 2] = c[:, :, 2] * patch_width
+    return np.concatenate([c, np.ones(c.shape[:2] + (1,))], axis=2)
+
+
+# --------------------------------------------------------------------------
+# a11: patch <-> image affine  (lib/utils/img_utils.py:63-111,141-155)
+# --------------------------------------------------------------------------
+
+def _affine_from_3pts(src, dst):
+    """Restates cv2.getAffineTransform (OpenCV imgproc/imgwarp.cpp): the 2x3
+    float64 M with M*[sx,sy,1]^T = [dx,dy]^T for three float32 point pairs.
+    Solved in float64 (OpenCV: 6x6 LU in double)."""
+    s = np.asarray(src, dtype=np.float32).astype(np.float64)
+    d = np.asarray(dst, dtype=np.float32).astype(np.float64)
+    a = np.concatenate([s, np.ones((3, 1))], axis=1)  # 3x3
+    m = np.linalg.solve(a, d)  # 3x2
+    return m.T.copy()
+
+
+def gen_trans_from_patch(c_x, c_y, src_width, src_height, dst_width, dst_height,
+                         scale, rot, inv=False):
+    """img_utils.py:72-105 incl. its float32 roundings: rotate_2d returns f32
+    (:69), src/dst point arrays are f32 (:91-99)."""
+    src_w = src_width * scale
+    src_h = src_height * scale
+    src_center = np.array([c_x, c_y], dtype=np.float64)
+    rot_rad = np.pi * rot / 180
+
+    def rotate_2d(pt, r):  # :63-69 (inputs are f32 arrays, math in f32*f64 -> f64, cast f32)
+        x, y = pt[0], pt[1]
+        sn, cs = np.sin(r), np.cos(r)
+        return np.array([x * cs - y * sn, x * sn + y * cs], dtype=np.float32)
+
+    src_downdir = rotate_2d(np.array([0, src_h * 0.5], dtype=np.float32), rot_rad)
+    src_rightdir = rotate_2d(np.array([src_w * 0.5, 0], dtype=np.float32), rot_rad)
+    dst_center = np.array([dst_width * 0.5, dst_height * 0.5], dtype=np.float32)
+    dst_downdir = np.array([0, dst_height * 0.5], dtype=np.float32)
+    dst_rightdir = np.array([dst_width * 0.5, 0], dtype=np.float32)
+    src = np.zeros((3, 2), dtype=np.float32)
+    src[0, :] = src_center
+    src[1, :] = src_center + src_downdir
+    src[2, :] = src_center + src_rightdir
+    dst = np.zeros((3, 2), dtype=np.float32)
+    dst[0, :] = dst_center
+    dst[1, :] = dst_center + dst_downdir
+    dst[2, :] = dst_center + dst_rightdir
+    if inv:
+        return _affine_from_3pts(dst, src)
+    return _affine_from_3pts(src, dst)
+
+
+def trans_coords_from_patch_to_org_3d(coords_in_patch, c_x, c_y, bb_w, bb_h,
+                                      patch_w, patch_h, rect_3d_w, rect_3d_h,
+                                      scale=1.0, rot=0):
+    """img_utils.py:141-155."""
+    out = np.array(coords_in_patch, dtype=np.float64, copy=True)
+    t = gen_trans_from_patch(c_x, c_y, bb_w, bb_h, patch_w, patch_h, scale, rot, inv=True)
+    xy1 = np.concatenate([out[:, 0:2], np.ones((out.shape[0], 1))], axis=1)
+    out[:, 0:2] = xy1 @ t.T
+    out[:, 2] = np.asarray(coords_in_patch)[:, 2] / patch_w * rect_3d_w
+    return out
+
+
+# --------------------------------------------------------------------------
+# a13: triangulators  (lib/utils/triangulation.py)
+# --------------------------------------------------------------------------
+
+def linear_eigen_triangulation(u1, P1, u2, P2, max_coordinate_value=1.e16):
+    """triangulation.py:8-27 = cv2.triangulatePoints (OpenCV
+    calib3d/triangulate.cpp icvTriangulatePoints): per point the 4x4 matrix
+    A with rows  x*P[2]-P[0], y*P[2]-P[1]  for each view; homogeneous solution
+    = right-singular vector of the smallest singular value; then /w (:24)."""
+    u1 = np.asarray(u1, dtype=np.float64)
+    u2 = np.asarray(u2, dtype=np.float64)
+    P = [np.asarray(P1, dtype=np.float64)[0:3, 0:4], np.asarray(P2, dtype=np.float64)[0:3, 0:4]]
+    n = len(u1)
+    X = np.zeros((n, 3))
+    for i in range(n):
+        A = np.zeros((4, 4))
+        for v, u in enumerate((u1[i], u2[i])):
+            A[2 * v + 0] = u[0] * P[v][2] - P[v][0]
+            A[2 * v + 1] = u[1] * P[v][2] - P[v][1]
+        _, _, vt = np.linalg.svd(A)
+        h = vt[-1]
+        X[i] = h[0:3] / h[3]
+    with np.errstate(invalid="ignore"):
+        status = np.max(np.abs(X), axis=1) <= max_coordinate_value
+    return X, status
+
+
+def _build_Ab(u1, P1, u2, P2):
+    """triangulation.py:139-150 (= :80-92): A rows C*P[:3,:3], b = -C*P[:3,3]
+    with C = [[-1,0,u],[0,-1,v]]."""
+    A = np.zeros((4, 3))
+    b = np.zeros(4)
+    for v, (u, P) in enumerate(((u1, P1), (u2, P2))):
+        C = np.array([[-1.0, 0.0, u[0]], [0.0, -1.0, u[1]]])
+        A[2 * v:2 * v + 2] = C @ P[0:3, 0:3]
+        b[2 * v:2 * v + 2] = -(C @ P[0:3, 3])
+    return A, b
+
+
+def linear_LS_triangulation(u1, P1, u2, P2):
+    """triangulation.py:34-97; cv2.solve(DECOMP_SVD) == least squares."""
+    u1 = np.asarray(u1, dtype=np.float64)
+    u2 = np.asarray(u2, dtype=np.float64)
+    P1 = np.asarray(P1, dtype=np.float64)
+    P2 = np.asarray(P2, dtype=np.float64)
+    X = np.zeros((len(u1), 3))
+    for i in range(len(u1)):
+        A, b = _build_Ab(u1[i], P1, u2[i], P2)
+        X[i] = np.linalg.lstsq(A, b, rcond=None)[0]
+    return X, np.ones(len(u1), dtype=bool)
+
+
+def iterative_LS_triangulation(u1, P1, u2, P2, tolerance=3.e-5):
+    """triangulation.py:104-181, including the CUMULATIVE re-weighting of A,b
+    (:165-169 multiply the already re-weighted rows again) and the status
+    arithmetic (:175-178; `i < 10` is always true)."""
+    u1 = np.asarray(u1, dtype=np.float64)
+    u2 = np.asarray(u2, dtype=np.float64)
+    P1 = np.asarray(P1, dtype=np.float64)
+    P2 = np.asarray(P2, dtype=np.float64)
+    n = len(u1)
+    X = np.zeros((n, 3))
+    status = np.zeros(n, dtype=int)
+    for xi in range(n):
+        A, b = _build_Ab(u1[xi], P1, u2[xi], P2)
+        d1 = d2 = 1.0
+        x = np.zeros(3)
+        d1n = d2n = 1.0
+        for _ in range(10):
+            x = np.linalg.lstsq(A, b, rcond=None)[0]
+            xh = np.array([x[0], x[1], x[2], 1.0])
+            d1n = P1[2, :].dot(xh)
+            d2n = P2[2, :].dot(xh)
+            if abs(d1n - d1) <= tolerance and abs(d2n - d2) <= tolerance:
+                break
+            A[0:2] *= 1 / d1n
+            A[2:4] *= 1 / d2n
+            b[0:2] *= 1 / d1n
+            b[2:4] *= 1 / d2n
+            d1, d2 = d1n, d2n
+        X[xi] = x
+        st = int(d1n > 0 and d2n > 0)
+        if d1n <= 0:
+            st -= 1
+        if d2n <= 0:
+            st -= 2
+        status[xi] = st
+    return X, status
+
+
+# --------------------------------------------------------------------------
+# a6/a12/a14/a15: cameras, pairing, projection to labels, self_supervision
+# --------------------------------------------------------------------------
+
+def projection_matrix(R, T, f, c):
+    """lib/utils/cameras.py:120-131,149-150: K.[R | R.(-T)] float64 3x4."""
+    R = np.asarray(R, dtype=np.float64)
+    T = np.asarray(T, dtype=np.float64).reshape(3, 1)
+    K = np.array([[f[0], 0., c[0]], [0., f[1], c[1]], [0., 0., 1.]], dtype=np.float64)
+    return K @ np.concatenate([R, R @ (-T)], axis=1)
+
+
+def triangulate_batch(kps, Pmats, method="iterative"):
+    """lib/utils/img_utils.py:193-209: sample i pairs with i + B/2; result
+    duplicated for both halves (:207-208)."""
+    fn = iterative_LS_triangulation if method == "iterative" else linear_eigen_triangulation
+    half = kps.shape[0] // 2
+    out = []
+    for i in range(half):
+        x, _ = fn(kps[i, :, 0:2], Pmats[i], kps[half + i, :, 0:2], Pmats[half + i])
+        out.append(x)
+    out = np.asarray(out)
+    return np.vstack([out, out])
+
+
+def labels_from_global_coords(X, meta):
+    """lib/utils/img_utils.py:212-243 + lib/utils/prep_h36m.py:170-204 +
+    lib/core/integral_loss.py:170-177.  meta: dict of arrays
+    scale, rot, center_x, center_y, width, height, T[B,3(,1)], R[B,3,3], f[B,2], c[B,2]."""
+    B, J = X.shape[0], X.shape[1]
+    label = np.zeros((B, J * 3), dtype=np.float32)
+    weight = np.ones((B, J * 3), dtype=np.float32)
+    for i in range(B):
+        R = np.asarray(meta["R"][i], dtype=np.float64)
+        T = np.asarray(meta["T"][i], dtype=np.float64).reshape(3)
+        f = np.asarray(meta["f"][i], dtype=np.float64).reshape(2)
+        c = np.asarray(meta["c"][i], dtype=np.float64).reshape(2)
+        cam = (X[i] - T) @ R.T                       # prep_h36m.py:186
+        jt = np.zeros((J, 3))
+        jt[:, 0] = cam[:, 0] / cam[:, 2] * f[0] + c[0]   # CamProj :170-175
+        jt[:, 1] = cam[:, 1] / cam[:, 2] * f[1] + c[1]
+        jt[:, 2] = cam[:, 2] - cam[0, 2]             # :199 (root joint 0)
+        scale = float(meta["scale"][i])
+        t = gen_trans_from_patch(float(meta["center_x"][i]), float(meta["center_y"][i]),
+                                 float(meta["width"][i]), float(meta["height"][i]),
+                                 256, 256, scale, float(meta["rot"][i]), inv=False)
+        xy1 = np.concatenate([jt[:, 0:2], np.ones((J, 1))], axis=1)
+        jt[:, 0:2] = xy1 @ t.T                       # img_utils.py:234-235
+        jt[:, 2] = jt[:, 2] / (2000. * scale) * 256.  # :236
+        jt[:, 0] = jt[:, 0] / 256. - 0.5             # integral_loss.py:171-173
+        jt[:, 1] = jt[:, 1] / 256. - 0.5
+        jt[:, 2] = jt[:, 2] / 256.
+        label[i] = jt.reshape(-1).astype(np.float32)
+    return label, weight
+
+
+def self_supervision(coords_norm, meta, method="iterative"):
+    """lib/utils/img_utils.py:166-190 downstream of the soft-argmax:
+    coords_norm [B, J*3] f32 -> (label, weight) [B, J*3] f32."""
+    res = joint_location_result(256, 256, coords_norm)
+    B = res.shape[0]
+    img = np.stack([
+        trans_coords_from_patch_to_org_3d(
+            res[i], float(meta["center_x"][i]), float(meta["center_y"][i]),
+            float(meta["width"][i]), float(meta["height"][i]), 256, 256, 2000, 2000,
+            scale=float(meta["scale"][i]), rot=float(meta["rot"][i]))
+        for i in range(B)])
+    X = triangulate_batch(img, np.asarray(meta["projection_matrix"]), method)
+    return labels_from_global_coords(X, meta) + (X, img)
+
+
+# --------------------------------------------------------------------------
+# synthetic generators -- shared by tests and bench
+# --------------------------------------------------------------------------
+
+def synthetic_cameras(rng, n_tuples, n_views=4):
+    """4 cameras per tuple on a ring r=4.5m+-0.5 at azimuths {45,135,225,315}+-10deg,
+    height 1.5m+-0.2, looking at the origin; f=(1145,1144), c=(512,515).
+    Returns R[n,v,3,3], T[n,v,3] (camera centre, world mm), f[n,v,2], c[n,v,2],
+    P[n,v,3,4] in the reference convention X_cam = R.(X - T) (cameras.py:149-150)."""
+    R = np.zeros((n_tuples, n_views, 3, 3))
+    T = np.zeros((n_tuples, n_views, 3))
+    f = np.tile(np.array([1145.0, 1144.0]), (n_tuples, n_views, 1))
+    c = np.tile(np.array([512.0, 515.0]), (n_tuples, n_views, 1))
+    P = np.zeros((n_tuples, n_views, 3, 4))
+    for t in range(n_tuples):
+        for v in range(n_views):
+            az = np.deg2rad(45.0 + 90.0 * v + rng.uniform(-10, 10))
+            r = 4500.0 + rng.uniform(-500, 500)
+            h = 1500.0 + rng.uniform(-200, 200)
+            C = np.array([r * np.cos(az), r * np.sin(az), h])
+            zc = -C / np.linalg.norm(C)                 # optical axis -> origin
+            up = np.array([0.0, 0.0, 1.0])
+            xc = np.cross(zc, up)
+            xc /= np.linalg.norm(xc)
+            yc = np.cross(zc, xc)
+            R[t, v] = np.stack([xc, yc, zc], axis=0)
+            T[t, v] = C
+            P[t, v] = projection_matrix(R[t, v], C, f[t, v], c[t, v])
+    return R, T, f, c, P
+
+
+def project(P, X):
+    """X[...,3] world -> pixel (u,v) with P 3x4."""
+    Xh = np.concatenate([X, np.ones(X.shape[:-1] + (1,))], axis=-1)
+    uvw = Xh @ P.T
+    return uvw[..., 0:2] / uvw[..., 2:3]

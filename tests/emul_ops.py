@@ -1,0 +1,324 @@
+"""TEST INFRASTRUCTURE: torch-CPU emulation of the libepb.so entry points with
+the SAME signatures as epipolarpose_b200.ops, written directly from the
+contracts in include/epb.h.  It lets the CPU test-suite exercise the host
+logic (network plan, geometry/tap tables, weight packing, autograd wiring,
+optimiser) without a GPU.  It is never imported by the product path."""
+import torch
+
+from epipolarpose_b200._lib import ConvGeom, EPB_MAX_TAPS
+
+launches = 0
+
+
+def make_geom(N, Hi, Wi, Cin, Ho, Wo, Cout, Hp, Wp, os, ph, pw, is_, taps, Tw,
+              in_relu=0, accumulate=0, precision=0):
+    g = ConvGeom()
+    g.N, g.Hi, g.Wi, g.Cin = N, Hi, Wi, Cin
+    g.Ho, g.Wo, g.Cout = Ho, Wo, Cout
+    g.Hp, g.Wp, g.os, g.ph, g.pw, g.is_ = Hp, Wp, os, ph, pw, is_
+    g.T = len(taps)
+    assert g.T <= EPB_MAX_TAPS
+    for i, (dh, dw, wt) in enumerate(taps):
+        g.dh[i], g.dw[i], g.wt[i] = dh, dw, wt
+    g.Tw = Tw
+    g.in_relu, g.accumulate, g.precision = in_relu, accumulate, precision
+    return g
+
+
+def _gather(g, x, t, in_scale, in_shift):
+    """[N,Hp,Wp,Cin] = f(x[n, i*is+dh, j*is+dw, :]) with zero outside."""
+    x = x.reshape(g.N, g.Hi, g.Wi, g.Cin)
+    if in_scale is not None:
+        x = x * in_scale + in_shift
+        if g.in_relu:
+            x = torch.relu(x)
+    dh, dw = g.dh[t], g.dw[t]
+    out = torch.zeros(g.N, g.Hp, g.Wp, g.Cin, dtype=x.dtype)
+    ii = torch.arange(g.Hp) * g.is_ + dh
+    jj = torch.arange(g.Wp) * g.is_ + dw
+    vi = (ii >= 0) & (ii < g.Hi)
+    vj = (jj >= 0) & (jj < g.Wi)
+    if vi.any() and vj.any():
+        sub = x[:, ii[vi]][:, :, jj[vj]]
+        tmp = out[:, vi]
+        tmp[:, :, vj] = sub
+        out[:, vi] = tmp
+    return out
+
+
+def conv_fprop(g, x, w, out, in_scale=None, in_shift=None, bias=None, stats=None):
+    W = w.reshape(g.Cout, g.Tw, g.Cin)
+    acc = torch.zeros(g.N, g.Hp, g.Wp, g.Cout, dtype=torch.float32)
+    for t in range(g.T):
+        acc += _gather(g, x, t, in_scale, in_shift) @ W[:, g.wt[t], :].T
+    if bias is not None:
+        acc += bias
+    o = out.view(g.N, g.Ho, g.Wo, g.Cout)
+    sl = o[:, g.ph::g.os, g.pw::g.os][:, :g.Hp, :g.Wp]
+    if g.accumulate:
+        acc = acc + sl
+    o[:, g.ph::g.os, g.pw::g.os][:, :g.Hp, :g.Wp] = acc
+    if stats is not None:
+        flat = acc.reshape(-1, g.Cout).double()
+        stats[:g.Cout] += flat.sum(0)
+        stats[g.Cout:] += (flat * flat).sum(0)
+
+
+def conv_wgrad(g, x, dout, dw, in_scale=None, in_shift=None):
+    DW = dw.view(g.Cout, g.Tw, g.Cin)
+    d = dout.view(g.N, g.Ho, g.Wo, g.Cout)[:, g.ph::g.os, g.pw::g.os][:, :g.Hp, :g.Wp]
+    d = d.reshape(-1, g.Cout)
+    for t in range(g.T):
+        a = _gather(g, x, t, in_scale, in_shift).reshape(-1, g.Cin)
+        DW[:, g.wt[t], :] += d.T @ a
+
+
+def pack_weight(src, dst, A, B, kh, kw, swap, ypad, unpack=0):
+    T = kh * kw
+    X, Y = (B, A) if swap else (A, B)
+    if not unpack:
+        s = src.reshape(A, B, T)
+        p = s.permute(1, 2, 0) if swap else s.permute(0, 2, 1)   # [X][T][Y]
+        d = dst.view(-1)[:X * T * ypad].view(X, T, ypad)
+        d.zero_()
+        d[:, :, :Y] = p
+    else:
+        p = src.view(-1)[:X * T * ypad].view(X, T, ypad)[:, :, :Y]
+        d = dst.view(A, B, T)
+        d.copy_(p.permute(2, 0, 1) if swap else p.permute(0, 2, 1))
+
+
+def nchw_to_nhwc(src, dst, N, C, H, W, Cpad):
+    d = dst.view(N, H, W, Cpad)
+    d.zero_()
+    d[..., :C] = src.view(N, C, H, W).permute(0, 2, 3, 1)
+
+
+def nhwc_to_nchw(src, dst, N, C, H, W, Cpad):
+    dst.view(N, C, H, W).copy_(src.view(N, H, W, Cpad)[..., :C].permute(0, 3, 1, 2))
+
+
+def channel_stats(x, M, C, stats):
+    f = x.reshape(M, C).double()
+    stats[:C] += f.sum(0)
+    stats[C:] += (f * f).sum(0)
+
+
+def bn_finalize(stats, M, C, gamma, beta, eps, momentum, running_mean, running_var, scale, shift,
+                mean, invstd):
+    mu = stats[:C] / M
+    var = (stats[C:] / M - mu * mu).clamp_min(0)
+    inv = 1.0 / torch.sqrt(var + eps)
+    scale.copy_((gamma.double() * inv).float())
+    shift.copy_((beta.double() - mu * gamma.double() * inv).float())
+    if mean is not None:
+        mean.copy_(mu.float())
+        invstd.copy_(inv.float())
+    if running_mean is not None:
+        running_mean.copy_(((1 - momentum) * running_mean.double() + momentum * mu).float())
+        unb = var * (M / max(M - 1, 1))
+        running_var.copy_(((1 - momentum) * running_var.double() + momentum * unb).float())
+
+
+def bn_eval_affine(C, gamma, beta, running_mean, running_var, eps, scale, shift):
+    inv = 1.0 / torch.sqrt(running_var + eps)
+    scale.copy_(gamma * inv)
+    shift.copy_(beta - running_mean * gamma * inv)
+
+
+def bn_act(x, scale, shift, r, rscale, rshift, relu, y, M, C):
+    v = x.reshape(M, C)
+    if scale is not None:
+        v = v * scale + shift
+    if r is not None:
+        q = r.reshape(M, C)
+        if rscale is not None:
+            q = q * rscale + rshift
+        v = v + q
+    if relu:
+        v = torch.relu(v)
+    y.view(M, C).copy_(v)
+
+
+def bn_relu_maxpool(x, scale, shift, y, argidx, N, H, W, C):
+    a = torch.relu(x.view(N, H, W, C) * scale + shift).permute(0, 3, 1, 2)
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    pad = torch.nn.functional.pad(a, (1, 1, 1, 1), value=float("-inf"))
+    best = torch.full((N, C, Ho, Wo), float("-inf"))
+    bi = torch.zeros((N, C, Ho, Wo), dtype=torch.uint8)
+    for kh in range(3):
+        for kw in range(3):
+            v = pad[:, :, kh:kh + 2 * Ho:2, kw:kw + 2 * Wo:2]
+            m = v > best
+            best = torch.where(m, v, best)
+            bi = torch.where(m, torch.full_like(bi, kh * 3 + kw), bi)
+    y.view(N, Ho, Wo, C).copy_(best.permute(0, 2, 3, 1))
+    argidx.view(N, Ho, Wo, C).copy_(bi.permute(0, 2, 3, 1))
+
+
+def maxpool_bwd(dy, argidx, dx, N, H, W, C):
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    g = dy.view(N, Ho, Wo, C)
+    k = argidx.view(N, Ho, Wo, C)
+    pad = torch.zeros(N, H + 2, W + 2, C)
+    for kh in range(3):
+        for kw in range(3):
+            sel = (k == kh * 3 + kw).float() * g
+            pad[:, kh:kh + 2 * Ho:2, kw:kw + 2 * Wo:2] += sel
+    dx.view(N, H, W, C).copy_(pad[:, 1:H + 1, 1:W + 1])
+
+
+def _masked(dy, x, y_out, scale, shift, relu, M, C):
+    g = dy.reshape(M, C)
+    if y_out is not None:
+        return g * (y_out.reshape(M, C) > 0).float()
+    if relu:
+        return g * ((x.reshape(M, C) * scale + shift) > 0).float()
+    return g
+
+
+def bn_bwd_reduce(dy, x, y_out, scale, shift, mean, invstd, relu, M, C, sums):
+    g = _masked(dy, x, y_out, scale, shift, relu, M, C).double()
+    xh = ((x.reshape(M, C) - mean) * invstd).double()
+    sums[:C] += g.sum(0)
+    sums[C:] += (g * xh).sum(0)
+
+
+def bn_bwd_apply(dy, x, y_out, scale, shift, mean, invstd, gamma, relu, sums, M, C, dx, dgamma,
+                 dbeta):
+    g = _masked(dy, x, y_out, scale, shift, relu, M, C)
+    xh = (x.reshape(M, C) - mean) * invstd
+    k1 = (sums[:C] / M).float()
+    k2 = (sums[C:] / M).float()
+    dx.view(M, C).copy_(gamma * invstd * (g - k1 - xh * k2))
+    if dgamma is not None:
+        dgamma.copy_(sums[C:].float())
+    if dbeta is not None:
+        dbeta.copy_(sums[:C].float())
+
+
+def add_masked(a, b, mask_src, dx, n):
+    q = b.reshape(-1)
+    if mask_src is not None:
+        q = q * (mask_src.reshape(-1) > 0).float()
+    dx.view(-1).copy_(a.reshape(-1) + q)
+
+
+def avgpool(x, y, N, HW, C):
+    y.view(N, C).copy_(x.reshape(N, HW, C).mean(1))
+
+
+def avgpool_bwd(dy, dx, N, HW, C, accumulate):
+    g = (dy.reshape(N, 1, C) / HW).expand(N, HW, C)
+    d = dx.view(N, HW, C)
+    if accumulate:
+        d += g
+    else:
+        d.copy_(g)
+
+
+def colsum(x, M, C, out):
+    out.copy_(x.reshape(M, C).double().sum(0).float())
+
+
+def _volume(logits, layout, N, J, D, H, W):
+    if layout == 0:
+        return logits.reshape(N, J, D, H, W)
+    return logits.reshape(N, H, W, J, D).permute(0, 3, 4, 1, 2)
+
+
+def softargmax_fwd(logits, layout, N, J, D, H, W, coords, lse):
+    v = _volume(logits, layout, N, J, D, H, W).reshape(N * J, -1)
+    m = v.max(1, keepdim=True).values
+    e = torch.exp(v - m)
+    s = e.sum(1, keepdim=True)
+    p = (e / s).reshape(N * J, D, H, W)
+    cx = (p.sum((1, 2)) * torch.arange(W)).sum(1) / W - 0.5
+    cy = (p.sum((1, 3)) * torch.arange(H)).sum(1) / H - 0.5
+    cz = (p.sum((2, 3)) * torch.arange(D)).sum(1) / D - 0.5
+    coords.view(N * J, 3).copy_(torch.stack([cx, cy, cz], 1))
+    lse.view(N * J, 2).copy_(torch.cat([m, 1.0 / s], 1))
+
+
+def softargmax_bwd(logits, layout, N, J, D, H, W, coords, lse, dcoords, dlogits):
+    v = _volume(logits, layout, N, J, D, H, W).reshape(N * J, D, H, W)
+    l = lse.view(N * J, 2)
+    p = torch.exp(v - l[:, 0, None, None, None]) * l[:, 1, None, None, None]
+    g = dcoords.view(N * J, 3)
+    c = coords.view(N * J, 3)
+    s = (g[:, 0, None, None, None] * torch.arange(W)[None, None, None, :] / W
+         + g[:, 1, None, None, None] * torch.arange(H)[None, None, :, None] / H
+         + g[:, 2, None, None, None] * torch.arange(D)[None, :, None, None] / D)
+    sbar = (g * (c + 0.5)).sum(1)
+    d = (p * (s - sbar[:, None, None, None])).reshape(N, J, D, H, W)
+    if layout == 0:
+        dlogits.view(N, J, D, H, W).copy_(d)
+    else:
+        dlogits.view(N, H, W, J, D).copy_(d.permute(0, 3, 4, 1, 2))
+
+
+def jointloss(x, t, w, n, kind, norm, div, loss, dx):
+    xv = x.reshape(-1).detach().clone().requires_grad_(True)
+    tv = t.reshape(-1)
+    a, b = xv, tv
+    if norm:
+        a = xv / xv.abs().sum()
+        b = tv / tv.abs().sum()
+    d = a - b
+    if kind == 0:
+        l = d * d
+    elif kind == 1:
+        l = d.abs()
+    else:
+        l = torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5)
+    tot = (l * w.reshape(-1)).sum() / div
+    tot.backward()
+    if loss is not None:
+        loss.view(-1)[0] = tot.detach()
+    if dx is not None:
+        dx.view(-1).copy_(xv.grad)
+
+
+def argmax2d(hm, NJ, H, W, idx, maxval, preds):
+    f = hm.reshape(NJ, H * W)
+    i = f.argmax(1)
+    m = f.max(1).values
+    if idx is not None:
+        idx.view(-1).copy_(i.int())
+    if maxval is not None:
+        maxval.view(-1).copy_(m)
+    if preds is not None:
+        mask = (m > 0).float()
+        preds.view(NJ, 2).copy_(torch.stack([(i % W).float() * mask,
+                                             torch.floor(i.float() / W) * mask], 1))
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step,
+              grad_scale=1.0):
+    g = grad * grad_scale
+    if weight_decay:
+        g = g + weight_decay * param
+    exp_avg.mul_(beta1).add_(g, alpha=1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = exp_avg_sq.sqrt() / (bc2 ** 0.5) + eps
+    param.addcdiv_(exp_avg, denom, value=-lr / bc1)
+
+
+def sgd_step(param, grad, buf, n, lr, momentum, weight_decay, nesterov, first_step,
+             grad_scale=1.0):
+    g = grad * grad_scale
+    if weight_decay:
+        g = g + weight_decay * param
+    if momentum:
+        if first_step:
+            buf.copy_(g)
+        else:
+            buf.mul_(momentum).add_(g)
+        g = g + momentum * buf if nesterov else buf
+    param.add_(g, alpha=-lr)
+
+
+def device_check():
+    pass

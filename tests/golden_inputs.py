@@ -1,0 +1,115 @@
+"""Seeded synthetic inputs shared by the golden-vector generator
+(tests/golden/make_golden.py, runs the reference in the build container) and
+by the tests (which run anywhere).  numpy Generator streams are stable across
+platforms, so only reference OUTPUTS need to be stored."""
+import numpy as np
+
+from oracle import restate
+
+# tag -> (N, J, D, H, W, seed, logit scale)
+SOFTARGMAX_CASES = {
+    "small": (2, 3, 8, 8, 8, 11, 3.0),
+    "cube16": (3, 5, 16, 16, 16, 12, 2.0),
+    "ragged": (1, 2, 4, 12, 20, 13, 4.0),     # D != H != W
+    "peaky": (2, 17, 16, 16, 16, 14, 12.0),
+}
+
+
+def logits(N, J, D, H, W, seed, scale):
+    rng = np.random.default_rng(seed)
+    return (scale * rng.standard_normal((N, J * D, H, W))).astype(np.float32)
+
+
+def labels(N, J, seed):
+    rng = np.random.default_rng(seed + 100)
+    gt = (rng.uniform(-0.5, 0.5, (N, J * 3))).astype(np.float32)
+    wt = (rng.uniform(0, 1, (N, J * 3)) > 0.2).astype(np.float32)
+    return gt, wt
+
+
+def argmax_heatmaps():
+    rng = np.random.default_rng(21)
+    hm = rng.standard_normal((3, 6, 16, 12)).astype(np.float32)
+    hm[0, 0] = -np.abs(hm[0, 0])            # all negative -> masked to (0,0)
+    hm[0, 1] = 0.0                           # all equal (ties) -> first index, masked (max == 0)
+    hm[0, 2, 5, 7] = 9.0
+    hm[0, 2, 9, 3] = 9.0                     # planted tie -> first occurrence (5,7)
+    hm[1, 0, 15, 11] = 50.0                  # last element
+    hm[1, 1, 0, 0] = 50.0                    # first element
+    hm[2, 3] = np.float32(0.25)              # positive constant
+    return hm
+
+
+def triangulation_case(n_pairs=16, J=17, seed=31, noise_px=3.0):
+    rng = np.random.default_rng(seed)
+    R, T, f, c, P = restate.synthetic_cameras(rng, n_pairs, 4)
+    X = rng.normal(0.0, 400.0, size=(n_pairs, J, 3))
+    P1, P2 = P[:, 0], P[:, 1]
+    u1 = np.stack([restate.project(P1[i], X[i]) for i in range(n_pairs)])
+    u2 = np.stack([restate.project(P2[i], X[i]) for i in range(n_pairs)])
+    u1 = u1 + rng.normal(0, noise_px, u1.shape)
+    u2 = u2 + rng.normal(0, noise_px, u2.shape)
+    return u1, u2, P1.copy(), P2.copy(), X
+
+
+def exact_projections(P1, P2, X):
+    u1 = np.stack([restate.project(P1[i], X[i]) for i in range(len(X))])
+    u2 = np.stack([restate.project(P2[i], X[i]) for i in range(len(X))])
+    return u1, u2
+
+
+def patch_case(B=6, J=5, seed=41):
+    rng = np.random.default_rng(seed)
+    coords = np.concatenate([rng.uniform(0, 256, (B, J, 2)), rng.uniform(-128, 128, (B, J, 1)),
+                             np.ones((B, J, 1))], axis=2)
+    boxes = np.stack([500 + rng.uniform(-50, 50, B), 500 + rng.uniform(-50, 50, B),
+                      800 + rng.uniform(-100, 100, B), 800 + rng.uniform(-100, 100, B),
+                      np.array([1.0, 1.0, 1.1, 0.85, 1.25, 0.9]),
+                      np.array([0.0, 0.0, 15.0, -30.0, 7.5, 0.0])], axis=1)
+    return coords, boxes
+
+
+def selfsup_case(n_tuples=2, J=4, D=16, seed=51):
+    """Batch of 2*n_tuples*... laid out [view0 | view1] of each tuple, logits whose
+    soft-argmax lands near the projection of a true 3-D pose."""
+    rng = np.random.default_rng(seed)
+    R, T, f, c, P = restate.synthetic_cameras(rng, n_tuples, 4)
+    B = 2 * n_tuples
+    views = [(t, 0) for t in range(n_tuples)] + [(t, 1) for t in range(n_tuples)]
+    meta = {"center_x": np.zeros(B), "center_y": np.zeros(B), "width": np.zeros(B),
+            "height": np.zeros(B), "scale": np.ones(B), "rot": np.zeros(B),
+            "R": np.zeros((B, 3, 3)), "T": np.zeros((B, 3, 1)), "f": np.zeros((B, 2)),
+            "c": np.zeros((B, 2)), "projection_matrix": np.zeros((B, 3, 4))}
+    logits = (0.5 * rng.standard_normal((B, J * D, D, D))).astype(np.float32)
+    X = rng.normal(0.0, 300.0, size=(n_tuples, J, 3))
+    for b, (t, v) in enumerate(views):
+        meta["R"][b], meta["T"][b, :, 0], meta["f"][b], meta["c"][b] = R[t, v], T[t, v], f[t, v], c[t, v]
+        meta["projection_matrix"][b] = P[t, v]
+        uv = restate.project(P[t, v], X[t])
+        meta["center_x"][b], meta["center_y"][b] = uv[:, 0].mean(), uv[:, 1].mean()
+        meta["width"][b] = meta["height"][b] = 700.0 + 20.0 * b
+        for j in range(J):   # plant a peak near the projected joint inside the patch
+            px = (uv[j, 0] - meta["center_x"][b]) / meta["width"][b] * D + D / 2
+            py = (uv[j, 1] - meta["center_y"][b]) / meta["height"][b] * D + D / 2
+            xi, yi = int(np.clip(px, 0, D - 1)), int(np.clip(py, 0, D - 1))
+            logits[b, j * D + D // 2, yi, xi] += 6.0
+    return logits, meta
+
+
+NET_CASES = {
+    "r18": dict(layers=18, J=3, D=8, HW=64, N=2, volume=True, seed=61,
+                grad_keys=["conv1.weight", "layer2.0.downsample.0.weight", "layer4.1.bn2.weight",
+                           "deconv_layers.7.weight", "final_layer.weight", "final_layer.bias"]),
+    "r50": dict(layers=50, J=2, D=8, HW=128, N=3, volume=True, seed=62,
+                grad_keys=["final_layer.weight", "final_layer.bias", "deconv_layers.7.weight"]),
+    "r50flat": dict(layers=50, J=3, D=4, HW=64, N=2, volume=False, seed=63,
+                    grad_keys=["depth_fc.weight", "final_layer.bias"]),
+}
+
+
+def images(N, HW, seed):
+    return np.random.default_rng(seed).standard_normal((N, 3, HW, HW)).astype(np.float32)
+
+
+def grad_like(shape, seed):
+    return np.random.default_rng(seed).standard_normal(tuple(shape)).astype(np.float32)

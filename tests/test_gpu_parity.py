@@ -1,0 +1,364 @@
+"""GPU (-m gpu): parity of the CUDA path (through the C ABI / the reference-
+shaped Python surface) against the oracle restatement and the golden vectors
+the unmodified reference produced.  Tolerances per BASELINE.json north_star:
+argmax indices bit-exact; triangulated joints <= 1e-4 mm; soft-argmax coords
+<= 1e-5 abs; heatmaps / gradients <= 1e-3 rel (max|d|/max|ref| per tensor)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, restate_net
+from tests import golden_inputs as gi
+from tests.conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from epipolarpose_b200 import ops
+    ops.device_check()
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------ soft-argmax + losses
+@pytest.mark.parametrize("tag", list(gi.SOFTARGMAX_CASES))
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_softargmax_loss_golden(golden, dev, tag, layout):
+    import lib.core.integral_loss as il
+    N, J, D, H, W, seed, scale = gi.SOFTARGMAX_CASES[tag]
+    if layout == "nchw" and W % 4:
+        pytest.skip("NCHW kernel needs W % 4 == 0")
+    g = golden("softargmax_" + tag)
+    x = torch.from_numpy(gi.logits(N, J, D, H, W, seed, scale)).to(dev)
+    if layout == "nhwc":
+        x = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)   # channels_last view
+    x.requires_grad_(True)
+    coords = il.softmax_integral_tensor(x, J, True, W, H, D)
+    assert np.max(np.abs(coords.detach().cpu().numpy() - g["coords"])) <= 1e-5
+    gt, wt = gi.labels(N, J, seed)
+    gt, wt = torch.from_numpy(gt).to(dev), torch.from_numpy(wt).to(dev)
+    for cls, key in ((il.L1JointLocationLoss, "l1"), (il.SmoothL1JointLocationLoss, "smoothl1")):
+        for norm in (False, True):
+            x.grad = None
+            loss = cls(J, norm=norm)(x, gt, wt)
+            loss.backward()
+            k = key + ("_norm" if norm else "")
+            assert abs(loss.item() - float(g[k + "_loss"])) <= 1e-5 * max(1.0, abs(float(g[k + "_loss"])))
+            grad = x.grad.cpu().numpy()
+            assert relerr(grad[:, :, ::3, ::3], g[k + "_grad_sample"]) <= 1e-3
+            assert relerr(np.abs(grad).sum((2, 3)), g[k + "_grad_sum_abs"]) <= 1e-3
+    if D == W:
+        res = il.get_joint_location_result(256, 256, x.detach())
+        assert np.max(np.abs(res - g["result"])) <= 256 * 1e-5
+
+
+def test_softargmax_full_size_properties(dev):
+    """BASELINE size (J=17, 64^3) on a few images: planted delta peaks decode to
+    their voxel; uniform logits decode to the volume centre; gradients of each
+    (n,j) volume sum to zero (softmax Jacobian annihilates constants)."""
+    import lib.core.integral_loss as il
+    N, J, D = 4, 17, 64
+    rng = np.random.default_rng(5)
+    x = torch.zeros((N, J * D, D, D), device=dev)
+    pos = rng.integers(0, D, size=(N, J, 3))
+    for n in range(N):
+        for j in range(J):
+            x[n, j * D + pos[n, j, 2], pos[n, j, 1], pos[n, j, 0]] = 60.0
+    for view in (x, x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)):
+        c = il.softmax_integral_tensor(view, J, True, D, D, D).cpu().numpy().reshape(N, J, 3)
+        assert np.max(np.abs((c + 0.5) * D - pos)) <= 1e-3
+    u = torch.zeros((1, J * D, D, D), device=dev)
+    c = il.softmax_integral_tensor(u, J, True, D, D, D).cpu().numpy()
+    assert np.max(np.abs(c - ((D - 1) / 2 / D - 0.5))) <= 1e-5
+    y = (2 * torch.randn((2, J * D, D, D), device=dev)).requires_grad_(True)
+    il.softmax_integral_tensor(y, J, True, D, D, D).sum().backward()
+    s = y.grad.reshape(2, J, -1).sum(-1).abs().max().item()
+    assert s <= 1e-5
+
+
+def test_softargmax_vs_oracle_medium(dev):
+    import lib.core.integral_loss as il
+    N, J, D = 2, 17, 32
+    logits = gi.logits(N, J, D, D, D, 77, 3.0)
+    ref = restate.softmax_integral(logits, J, D, D, D)
+    for lay in (0, 1):
+        x = torch.from_numpy(logits).to(dev)
+        if lay:
+            x = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        c = il.softmax_integral_tensor(x, J, True, D, D, D).cpu().numpy()
+        assert np.max(np.abs(c - ref)) <= 1e-5
+        g = np.random.default_rng(3).standard_normal((N, J * 3)).astype(np.float32)
+        x.requires_grad_(True)
+        il.softmax_integral_tensor(x, J, True, D, D, D).backward(torch.from_numpy(g).to(dev))
+        gref = restate.softmax_integral_grad(logits, g, J, D, D, D)
+        assert relerr(x.grad.cpu().numpy(), gref) <= 1e-3
+
+
+# ------------------------------------------------------------------ argmax
+def test_argmax_bit_exact(golden, dev):
+    import lib.core.inference as inf
+    g = golden("argmax")
+    hm = gi.argmax_heatmaps()
+    preds, maxvals = inf.get_max_preds(hm)
+    assert np.array_equal(preds, g["preds"]) and np.array_equal(maxvals, g["maxvals"])
+    big = np.random.default_rng(9).standard_normal((32, 17, 64, 64)).astype(np.float32)
+    big[:, :, 10, 10] = big.max() + 1          # ties across maps at a fixed location
+    big[3, 2, 5, 5] = big[3, 2, 10, 10]        # earlier tie wins
+    p, m, idx = inf.get_max_preds_device(torch.from_numpy(big).to(dev))
+    rp, rm, ridx = restate.get_max_preds(big)
+    assert np.array_equal(idx.cpu().numpy(), ridx.astype(np.int32))
+    assert np.array_equal(p.cpu().numpy(), rp) and np.array_equal(m.cpu().numpy(), rm)
+    e = inf.get_max_preds_device(torch.zeros((0, 17, 64, 64), device=dev))
+    assert e[0].shape == (0, 17, 2)
+
+
+# ------------------------------------------------------------------ geometry (fp64)
+def test_triangulators_golden(golden, dev):
+    import lib.utils.triangulation as tri
+    g = golden("triangulation")
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    for name in ("linear_eigen_triangulation", "linear_LS_triangulation", "iterative_LS_triangulation"):
+        for i in range(len(u1)):
+            x, st = getattr(tri, name)(u1[i], P1[i], u2[i], P2[i])
+            assert np.max(np.abs(x - g[name + "_x"][i])) <= 1e-4, name     # mm
+            assert np.array_equal(np.asarray(st).astype(np.int64), g[name + "_status"][i])
+    u1e, u2e = gi.exact_projections(P1, P2, X)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for m in ("linear_eigen", "linear_LS", "iterative_LS"):
+        Xg, _ = tri.triangulate_pairs(t(u1e), t(u2e), t(P1), t(P2), m)
+        assert np.max(np.abs(Xg.cpu().numpy() - X)) <= 1e-6             # known answer
+
+
+def test_triangulation_large_vs_oracle(dev):
+    import lib.utils.triangulation as tri
+    u1, u2, P1, P2, X = gi.triangulation_case(n_pairs=64, J=17, seed=99)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for m, fn in (("linear_eigen", restate.linear_eigen_triangulation),
+                  ("iterative_LS", restate.iterative_LS_triangulation)):
+        Xg, st = tri.triangulate_pairs(t(u1), t(u2), t(P1), t(P2), m)
+        Xg = Xg.cpu().numpy()
+        for i in range(0, 64, 7):
+            xr, sr = fn(u1[i], P1[i], u2[i], P2[i])
+            assert np.max(np.abs(Xg[i] - xr)) <= 1e-4
+    e, _ = tri.triangulate_pairs(t(u1[:0]), t(u2[:0]), t(P1[:0]), t(P2[:0]))
+    assert e.shape == (0, 17, 3)
+    # a point behind camera 1 gets the reference's negative status
+    Xb = X[:1].copy()
+    x, st = tri.iterative_LS_triangulation(u1[0], P1[0], u2[0], P2[0])
+    xr, sr = restate.iterative_LS_triangulation(u1[0], P1[0], u2[0], P2[0])
+    assert np.array_equal(st, sr)
+
+
+def test_patch_to_image_and_selfsup_golden(golden, dev):
+    import lib.utils.img_utils as iu
+    g = golden("patch_to_image")
+    coords, boxes = gi.patch_case()
+    out = iu.trans_coords_from_patch_to_org_3d_batch(coords, boxes[:, 0], boxes[:, 1], boxes[:, 2],
+                                                     boxes[:, 3], 256, 256, 2000, boxes[:, 4], boxes[:, 5])
+    assert np.max(np.abs(out - g["kps"])) <= 5e-3      # inputs pass through float32 patch units
+    one = iu.trans_coords_from_patch_to_org_3d(coords[1], *boxes[1, :4], 256, 256, 2000, 2000,
+                                               scale=boxes[1, 4], rot=boxes[1, 5])
+    assert np.max(np.abs(one - g["kps"][1])) <= 5e-3
+    gs = golden("selfsup")
+    logits, meta = gi.selfsup_case()
+    mt = {k: torch.from_numpy(v) for k, v in meta.items()}
+    label, weight = iu.self_supervision(torch.from_numpy(logits).to(dev), mt)
+    assert np.max(np.abs(label - gs["label"])) <= 2e-5
+    assert np.array_equal(weight, gs["weight"])
+
+
+# ------------------------------------------------------------------ conv / BN kernels vs torch fp32
+def _rand(dev, *s):
+    return torch.randn(*s, device=dev)
+
+
+@pytest.mark.parametrize("cfg", [
+    ("conv", 32, 64, 1, 1, 0, 14), ("conv", 64, 64, 3, 1, 1, 14), ("conv", 64, 128, 3, 2, 1, 14),
+    ("conv", 64, 256, 1, 2, 0, 14), ("conv", 3, 64, 7, 2, 3, 30), ("deconv", 64, 32, 4, 2, 1, 7),
+    ("conv", 32, 40, 3, 1, 1, 9),
+])
+@pytest.mark.parametrize("precision", [0, 3])
+def test_conv_family_vs_torch(dev, cfg, precision):
+    """fprop / dgrad / wgrad of one layer (through net.Conv geometry + C ABI)
+    against torch fp32 on identical tensors: <= 1e-3 rel per the north star
+    (the fp32 and 3xTF32 paths sit near 1e-5)."""
+    from epipolarpose_b200 import net, ops
+    import torch.nn.functional as F
+    kind, cin, cout, k, s, p, hw = cfg
+    N = 3
+    conv = net.Conv("t", kind, cin, cout, k, s, p, 0)
+    eng = net.Engine(None, precision=precision)
+    eng.dev = dev
+    w = _rand(dev, *((cout, cin, k, k) if kind == "conv" else (cin, cout, k, k))) * 0.1
+    x = _rand(dev, N, cin, hw, hw)
+    sc, sh = torch.rand(cin, device=dev) + 0.5, _rand(dev, cin) * 0.1
+    xa = torch.relu(x * sc[None, :, None, None] + sh[None, :, None, None]).requires_grad_(True)
+    wt = w.clone().requires_grad_(True)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref = F.conv2d(xa, wt, None, s, p) if kind == "conv" else F.conv_transpose2d(xa, wt, None, s, p)
+        gout = _rand(dev, *ref.shape)
+        ref.backward(gout)
+    xn = torch.zeros(N, hw, hw, conv.cin_p, device=dev)
+    ops.nchw_to_nhwc(x.contiguous(), xn, N, cin, hw, hw, conv.cin_p)
+    scp = torch.ones(conv.cin_p, device=dev); scp[:cin] = sc
+    shp = torch.zeros(conv.cin_p, device=dev); shp[:cin] = sh
+    wf, wd = conv.pack(ops, w)
+    stats = torch.zeros(2 * conv.cout_p, device=dev, dtype=torch.float64)
+    out, Ho, Wo = eng._conv_fwd(conv, xn, N, hw, hw, wf, affine=(scp, shp), stats=stats)
+    o = out[..., :cout].permute(0, 3, 1, 2)
+    assert relerr(o.cpu().numpy(), ref.detach().cpu().numpy()) <= 1e-3
+    st_ref = torch.cat([ref.detach().double().sum((0, 2, 3)), (ref.detach().double() ** 2).sum((0, 2, 3))])
+    st = torch.cat([stats[:cout], stats[conv.cout_p:conv.cout_p + cout]])
+    assert relerr(st.cpu().numpy(), st_ref.cpu().numpy()) <= 1e-3
+    gn = torch.zeros(N, Ho, Wo, conv.cout_p, device=dev)
+    ops.nchw_to_nhwc(gout.contiguous(), gn, N, cout, Ho, Wo, conv.cout_p)
+    din = eng._conv_dgrad(conv, gn, N, hw, hw, wd)
+    assert relerr(din[..., :cin].permute(0, 3, 1, 2).cpu().numpy(), xa.grad.cpu().numpy()) <= 1e-3
+    gw = torch.zeros_like(w)
+    eng._conv_wgrad(conv, xn, gn, N, hw, hw, gw, affine=(scp, shp))
+    assert relerr(gw.cpu().numpy(), wt.grad.cpu().numpy()) <= 1e-3
+
+
+def test_bn_pool_kernels_vs_torch(dev):
+    from epipolarpose_b200 import ops
+    import torch.nn.functional as F
+    N, H, W, C = 3, 18, 14, 64
+    x = _rand(dev, N, H, W, C) * 2 + 0.3
+    M = N * H * W
+    stats = torch.zeros(2 * C, device=dev, dtype=torch.float64)
+    ops.channel_stats(x, M, C, stats)
+    xd = x.double().reshape(M, C)
+    assert relerr(stats[:C].cpu().numpy(), xd.sum(0).cpu().numpy()) <= 1e-6
+    assert relerr(stats[C:].cpu().numpy(), (xd * xd).sum(0).cpu().numpy()) <= 1e-6
+    gamma, beta = torch.rand(C, device=dev) + 0.5, _rand(dev, C)
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    sc, sh, mu, inv = (torch.empty(C, device=dev) for _ in range(4))
+    ops.bn_finalize(stats, M, C, gamma, beta, 1e-5, 0.1, rm, rv, sc, sh, mu, inv)
+    xc = x.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    gt, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yref = F.batch_norm(xc, rm2, rv2, gt, bt, True, 0.1, 1e-5)
+    assert relerr(rm.cpu().numpy(), rm2.cpu().numpy()) <= 1e-5 and relerr(rv.cpu().numpy(), rv2.cpu().numpy()) <= 1e-5
+    # stem: bn + relu + maxpool, forward and backward
+    pref = F.max_pool2d(torch.relu(yref), 3, 2, 1)
+    Ho, Wo = pref.shape[2], pref.shape[3]
+    y = torch.empty(N, Ho, Wo, C, device=dev)
+    arg = torch.empty(N, Ho, Wo, C, device=dev, dtype=torch.uint8)
+    ops.bn_relu_maxpool(x, sc, sh, y, arg, N, H, W, C)
+    assert relerr(y.permute(0, 3, 1, 2).cpu().numpy(), pref.detach().cpu().numpy()) <= 1e-5
+    g = _rand(dev, *pref.shape)
+    pref.backward(g)
+    gp = torch.empty(N, H, W, C, device=dev)
+    ops.maxpool_bwd(g.permute(0, 2, 3, 1).contiguous(), arg, gp, N, H, W, C)
+    sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
+    ops.bn_bwd_reduce(gp, x, None, sc, sh, mu, inv, 1, M, C, sums)
+    dx, dg, db = torch.empty_like(x), torch.empty(C, device=dev), torch.empty(C, device=dev)
+    ops.bn_bwd_apply(gp, x, None, sc, sh, mu, inv, gamma, 1, sums, M, C, dx, dg, db)
+    assert relerr(dx.permute(0, 3, 1, 2).cpu().numpy(), xc.grad.cpu().numpy()) <= 1e-4
+    assert relerr(dg.cpu().numpy(), gt.grad.cpu().numpy()) <= 1e-4
+    assert relerr(db.cpu().numpy(), bt.grad.cpu().numpy()) <= 1e-4
+    # residual add + relu
+    r = _rand(dev, N, H, W, C)
+    out = torch.empty_like(x)
+    ops.bn_act(x, sc, sh, r, None, None, 1, out, M, C)
+    ref = torch.relu(yref.detach().permute(0, 2, 3, 1) + r)
+    assert relerr(out.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+
+
+# ------------------------------------------------------------------ whole network
+@pytest.mark.parametrize("tag", list(gi.NET_CASES))
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_network_vs_reference_golden(golden, dev, tag, precision):
+    """Module surface (get_pose_net / state_dict / train / eval) on the GPU
+    against outputs of the UNMODIFIED reference module on the same weights."""
+    import lib.models as models
+    from oracle import refshim
+    c = gi.NET_CASES[tag]
+    g = golden("net_" + tag)
+    cfg = refshim.make_cfg(num_layers=c["layers"], num_joints=c["J"], volume=c["volume"],
+                           depth_res=c["D"], image_size=(c["HW"], c["HW"]))
+    model = models.pose3d_resnet.get_pose_net(cfg, False, precision=precision)
+    shapes = restate_net.param_shapes(num_layers=c["layers"], num_joints=c["J"], volume=c["volume"],
+                                      depth_res=c["D"])
+    model.load_state_dict(restate_net.init_state(shapes, c["seed"]))
+    model = model.to(dev).train()
+    x = torch.from_numpy(gi.images(c["N"], c["HW"], c["seed"])).to(dev)
+    out = model(x)
+    outs = out if isinstance(out, tuple) else (out,)
+    for i, o in enumerate(outs):
+        assert tuple(o.shape) == g["out%d" % i].shape
+        assert relerr(o.detach().cpu().numpy(), g["out%d" % i]) <= 1e-3
+    gs = [torch.from_numpy(gi.grad_like(o.shape, c["seed"] + 1 + i)).to(dev) for i, o in enumerate(outs)]
+    sum((o * gg).sum() for o, gg in zip(outs, gs)).backward()
+    named = dict(model.named_parameters())
+    assert relerr(named["final_layer.bias"].grad.cpu().numpy(), g["grad/final_layer.bias"]) <= 1e-3
+    sd = model.state_dict()
+    assert relerr(sd["bn1.running_mean"].cpu().numpy(), g["bn1.running_mean"]) <= 1e-4
+    assert relerr(sd["bn1.running_var"].cpu().numpy(), g["bn1.running_var"]) <= 1e-4
+    assert int(sd["bn1.num_batches_tracked"]) == 1
+    model.eval()
+    with torch.no_grad():
+        e = model(x)
+    e = e[0] if isinstance(e, tuple) else e
+    assert relerr(e.cpu().numpy(), g["eval_out0"]) <= 1e-3
+
+
+def test_network_gradients_vs_oracle_fp64(dev):
+    """All parameter gradients of an R18 net under the real integral loss
+    against the float64 oracle.  Bar: 1e-3 rel, or -- for tensors where the
+    fp32 torch oracle itself is further than that from float64 (chaotic
+    random-init trunk) -- no worse than 2x the fp32 oracle's own error."""
+    import lib.models as models
+    import lib.core.integral_loss as il
+    from oracle import refshim
+    J, D, HW, N = 3, 16, 64, 4
+    cfg = refshim.make_cfg(num_layers=18, num_joints=J, volume=True, depth_res=D, image_size=(HW, HW))
+    shapes = restate_net.param_shapes(num_layers=18, num_joints=J, volume=True, depth_res=D)
+    sd = restate_net.init_state(shapes, 5)
+    x = gi.images(N, HW, 5)
+    gt, wt = gi.labels(N, J, 5)
+
+    def oracle(dt):
+        p = {k: (v.to(dt).clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+                 else (v.to(dt) if v.is_floating_point() else v)) for k, v in sd.items()}
+        o = restate_net.forward(p, torch.from_numpy(x).to(dt), num_layers=18, training=True)
+        sm = torch.softmax(o.reshape(N, J, -1), 2).reshape(N, J, D, D, D)
+        ar = torch.arange(D, dtype=dt)
+        cx = (sm.sum((2, 3)) * ar).sum(2) / D - 0.5
+        cy = (sm.sum((2, 4)) * ar).sum(2) / D - 0.5
+        cz = (sm.sum((3, 4)) * ar).sum(2) / D - 0.5
+        c = torch.stack([cx, cy, cz], 2).reshape(N, J * 3)
+        loss = ((c - torch.from_numpy(gt).to(dt)).abs() * torch.from_numpy(wt).to(dt)).sum() / N
+        loss.backward()
+        return loss.item(), {k: v.grad for k, v in p.items() if getattr(v, "grad", None) is not None}
+
+    l64, g64 = oracle(torch.float64)
+    l32, g32 = oracle(torch.float32)
+    model = models.pose3d_resnet.get_pose_net(cfg, False, precision="tf32x3")
+    model.load_state_dict(sd)
+    model = model.to(dev).train()
+    loss = il.L1JointLocationLoss(J)(model(torch.from_numpy(x).to(dev)), torch.from_numpy(gt).to(dev),
+                                     torch.from_numpy(wt).to(dev))
+    loss.backward()
+    assert abs(loss.item() - l64) <= 1e-4 * abs(l64)
+    for k, p in model.named_parameters():
+        ours = relerr(p.grad.cpu().numpy(), g64[k].numpy())
+        base = relerr(g32[k].numpy(), g64[k].numpy())
+        assert ours <= max(1e-3, 2 * base), (k, ours, base)
+
+
+def test_fused_adam_matches_torch(dev):
+    import lib.utils.utils as U
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in ((7, 3), (64,), (5, 5, 3))]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    a, b = U.FusedAdam(ps, lr=1e-2), torch.optim.Adam(qs, lr=1e-2)
+    for it in range(5):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad, q.grad = g.clone(), g.clone()
+        a.step(); b.step()
+    for p, q in zip(ps, qs):
+        assert relerr(p.detach().cpu().numpy(), q.detach().cpu().numpy()) <= 1e-5

@@ -1,0 +1,110 @@
+"""CPU: pins the oracle restatements (oracle/restate.py, oracle/restate_net.py)
+against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  The reference ships no tests of its own
+(SURVEY.md section 4), so these vectors are the pin."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, restate_net
+from tests import golden_inputs as gi
+from tests.conftest import relerr
+
+
+@pytest.mark.parametrize("tag", list(gi.SOFTARGMAX_CASES))
+def test_softargmax_and_losses(golden, tag):
+    N, J, D, H, W, seed, scale = gi.SOFTARGMAX_CASES[tag]
+    g = golden("softargmax_" + tag)
+    logits = gi.logits(N, J, D, H, W, seed, scale)
+    coords = restate.softmax_integral(logits, J, W, H, D)
+    assert np.max(np.abs(coords - g["coords"])) <= 2e-6          # fp32 accumulation order only
+    gt, wt = gi.labels(N, J, seed)
+    for kind, key in (("l1", "l1"), ("smoothl1", "smoothl1")):
+        for norm in (False, True):
+            k = key + ("_norm" if norm else "")
+            loss, dcoords = restate.weighted_loss(kind, g["coords"], gt, wt, True, norm)
+            assert abs(loss - float(g[k + "_loss"])) <= 1e-5 * max(1.0, abs(loss))
+            grad = restate.softmax_integral_grad(logits, dcoords, J, W, H, D)
+            ref_sample = g[k + "_grad_sample"]
+            assert relerr(grad[:, :, ::3, ::3], ref_sample) <= 2e-4
+            assert relerr(np.abs(grad).sum((2, 3)), g[k + "_grad_sum_abs"]) <= 2e-4
+    loss, _ = restate.weighted_loss("mse", g["coords"], gt, wt, True, False)
+    assert abs(loss - float(g["mse_loss"])) <= 1e-5 * max(1.0, abs(loss))
+    if D == W:
+        res = restate.joint_location_result(256, 256, g["coords"])
+        assert np.max(np.abs(res - g["result"])) <= 1e-4
+
+
+def test_argmax(golden):
+    g = golden("argmax")
+    preds, maxvals, _ = restate.get_max_preds(gi.argmax_heatmaps())
+    assert np.array_equal(preds, g["preds"])                     # bit-exact indices
+    assert np.array_equal(maxvals, g["maxvals"])
+
+
+def test_triangulators(golden):
+    g = golden("triangulation")
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    for name, fn in (("linear_eigen_triangulation", restate.linear_eigen_triangulation),
+                     ("linear_LS_triangulation", restate.linear_LS_triangulation),
+                     ("iterative_LS_triangulation", restate.iterative_LS_triangulation)):
+        for i in range(len(u1)):
+            x, st = fn(u1[i], P1[i], u2[i], P2[i])
+            assert np.max(np.abs(x - g[name + "_x"][i])) <= 1e-6, name   # mm; bar is 1e-4
+            assert np.array_equal(np.asarray(st).astype(np.int64), g[name + "_status"][i])
+    u1e, u2e = gi.exact_projections(P1, P2, X)
+    for i in range(len(u1)):   # known-answer: noise-free projections triangulate back
+        assert np.max(np.abs(restate.linear_eigen_triangulation(u1e[i], P1[i], u2e[i], P2[i])[0] - X[i])) <= 1e-7
+        assert np.max(np.abs(restate.iterative_LS_triangulation(u1e[i], P1[i], u2e[i], P2[i])[0] - X[i])) <= 1e-7
+    assert np.max(np.abs(g["exact_eigen"] - X)) <= 1e-7 and np.max(np.abs(g["exact_iter"] - X)) <= 1e-7
+
+
+def test_patch_to_image(golden):
+    g = golden("patch_to_image")
+    coords, boxes = gi.patch_case()
+    for i in range(len(coords)):
+        out = restate.trans_coords_from_patch_to_org_3d(coords[i], *boxes[i, :4], 256, 256, 2000, 2000,
+                                                        scale=boxes[i, 4], rot=boxes[i, 5])
+        assert np.max(np.abs(out - g["kps"][i])) <= 1e-9
+
+
+def test_self_supervision_chain(golden):
+    g = golden("selfsup")
+    logits, meta = gi.selfsup_case()
+    J, D = 4, 16
+    coords = restate.softmax_integral(logits, J, D, D, D)
+    label, weight, X, img = restate.self_supervision(coords, meta)
+    assert np.max(np.abs(label - g["label"])) <= 5e-6
+    assert np.array_equal(weight, g["weight"])
+
+
+@pytest.mark.parametrize("tag", list(gi.NET_CASES))
+def test_network_restatement(golden, tag):
+    c = gi.NET_CASES[tag]
+    g = golden("net_" + tag)
+    shapes = restate_net.param_shapes(num_layers=c["layers"], num_joints=c["J"], volume=c["volume"],
+                                      depth_res=c["D"])
+    sd = restate_net.init_state(shapes, c["seed"])
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    x = torch.from_numpy(gi.images(c["N"], c["HW"], c["seed"]))
+    new_stats = {}
+    out = restate_net.forward(p, x, num_layers=c["layers"], volume=c["volume"],
+                              image_size=(c["HW"], c["HW"]), training=True, new_stats=new_stats)
+    outs = out if isinstance(out, tuple) else (out,)
+    for i, o in enumerate(outs):
+        assert relerr(o.detach().numpy(), g["out%d" % i]) <= 5e-4   # fp32 reassociation (tiny-batch BN)
+    gs = [torch.from_numpy(gi.grad_like(o.shape, c["seed"] + 1 + i)) for i, o in enumerate(outs)]
+    sum((o * gg).sum() for o, gg in zip(outs, gs)).backward()
+    # heads are well conditioned; deep-trunk gradients of a random-init net are chaotic in fp32
+    for k in ("final_layer.bias",):
+        assert relerr(p[k].grad.numpy(), g["grad/" + k]) <= 1e-3
+    assert relerr(new_stats["bn1.running_mean"].numpy(), g["bn1.running_mean"]) <= 1e-5
+    assert relerr(new_stats["bn1.running_var"].numpy(), g["bn1.running_var"]) <= 1e-5
+    sd_eval = dict(sd)
+    sd_eval.update(new_stats)          # the reference's eval pass ran after the running-stat update
+    with torch.no_grad():
+        e = restate_net.forward(sd_eval, x, num_layers=c["layers"], volume=c["volume"],
+                                image_size=(c["HW"], c["HW"]), training=False)
+    e = e[0] if isinstance(e, tuple) else e
+    assert relerr(e.numpy(), g["eval_out0"]) <= 5e-4

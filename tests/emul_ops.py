@@ -258,21 +258,22 @@ def softargmax_bwd(logits, layout, N, J, D, H, W, coords, lse, dcoords, dlogits)
 
 
 def jointloss(x, t, w, n, kind, norm, div, loss, dx):
-    xv = x.reshape(-1).detach().clone().requires_grad_(True)
-    tv = t.reshape(-1)
-    a, b = xv, tv
-    if norm:
-        a = xv / xv.abs().sum()
-        b = tv / tv.abs().sum()
-    d = a - b
-    if kind == 0:
-        l = d * d
-    elif kind == 1:
-        l = d.abs()
-    else:
-        l = torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5)
-    tot = (l * w.reshape(-1)).sum() / div
-    tot.backward()
+    with torch.enable_grad():
+        xv = x.reshape(-1).detach().clone().requires_grad_(True)
+        tv = t.reshape(-1)
+        a, b = xv, tv
+        if norm:
+            a = xv / xv.abs().sum()
+            b = tv / tv.abs().sum()
+        d = a - b
+        if kind == 0:
+            l = d * d
+        elif kind == 1:
+            l = d.abs()
+        else:
+            l = torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5)
+        tot = (l * w.reshape(-1)).sum() / div
+        tot.backward()
     if loss is not None:
         loss.view(-1)[0] = tot.detach()
     if dx is not None:

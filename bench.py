@@ -309,13 +309,34 @@ def run_gpu(args):
 
 
 # ---------------------------------------------------------------------------- CPU arm
+def pick_cpu_threads():
+    """torch-CPU convolutions do not scale to every hardware thread of the box
+    (128 threads were 100x SLOWER than 16 on the B200 hosts): time a small
+    forward at a few thread counts and give the reference arm the fastest."""
+    from oracle import restate_net
+    ncpu = os.cpu_count() or 1
+    sd = restate_net.init_state(restate_net.param_shapes(18, 2, True, 8), 0)
+    x = torch.randn(4, 3, 128, 128)
+    best, best_t = 1, float("inf")
+    for th in sorted({min(ncpu, c) for c in (8, 16, 32, 64)}):
+        torch.set_num_threads(th)
+        with torch.no_grad():
+            restate_net.forward(sd, x, num_layers=18, training=True)
+            t0 = time.perf_counter()
+            restate_net.forward(sd, x, num_layers=18, training=True)
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = th, dt
+    return best
+
+
 def cpu_reference(steps, warmup, tuples, layers=50):
     """The reference's CPU implementation of the step, restated (oracle port):
     torch-CPU fp32 PoseResNet fwd/bwd + Adam on all host threads, float64
     numpy geometry single-threaded as in the reference's Python loops."""
     from oracle import restate, restate_net
     from lib.dataset.synthetic import ring_camera
-    cores = os.cpu_count() or 1
+    cores = pick_cpu_threads()
     torch.set_num_threads(cores)
     n_img = tuples * VIEWS
     shapes = restate_net.param_shapes(layers, J, True, D)

@@ -395,8 +395,10 @@ epb_encode_tiled_fn epb_get_encode_tiled() {
   return fn;
 }
 
+bool epb_conv_wgrad_tc_supported(const epb_conv_geom* g);
+
 bool epb_conv_tc_supported(const epb_conv_geom* g, bool wgrad) {
-  if (wgrad) return false;
+  if (wgrad) return epb_conv_wgrad_tc_supported(g);
   return g->Cin % 32 == 0 && g->Cout % 32 == 0 && g->Cout >= 32;
 }
 
@@ -443,8 +445,3 @@ int epb_conv_fprop_tc(const epb_conv_geom* g, const float* in, const float* w,
   return EPB_EINVAL;
 }
 
-int epb_conv_wgrad_tc(const epb_conv_geom*, const float*, const float*, const float*, const float*,
-                      float*, cudaStream_t) {
-  epb_set_error("tcgen05 wgrad path not built");
-  return EPB_EINVAL;
-}

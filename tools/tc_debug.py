@@ -45,8 +45,32 @@ def run(kind, cin, cout, k, s, p, hw, N, precision, affine=True, verbose=True):
     st_ref = torch.cat([ref.double().sum((0, 2, 3)), (ref.double() ** 2).sum((0, 2, 3))])
     st = torch.cat([stats[:cout], stats[conv.cout_p:conv.cout_p + cout]])
     srel = ((st - st_ref).abs().max() / st_ref.abs().max()).item()
-    print("%-6s cin %4d cout %4d k%d s%d hw %3d N %d prec %d : rel err %.3e  stats rel %.3e"
-          % (kind, cin, cout, k, s, hw, N, precision, rel, srel), flush=True)
+    # dgrad + wgrad through the same geometry
+    gout = torch.randn_like(ref)
+    xa_ = xa.detach().clone().requires_grad_(True); w_ = w.detach().clone().requires_grad_(True)
+    r2 = (F.conv2d(xa_.double(), w_.double(), None, s, p) if kind == "conv"
+          else F.conv_transpose2d(xa_.double(), w_.double(), None, s, p))
+    gx, gw_ref = torch.autograd.grad(r2, (xa_, w_), gout.double())
+    gn = torch.zeros(N, Ho, Wo, conv.cout_p, device=dev)
+    ops.nchw_to_nhwc(gout.contiguous(), gn, N, cout, Ho, Wo, conv.cout_p)
+    drel = wrel = float("nan")
+    try:
+        din = eng._conv_dgrad(conv, gn, N, hw, hw, wd)
+        torch.cuda.synchronize()
+        drel = ((din[..., :cin].permute(0, 3, 1, 2) - gx.float()).abs().max() / gx.abs().max()).item()
+        gw = torch.zeros_like(w)
+        eng._conv_wgrad(conv, xn, gn, N, hw, hw, gw, affine=(sc, sh) if affine else None)
+        torch.cuda.synchronize()
+        wrel = ((gw - gw_ref.float()).abs().max() / gw_ref.abs().max()).item()
+    except Exception as e:
+        print("   dgrad/wgrad FAILED", repr(e)[:300])
+    print("%-6s cin %4d cout %4d k%d s%d hw %3d N %d prec %d : fprop %.3e stats %.3e dgrad %.3e wgrad %.3e"
+          % (kind, cin, cout, k, s, hw, N, precision, rel, srel, drel, wrel), flush=True)
+    if verbose and wrel > 5e-3:
+        e = (gw - gw_ref.float()).abs()
+        print("   wgrad bad: shape", tuple(gw.shape), "ratio sample",
+              (gw.flatten()[:8] / gw_ref.float().flatten()[:8]).cpu().numpy().round(3).tolist(),
+              "bad frac %.3f" % (e > 1e-2 * gw_ref.abs().max()).float().mean().item())
     if verbose and rel > 5e-3:
         e2 = err.permute(0, 2, 3, 1).reshape(-1, cout)      # [pixels][cout]
         r2 = ref.permute(0, 2, 3, 1).reshape(-1, cout)

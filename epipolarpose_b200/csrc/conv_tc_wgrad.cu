@@ -7,9 +7,9 @@
 // reduction index m strides over pixel rows), so no transposition is needed:
 // producer warps gather 32 pixel rows per stage (dout rows and the tap-shifted
 // input rows with the fused BatchNorm+ReLU of the producing layer), split them
-// into TF32 hi (+ lo for 3xTF32) and store them in the SWIZZLE_128B MN-major
-// layout (128-byte rows = 32 consecutive channels of one pixel; 8 pixel rows
-// form a 1024-byte atom).  One thread issues tcgen05.mma kind::tf32 with
+// into TF32 hi (+ lo for 3xTF32) and store them in the SWIZZLE_128B_BASE32B
+// MN-major layout (128-byte rows = 32 consecutive channels of one pixel; 4 pixel
+// rows form a 512-byte atom; the only layout tcgen05 takes for 32-bit MN-major).  One thread issues tcgen05.mma kind::tf32 with
 // M = 128 (co), N = ci tile, K = 8 pixels; FP32 accumulators live in TMEM for
 // the CTA's whole pixel range (split-K over pixels across CTAs), then the
 // epilogue adds the partial tile to dw with vector reductions
@@ -44,11 +44,16 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
                : "memory");
 }
 
-// store one float4 (4 consecutive channels `ch4*4..` of pixel row r) into the MN-major
-// SWIZZLE_128B tile: chunk c = ch4 / 8 (32 channels), 16-byte slot j = ch4 % 8
+// Store one float4 (4 consecutive channels `ch4*4..` of pixel row r) into the MN-major
+// tile.  For 32-bit MN-major operands tcgen05 accepts only the SWIZZLE_128B_BASE32B
+// layout: 128-byte rows (32 consecutive channels of one pixel), pixel rows at a 128-byte
+// pitch, atoms of 4 rows (512 B), and the 32-byte chunk index (address bits 5-6) XORed with
+// the row index mod 4 (address bits 7-8).  chunk c = ch4 / 8 selects the 32-channel column
+// block (LBO apart), ch4 % 8 the 16-byte slot inside the row.
 __device__ __forceinline__ void st_mn(uint8_t* tile, int r, int ch4, float4 v) {
+  const int slot = ch4 & 7;
   const uint32_t off = (uint32_t)(ch4 >> 3) * (KPIX * 128) + (uint32_t)r * 128u +
-                       (uint32_t)(((ch4 & 7) ^ (r & 7)) << 4);
+                       (uint32_t)((((slot >> 1) ^ (r & 3)) << 5) | ((slot & 1) << 4));
   *reinterpret_cast<float4*>(tile + off) = v;
 }
 
@@ -201,7 +206,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
     // ======================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_tf32(WM, BNW, 1, 1);     // both operands MN-major
-      constexpr uint32_t LBO = KPIX * 128, SBO = 1024;
+      constexpr uint32_t LBO = KPIX * 128, SBO = 512;   // chunk stride, 4-row k-atom stride
       int stage = 0;
       uint32_t phase = 0;
       for (int st = 0; st < nstages; ++st) {

@@ -6,7 +6,7 @@
 // descriptor"):
 //   smem descriptor: [0,14) start addr >> 4 | [16,30) leading byte offset >> 4 |
 //                    [32,46) stride byte offset >> 4 | [46,48) version = 1 |
-//                    [61,64) layout (2 = SWIZZLE_128B)
+//                    [61,64) layout (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B)
 //   instr descriptor (kind::tf32/f16): [4,6) D format (1 = f32) | [7,10) A format
 //                    (2 = tf32) | [10,13) B format | 15 A major (1 = MN) |
 //                    16 B major | [17,23) N >> 3 | [24,29) M >> 4
@@ -138,13 +138,13 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// MN-major operand, SWIZZLE_128B: 128-byte rows hold 32 consecutive MN
-// elements of one k; 8 k-rows form a 1024 B atom (SBO = stride between
+// MN-major 32-bit operand, SWIZZLE_128B_BASE32B (layout type 1): 128-byte rows hold 32
+// consecutive MN elements of one k; 4 k-rows form a 512 B atom (SBO = stride between
 // k-atoms); LBO = byte stride between successive 32-element MN chunks.
 __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t addr, uint32_t lbo_bytes,
                                                        uint32_t sbo_bytes) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+         ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) |

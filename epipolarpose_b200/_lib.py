@@ -31,6 +31,7 @@ _PROTOS = {
     "epb_conv_fprop": (c_int, [ctypes.POINTER(ConvGeom), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "epb_conv_wgrad": (c_int, [ctypes.POINTER(ConvGeom), c_p, c_p, c_p, c_p, c_p, c_p]),
     "epb_pack_weight": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "epb_im2col": (c_int, [c_p, c_p] + [c_int] * 12 + [c_p]),
     "epb_nchw_to_nhwc": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p]),
     "epb_nhwc_to_nchw": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p]),
     "epb_channel_stats": (c_int, [c_p, c_i64, c_int, c_p, c_p]),

@@ -124,27 +124,39 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         rows->pix_base[p] = -1;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int kb = 0; kb < KB; ++kb) {
+      // software pipeline: the global loads of k-block kb+1 are in flight while
+      // k-block kb is converted and stored (one exposed L2/HBM latency per TILE,
+      // not per k-block)
+      float4 v[8], vn[8];
+      unsigned okm = 0, okn = 0;
+      auto issue = [&](int kb, float4 (&dst)[8], unsigned& mask) {
         const int t = kb / CB, cb = kb - t * CB;
         const int dh = g.dh[t], dw = g.dw[t];
         const int ch = cb * BKE + c4 * 4;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in_scale) {
-          sc = *reinterpret_cast<const float4*>(in_scale + ch);
-          sh = *reinterpret_cast<const float4*>(in_shift + ch);
-        }
-        float4 v[8];
-        bool ok[8];
+        mask = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int r = warp * 32 + q * 4 + rsub;
           const int pb = rows->pix_base[r];
           const int ih = rows->ih0[r] + dh, iw = rows->iw0[r] + dw;
-          ok[q] = (pb >= 0) && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
-          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[q])
-            v[q] = *reinterpret_cast<const float4*>(
+          const bool ok = (pb >= 0) && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
+          dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            dst[q] = *reinterpret_cast<const float4*>(
                 in + ((int64_t)pb + (int64_t)ih * g.Wi + iw) * g.Cin + ch);
+            mask |= 1u << q;
+          }
+        }
+      };
+      issue(0, v, okm);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb + 1 < KB) issue(kb + 1, vn, okn);
+        const int cb = kb % CB;
+        const int ch = cb * BKE + c4 * 4;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in_scale) {
+          sc = *reinterpret_cast<const float4*>(in_scale + ch);
+          sh = *reinterpret_cast<const float4*>(in_shift + ch);
         }
         tc::mbar_wait(empty_bar(stage), phase ^ 1);
         uint8_t* a_hi = sm + stage * C::STAGE;
@@ -152,7 +164,7 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         for (int q = 0; q < 8; ++q) {
           const int r = warp * 32 + q * 4 + rsub;
           float4 x = v[q];
-          if (in_scale && ok[q]) {
+          if (in_scale && ((okm >> q) & 1u)) {
             x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
             x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
             if (g.in_relu) {
@@ -173,6 +185,9 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(full_bar(stage));
         if (++stage == C::S) { stage = 0; phase ^= 1; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = vn[q];
+        okm = okn;
       }
     }
   } else if (warp == kProducerWarps) {

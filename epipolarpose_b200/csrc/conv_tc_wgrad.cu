@@ -5,37 +5,42 @@
 // GEMM view: D[co, ci] with the reduction over pixels m.  Both operands are
 // "MN-major" for the tensor core (channels are contiguous in NHWC memory, the
 // reduction index m strides over pixel rows), so no transposition is needed:
-// producer warps gather 32 pixel rows per stage (dout rows and the tap-shifted
+// producer warps gather 32 pixel rows per tile (dout rows, and the tap-shifted
 // input rows with the fused BatchNorm+ReLU of the producing layer), split them
 // into TF32 hi (+ lo for 3xTF32) and store them in the SWIZZLE_128B_BASE32B
 // MN-major layout (128-byte rows = 32 consecutive channels of one pixel; 4 pixel
-// rows form a 512-byte atom; the only layout tcgen05 takes for 32-bit MN-major).  One thread issues tcgen05.mma kind::tf32 with
-// M = 128 (co), N = ci tile, K = 8 pixels; FP32 accumulators live in TMEM for
-// the CTA's whole pixel range (split-K over pixels across CTAs), then the
-// epilogue adds the partial tile to dw with vector reductions
-// (red.global.add.v4.f32).
+// rows form a 512-byte atom; the only layout tcgen05 takes for 32-bit MN-major).
 //
-// Work item = (co tile, tap, ci tile, pixel split); one work item per CTA.
+// One CTA = (co tile of 128, a group of NB "slots" = (tap, ci tile) pairs, a
+// split of the pixel range).  The dout tile A(p) of pixel block p is produced
+// ONCE and multiplied against the NB input tiles B(p, b) (two smem rings), each
+// slot accumulating into its own TMEM columns (NB * BNW <= 512 fp32 columns), so
+// dout is gathered once per NB taps instead of once per tap.  Global loads of the
+// next tile are in flight while the current one is converted and stored.  One
+// thread issues tcgen05.mma kind::tf32 (M = 128, N = BNW, K = 8 pixels); the
+// epilogue adds the partial tiles to dw with red.global.add.v4.f32 (split-K).
 #include "conv_common.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int WM = 128;          // co rows per tile (UMMA M); rows >= Cout are zero
-constexpr int KPIX = 32;         // pixels per pipeline stage (4 MMAs of K = 8)
+constexpr int KPIX = 32;         // pixels per tile (4 MMAs of K = 8)
 constexpr int kProdWarps = 8;
-constexpr int kThreadsW = 32 * (kProdWarps + 1);   // 8 producer/epilogue warps + 1 MMA warp
+constexpr int kProd = 32 * kProdWarps;
+constexpr int kThreadsW = kProd + 32;      // + 1 MMA warp
+constexpr int kMaxSlots = 16;
 
 template <int BNW, int NS>
 struct WCfg {
   static constexpr int PL = (NS == 3) ? 2 : 1;
-  static constexpr int A_BYTES = WM * KPIX * 4 * PL;     // dout tile  (hi[,lo])
-  static constexpr int B_BYTES = BNW * KPIX * 4 * PL;    // input tile (hi[,lo])
-  static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int S_ = (200 * 1024) / STAGE;
-  static constexpr int S = S_ > 6 ? 6 : S_;
-  static constexpr int TMEM_COLS = BNW <= 32 ? 32 : (BNW <= 64 ? 64 : 128);
-  static constexpr int SMEM = S * STAGE + 1024 + 256;
+  static constexpr int A_TILE = WM * KPIX * 4 * PL;      // dout tile  (hi[,lo])
+  static constexpr int B_TILE = BNW * KPIX * 4 * PL;     // input tile (hi[,lo])
+  static constexpr int SA = 2;
+  static constexpr int SB_ = (196 * 1024 - SA * A_TILE) / B_TILE;
+  static constexpr int SB = SB_ > 8 ? 8 : SB_;
+  static constexpr int NB_MAX = (512 / BNW) > kMaxSlots ? kMaxSlots : (512 / BNW);
+  static constexpr int SMEM = SA * A_TILE + SB * B_TILE + 1024 + 512;
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -57,108 +62,173 @@ __device__ __forceinline__ void st_mn(uint8_t* tile, int r, int ch4, float4 v) {
   *reinterpret_cast<float4*>(tile + off) = v;
 }
 
+struct PixCoord { int n, i, j; };
+
 template <int BNW, int NS>
 __global__ void __launch_bounds__(kThreadsW, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __restrict__ in,
                      const float* __restrict__ dout, const float* __restrict__ in_scale,
                      const float* __restrict__ in_shift, float* __restrict__ dw, int co_tiles,
-                     int ci_tiles, int rows_per_split) {
+                     int ci_tiles, int groups, int nb_per_group, int rows_per_split) {
   using C = WCfg<BNW, NS>;
+  constexpr int QA = WM / 4;                 // float4 per dout row (32)
+  constexpr int QB = BNW / 4;                // float4 per input row
+  constexpr int RA = kProd / QA;             // dout rows covered per pass (8)
+  constexpr int RB = kProd / QB;             // input rows covered per pass
+  constexpr int PA = KPIX / RA;              // passes (4)
+  constexpr int PB = KPIX / RB;              // passes (BNW=128:4, 64:2, 32:1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  uint8_t* ctrl = sm + C::S * C::STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);       // full[S], empty[S], done
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl + 8 * 16);
+  uint8_t* smB = sm + C::SA * C::A_TILE;
+  uint8_t* ctrl = smB + C::SB * C::B_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);   // fullA[2] emptyA[2] fullB[8] emptyB[8] done
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl + 8 * 24);
   const uint32_t bar0 = tc::smem_u32(bars);
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (6 + s); };
-  const uint32_t done_bar = bar0 + 8u * 12;
+  auto fullA = [&](int s) { return bar0 + 8u * s; };
+  auto emptyA = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto fullB = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto emptyB = [&](int s) { return bar0 + 8u * (12 + s); };
+  const uint32_t done_bar = bar0 + 8u * 20;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // work item decode
+  // work item decode: blockIdx.x = ((split * co_tiles + cot) * groups + grp)
   int w = blockIdx.x;
-  const int cit = w % ci_tiles; w /= ci_tiles;
-  const int t = w % g.T; w /= g.T;
+  const int grp = w % groups; w /= groups;
   const int cot = w % co_tiles;
   const int split = w / co_tiles;
-  const int64_t M = (int64_t)g.N * g.Hp * g.Wp;
-  const int64_t mbeg = (int64_t)split * rows_per_split;
-  const int64_t mend = mbeg + rows_per_split < M ? mbeg + rows_per_split : M;
-  const int nstages = (int)((mend - mbeg + KPIX - 1) / KPIX);
-  const int co0 = cot * WM, ci0 = cit * BNW;
+  const int total_slots = g.T * ci_tiles;
+  const int slot0 = grp * nb_per_group;
+  const int NB = min(nb_per_group, total_slots - slot0);
+  const int M = g.N * g.Hp * g.Wp;
+  const int mbeg = split * rows_per_split;
+  const int mend = min(M, mbeg + rows_per_split);
+  const int nblk = (mend - mbeg + KPIX - 1) / KPIX;
+  const int co0 = cot * WM;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::S; ++s) {
-      tc::mbar_init(full_bar(s), kProdWarps);
-      tc::mbar_init(empty_bar(s), 1);
-    }
+    for (int s = 0; s < C::SA; ++s) { tc::mbar_init(fullA(s), kProdWarps); tc::mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < C::SB; ++s) { tc::mbar_init(fullB(s), kProdWarps); tc::mbar_init(emptyB(s), 1); }
     tc::mbar_init(done_bar, 1);
     tc::fence_barrier_init();
   }
-  if (warp == kProdWarps) tc::tmem_alloc<C::TMEM_COLS>(tc::smem_u32(tmem_ptr));
+  if (warp == kProdWarps) tc::tmem_alloc<512>(tc::smem_u32(tmem_ptr));
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < kProdWarps) {
-    // ======================================== producers: 4 pixel rows per warp per stage
-    const int dh = g.dh[t], dwv = g.dw[t];
-    const int co = co0 + lane * 4;            // this lane's 4 dout channels
+    // ======================================================== producers (256 threads)
+    const int tid = threadIdx.x;
+    const int qa = tid % QA, ra0 = tid / QA;        // dout: float4 slot, first row
+    const int qb = tid % QB, rb0 = tid / QB;        // input: float4 slot, first row
+    const int co = co0 + qa * 4;
     const bool co_ok = co < g.Cout;
-    const int ci = ci0 + lane * 4;            // this lane's 4 input channels
-    const bool ci_ok = (lane * 4 < BNW) && ci < g.Cin;
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in_scale && ci_ok) {
-      sc = *reinterpret_cast<const float4*>(in_scale + ci);
-      sh = *reinterpret_cast<const float4*>(in_shift + ci);
-    }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int st = 0; st < nstages; ++st) {
-      float4 a[4], b[4];
-      bool bok[4];
+    // pixel coordinates of this thread's rows of the CURRENT block (advance by 32 px per block)
+    PixCoord ca[PA], cb[PB];
+    auto decode = [&](int m, PixCoord& c) {
+      const unsigned um = (unsigned)m;
+      c.j = (int)(um % (unsigned)g.Wp);
+      const unsigned q = um / (unsigned)g.Wp;
+      c.i = (int)(q % (unsigned)g.Hp);
+      c.n = (int)(q / (unsigned)g.Hp);
+    };
+    auto advance = [&](PixCoord& c) {
+      c.j += KPIX;
+      while (c.j >= g.Wp) { c.j -= g.Wp; if (++c.i == g.Hp) { c.i = 0; ++c.n; } }
+    };
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t m = mbeg + (int64_t)st * KPIX + warp * 4 + q;
-        a[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        b[q] = a[q];
-        bok[q] = false;
-        if (m < mend) {
-          const int j = (int)(m % g.Wp);
-          const int i = (int)((m / g.Wp) % g.Hp);
-          const int n = (int)(m / ((int64_t)g.Wp * g.Hp));
-          if (co_ok)
-            a[q] = *reinterpret_cast<const float4*>(
-                dout + (((int64_t)n * g.Ho + (i * g.os + g.ph)) * g.Wo + (j * g.os + g.pw)) * g.Cout + co);
-          const int ih = i * g.is + dh, iw = j * g.is + dwv;
-          if (ci_ok && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi) {
-            b[q] = *reinterpret_cast<const float4*>(
-                in + (((int64_t)n * g.Hi + ih) * g.Wi + iw) * g.Cin + ci);
-            bok[q] = true;
+    for (int k = 0; k < PA; ++k) decode(mbeg + ra0 + k * RA, ca[k]);
+#pragma unroll
+    for (int k = 0; k < PB; ++k) decode(mbeg + rb0 + k * RB, cb[k]);
+
+    constexpr int NREG = PA > PB ? PA : PB;
+    float4 cur[NREG], nxt[NREG];
+    unsigned curm = 0, nxtm = 0;
+    // tile sequence: u = blk * (NB + 1) + e ; e == 0 -> dout tile, e >= 1 -> input slot e-1
+    const int per_blk = NB + 1;
+    const int total = nblk * per_blk;
+    auto issue = [&](int u, float4 (&dst)[NREG], unsigned& mask) {
+      const int blk = u / per_blk, e = u - blk * per_blk;
+      const int mrow0 = mbeg + blk * KPIX;
+      mask = 0;
+      if (e == 0) {
+#pragma unroll
+        for (int k = 0; k < PA; ++k) {
+          dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (co_ok && mrow0 + ra0 + k * RA < mend)
+            dst[k] = *reinterpret_cast<const float4*>(
+                dout + (((int64_t)ca[k].n * g.Ho + (ca[k].i * g.os + g.ph)) * g.Wo +
+                        (ca[k].j * g.os + g.pw)) * g.Cout + co);
+        }
+      } else {
+        const int sl = slot0 + e - 1;
+        const int t = sl / ci_tiles, cit = sl - t * ci_tiles;
+        const int ci = cit * BNW + qb * 4;
+        const int dh = g.dh[t], dwv = g.dw[t];
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+          dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int ih = cb[k].i * g.is + dh, iw = cb[k].j * g.is + dwv;
+          if (ci < g.Cin && mrow0 + rb0 + k * RB < mend && ih >= 0 && ih < g.Hi && iw >= 0 &&
+              iw < g.Wi) {
+            dst[k] = *reinterpret_cast<const float4*>(
+                in + (((int64_t)cb[k].n * g.Hi + ih) * g.Wi + iw) * g.Cin + ci);
+            mask |= 1u << k;
           }
         }
       }
-      tc::mbar_wait(empty_bar(stage), phase ^ 1);
-      uint8_t* a_hi = sm + stage * C::STAGE;
-      uint8_t* b_hi = a_hi + C::A_BYTES;
+    };
+    auto split_store = [&](uint8_t* tile, int tile_plane_bytes, int r, int ch4, float4 x) {
+      const float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
+                                    tc::to_tf32(x.w));
+      st_mn(tile, r, ch4, hi);
+      if (NS == 3)
+        st_mn(tile + tile_plane_bytes, r, ch4,
+              make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+    };
+
+    if (total > 0) issue(0, cur, curm);
+    for (int u = 0; u < total; ++u) {
+      const int blk = u / per_blk, e = u - blk * per_blk;
+      // coordinates must describe the NEXT tile's pixel block when its loads are issued
+      if (u + 1 < total) {
+        if (e + 1 == per_blk) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = warp * 4 + q;
-        {
-          const float4 x = a[q];
-          const float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
-                                        tc::to_tf32(x.w));
-          st_mn(a_hi, r, lane, hi);
-          if (NS == 3)
-            st_mn(a_hi + WM * KPIX * 4, r, lane,
-                  make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+          for (int k = 0; k < PA; ++k) advance(ca[k]);
+#pragma unroll
+          for (int k = 0; k < PB; ++k) advance(cb[k]);
         }
-        if (lane * 4 < BNW) {
-          float4 x = b[q];
-          if (in_scale && bok[q]) {
+        issue(u + 1, nxt, nxtm);
+      }
+      if (e == 0) {
+        const int s = blk % C::SA;
+        tc::mbar_wait(emptyA(s), ((blk / C::SA) & 1) ^ 1);
+        uint8_t* tile = sm + s * C::A_TILE;
+#pragma unroll
+        for (int k = 0; k < PA; ++k) split_store(tile, WM * KPIX * 4, ra0 + k * RA, qa, cur[k]);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(fullA(s));
+      } else {
+        const int qn = blk * NB + (e - 1);
+        const int s = qn % C::SB;
+        const int sl = slot0 + e - 1;
+        const int cit = sl % ci_tiles;
+        const int ci = cit * BNW + qb * 4;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in_scale && ci < g.Cin) {
+          sc = *reinterpret_cast<const float4*>(in_scale + ci);
+          sh = *reinterpret_cast<const float4*>(in_shift + ci);
+        }
+        tc::mbar_wait(emptyB(s), ((qn / C::SB) & 1) ^ 1);
+        uint8_t* tile = smB + s * C::B_TILE;
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+          float4 x = cur[k];
+          if (in_scale && ((curm >> k) & 1u)) {
             x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
             x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
             if (g.in_relu) {
@@ -166,70 +236,75 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
               x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
             }
           }
-          const float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
-                                        tc::to_tf32(x.w));
-          st_mn(b_hi, r, lane, hi);
-          if (NS == 3)
-            st_mn(b_hi + BNW * KPIX * 4, r, lane,
-                  make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+          split_store(tile, BNW * KPIX * 4, rb0 + k * RB, qb, x);
         }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(fullB(s));
       }
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(full_bar(stage));
-      if (++stage == C::S) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int k = 0; k < NREG; ++k) cur[k] = nxt[k];
+      curm = nxtm;
     }
-    // ======================================== epilogue (warps 0-3: one TMEM lane quarter each)
+    // ======================================================== epilogue (warps 0-3)
     if (warp < 4) {
       tc::mbar_wait(done_bar, 0);
       tc::tc_fence_after();
-      const int row = warp * 32 + lane;
-      const int corow = co0 + row;
+      const int corow = co0 + warp * 32 + lane;
       const int64_t wrow = (int64_t)g.Tw * g.Cin;
+      for (int b = 0; b < NB; ++b) {
+        const int sl = slot0 + b;
+        const int t = sl / ci_tiles, cit = sl - t * ci_tiles;
 #pragma unroll 1
-      for (int chunk = 0; chunk < BNW / 32; ++chunk) {
-        uint32_t r[32];
-        tc::tmem_ld32(tmem_base + chunk * 32 + ((uint32_t)(warp * 32) << 16), r);
-        tc::tmem_ld_wait();
-        const int c0 = ci0 + chunk * 32;
-        if (corow < g.Cout && c0 < g.Cin) {
-          float* dst = dw + (int64_t)corow * wrow + (int64_t)g.wt[t] * g.Cin + c0;
+        for (int chunk = 0; chunk < BNW / 32; ++chunk) {
+          uint32_t r[32];
+          tc::tmem_ld32(tmem_base + b * BNW + chunk * 32 + ((uint32_t)(warp * 32) << 16), r);
+          tc::tmem_ld_wait();
+          const int c0 = cit * BNW + chunk * 32;
+          if (nblk > 0 && corow < g.Cout && c0 < g.Cin) {
+            float* dst = dw + (int64_t)corow * wrow + (int64_t)g.wt[t] * g.Cin + c0;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            if (c0 + c < g.Cin)
-              red_add_v4(dst + c, __uint_as_float(r[c]), __uint_as_float(r[c + 1]),
-                         __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+            for (int c = 0; c < 32; c += 4)
+              if (c0 + c < g.Cin)
+                red_add_v4(dst + c, __uint_as_float(r[c]), __uint_as_float(r[c + 1]),
+                           __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+          }
         }
       }
     }
   } else {
-    // ======================================== MMA issuer
+    // ======================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_tf32(WM, BNW, 1, 1);     // both operands MN-major
       constexpr uint32_t LBO = KPIX * 128, SBO = 512;   // chunk stride, 4-row k-atom stride
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int st = 0; st < nstages; ++st) {
-        tc::mbar_wait(full_bar(stage), phase);
-        tc::tc_fence_after();
-        const uint32_t a_hi = base + stage * C::STAGE;
-        const uint32_t b_hi = a_hi + C::A_BYTES;
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int sa = blk % C::SA;
+        tc::mbar_wait(fullA(sa), (blk / C::SA) & 1);
+        const uint32_t a_hi = base + sa * C::A_TILE;
+        for (int b = 0; b < NB; ++b) {
+          const int qn = blk * NB + b;
+          const int sb = qn % C::SB;
+          tc::mbar_wait(fullB(sb), (qn / C::SB) & 1);
+          tc::tc_fence_after();
+          const uint32_t b_hi = base + C::SA * C::A_TILE + sb * C::B_TILE;
+          const uint32_t d_tmem = tmem_base + b * BNW;
 #pragma unroll
-        for (int ks = 0; ks < KPIX / 8; ++ks) {
-          const uint64_t ah = tc::desc_mnmajor_sw128(a_hi + ks * 1024, LBO, SBO);
-          const uint64_t bh = tc::desc_mnmajor_sw128(b_hi + ks * 1024, LBO, SBO);
-          if (NS == 3) {
-            const uint64_t al = tc::desc_mnmajor_sw128(a_hi + WM * KPIX * 4 + ks * 1024, LBO, SBO);
-            const uint64_t bl = tc::desc_mnmajor_sw128(b_hi + BNW * KPIX * 4 + ks * 1024, LBO, SBO);
-            tc::mma_tf32(tmem_base, al, bh, idesc, (st | ks) != 0);
-            tc::mma_tf32(tmem_base, ah, bl, idesc, 1);
-            tc::mma_tf32(tmem_base, ah, bh, idesc, 1);
-          } else {
-            tc::mma_tf32(tmem_base, ah, bh, idesc, (st | ks) != 0);
+          for (int ks = 0; ks < KPIX / 8; ++ks) {
+            const uint64_t ah = tc::desc_mnmajor_sw128(a_hi + ks * 1024, LBO, SBO);
+            const uint64_t bh = tc::desc_mnmajor_sw128(b_hi + ks * 1024, LBO, SBO);
+            if (NS == 3) {
+              const uint64_t al = tc::desc_mnmajor_sw128(a_hi + WM * KPIX * 4 + ks * 1024, LBO, SBO);
+              const uint64_t bl = tc::desc_mnmajor_sw128(b_hi + BNW * KPIX * 4 + ks * 1024, LBO, SBO);
+              tc::mma_tf32(d_tmem, al, bh, idesc, (blk | ks) != 0);
+              tc::mma_tf32(d_tmem, ah, bl, idesc, 1);
+              tc::mma_tf32(d_tmem, ah, bh, idesc, 1);
+            } else {
+              tc::mma_tf32(d_tmem, ah, bh, idesc, (blk | ks) != 0);
+            }
           }
+          tc::mma_commit(emptyB(sb));
         }
-        tc::mma_commit(empty_bar(stage));
-        if (++stage == C::S) { stage = 0; phase ^= 1; }
+        tc::mma_commit(emptyA(sa));
       }
       tc::mma_commit(done_bar);
     }
@@ -238,7 +313,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
   __syncthreads();
   if (warp == kProdWarps) {
     tc::tc_fence_after();
-    tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    tc::tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -247,11 +322,16 @@ int launch_wgrad(const epb_conv_geom* g, const float* in, const float* dout, con
                  const float* in_shift, float* dw, cudaStream_t st) {
   using C = WCfg<BNW, NS>;
   const int64_t M = (int64_t)g->N * g->Hp * g->Wp;
+  EPB_CHECK_ARG(M < (1LL << 31));
   const int co_tiles = (g->Cout + WM - 1) / WM;
   const int ci_tiles = (g->Cin + BNW - 1) / BNW;
-  const int64_t tiles = (int64_t)co_tiles * ci_tiles * g->T;
+  const int total_slots = g->T * ci_tiles;
+  const int groups = (total_slots + C::NB_MAX - 1) / C::NB_MAX;
+  const int nb = (total_slots + groups - 1) / groups;          // balanced group size
+  const int groups2 = (total_slots + nb - 1) / nb;
+  const int64_t tiles = (int64_t)co_tiles * groups2;
   int64_t splits = (2 * kNumSMs + tiles - 1) / tiles;
-  const int64_t max_splits = (M + 8 * KPIX - 1) / (8 * KPIX);     // >= 8 stages per CTA
+  const int64_t max_splits = (M + 8 * KPIX - 1) / (8 * KPIX);   // >= 8 pixel blocks per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int64_t rows = (M + splits - 1) / splits;
@@ -266,7 +346,7 @@ int launch_wgrad(const epb_conv_geom* g, const float* in, const float* dout, con
   const int64_t grid = tiles * splits;
   EPB_CHECK_ARG(grid < (1LL << 31));
   conv_wgrad_tc_kernel<BNW, NS><<<(unsigned)grid, kThreadsW, C::SMEM, st>>>(
-      *g, in, dout, in_scale, in_shift, dw, co_tiles, ci_tiles, (int)rows);
+      *g, in, dout, in_scale, in_shift, dw, co_tiles, ci_tiles, groups2, nb, (int)rows);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

@@ -60,6 +60,37 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
+// col[m][kk], kk = (r*kw + s)*C + c (zero for kk >= kh*kw*C and for padding pixels):
+// the 7x7 stem (C = 3) becomes a K-major GEMM operand for the tensor-core path.
+__global__ void im2col_kernel(const float* __restrict__ in, float4* __restrict__ col, int N, int Hi,
+                              int Wi, int pitch, int C, int kh, int kw, int stride, int pad, int Ho,
+                              int Wo, int Kpad) {
+  const int K4 = Kpad >> 2, K = kh * kw * C;
+  const int64_t total = (int64_t)N * Ho * Wo * K4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int k4 = (int)(i % K4);
+    int64_t m = i / K4;
+    const int ow = (int)(m % Wo); m /= Wo;
+    const int oh = (int)(m % Ho);
+    const int n = (int)(m / Ho);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int kk = k4 * 4 + e;
+      v[e] = 0.f;
+      if (kk < K) {
+        const int t = kk / C, c = kk - t * C;
+        const int r = t / kw, sx = t - r * kw;
+        const int ih = oh * stride - pad + r, iw = ow * stride - pad + sx;
+        if (ih >= 0 && ih < Hi && iw >= 0 && iw < Wi)
+          v[e] = __ldg(in + ((int64_t)(n * Hi + ih) * Wi + iw) * pitch + c);
+      }
+    }
+    col[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                             float4* __restrict__ m, float4* __restrict__ v, int64_t n4, float lr,
                             float b1, float b2, float eps, float wd, float bc1, float rsqrt_bc2,
@@ -155,6 +186,21 @@ extern "C" __attribute__((visibility("default"))) int epb_nhwc_to_nchw(const flo
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (Cpad + 31) / 32, N);
   nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, dst, C, HW, Cpad);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_im2col(const float* in, float* col, int N, int Hi, int Wi, int pitch, int C, int kh,
+                          int kw, int stride, int pad, int Ho, int Wo, int Kpad,
+                          epb_stream_t stream) {
+  EPB_CHECK_ARG(in && col && N > 0 && Hi > 0 && Wi > 0 && C > 0 && pitch >= C);
+  EPB_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && Ho > 0 && Wo > 0);
+  EPB_CHECK_ARG(Kpad % 4 == 0 && Kpad >= kh * kw * C);
+  const int64_t total = (int64_t)N * Ho * Wo * (Kpad / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+  im2col_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(
+      in, reinterpret_cast<float4*>(col), N, Hi, Wi, pitch, C, kh, kw, stride, pad, Ho, Wo, Kpad);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

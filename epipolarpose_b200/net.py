@@ -119,6 +119,9 @@ class PoseNetPlan:
         self.image_size = tuple(image_size)
         self.exp = 4 if self.kind == "bottleneck" else 1
         self.stem = Conv("conv1", "conv", 3, 64, 7, 2, 3)
+        # the stem runs as a 1x1 conv over its patch matrix (K = 7*7*3 = 147 -> 160)
+        self.stem_kpad = _pad(7 * 7 * 3, 32)
+        self.stem_col = Conv("conv1", "conv", self.stem_kpad, 64, 1, 1, 0)
         self.blocks = []
         inpl = 64
         for li, (planes, nb) in enumerate(zip((64, 128, 256, 512), self.layers)):
@@ -294,16 +297,25 @@ class Engine:
             return wf
 
         # ---- stem (pose3d_resnet.py:186-189)
-        stem = plan.stem
+        stem, scol, kpad = plan.stem, plan.stem_col, plan.stem_kpad
         x = self._new(N, H, W, stem.cin_p)
         ops.nchw_to_nhwc(x_nchw, x, N, 3, H, W, stem.cin_p)
-        z0, H1, W1 = self._conv_fwd(stem, x, N, H, W, packed(stem), stats=stats_of("bn1", 64))
+        H1, W1 = stem.out_hw(H, W)
+        col = self._new(N, H1, W1, kpad)
+        ops.im2col(x, col, N, H, W, stem.cin_p, 3, 7, 7, 2, 3, H1, W1, kpad)
+        # conv1.weight [64,3,7,7] -> [64][(r,s,c)] -> zero-padded [64][kpad]
+        w147 = torch.empty(64 * 147, device=self.dev, dtype=torch.float32)
+        ops.pack_weight(params["conv1.weight"], w147, 64, 3, 7, 7, 0, 3)
+        wcol = torch.zeros((64, kpad, 1, 1), device=self.dev, dtype=torch.float32)
+        wcol.view(64, kpad)[:, :147] = w147.view(64, 147)
+        wf_col, _ = scol.pack(ops, wcol)
+        z0, _, _ = self._conv_fwd(scol, col, N, H1, W1, wf_col, stats=stats_of("bn1", 64))
         b0 = bn("bn1", 64, N * H1 * W1)
         H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
         cur = self._new(N, H2, W2, 64)
         argidx = self._new(N, H2, W2, 64, dtype=torch.uint8)
         ops.bn_relu_maxpool(z0, b0.scale, b0.shift, cur, argidx, N, H1, W1, 64)
-        S["stem"] = (x, z0, argidx, H1, W1, H2, W2)
+        S["stem"] = (col, z0, argidx, H1, W1, H2, W2)
         h, w = H2, W2
 
         # ---- residual stages (:191-194)
@@ -457,8 +469,12 @@ class Engine:
                 ops.add_masked(g, dcur, out, nd, g.numel())
                 dcur = nd
         # ---- stem
-        x, z0, argidx, H1, W1, H2, W2 = S["stem"]
+        col, z0, argidx, H1, W1, H2, W2 = S["stem"]
         gpool = self._new(N, H1, W1, 64)
         ops.maxpool_bwd(dcur, argidx, gpool, N, H1, W1, 64)
         dz0 = self._bn_bwd(S["bn"]["bn1"], gpool, z0, None, 1, params, grads)
-        self._conv_wgrad(plan.stem, x, dz0, N, S["H"], S["W"], grads["conv1.weight"])
+        kpad = plan.stem_kpad
+        gcol = torch.zeros((64, kpad, 1, 1), device=self.dev, dtype=torch.float32)
+        self._conv_wgrad(plan.stem_col, col, dz0, N, H1, W1, gcol)
+        g147 = gcol.view(64, kpad)[:, :147].contiguous()
+        ops.pack_weight(g147, grads["conv1.weight"], 64, 3, 7, 7, 0, 3, 1)

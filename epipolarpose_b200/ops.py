@@ -80,6 +80,11 @@ def pack_weight(src, dst, A, B, kh, kw, swap, ypad, unpack=0):
     _call("epb_pack_weight", _p(src), _p(dst), A, B, kh, kw, swap, ypad, unpack, _stream())
 
 
+def im2col(x, col, N, Hi, Wi, pitch, C, kh, kw, stride, pad, Ho, Wo, Kpad):
+    _call("epb_im2col", _p(x), _p(col), N, Hi, Wi, pitch, C, kh, kw, stride, pad, Ho, Wo, Kpad,
+          _stream())
+
+
 def nchw_to_nhwc(src, dst, N, C, H, W, Cpad):
     _call("epb_nchw_to_nhwc", _p(src), _p(dst), N, C, H, W, Cpad, _stream())
 

@@ -101,6 +101,15 @@ int epb_conv_wgrad(const epb_conv_geom* g, const float* in, const float* dout,
 int epb_pack_weight(const float* src, float* dst, int A, int B, int kh, int kw,
                     int swap, int Ypad, int unpack, epb_stream_t stream);
 
+/* Patch matrix of a small-Cin convolution (the 7x7 stem, pose3d_resnet.py:99):
+ * col[m][(r*kw+s)*C + c] = in[n, oh*stride-pad+r, ow*stride-pad+s, c] (0 outside
+ * the image and for columns >= kh*kw*C), row pitch Kpad floats, so the layer
+ * runs as a 1x1 conv on the tensor-core path.  `in` is NHWC with `pitch` floats
+ * per pixel. */
+int epb_im2col(const float* in, float* col, int N, int Hi, int Wi, int pitch,
+               int C, int kh, int kw, int stride, int pad, int Ho, int Wo,
+               int Kpad, epb_stream_t stream);
+
 /* NCHW <-> NHWC float32 with channel padding (module boundary only:
  * pose3d_resnet.py:185 takes NCHW images, returns NCHW heatmaps). */
 int epb_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W,

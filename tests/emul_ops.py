@@ -88,6 +88,17 @@ def pack_weight(src, dst, A, B, kh, kw, swap, ypad, unpack=0):
         d.copy_(p.permute(2, 0, 1) if swap else p.permute(0, 2, 1))
 
 
+def im2col(x, col, N, Hi, Wi, pitch, C, kh, kw, stride, pad, Ho, Wo, Kpad):
+    xs = x.reshape(N, Hi, Wi, pitch)[..., :C]
+    xp = torch.nn.functional.pad(xs, (0, 0, pad, pad, pad, pad))
+    out = torch.zeros(N, Ho, Wo, Kpad)
+    for r in range(kh):
+        for s in range(kw):
+            t = r * kw + s
+            out[..., t * C:(t + 1) * C] = xp[:, r:r + stride * Ho:stride, s:s + stride * Wo:stride]
+    col.view(N, Ho, Wo, Kpad).copy_(out)
+
+
 def nchw_to_nhwc(src, dst, N, C, H, W, Cpad):
     d = dst.view(N, H, W, Cpad)
     d.zero_()

@@ -11,6 +11,7 @@ extern "C" __attribute__((visibility("default"))) int epb_conv_fprop(const epb_c
   EPB_CHECK_ARG(in && w && out);
   EPB_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr));
   EPB_CHECK_ARG(g->precision == 0 || g->precision == 1 || g->precision == 3);
+  EPB_CHECK_ARG(!(stats && g->accumulate));   // statistics describe a freshly written output
   if (g->precision != 0 && epb_conv_tc_supported(g, false))
     return epb_conv_fprop_tc(g, in, w, in_scale, in_shift, bias, out, stats, as_stream(stream));
   return epb_conv_fprop_simt(g, in, w, in_scale, in_shift, bias, out, stats, as_stream(stream));

@@ -42,8 +42,10 @@ struct Cfg {
   static constexpr int S_ = kSmemBudget / STAGE;
   static constexpr int S = S_ > 8 ? 8 : S_;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int EPI_PITCH = 36;                          // floats per staged row (144 B)
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;       // one 32x32 block per epilogue warp
   static constexpr int SMEM = S * STAGE + 1024 /*align*/ + 1024 /*barriers, rowinfo*/ +
-                              BM * 3 * 4 + 2 * BN * 4;
+                              BM * 3 * 4 + 2 * BN * 4 + EPI_BYTES;
 };
 
 struct RowInfo {
@@ -69,6 +71,7 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl + 8 * (2 * 8 + 4));
   RowInfo* rows = reinterpret_cast<RowInfo*>(ctrl + 1024);
   float* sstat = reinterpret_cast<float*>(ctrl + 1024 + sizeof(RowInfo));   // [2][BN]
+  float* epi_stage = sstat + 2 * BN;                                         // [4][32][EPI_PITCH]
   const uint32_t bar0 = tc::smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
@@ -267,6 +270,8 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
       }
       tc::mbar_wait(tfull_bar(as), aphase);
       tc::tc_fence_after();
+      float* stg = epi_stage + (warp - (kProducerWarps + 2)) * 32 * C::EPI_PITCH;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         const int col0 = nt * BN + chunk * 32;
@@ -274,53 +279,51 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         uint32_t r[32];
         tc::tmem_ld32(tmem_base + as * BN + chunk * 32 + ((uint32_t)(q * 32) << 16), r);
         tc::tmem_ld_wait();
-        float v[32];
+        // stage this warp's 32x32 block (row = TMEM lane) so that the global stores below
+        // write whole 128-byte lines (4 rows per warp instruction) instead of 32 scattered
+        // 16-byte pieces
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]);
-        if (bias) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+        for (int c = 0; c < 32; c += 4) {
+          float4 x = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
+                                 __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+          if (bias) {
             const float4 b = *reinterpret_cast<const float4*>(bias + col0 + c);
-            v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
           }
+          *reinterpret_cast<float4*>(stg + lane * C::EPI_PITCH + c) = x;
         }
-        if (valid) {
-          float4* o4 = reinterpret_cast<float4*>(orow + col0);
-          if (g.accumulate) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 pv = o4[c];
-              v[4 * c] += pv.x; v[4 * c + 1] += pv.y; v[4 * c + 2] += pv.z; v[4 * c + 3] += pv.w;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            o4[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        }
+        __syncwarp();
         if (stats) {
-          // column sums over this warp's 32 rows: transpose-reduce (31 shuffles per quantity)
-          float s1[32], s2[32];
+          // lane = column: sum over the 32 staged rows (bank = 4*row + lane: conflict free)
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float x = valid ? v[c] : 0.f;
-            s1[c] = x;
-            s2[c] = x * x;
+          for (int rr = 0; rr < 32; ++rr) {
+            const float x = ((vmask >> rr) & 1u) ? stg[rr * C::EPI_PITCH + lane] : 0.f;
+            s1 += x;
+            s2 = fmaf(x, x, s2);
           }
+          atomicAdd(&sstat[chunk * 32 + lane], s1);
+          atomicAdd(&sstat[BN + chunk * 32 + lane], s2);
+        }
+        {
+          const int c4 = lane & 7, rsub = lane >> 3;
 #pragma unroll
-          for (int w = 16; w >= 1; w >>= 1) {
-            const bool up = (lane & w) != 0;
-#pragma unroll
-            for (int c = 0; c < w; ++c) {
-              const float keep1 = up ? s1[c + w] : s1[c], send1 = up ? s1[c] : s1[c + w];
-              const float keep2 = up ? s2[c + w] : s2[c], send2 = up ? s2[c] : s2[c + w];
-              s1[c] = keep1 + __shfl_xor_sync(0xffffffffu, send1, w);
-              s2[c] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            float* prow = reinterpret_cast<float*>(
+                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(orow), rr));
+            if (prow) {
+              float4 x = *reinterpret_cast<const float4*>(stg + rr * C::EPI_PITCH + c4 * 4);
+              float4* o = reinterpret_cast<float4*>(prow + col0) + c4;
+              if (g.accumulate) {
+                const float4 pv = *o;
+                x.x += pv.x; x.y += pv.y; x.z += pv.z; x.w += pv.w;
+              }
+              *o = x;
             }
           }
-          // lane l now holds the sums of column bitrev-free index: column = lane
-          atomicAdd(&sstat[chunk * 32 + lane], s1[0]);
-          atomicAdd(&sstat[BN + chunk * 32 + lane], s2[0]);
         }
+        __syncwarp();
       }
       tc::tc_fence_before();
       __syncwarp();

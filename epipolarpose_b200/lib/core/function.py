@@ -33,6 +33,25 @@ def _online_tri(config):
     return bool(train is not None and getattr(train, 'ONLINE_TRIANGULATION', False))
 
 
+def online_epipolar_loss(criterion, preds, meta, method="iterative"):
+    """criterion(preds, labels(preds), 1) with the labels produced by the epipolar
+    self-supervision path from the SAME soft-argmax coordinates the loss uses
+    (labels carry no gradient, reference integral_loss.py:88-91)."""
+    from .integral_loss import softmax_integral_tensor, _WeightedLossFn
+    from ..utils.img_utils import (patch_to_image_device, triangulate_device,
+                                   labels_from_global_coords_device)
+    J = criterion.num_joints
+    W, H = preds.shape[-1], preds.shape[-2]
+    D = preds.shape[-3] // J
+    coords = softmax_integral_tensor(preds, J, True, W, H, D)
+    with torch.no_grad():
+        kps = patch_to_image_device(coords.detach(), meta)
+        X = triangulate_device(kps, meta, method)
+        label, weight = labels_from_global_coords_device(X, meta)
+    return _WeightedLossFn.apply(coords, label, weight, criterion._kind, criterion.size_average,
+                                 criterion.norm)
+
+
 def train_integral(config, train_loader, model, criterion, optimizer, epoch):
     batch_time = AverageMeter()
     data_time = AverageMeter()
@@ -50,11 +69,13 @@ def train_integral(config, train_loader, model, criterion, optimizer, epoch):
         batch_size = batch_data.size(0)
         preds = model(batch_data)
         if online:
-            batch_label, batch_label_weight = self_supervision_device(preds.detach(), meta, method)
+            # one soft-argmax pass serves both the epipolar labels and the loss
+            loss = online_epipolar_loss(criterion, preds, meta, method)
+            batch_label = batch_label_weight = None
         else:
             batch_label = batch_label.cuda(non_blocking=True)
             batch_label_weight = batch_label_weight.cuda(non_blocking=True)
-        loss = criterion(preds, batch_label, batch_label_weight)
+            loss = criterion(preds, batch_label, batch_label_weight)
         del batch_data, batch_label, batch_label_weight, preds
         loss.backward()
         optimizer.step()

@@ -1,0 +1,38 @@
+"""Key metrics + warp-stall breakdown of a .ncu-rep (run where ncu is installed)."""
+import csv, io, subprocess, sys
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, vals = rows[0], rows[-1]
+d = dict(zip(hdr, vals))
+keys = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "gpu__time_duration.sum", "sm__cycles_active.avg",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_st.sum",
+        "lts__t_sectors_op_write.sum", "lts__t_sectors_op_read.sum", "lts__t_requests_srcunit_tex_op_write.sum"]
+for k in keys:
+    for h in hdr:
+        if h == k:
+            print("%-70s %s" % (h, d[h]))
+stalls = [(h, float(d[h].replace(",", ""))) for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")] or \
+         [(h, float(d[h].replace(",", ""))) for h in hdr if "warp_issue_stalled" in h and h.endswith(".pct")]
+for h, v in sorted(stalls, key=lambda x: -x[1])[:10]:
+    print("  stall %-66s %.3f" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("smsp__average_warp_latency_issue_stalled_", ""), v))
+if len(sys.argv) > 2:
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(src)))
+    h = rows[0]
+    try:
+        isrc = h.index("Source"); ismp = [i for i, x in enumerate(h) if x.startswith("# Samples") or x == "Warp Stall Sampling (All Samples)"][0]
+        body = [r for r in rows[1:] if len(r) > ismp and r[ismp].replace(",", "").isdigit()]
+        body.sort(key=lambda r: -int(r[ismp].replace(",", "")))
+        tot = sum(int(r[ismp].replace(",", "")) for r in body) or 1
+        for r in body[:int(sys.argv[2])]:
+            print("  %5.1f%%  %s" % (100.0 * int(r[ismp].replace(",", "")) / tot, r[isrc][:110]))
+    except Exception as e:
+        print("source page parse failed", e, h[:12])

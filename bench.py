@@ -229,8 +229,10 @@ def run_gpu(args):
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
+    h0 = time.perf_counter()
     for i in range(args.steps):
         loss = step(dev_batches[i % 2])       # 2 x 100 MB inputs + >25 GB activations >> 126 MB L2
+    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
@@ -295,7 +297,7 @@ def run_gpu(args):
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT,
                 "h2d_bytes_per_step": int(host_batches[0].numel() * 4),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
         "roofline": {"bound": "tensor", "kernel": "conv implicit-GEMM family (fprop/dgrad/wgrad)",
                      "achieved": round(achieved, 3), "peak": round(tensor_peak, 1),
                      "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 5),

@@ -5,13 +5,13 @@
 //   BatchNorm+ReLU applied on the fly.
 //
 // One persistent CTA per SM, warp-specialised:
-//   warps 0-3  A producers: gather 128 pixel rows x 32 channels (128-byte rows),
+//   warps 0-7  A producers: gather 128 pixel rows x 32 channels (128-byte rows),
 //              fused BN+ReLU, split into TF32 hi (+ lo for the 3xTF32 mode) and
 //              store into the SWIZZLE_128B K-major smem layout tcgen05 reads;
-//   warp  4    B producer: TMA loads of the packed weight tile (hi / lo planes);
-//   warp  5    MMA issuer: one thread issues tcgen05.mma kind::tf32 (M=128,
+//   warp  8    B producer: TMA loads of the packed weight tile (hi / lo planes);
+//   warp  9    MMA issuer: one thread issues tcgen05.mma kind::tf32 (M=128,
 //              N=BN, K=8) with FP32 accumulators in TMEM (double buffered);
-//   warps 6-9  epilogue: tcgen05.ld TMEM -> registers -> bias / accumulate ->
+//   warps 10-13 epilogue: tcgen05.ld TMEM -> registers -> bias / accumulate ->
 //              global, plus per-channel sum / sum-of-squares for the following
 //              BatchNorm (warp transpose-reduce, smem, one double atomic per
 //              column per tile).
@@ -28,9 +28,10 @@ namespace {
 
 constexpr int BM = 128;          // pixel rows per tile == UMMA M
 constexpr int BKE = 32;          // tf32 elements per k-block (128 bytes)
-constexpr int kProducerWarps = 4;
+constexpr int kProducerWarps = 8;       // 256 gather threads: bytes in flight, not issue rate, bound the A stream
+constexpr int kPrefetch = 4;            // k-blocks of global loads in flight per thread (register ring)
 constexpr int kEpiWarps = 4;
-constexpr int kThreads = 32 * (kProducerWarps + 2 + kEpiWarps);   // 320
+constexpr int kThreads = 32 * (kProducerWarps + 2 + kEpiWarps);   // 448
 constexpr int kSmemBudget = 200 * 1024;
 
 template <int BN, int NS>
@@ -104,42 +105,43 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < kProducerWarps) {
-    // =================================================== A producers (128 threads)
-    const int p = threadIdx.x;                 // 0..127: row whose geometry this thread computes
+    // =================================================== A producers (256 threads)
+    const int p = threadIdx.x;                 // threads 0..127 also compute one row's geometry
     const int c4 = lane & 7;                   // 16-byte chunk within the 128-byte row
     const int rsub = lane >> 3;                // 0..3
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / n_tiles;
-      const int64_t m = (int64_t)mt * BM + p;
-      // producers of the previous tile are done reading rowinfo (they all passed
-      // their last k-block) once every producer reaches this barrier
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (m < M) {
-        const int j = (int)(m % g.Wp);
-        const int i = (int)((m / g.Wp) % g.Hp);
-        const int n = (int)(m / ((int64_t)g.Wp * g.Hp));
-        rows->pix_base[p] = n * g.Hi * g.Wi;
-        rows->ih0[p] = i * g.is;
-        rows->iw0[p] = j * g.is;
-      } else {
-        rows->pix_base[p] = -1;
+      // producers of the previous tile are done reading rowinfo once all reach this barrier
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (p < BM) {
+        const int64_t m = (int64_t)mt * BM + p;
+        if (m < M) {
+          const unsigned um = (unsigned)m;
+          const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
+          const unsigned i = qq % (unsigned)g.Hp, n = qq / (unsigned)g.Hp;
+          rows->pix_base[p] = (int)n * g.Hi * g.Wi;
+          rows->ih0[p] = (int)i * g.is;
+          rows->iw0[p] = (int)j * g.is;
+        } else {
+          rows->pix_base[p] = -1;
+        }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // software pipeline: the global loads of k-block kb+1 are in flight while
-      // k-block kb is converted and stored (one exposed L2/HBM latency per TILE,
-      // not per k-block)
-      float4 v[8], vn[8];
-      unsigned okm = 0, okn = 0;
-      auto issue = [&](int kb, float4 (&dst)[8], unsigned& mask) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // Register ring of kPrefetch k-blocks: the loads of k-blocks kb+1..kb+3 are in flight
+      // while k-block kb is converted and stored.  These layers stream activations from
+      // HBM (~1.5 us latency): 256 threads x 4 x 16 B x 4 slots = 64 KB in flight per SM.
+      float4 buf[kPrefetch][4];
+      unsigned okm[kPrefetch];
+      auto issue = [&](int kb, float4 (&dst)[4], unsigned& mask) {
         const int t = kb / CB, cb = kb - t * CB;
         const int dh = g.dh[t], dw = g.dw[t];
         const int ch = cb * BKE + c4 * 4;
         mask = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = warp * 32 + q * 4 + rsub;
+        for (int q = 0; q < 4; ++q) {
+          const int r = warp * 16 + q * 4 + rsub;
           const int pb = rows->pix_base[r];
           const int ih = rows->ih0[r] + dh, iw = rows->iw0[r] + dw;
           const bool ok = (pb >= 0) && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
@@ -151,9 +153,7 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           }
         }
       };
-      issue(0, v, okm);
-      for (int kb = 0; kb < KB; ++kb) {
-        if (kb + 1 < KB) issue(kb + 1, vn, okn);
+      auto process = [&](int kb, const float4 (&v)[4], unsigned mask) {
         const int cb = kb % CB;
         const int ch = cb * BKE + c4 * 4;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -164,10 +164,10 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         tc::mbar_wait(empty_bar(stage), phase ^ 1);
         uint8_t* a_hi = sm + stage * C::STAGE;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = warp * 32 + q * 4 + rsub;
+        for (int q = 0; q < 4; ++q) {
+          const int r = warp * 16 + q * 4 + rsub;
           float4 x = v[q];
-          if (in_scale && ((okm >> q) & 1u)) {
+          if (in_scale && ((mask >> q) & 1u)) {
             x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
             x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
             if (g.in_relu) {
@@ -188,9 +188,20 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(full_bar(stage));
         if (++stage == C::S) { stage = 0; phase ^= 1; }
+      };
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = vn[q];
-        okm = okn;
+      for (int d = 0; d < kPrefetch - 1; ++d)
+        if (d < KB) issue(d, buf[d], okm[d]);
+      for (int kb0 = 0; kb0 < KB; kb0 += kPrefetch) {
+#pragma unroll
+        for (int d = 0; d < kPrefetch; ++d) {
+          const int kb = kb0 + d;
+          if (kb < KB) {
+            const int nx = kb + kPrefetch - 1;
+            if (nx < KB) issue(nx, buf[(d + kPrefetch - 1) % kPrefetch], okm[(d + kPrefetch - 1) % kPrefetch]);
+            process(kb, buf[d], okm[d]);
+          }
+        }
       }
     }
   } else if (warp == kProducerWarps) {

@@ -145,16 +145,23 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
     for (int k = 0; k < PB; ++k) decode(mbeg + rb0 + k * RB, cb[k]);
 
     constexpr int NREG = PA > PB ? PA : PB;
-    float4 cur[NREG], nxt[NREG];
-    unsigned curm = 0, nxtm = 0;
+    constexpr int PD = 4;                         // register ring: 3 tiles of loads in flight
+    float4 buf[PD][NREG];
+    unsigned msk[PD];
     // tile sequence: u = blk * (NB + 1) + e ; e == 0 -> dout tile, e >= 1 -> input slot e-1
     const int per_blk = NB + 1;
     const int total = nblk * per_blk;
-    auto issue = [&](int u, float4 (&dst)[NREG], unsigned& mask) {
-      const int blk = u / per_blk, e = u - blk * per_blk;
-      const int mrow0 = mbeg + blk * KPIX;
+    int iu = 0, ie = 0, iblk = 0;                 // issue cursor (runs PD-1 tiles ahead)
+    auto issue_next = [&](float4 (&dst)[NREG], unsigned& mask) {
+      if (ie == 0 && iu > 0) {                    // the cursor enters the next pixel block
+#pragma unroll
+        for (int k = 0; k < PA; ++k) advance(ca[k]);
+#pragma unroll
+        for (int k = 0; k < PB; ++k) advance(cb[k]);
+      }
+      const int mrow0 = mbeg + iblk * KPIX;
       mask = 0;
-      if (e == 0) {
+      if (ie == 0) {
 #pragma unroll
         for (int k = 0; k < PA; ++k) {
           dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -164,7 +171,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
                         (ca[k].j * g.os + g.pw)) * g.Cout + co);
         }
       } else {
-        const int sl = slot0 + e - 1;
+        const int sl = slot0 + ie - 1;
         const int t = sl / ci_tiles, cit = sl - t * ci_tiles;
         const int ci = cit * BNW + qb * 4;
         const int dh = g.dh[t], dwv = g.dw[t];
@@ -180,6 +187,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
           }
         }
       }
+      ++iu;
+      if (++ie == per_blk) { ie = 0; ++iblk; }
     };
     auto split_store = [&](uint8_t* tile, int tile_plane_bytes, int r, int ch4, float4 x) {
       const float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
@@ -189,20 +198,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         st_mn(tile + tile_plane_bytes, r, ch4,
               make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
     };
-
-    if (total > 0) issue(0, cur, curm);
-    for (int u = 0; u < total; ++u) {
+    auto process = [&](int u, const float4 (&cur)[NREG], unsigned curm) {
       const int blk = u / per_blk, e = u - blk * per_blk;
-      // coordinates must describe the NEXT tile's pixel block when its loads are issued
-      if (u + 1 < total) {
-        if (e + 1 == per_blk) {
-#pragma unroll
-          for (int k = 0; k < PA; ++k) advance(ca[k]);
-#pragma unroll
-          for (int k = 0; k < PB; ++k) advance(cb[k]);
-        }
-        issue(u + 1, nxt, nxtm);
-      }
       if (e == 0) {
         const int s = blk % C::SA;
         tc::mbar_wait(emptyA(s), ((blk / C::SA) & 1) ^ 1);
@@ -242,9 +239,19 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(fullB(s));
       }
+    };
 #pragma unroll
-      for (int k = 0; k < NREG; ++k) cur[k] = nxt[k];
-      curm = nxtm;
+    for (int d = 0; d < PD - 1; ++d)
+      if (d < total) issue_next(buf[d], msk[d]);
+    for (int u0 = 0; u0 < total; u0 += PD) {
+#pragma unroll
+      for (int d = 0; d < PD; ++d) {
+        const int u = u0 + d;
+        if (u < total) {
+          if (u + PD - 1 < total) issue_next(buf[(d + PD - 1) % PD], msk[(d + PD - 1) % PD]);
+          process(u, buf[d], msk[d]);
+        }
+      }
     }
     // ======================================================== epilogue (warps 0-3)
     if (warp < 4) {

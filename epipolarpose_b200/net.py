@@ -35,6 +35,7 @@ class Conv:
         self.bias = bias
         self.cin_p = _pad(cin, 4)
         self.cout_p = _pad(cout, 4)
+        self._gcache = {}
 
     def out_hw(self, h, w):
         if self.kind == "conv":
@@ -75,15 +76,21 @@ class Conv:
         return geoms
 
     def fprop_geoms(self, ops, N, H, W, precision):
-        Ho, Wo = self.out_hw(H, W)
-        f = self._gather_geoms if self.kind == "conv" else self._scatter_geoms
-        return f(ops, N, H, W, self.cin_p, Ho, Wo, self.cout_p, precision)
+        key = ("f", id(ops), N, H, W, precision)
+        if key not in self._gcache:           # geometry tables are static per shape: build once
+            Ho, Wo = self.out_hw(H, W)
+            f = self._gather_geoms if self.kind == "conv" else self._scatter_geoms
+            self._gcache[key] = f(ops, N, H, W, self.cin_p, Ho, Wo, self.cout_p, precision)
+        return self._gcache[key]
 
     def dgrad_geoms(self, ops, N, H, W, precision):
         """src = dOut [N,Ho,Wo,cout], dst = dIn [N,H,W,cin]."""
-        Ho, Wo = self.out_hw(H, W)
-        f = self._scatter_geoms if self.kind == "conv" else self._gather_geoms
-        return f(ops, N, Ho, Wo, self.cout_p, H, W, self.cin_p, precision)
+        key = ("d", id(ops), N, H, W, precision)
+        if key not in self._gcache:
+            Ho, Wo = self.out_hw(H, W)
+            f = self._scatter_geoms if self.kind == "conv" else self._gather_geoms
+            self._gcache[key] = f(ops, N, Ho, Wo, self.cout_p, H, W, self.cin_p, precision)
+        return self._gcache[key]
 
     # ---- weights --------------------------------------------------------------
     def pack(self, ops, w):
@@ -209,6 +216,7 @@ class Engine:
             if g is None:
                 continue
             g.in_relu = relu if affine is not None else 0
+            g.accumulate = 0
             ops.conv_fprop(g, x, wf, out, sc, sh, bias, stats)
         return out, Ho, Wo
 
@@ -226,6 +234,7 @@ class Engine:
             if g is None:
                 continue
             g.accumulate = 1 if accumulate_into is not None else 0
+            g.in_relu = 0
             ops.conv_fprop(g, dout, wd, din, None, None, None, None)
         return din
 

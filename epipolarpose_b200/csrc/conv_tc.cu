@@ -134,10 +134,32 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
       // HBM (~1.5 us latency): 256 threads x 4 x 16 B x 4 slots = 64 KB in flight per SM.
       float4 buf[kPrefetch][4];
       unsigned okm[kPrefetch];
-      auto issue = [&](int kb, float4 (&dst)[4], unsigned& mask) {
-        const int t = kb / CB, cb = kb - t * CB;
-        const int dh = g.dh[t], dw = g.dw[t];
-        const int ch = cb * BKE + c4 * 4;
+      int it = 0, icb = 0, pcb = 0;            // issue cursor (tap, channel block); consume cursor
+      // Warm L2 for the NEXT tile of this CTA while the current one is processed: one
+      // prefetch per 128-byte line of the (un-shifted) pixel row.  These layers stream
+      // their activations from HBM exactly once; without this every k-block pays the
+      // DRAM latency with only the register ring's bytes in flight.
+      {
+        const int ntile = tile + gridDim.x;
+        if (p < BM && ntile < total_tiles && ntile / n_tiles != mt) {
+          const int64_t mn = (int64_t)(ntile / n_tiles) * BM + p;
+          if (mn < M) {
+            const unsigned um = (unsigned)mn;
+            const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
+            const unsigned i = qq % (unsigned)g.Hp, n = qq / (unsigned)g.Hp;
+            int ih = (int)i * g.is, iw = (int)j * g.is;
+            ih = ih < g.Hi ? ih : g.Hi - 1;
+            iw = iw < g.Wi ? iw : g.Wi - 1;
+            const float* rowp = in + (((int64_t)n * g.Hi + ih) * g.Wi + iw) * g.Cin;
+            for (int c = 0; c < g.Cin; c += 32)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + c));
+          }
+        }
+      }
+      auto issue = [&](float4 (&dst)[4], unsigned& mask) {
+        const int dh = g.dh[it], dw = g.dw[it];
+        const int ch = icb * BKE + c4 * 4;
+        if (++icb == CB) { icb = 0; ++it; }
         mask = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -153,9 +175,9 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           }
         }
       };
-      auto process = [&](int kb, const float4 (&v)[4], unsigned mask) {
-        const int cb = kb % CB;
-        const int ch = cb * BKE + c4 * 4;
+      auto process = [&](const float4 (&v)[4], unsigned mask) {
+        const int ch = pcb * BKE + c4 * 4;
+        if (++pcb == CB) pcb = 0;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in_scale) {
           sc = *reinterpret_cast<const float4*>(in_scale + ch);
@@ -191,15 +213,15 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
       };
 #pragma unroll
       for (int d = 0; d < kPrefetch - 1; ++d)
-        if (d < KB) issue(d, buf[d], okm[d]);
+        if (d < KB) issue(buf[d], okm[d]);
       for (int kb0 = 0; kb0 < KB; kb0 += kPrefetch) {
 #pragma unroll
         for (int d = 0; d < kPrefetch; ++d) {
           const int kb = kb0 + d;
           if (kb < KB) {
             const int nx = kb + kPrefetch - 1;
-            if (nx < KB) issue(nx, buf[(d + kPrefetch - 1) % kPrefetch], okm[(d + kPrefetch - 1) % kPrefetch]);
-            process(kb, buf[d], okm[d]);
+            if (nx < KB) issue(buf[(d + kPrefetch - 1) % kPrefetch], okm[(d + kPrefetch - 1) % kPrefetch]);
+            process(buf[d], okm[d]);
           }
         }
       }
@@ -212,9 +234,10 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % n_tiles;
+        int t = 0, cb = 0;
         for (int kb = 0; kb < KB; ++kb) {
-          const int t = kb / CB, cb = kb - t * CB;
           const int kx = g.wt[t] * g.Cin + cb * BKE;
+          if (++cb == CB) { cb = 0; ++t; }
           tc::mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t b_dst = base + stage * C::STAGE + C::A_BYTES;
           tc::mbar_arrive_expect_tx(full_bar(stage), C::B_BYTES);

@@ -152,6 +152,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
     const int per_blk = NB + 1;
     const int total = nblk * per_blk;
     int iu = 0, ie = 0, iblk = 0;                 // issue cursor (runs PD-1 tiles ahead)
+    const int t_first = slot0 / ci_tiles, cit_first = slot0 - t_first * ci_tiles;
+    int it = t_first, icit = cit_first;           // tap / ci tile of the cursor's input slot
     auto issue_next = [&](float4 (&dst)[NREG], unsigned& mask) {
       if (ie == 0 && iu > 0) {                    // the cursor enters the next pixel block
 #pragma unroll
@@ -162,6 +164,26 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
       const int mrow0 = mbeg + iblk * KPIX;
       mask = 0;
       if (ie == 0) {
+        // warm L2 eight pixel blocks ahead (rows of one block are contiguous when the phase
+        // grid is dense): the register ring alone keeps too few bytes in flight for HBM
+        const int pfm = mrow0 + 8 * KPIX;
+        if (pfm < mend) {
+          if (g.os == 1) {
+            const int lines = (KPIX * WM * 4) / 128;         // co tile: 4 lines per row
+            for (int l = tid; l < lines; l += kProd) {
+              const int r = l >> 2, c = (l & 3) * 32;
+              if (co0 + c < g.Cout)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(dout + (int64_t)(pfm + r) * g.Cout + co0 + c));
+            }
+          }
+          if (g.is == 1 && g.Hp == g.Hi && g.Wp == g.Wi) {
+            const int lpr = g.Cin >> 5;                       // lines per input row
+            for (int l = tid; l < KPIX * lpr; l += kProd) {
+              const int r = l / lpr, c = (l - r * lpr) * 32;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (int64_t)(pfm + r) * g.Cin + c));
+            }
+          }
+        }
 #pragma unroll
         for (int k = 0; k < PA; ++k) {
           dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -171,10 +193,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
                         (ca[k].j * g.os + g.pw)) * g.Cout + co);
         }
       } else {
-        const int sl = slot0 + ie - 1;
-        const int t = sl / ci_tiles, cit = sl - t * ci_tiles;
-        const int ci = cit * BNW + qb * 4;
-        const int dh = g.dh[t], dwv = g.dw[t];
+        const int ci = icit * BNW + qb * 4;
+        const int dh = g.dh[it], dwv = g.dw[it];
+        if (++icit == ci_tiles) { icit = 0; ++it; }
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
           dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -188,7 +209,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         }
       }
       ++iu;
-      if (++ie == per_blk) { ie = 0; ++iblk; }
+      if (++ie == per_blk) { ie = 0; ++iblk; it = t_first; icit = cit_first; }
     };
     auto split_store = [&](uint8_t* tile, int tile_plane_bytes, int r, int ch4, float4 x) {
       const float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
@@ -198,11 +219,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         st_mn(tile + tile_plane_bytes, r, ch4,
               make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
     };
-    auto process = [&](int u, const float4 (&cur)[NREG], unsigned curm) {
-      const int blk = u / per_blk, e = u - blk * per_blk;
+    int pe = 0, pblk = 0, pcit = cit_first;       // consume cursor
+    int sA = 0, sB = 0;
+    uint32_t phA = 0, phB = 0;
+    auto process = [&](const float4 (&cur)[NREG], unsigned curm) {
+      const int e = pe;
       if (e == 0) {
-        const int s = blk % C::SA;
-        tc::mbar_wait(emptyA(s), ((blk / C::SA) & 1) ^ 1);
+        const int s = sA;
+        tc::mbar_wait(emptyA(s), phA ^ 1);
+        if (++sA == C::SA) { sA = 0; phA ^= 1; }
         uint8_t* tile = sm + s * C::A_TILE;
 #pragma unroll
         for (int k = 0; k < PA; ++k) split_store(tile, WM * KPIX * 4, ra0 + k * RA, qa, cur[k]);
@@ -210,17 +235,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(fullA(s));
       } else {
-        const int qn = blk * NB + (e - 1);
-        const int s = qn % C::SB;
-        const int sl = slot0 + e - 1;
-        const int cit = sl % ci_tiles;
-        const int ci = cit * BNW + qb * 4;
+        const int s = sB;
+        const int ci = pcit * BNW + qb * 4;
+        if (++pcit == ci_tiles) pcit = 0;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in_scale && ci < g.Cin) {
           sc = *reinterpret_cast<const float4*>(in_scale + ci);
           sh = *reinterpret_cast<const float4*>(in_shift + ci);
         }
-        tc::mbar_wait(emptyB(s), ((qn / C::SB) & 1) ^ 1);
+        tc::mbar_wait(emptyB(s), phB ^ 1);
+        if (++sB == C::SB) { sB = 0; phB ^= 1; }
         uint8_t* tile = smB + s * C::B_TILE;
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
@@ -239,6 +263,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(fullB(s));
       }
+      if (++pe == per_blk) { pe = 0; ++pblk; pcit = cit_first; }
     };
 #pragma unroll
     for (int d = 0; d < PD - 1; ++d)
@@ -249,7 +274,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         const int u = u0 + d;
         if (u < total) {
           if (u + PD - 1 < total) issue_next(buf[(d + PD - 1) % PD], msk[(d + PD - 1) % PD]);
-          process(u, buf[d], msk[d]);
+          process(buf[d], msk[d]);
         }
       }
     }
@@ -284,14 +309,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_tf32(WM, BNW, 1, 1);     // both operands MN-major
       constexpr uint32_t LBO = KPIX * 128, SBO = 512;   // chunk stride, 4-row k-atom stride
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       for (int blk = 0; blk < nblk; ++blk) {
-        const int sa = blk % C::SA;
-        tc::mbar_wait(fullA(sa), (blk / C::SA) & 1);
+        tc::mbar_wait(fullA(sa), pha);
         const uint32_t a_hi = base + sa * C::A_TILE;
         for (int b = 0; b < NB; ++b) {
-          const int qn = blk * NB + b;
-          const int sb = qn % C::SB;
-          tc::mbar_wait(fullB(sb), (qn / C::SB) & 1);
+          tc::mbar_wait(fullB(sb), phb);
           tc::tc_fence_after();
           const uint32_t b_hi = base + C::SA * C::A_TILE + sb * C::B_TILE;
           const uint32_t d_tmem = tmem_base + b * BNW;
@@ -310,8 +334,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
             }
           }
           tc::mma_commit(emptyB(sb));
+          if (++sb == C::SB) { sb = 0; phb ^= 1; }
         }
         tc::mma_commit(emptyA(sa));
+        if (++sa == C::SA) { sa = 0; pha ^= 1; }
       }
       tc::mma_commit(done_bar);
     }

@@ -129,6 +129,57 @@ __global__ void adam_kernel1(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// Device-side hyper-parameters (CUDA-graph friendly): hyper = [lr, beta1, beta2, eps, wd,
+// grad_scale], *step_dev = 1-based step count (incremented by the caller before the launch).
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                const float* __restrict__ hyper, const int* __restrict__ step_dev) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4],
+              gscale = hyper[5];
+  const double st = (double)*step_dev;
+  const float bc1 = (float)(1.0 - pow((double)b1, st));
+  const float rsqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, st)));
+  const float step = lr / bc1;
+  const int64_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    float* P = &pp.x; float* G = &gg.x; float* Mv = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr = G[k] * gscale;
+      if (wd != 0.f) gr += wd * P[k];
+      Mv[k] = b1 * Mv[k] + (1.f - b1) * gr;
+      V[k] = b2 * V[k] + (1.f - b2) * gr * gr;
+      P[k] -= step * (Mv[k] / (sqrtf(V[k]) * rsqrt_bc2 + eps));
+    }
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+}
+
+// hyper = [lr, momentum, wd, nesterov, grad_scale]; first step when *step_dev == 1
+__global__ void sgd_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                               float* __restrict__ buf, int64_t n, const float* __restrict__ hyper,
+                               const int* __restrict__ step_dev) {
+  const float lr = hyper[0], mom = hyper[1], wd = hyper[2], gscale = hyper[4];
+  const bool nesterov = hyper[3] != 0.f, first = (*step_dev == 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gscale;
+    if (wd != 0.f) gr += wd * p[i];
+    if (mom != 0.f) {
+      const float b = first ? gr : mom * buf[i] + gr;
+      buf[i] = b;
+      gr = nesterov ? gr + mom * b : b;
+    }
+    p[i] -= lr * gr;
+  }
+}
+
 __global__ void sgd_kernel1(float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ buf, int64_t n, float lr, float mom, float wd,
                             int nesterov, int first, float gscale) {
@@ -267,6 +318,30 @@ extern "C" __attribute__((visibility("default"))) int epb_sgd_step(float* param,
       reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad),
       reinterpret_cast<float4*>(momentum_buf), n / 4, lr, momentum, weight_decay, nesterov,
       first_step, grad_scale);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                 int64_t n, const float* hyper, const int* step_dev,
+                                 epb_stream_t stream) {
+  EPB_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && hyper && step_dev && n > 0 && n % 4 == 0);
+  EPB_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16) == 0);
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  adam_dev_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n,
+                                                              hyper, step_dev);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_sgd_step_dev(float* param, const float* grad, float* momentum_buf, int64_t n,
+                                const float* hyper, const int* step_dev, epb_stream_t stream) {
+  EPB_CHECK_ARG(param && grad && momentum_buf && hyper && step_dev && n > 0);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  sgd_dev_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(param, grad, momentum_buf, n, hyper,
+                                                             step_dev);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

@@ -52,6 +52,75 @@ def online_epipolar_loss(criterion, preds, meta, method="iterative"):
                                  criterion.norm)
 
 
+class GraphedTrainStep:
+    """One training step (forward, loss, backward incl. the gradient all-reduce, optimiser)
+    captured ONCE in a CUDA graph and replayed: the step is ~3000 kernel launches whose
+    Python/driver issue time is otherwise comparable to the GPU time.  Inputs are copied
+    into static device buffers; hyper-parameters and the step counter live in device
+    memory (FusedAdam / FusedSGD), so LR schedules keep working.  The first call runs
+    eagerly (sizes workspaces, one-time attributes), the second captures and replays."""
+
+    def __init__(self, model, criterion, optimizer, online=False, method="iterative"):
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        self.online, self.method = online, method
+        self.graph = None
+        self.key = None
+        self.calls = 0
+
+    def _eager(self, x, label, weight, geom):
+        self.optimizer.zero_grad()
+        preds = self.model(x)
+        if self.online:
+            loss = online_epipolar_loss(self.criterion, preds, {"_packed": geom}, self.method)
+        else:
+            loss = self.criterion(preds, label, weight)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def __call__(self, batch_data, label=None, weight=None, meta=None):
+        dev = next(self.model.parameters()).device
+        B = batch_data.shape[0]
+        geom = None
+        if self.online:
+            from ..utils.img_utils import pack_meta
+            geom = pack_meta(meta, B, dev)
+        key = (tuple(batch_data.shape), self.online)
+        self.calls += 1
+        if self.graph is not None and key == self.key:
+            self.sx.copy_(batch_data, non_blocking=True)
+            if self.online:
+                for k in self.sgeom:
+                    self.sgeom[k].copy_(geom[k], non_blocking=True)
+            else:
+                self.slabel.copy_(label, non_blocking=True)
+                self.sweight.copy_(weight, non_blocking=True)
+            if hasattr(self.optimizer, "sync_hyper"):
+                self.optimizer.sync_hyper()
+            self.graph.replay()
+            return self.sloss
+        x = batch_data.to(dev, non_blocking=True)
+        if not self.online:
+            label, weight = label.to(dev, non_blocking=True), weight.to(dev, non_blocking=True)
+        if self.calls == 1 or self.graph is not None or not torch.cuda.is_available():
+            return self._eager(x, label, weight, geom)       # warm-up / odd-shaped batch
+        # second call with this shape: capture, then replay (capture itself does not execute)
+        self.key = key
+        self.sx = x.clone()
+        self.sgeom = {k: v.clone() for k, v in geom.items()} if self.online else None
+        self.slabel = label.clone() if not self.online else None
+        self.sweight = weight.clone() if not self.online else None
+        if hasattr(self.optimizer, "sync_hyper"):
+            self.optimizer.sync_hyper()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.sloss = self._eager(self.sx, self.slabel, self.sweight, self.sgeom)
+        self.graph.replay()
+        return self.sloss
+
+
 def train_integral(config, train_loader, model, criterion, optimizer, epoch):
     batch_time = AverageMeter()
     data_time = AverageMeter()
@@ -60,27 +129,40 @@ def train_integral(config, train_loader, model, criterion, optimizer, epoch):
     online = _online_tri(config)
     method = getattr(config.TRAIN, 'TRIANGULATION_METHOD', 'iterative') if online else None
     pending = []           # (device loss, batch size) not yet folded into `losses`
+    use_graph = bool(getattr(config.TRAIN, 'CUDA_GRAPH', True)) and hasattr(criterion, '_kind')
+    stepper = getattr(model, '_epb_graphed_step', None)
+    if use_graph and (stepper is None or stepper.optimizer is not optimizer
+                      or stepper.criterion is not criterion or stepper.online != online):
+        stepper = GraphedTrainStep(model, criterion, optimizer, online, method)
+        model._epb_graphed_step = stepper
     end = time.time()
     for i, data in enumerate(train_loader):
         data_time.update(time.time() - end)
         batch_data, batch_label, batch_label_weight, meta = data
-        optimizer.zero_grad()
-        batch_data = batch_data.cuda(non_blocking=True)
         batch_size = batch_data.size(0)
-        preds = model(batch_data)
-        if online:
-            # one soft-argmax pass serves both the epipolar labels and the loss
-            loss = online_epipolar_loss(criterion, preds, meta, method)
-            batch_label = batch_label_weight = None
+        if use_graph:
+            loss = stepper(batch_data, batch_label, batch_label_weight, meta)
+            if stepper.graph is not None:
+                loss = loss.clone()      # the static loss buffer is overwritten by the next replay
+            pending.append((loss, batch_size))
+            del loss
         else:
-            batch_label = batch_label.cuda(non_blocking=True)
-            batch_label_weight = batch_label_weight.cuda(non_blocking=True)
-            loss = criterion(preds, batch_label, batch_label_weight)
-        del batch_data, batch_label, batch_label_weight, preds
-        loss.backward()
-        optimizer.step()
-        pending.append((loss.detach(), batch_size))
-        del loss
+            optimizer.zero_grad()
+            batch_data = batch_data.cuda(non_blocking=True)
+            preds = model(batch_data)
+            if online:
+                # one soft-argmax pass serves both the epipolar labels and the loss
+                loss = online_epipolar_loss(criterion, preds, meta, method)
+                batch_label = batch_label_weight = None
+            else:
+                batch_label = batch_label.cuda(non_blocking=True)
+                batch_label_weight = batch_label_weight.cuda(non_blocking=True)
+                loss = criterion(preds, batch_label, batch_label_weight)
+            del batch_data, batch_label, batch_label_weight, preds
+            loss.backward()
+            optimizer.step()
+            pending.append((loss.detach(), batch_size))
+            del loss
         if i % config.PRINT_FREQ == 0:
             for lv, bs in pending:
                 losses.update(lv.item(), bs)      # the only device sync of the loop

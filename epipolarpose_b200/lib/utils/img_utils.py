@@ -42,6 +42,19 @@ def _cams(meta, B, dev):
                      dim=1).contiguous()
 
 
+def pack_meta(meta, B, dev):
+    """Collated `meta` -> device float64 tensors {box [B,6], cam [B,16], P [B,3,4]} (the
+    form the kernels consume; static-shaped, so a CUDA graph can re-read them)."""
+    if isinstance(meta, dict) and "_packed" in meta:
+        return meta["_packed"]
+    out = {"box": _boxes(meta, B, dev)}
+    if 'R' in meta:
+        out["cam"] = _cams(meta, B, dev)
+    if 'projection_matrix' in meta:
+        out["P"] = _t64(meta['projection_matrix'], dev).reshape(B, -1, 4)[:, 0:3, :].contiguous()
+    return out
+
+
 def patch_to_image_device(coords_norm, meta, patch_w=256, patch_h=256, rect_3d_w=2000):
     """coords_norm [B, J*3] float32 (soft-argmax output) -> kps [B,J,4] float64."""
     ops = _backend[0]
@@ -49,8 +62,8 @@ def patch_to_image_device(coords_norm, meta, patch_w=256, patch_h=256, rect_3d_w
     J = coords_norm.shape[1] // 3
     dev = coords_norm.device
     kps = torch.empty((B, J, 4), device=dev, dtype=torch.float64)
-    ops.patch_to_image(coords_norm.contiguous(), _boxes(meta, B, dev), B, J, patch_w, patch_h,
-                       rect_3d_w, kps)
+    ops.patch_to_image(coords_norm.contiguous(), pack_meta(meta, B, dev)["box"], B, J, patch_w,
+                       patch_h, rect_3d_w, kps)
     return kps
 
 
@@ -59,7 +72,7 @@ def triangulate_device(kps, meta, method="iterative"):
     same world-frame result."""
     B, J = kps.shape[0], kps.shape[1]
     half = B // 2
-    P = _t64(meta['projection_matrix'], kps.device).reshape(B, -1, 4)[:, 0:3, :].contiguous()
+    P = pack_meta(meta, B, kps.device)["P"]
     X, _ = _tri.triangulate_pairs(kps[:half], kps[half:2 * half], P[:half], P[half:2 * half],
                                   method=method, stride_u=kps.shape[2])
     return torch.cat([X, X], dim=0)
@@ -71,8 +84,9 @@ def labels_from_global_coords_device(X, meta, patch_w=256., patch_h=256., rect_3
     dev = X.device
     label = torch.empty((B, J * 3), device=dev, dtype=torch.float32)
     weight = torch.empty((B, J * 3), device=dev, dtype=torch.float32)
-    ops.project_labels(X.contiguous(), _cams(meta, B, dev), _boxes(meta, B, dev), B, J, patch_w,
-                       patch_h, rect_3d_w, label, weight)
+    pm = pack_meta(meta, B, dev)
+    ops.project_labels(X.contiguous(), pm["cam"], pm["box"], B, J, patch_w, patch_h, rect_3d_w,
+                       label, weight)
     return label, weight
 
 

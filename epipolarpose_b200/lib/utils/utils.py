@@ -84,25 +84,50 @@ class _FlatOptimizer(torch.optim.Optimizer):
 
 
 class FusedAdam(_FlatOptimizer):
+    """torch.optim.Adam semantics; hyper-parameters and the step count live in device
+    memory (epb_adam_step_dev) so that a captured CUDA graph of the training step keeps
+    following the LR schedule."""
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    def _hyper(self, group):
+        b1, b2 = group['betas']
+        return [group['lr'], b1, b2, group['eps'], group['weight_decay'], 1.0]
+
+    def sync_hyper(self):
+        """Push host-side hyper-parameters (e.g. after lr_scheduler.step()) to the device."""
+        for gi, (group, info) in enumerate(zip(self.param_groups, self._flat)):
+            st = self.state.setdefault('flat%d' % gi, {})
+            h = self._hyper(group)
+            if st.get('hyper_host') != h:
+                dev = info['buf'].device
+                if 'hyper' not in st:
+                    st['hyper'] = torch.zeros(len(h), device=dev, dtype=torch.float32)
+                st['hyper'].copy_(torch.tensor(h, dtype=torch.float32), non_blocking=True)
+                st['hyper_host'] = h
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         ops = _backend[0]
+        capturing = info_dev_is_capturing()
+        if not capturing:
+            self.sync_hyper()
         for gi, (group, info) in enumerate(zip(self.param_groups, self._flat)):
             st = self.state.setdefault('flat%d' % gi, {})
-            if not st:
+            if 'exp_avg' not in st:
                 st['step'] = 0
+                st['step_dev'] = torch.zeros(1, device=info['buf'].device, dtype=torch.int32)
                 st['exp_avg'] = torch.zeros_like(info['buf'])
                 st['exp_avg_sq'] = torch.zeros_like(info['buf'])
             st['step'] += 1
+            st['step_dev'] += 1
             b1, b2 = group['betas']
             gflat = self._grads_are_flat(group, info)
-            if gflat is not None:
-                ops.adam_step(info['buf'], gflat, st['exp_avg'], st['exp_avg_sq'], info['n'],
-                              group['lr'], b1, b2, group['eps'], group['weight_decay'], st['step'])
+            if gflat is not None and info['n'] % 4 == 0:
+                ops.adam_step_dev(info['buf'], gflat, st['exp_avg'], st['exp_avg_sq'], info['n'],
+                                  st['hyper'], st['step_dev'])
                 continue
             for p, o, s in zip(group['params'], info['offs'], info['sizes']):
                 if p.grad is None:
@@ -118,26 +143,45 @@ class FusedSGD(_FlatOptimizer):
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay,
                                       nesterov=nesterov))
 
+    def _hyper(self, group):
+        return [group['lr'], group['momentum'], group['weight_decay'],
+                1.0 if group['nesterov'] else 0.0, 1.0]
+
+    sync_hyper = FusedAdam.sync_hyper
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         ops = _backend[0]
+        if not info_dev_is_capturing():
+            self.sync_hyper()
         for gi, (group, info) in enumerate(zip(self.param_groups, self._flat)):
             st = self.state.setdefault('flat%d' % gi, {})
-            first = not st
-            if first:
+            if 'buf' not in st:
+                st['step'] = 0
+                st['step_dev'] = torch.zeros(1, device=info['buf'].device, dtype=torch.int32)
                 st['buf'] = torch.zeros_like(info['buf'])
+            st['step'] += 1
+            st['step_dev'] += 1
             gflat = self._grads_are_flat(group, info)
-            args = (group['lr'], group['momentum'], group['weight_decay'], group['nesterov'], first)
             if gflat is not None:
-                ops.sgd_step(info['buf'], gflat, st['buf'], info['n'], *args)
+                ops.sgd_step_dev(info['buf'], gflat, st['buf'], info['n'], st['hyper'], st['step_dev'])
                 continue
+            args = (group['lr'], group['momentum'], group['weight_decay'], group['nesterov'],
+                    st['step'] == 1)
             for p, o, s in zip(group['params'], info['offs'], info['sizes']):
                 if p.grad is None:
                     continue
                 ops.sgd_step(info['buf'][o:o + s], p.grad.contiguous().reshape(-1),
                              st['buf'][o:o + s], s, *args)
         return loss
+
+
+def info_dev_is_capturing():
+    try:
+        return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    except Exception:
+        return False
 
 
 def get_optimizer(cfg, model):

@@ -203,3 +203,13 @@ def sgd_step(param, grad, buf, n, lr, momentum, weight_decay, nesterov, first_st
              grad_scale=1.0):
     _call("epb_sgd_step", _p(param), _p(grad), _p(buf), n, lr, momentum, weight_decay,
           int(nesterov), int(first_step), grad_scale, _stream())
+
+
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, n, hyper, step_dev):
+    _call("epb_adam_step_dev", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, _p(hyper),
+          _p(step_dev, torch.int32), _stream())
+
+
+def sgd_step_dev(param, grad, buf, n, hyper, step_dev):
+    _call("epb_sgd_step_dev", _p(param), _p(grad), _p(buf), n, _p(hyper),
+          _p(step_dev, torch.int32), _stream())

@@ -246,6 +246,19 @@ int epb_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n
                  float lr, float momentum, float weight_decay, int nesterov,
                  int first_step, float grad_scale, epb_stream_t stream);
 
+/* Same updates with the hyper-parameters and the step count read from DEVICE
+ * memory, so that a whole training step can be captured in a CUDA graph and
+ * replayed while the LR schedule (scripts/train.py:107-109) keeps changing:
+ * adam hyper = [lr, beta1, beta2, eps, weight_decay, grad_scale];
+ * sgd  hyper = [lr, momentum, weight_decay, nesterov, grad_scale];
+ * *step_dev is the 1-based step (the caller increments it before the call). */
+int epb_adam_step_dev(float* param, const float* grad, float* exp_avg,
+                      float* exp_avg_sq, int64_t n, const float* hyper,
+                      const int* step_dev, epb_stream_t stream);
+int epb_sgd_step_dev(float* param, const float* grad, float* momentum_buf,
+                     int64_t n, const float* hyper, const int* step_dev,
+                     epb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

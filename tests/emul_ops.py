@@ -332,5 +332,15 @@ def sgd_step(param, grad, buf, n, lr, momentum, weight_decay, nesterov, first_st
     param.add_(g, alpha=-lr)
 
 
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, n, hyper, step_dev):
+    lr, b1, b2, eps, wd, gs = [float(v) for v in hyper]
+    adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, b1, b2, eps, wd, int(step_dev), gs)
+
+
+def sgd_step_dev(param, grad, buf, n, hyper, step_dev):
+    lr, mom, wd, nest, gs = [float(v) for v in hyper]
+    sgd_step(param, grad, buf, n, lr, mom, wd, nest != 0, int(step_dev) == 1, gs)
+
+
 def device_check():
     pass

@@ -381,3 +381,51 @@ def test_fused_adam_matches_torch(dev):
         a.step(); b.step()
     for p, q in zip(ps, qs):
         assert relerr(p.detach().cpu().numpy(), q.detach().cpu().numpy()) <= 1e-5
+
+
+def test_graphed_train_step_matches_eager(dev):
+    """train_integral with the CUDA-graph stepper (default) against the eager loop: same
+    losses and parameters after several steps (LR change in between included)."""
+    import copy
+    import lib.models as models
+    import lib.core.integral_loss as il
+    import lib.core.function as fn
+    import lib.utils.utils as U
+    from lib.core.config import config, reset_config
+    from oracle import refshim
+    from tests import golden_inputs as gi
+    J, D, HW = 4, 16, 64
+    logits_np, meta_np = gi.selfsup_case(n_tuples=2, J=J, D=D)
+    B = logits_np.shape[0]
+    meta = {k: torch.from_numpy(v) for k, v in meta_np.items()}
+    cfg = refshim.make_cfg(num_layers=18, num_joints=J, volume=True, depth_res=D, image_size=(HW, HW))
+    sd = restate_net.init_state(restate_net.param_shapes(18, J, True, D), 3)
+    batches = [(torch.from_numpy(gi.images(B, HW, 40 + i)), torch.zeros(B, J * 3), torch.ones(B, J * 3), meta)
+               for i in range(5)]
+
+    class Loader(list):
+        dataset = None
+    results = {}
+    for mode in (False, True):
+        reset_config()
+        config.PRINT_FREQ = 1
+        config.TRAIN.ONLINE_TRIANGULATION = True
+        config.TRAIN.CUDA_GRAPH = mode
+        model = models.pose3d_resnet.get_pose_net(cfg, False)
+        model.load_state_dict(sd)
+        model = model.to(dev)
+        crit = il.SmoothL1JointLocationLoss(J)
+        opt = U.FusedAdam(list(model.parameters()), lr=1e-3)
+        l1 = fn.train_integral(config, Loader(batches[:3]), model, crit, opt, 0)
+        for gr in opt.param_groups:
+            gr["lr"] = 1e-4                       # scheduler step between epochs
+        l2 = fn.train_integral(config, Loader(batches[3:]), model, crit, opt, 1)
+        torch.cuda.synchronize()
+        results[mode] = (l1, l2, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+        assert int(results[mode][2]["bn1.num_batches_tracked"]) == 5
+    reset_config()
+    assert abs(results[True][0] - results[False][0]) <= 1e-4 * abs(results[False][0])
+    assert abs(results[True][1] - results[False][1]) <= 1e-4 * abs(results[False][1])
+    for k, v in results[False][2].items():
+        if v.is_floating_point():
+            assert relerr(results[True][2][k].numpy(), v.numpy()) <= 2e-3, k

@@ -40,7 +40,7 @@ struct WCfg {
   static constexpr int SB_ = (196 * 1024 - SA * A_TILE) / B_TILE;
   static constexpr int SB = SB_ > 8 ? 8 : SB_;
   static constexpr int NB_MAX = (512 / BNW) > kMaxSlots ? kMaxSlots : (512 / BNW);
-  static constexpr int SMEM = SA * A_TILE + SB * B_TILE + 1024 + 512;
+  static constexpr int SMEM = SA * A_TILE + SB * B_TILE + 1024 + 2048;
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -85,6 +85,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
   uint8_t* ctrl = smB + C::SB * C::B_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);   // fullA[2] emptyA[2] fullB[8] emptyB[8] done
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl + 8 * 24);
+  int* slot_t = reinterpret_cast<int*>(ctrl + 256);          // [kMaxSlots] tap of each slot
+  int* slot_cit = slot_t + kMaxSlots;                        // [kMaxSlots] ci tile of each slot
+  int* rowtab = slot_cit + kMaxSlots;                        // [2 groups][4][KPIX]
   const uint32_t bar0 = tc::smem_u32(bars);
   auto fullA = [&](int s) { return bar0 + 8u * s; };
   auto emptyA = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -108,10 +111,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
   const int co0 = cot * WM;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::SA; ++s) { tc::mbar_init(fullA(s), kProdWarps); tc::mbar_init(emptyA(s), 1); }
-    for (int s = 0; s < C::SB; ++s) { tc::mbar_init(fullB(s), kProdWarps); tc::mbar_init(emptyB(s), 1); }
+    for (int s = 0; s < C::SA; ++s) { tc::mbar_init(fullA(s), kProdWarps / 2); tc::mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < C::SB; ++s) { tc::mbar_init(fullB(s), kProdWarps / 2); tc::mbar_init(emptyB(s), 1); }
     tc::mbar_init(done_bar, 1);
     tc::fence_barrier_init();
+    for (int b = 0; b < NB; ++b) {
+      slot_t[b] = (slot0 + b) / ci_tiles;
+      slot_cit[b] = (slot0 + b) % ci_tiles;
+    }
   }
   if (warp == kProdWarps) tc::tmem_alloc<512>(tc::smem_u32(tmem_ptr));
   tc::tc_fence_before();
@@ -120,96 +127,95 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < kProdWarps) {
-    // ======================================================== producers (256 threads)
-    const int tid = threadIdx.x;
-    const int qa = tid % QA, ra0 = tid / QA;        // dout: float4 slot, first row
-    const int qb = tid % QB, rb0 = tid / QB;        // input: float4 slot, first row
+    // ======================================================== producers (2 groups of 4 warps)
+    // Tiles alternate between the two groups (group = u & 1): each warp pays the per-tile
+    // fixed costs (mbarrier wait, proxy fence, arrive) for every OTHER tile while the two
+    // groups overlap; inside a group the loads of its next tile are in flight (register
+    // double buffer) while the current tile is converted and stored.
+    constexpr int GT = kProd / 2;                  // threads per group (128)
+    constexpr int RAg = GT / QA, PAg = KPIX / RAg; // dout rows per pass / passes (4, 8)
+    constexpr int RBg = GT / QB, PBg = KPIX / RBg; // input rows per pass / passes
+    constexpr int NREG = PAg > PBg ? PAg : PBg;
+    const int grpi = warp >> 2;
+    const int tg = threadIdx.x & (GT - 1);
+    const int qa = tg % QA, ra0 = tg / QA;
+    const int qb = tg % QB, rb0 = tg / QB;
     const int co = co0 + qa * 4;
     const bool co_ok = co < g.Cout;
-    // pixel coordinates of this thread's rows of the CURRENT block (advance by 32 px per block)
-    PixCoord ca[PA], cb[PB];
-    auto decode = [&](int m, PixCoord& c) {
-      const unsigned um = (unsigned)m;
-      c.j = (int)(um % (unsigned)g.Wp);
-      const unsigned q = um / (unsigned)g.Wp;
-      c.i = (int)(q % (unsigned)g.Hp);
-      c.n = (int)(q / (unsigned)g.Hp);
-    };
-    auto advance = [&](PixCoord& c) {
-      c.j += KPIX;
-      while (c.j >= g.Wp) { c.j -= g.Wp; if (++c.i == g.Hp) { c.i = 0; ++c.n; } }
-    };
-#pragma unroll
-    for (int k = 0; k < PA; ++k) decode(mbeg + ra0 + k * RA, ca[k]);
-#pragma unroll
-    for (int k = 0; k < PB; ++k) decode(mbeg + rb0 + k * RB, cb[k]);
-
-    constexpr int NREG = PA > PB ? PA : PB;
-    constexpr int PD = 4;                         // register ring: 3 tiles of loads in flight
-    float4 buf[PD][NREG];
-    unsigned msk[PD];
-    // tile sequence: u = blk * (NB + 1) + e ; e == 0 -> dout tile, e >= 1 -> input slot e-1
+    int* rt = rowtab + grpi * 4 * KPIX;           // [dout pixel | n*Hi*Wi | i*is | j*is][KPIX]
     const int per_blk = NB + 1;
     const int total = nblk * per_blk;
-    int iu = 0, ie = 0, iblk = 0;                 // issue cursor (runs PD-1 tiles ahead)
-    const int t_first = slot0 / ci_tiles, cit_first = slot0 - t_first * ci_tiles;
-    int it = t_first, icit = cit_first;           // tap / ci tile of the cursor's input slot
+    float4 buf[2][NREG];
+    unsigned msk[2];
+    int ie = grpi, iblk = 0, tab_blk = -1;        // issue cursor of this group
+    while (ie >= per_blk) { ie -= per_blk; ++iblk; }
     auto issue_next = [&](float4 (&dst)[NREG], unsigned& mask) {
-      if (ie == 0 && iu > 0) {                    // the cursor enters the next pixel block
-#pragma unroll
-        for (int k = 0; k < PA; ++k) advance(ca[k]);
-#pragma unroll
-        for (int k = 0; k < PB; ++k) advance(cb[k]);
-      }
-      const int mrow0 = mbeg + iblk * KPIX;
-      mask = 0;
-      if (ie == 0) {
-        // warm L2 eight pixel blocks ahead (rows of one block are contiguous when the phase
-        // grid is dense): the register ring alone keeps too few bytes in flight for HBM
-        const int pfm = mrow0 + 8 * KPIX;
-        if (pfm < mend) {
+      if (tab_blk != iblk) {                      // the cursor entered a new pixel block
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grpi) : "memory");
+        if (tg < KPIX) {
+          const int m = mbeg + iblk * KPIX + tg;
+          if (m < mend) {
+            const unsigned um = (unsigned)m;
+            const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
+            const unsigned i = qq % (unsigned)g.Hp, n = qq / (unsigned)g.Hp;
+            rt[tg] = ((int)n * g.Ho + ((int)i * g.os + g.ph)) * g.Wo + ((int)j * g.os + g.pw);
+            rt[KPIX + tg] = (int)n * g.Hi * g.Wi;
+            rt[2 * KPIX + tg] = (int)i * g.is;
+            rt[3 * KPIX + tg] = (int)j * g.is;
+          } else {
+            rt[tg] = -1;
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grpi) : "memory");
+        tab_blk = iblk;
+        // warm L2 eight pixel blocks ahead (rows of a block are contiguous when the phase
+        // grid is dense): the register buffers alone keep too few bytes in flight for HBM
+        const int pfm = mbeg + (iblk + 8) * KPIX;
+        if (grpi == 0 && pfm < mend) {
           if (g.os == 1) {
-            const int lines = (KPIX * WM * 4) / 128;         // co tile: 4 lines per row
-            for (int l = tid; l < lines; l += kProd) {
+            const int lines = (KPIX * WM * 4) / 128;
+            for (int l = tg; l < lines; l += GT) {
               const int r = l >> 2, c = (l & 3) * 32;
               if (co0 + c < g.Cout)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(dout + (int64_t)(pfm + r) * g.Cout + co0 + c));
             }
           }
           if (g.is == 1 && g.Hp == g.Hi && g.Wp == g.Wi) {
-            const int lpr = g.Cin >> 5;                       // lines per input row
-            for (int l = tid; l < KPIX * lpr; l += kProd) {
+            const int lpr = g.Cin >> 5;
+            for (int l = tg; l < KPIX * lpr; l += GT) {
               const int r = l / lpr, c = (l - r * lpr) * 32;
               asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (int64_t)(pfm + r) * g.Cin + c));
             }
           }
         }
+      }
+      mask = 0;
+      if (ie == 0) {
 #pragma unroll
-        for (int k = 0; k < PA; ++k) {
+        for (int k = 0; k < PAg; ++k) {
           dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (co_ok && mrow0 + ra0 + k * RA < mend)
-            dst[k] = *reinterpret_cast<const float4*>(
-                dout + (((int64_t)ca[k].n * g.Ho + (ca[k].i * g.os + g.ph)) * g.Wo +
-                        (ca[k].j * g.os + g.pw)) * g.Cout + co);
+          const int dp = rt[ra0 + k * RAg];
+          if (co_ok && dp >= 0)
+            dst[k] = *reinterpret_cast<const float4*>(dout + (int64_t)dp * g.Cout + co);
         }
       } else {
-        const int ci = icit * BNW + qb * 4;
-        const int dh = g.dh[it], dwv = g.dw[it];
-        if (++icit == ci_tiles) { icit = 0; ++it; }
+        const int sl = ie - 1;
+        const int ci = slot_cit[sl] * BNW + qb * 4;
+        const int dh = g.dh[slot_t[sl]], dwv = g.dw[slot_t[sl]];
 #pragma unroll
-        for (int k = 0; k < PB; ++k) {
+        for (int k = 0; k < PBg; ++k) {
           dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int ih = cb[k].i * g.is + dh, iw = cb[k].j * g.is + dwv;
-          if (ci < g.Cin && mrow0 + rb0 + k * RB < mend && ih >= 0 && ih < g.Hi && iw >= 0 &&
-              iw < g.Wi) {
+          const int r = rb0 + k * RBg;
+          const int ih = rt[2 * KPIX + r] + dh, iw = rt[3 * KPIX + r] + dwv;
+          if (ci < g.Cin && rt[r] >= 0 && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi) {
             dst[k] = *reinterpret_cast<const float4*>(
-                in + (((int64_t)cb[k].n * g.Hi + ih) * g.Wi + iw) * g.Cin + ci);
+                in + ((int64_t)rt[KPIX + r] + (int64_t)ih * g.Wi + iw) * g.Cin + ci);
             mask |= 1u << k;
           }
         }
       }
-      ++iu;
-      if (++ie == per_blk) { ie = 0; ++iblk; it = t_first; icit = cit_first; }
+      ie += 2;
+      while (ie >= per_blk) { ie -= per_blk; ++iblk; }
     };
     auto split_store = [&](uint8_t* tile, int tile_plane_bytes, int r, int ch4, float4 x) {
       const float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
@@ -219,35 +225,31 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         st_mn(tile + tile_plane_bytes, r, ch4,
               make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
     };
-    int pe = 0, pblk = 0, pcit = cit_first;       // consume cursor
-    int sA = 0, sB = 0;
-    uint32_t phA = 0, phB = 0;
+    int pe = grpi, pblk = 0;                      // consume cursor of this group
+    while (pe >= per_blk) { pe -= per_blk; ++pblk; }
     auto process = [&](const float4 (&cur)[NREG], unsigned curm) {
-      const int e = pe;
-      if (e == 0) {
-        const int s = sA;
-        tc::mbar_wait(emptyA(s), phA ^ 1);
-        if (++sA == C::SA) { sA = 0; phA ^= 1; }
+      if (pe == 0) {
+        const int s = pblk % C::SA;
+        tc::mbar_wait(emptyA(s), ((pblk / C::SA) & 1) ^ 1);
         uint8_t* tile = sm + s * C::A_TILE;
 #pragma unroll
-        for (int k = 0; k < PA; ++k) split_store(tile, WM * KPIX * 4, ra0 + k * RA, qa, cur[k]);
+        for (int k = 0; k < PAg; ++k) split_store(tile, WM * KPIX * 4, ra0 + k * RAg, qa, cur[k]);
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(fullA(s));
       } else {
-        const int s = sB;
-        const int ci = pcit * BNW + qb * 4;
-        if (++pcit == ci_tiles) pcit = 0;
+        const int qn = pblk * NB + (pe - 1);
+        const int s = qn % C::SB;
+        const int ci = slot_cit[pe - 1] * BNW + qb * 4;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in_scale && ci < g.Cin) {
           sc = *reinterpret_cast<const float4*>(in_scale + ci);
           sh = *reinterpret_cast<const float4*>(in_shift + ci);
         }
-        tc::mbar_wait(emptyB(s), phB ^ 1);
-        if (++sB == C::SB) { sB = 0; phB ^= 1; }
+        tc::mbar_wait(emptyB(s), ((qn / C::SB) & 1) ^ 1);
         uint8_t* tile = smB + s * C::B_TILE;
 #pragma unroll
-        for (int k = 0; k < PB; ++k) {
+        for (int k = 0; k < PBg; ++k) {
           float4 x = cur[k];
           if (in_scale && ((curm >> k) & 1u)) {
             x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
@@ -257,23 +259,24 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
               x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
             }
           }
-          split_store(tile, BNW * KPIX * 4, rb0 + k * RB, qb, x);
+          split_store(tile, BNW * KPIX * 4, rb0 + k * RBg, qb, x);
         }
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(fullB(s));
       }
-      if (++pe == per_blk) { pe = 0; ++pblk; pcit = cit_first; }
+      pe += 2;
+      while (pe >= per_blk) { pe -= per_blk; ++pblk; }
     };
+    // this group's tiles: u = grpi, grpi + 2, ...
+    const int mine = (total - grpi + 1) / 2;
+    if (mine > 0) issue_next(buf[0], msk[0]);
+    for (int k0 = 0; k0 < mine; k0 += 2) {
 #pragma unroll
-    for (int d = 0; d < PD - 1; ++d)
-      if (d < total) issue_next(buf[d], msk[d]);
-    for (int u0 = 0; u0 < total; u0 += PD) {
-#pragma unroll
-      for (int d = 0; d < PD; ++d) {
-        const int u = u0 + d;
-        if (u < total) {
-          if (u + PD - 1 < total) issue_next(buf[(d + PD - 1) % PD], msk[(d + PD - 1) % PD]);
+      for (int d = 0; d < 2; ++d) {
+        const int k = k0 + d;
+        if (k < mine) {
+          if (k + 1 < mine) issue_next(buf[d ^ 1], msk[d ^ 1]);
           process(buf[d], msk[d]);
         }
       }
@@ -285,8 +288,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
       const int corow = co0 + warp * 32 + lane;
       const int64_t wrow = (int64_t)g.Tw * g.Cin;
       for (int b = 0; b < NB; ++b) {
-        const int sl = slot0 + b;
-        const int t = sl / ci_tiles, cit = sl - t * ci_tiles;
+        const int t = slot_t[b], cit = slot_cit[b];
 #pragma unroll 1
         for (int chunk = 0; chunk < BNW / 32; ++chunk) {
           uint32_t r[32];

@@ -66,6 +66,21 @@ class GraphedTrainStep:
         self.graph = None
         self.key = None
         self.calls = 0
+        # eager warm-up and capture share ONE side stream so that the parameters'
+        # AccumulateGrad nodes are never bound to the legacy default stream (which
+        # may not join a capture)
+        self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+
+    def eager_step(self, x, label, weight, geom):
+        """One un-captured step on the stepper's side stream."""
+        if self.stream is None:
+            return self._eager(x, label, weight, geom)
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = self._eager(x, label, weight, geom)
+        cur.wait_stream(self.stream)
+        return out
 
     def _eager(self, x, label, weight, geom):
         self.optimizer.zero_grad()
@@ -103,7 +118,7 @@ class GraphedTrainStep:
         if not self.online:
             label, weight = label.to(dev, non_blocking=True), weight.to(dev, non_blocking=True)
         if self.calls == 1 or self.graph is not None or not torch.cuda.is_available():
-            return self._eager(x, label, weight, geom)       # warm-up / odd-shaped batch
+            return self.eager_step(x, label, weight, geom)   # warm-up / odd-shaped batch
         # second call with this shape: capture, then replay (capture itself does not execute)
         self.key = key
         self.sx = x.clone()
@@ -115,7 +130,7 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=self.stream):
             self.sloss = self._eager(self.sx, self.slabel, self.sweight, self.sgeom)
         self.graph.replay()
         return self.sloss

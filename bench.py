@@ -314,14 +314,15 @@ def run_gpu(args):
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT,
                 "h2d_bytes_per_step": int(host_batches[0].numel() * 4),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
+        "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
         "cuda_graph": bool(use_graph),
         "roofline": {"bound": "tensor", "kernel": "conv implicit-GEMM family (fprop/dgrad/wgrad)",
                      "achieved": round(achieved, 3), "peak": round(tensor_peak, 1),
                      "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 5),
                      "traffic": None, "peak_source": which + " bf16_tflops_sustained / 2 (tf32)",
                      "launches_per_step": n_conv_launch,
-                     "share_of_step": round(conv_ms / eager_ms, 4) if eager_ms > 0 else None,
+                     "share_of_step": round(conv_ms / ms_step, 4) if ms_step > 0 else None,
                      "measured": "CUDA events around each launch of %d eager step(s) run right "
                                  "after the timed region (eager step %.2f ms)" % (n_inst, eager_ms)},
     }

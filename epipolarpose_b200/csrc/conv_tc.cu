@@ -29,7 +29,7 @@ namespace {
 constexpr int BM = 128;          // pixel rows per tile == UMMA M
 constexpr int BKE = 32;          // tf32 elements per k-block (128 bytes)
 constexpr int kProducerWarps = 8;       // 256 gather threads: bytes in flight, not issue rate, bound the A stream
-constexpr int kPrefetch = 4;            // k-blocks of global loads in flight per thread (register ring)
+
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (kProducerWarps + 2 + kEpiWarps);   // 448
 constexpr int kSmemBudget = 200 * 1024;
@@ -87,7 +87,7 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::S; ++s) {
-      tc::mbar_init(full_bar(s), kProducerWarps + 1);
+      tc::mbar_init(full_bar(s), kProducerWarps / 2 + 1);
       tc::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -109,8 +109,8 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
     const int p = threadIdx.x;                 // threads 0..127 also compute one row's geometry
     const int c4 = lane & 7;                   // 16-byte chunk within the 128-byte row
     const int rsub = lane >> 3;                // 0..3
-    int stage = 0;
-    uint32_t phase = 0;
+    int base_stage = 0;                        // ring slot / phase of the tile's k-block 0
+    uint32_t base_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / n_tiles;
       // producers of the previous tile are done reading rowinfo once all reach this barrier
@@ -129,16 +129,23 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // Register ring of kPrefetch k-blocks: the loads of k-blocks kb+1..kb+3 are in flight
-      // while k-block kb is converted and stored.  These layers stream activations from
-      // HBM (~1.5 us latency): 256 threads x 4 x 16 B x 4 slots = 64 KB in flight per SM.
-      float4 buf[kPrefetch][4];
-      unsigned okm[kPrefetch];
-      int it = 0, icb = 0, pcb = 0;            // issue cursor (tap, channel block); consume cursor
+      // Two groups of 4 warps alternate k-blocks (group = kb & 1): each warp pays the
+      // per-k-block fixed costs (mbarrier wait, proxy fence, arrive) for every OTHER
+      // k-block while the groups overlap; inside a group the loads of its next k-block
+      // are in flight (register double buffer) while the current one is converted.
+      float4 buf[2][8];
+      unsigned okm[2];
+      const int grp = warp >> 2, wg = warp & 3;
+      int st = base_stage + grp;
+      uint32_t ph = base_phase;
+      if (st >= C::S) { st -= C::S; ph ^= 1; }
+      int it = 0, icb = grp, pcb = grp;          // issue cursor (tap, channel block); consume cursor
+      while (icb >= CB) { icb -= CB; ++it; }
+      while (pcb >= CB) pcb -= CB;
       // Warm L2 for the NEXT tile of this CTA while the current one is processed: one
       // prefetch per 128-byte line of the (un-shifted) pixel row.  These layers stream
       // their activations from HBM exactly once; without this every k-block pays the
-      // DRAM latency with only the register ring's bytes in flight.
+      // DRAM latency with only the register buffers' bytes in flight.
       {
         const int ntile = tile + gridDim.x;
         if (p < BM && ntile < total_tiles && ntile / n_tiles != mt) {
@@ -156,14 +163,15 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           }
         }
       }
-      auto issue = [&](float4 (&dst)[4], unsigned& mask) {
+      auto issue = [&](float4 (&dst)[8], unsigned& mask) {
         const int dh = g.dh[it], dw = g.dw[it];
         const int ch = icb * BKE + c4 * 4;
-        if (++icb == CB) { icb = 0; ++it; }
+        icb += 2;
+        while (icb >= CB) { icb -= CB; ++it; }
         mask = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = warp * 16 + q * 4 + rsub;
+        for (int q = 0; q < 8; ++q) {
+          const int r = wg * 32 + q * 4 + rsub;
           const int pb = rows->pix_base[r];
           const int ih = rows->ih0[r] + dh, iw = rows->iw0[r] + dw;
           const bool ok = (pb >= 0) && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
@@ -175,19 +183,20 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           }
         }
       };
-      auto process = [&](const float4 (&v)[4], unsigned mask) {
+      auto process = [&](const float4 (&v)[8], unsigned mask) {
         const int ch = pcb * BKE + c4 * 4;
-        if (++pcb == CB) pcb = 0;
+        pcb += 2;
+        while (pcb >= CB) pcb -= CB;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in_scale) {
           sc = *reinterpret_cast<const float4*>(in_scale + ch);
           sh = *reinterpret_cast<const float4*>(in_shift + ch);
         }
-        tc::mbar_wait(empty_bar(stage), phase ^ 1);
-        uint8_t* a_hi = sm + stage * C::STAGE;
+        tc::mbar_wait(empty_bar(st), ph ^ 1);
+        uint8_t* a_hi = sm + st * C::STAGE;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = warp * 16 + q * 4 + rsub;
+        for (int q = 0; q < 8; ++q) {
+          const int r = wg * 32 + q * 4 + rsub;
           float4 x = v[q];
           if (in_scale && ((mask >> q) & 1u)) {
             x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
@@ -208,22 +217,26 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(full_bar(stage));
-        if (++stage == C::S) { stage = 0; phase ^= 1; }
+        if (lane == 0) tc::mbar_arrive(full_bar(st));
+        st += 2;
+        if (st >= C::S) { st -= C::S; ph ^= 1; }
       };
+      const int mine = (KB - grp + 1) / 2;
+      if (mine > 0) issue(buf[0], okm[0]);
+      for (int k0 = 0; k0 < mine; k0 += 2) {
 #pragma unroll
-      for (int d = 0; d < kPrefetch - 1; ++d)
-        if (d < KB) issue(buf[d], okm[d]);
-      for (int kb0 = 0; kb0 < KB; kb0 += kPrefetch) {
-#pragma unroll
-        for (int d = 0; d < kPrefetch; ++d) {
-          const int kb = kb0 + d;
-          if (kb < KB) {
-            const int nx = kb + kPrefetch - 1;
-            if (nx < KB) issue(buf[(d + kPrefetch - 1) % kPrefetch], okm[(d + kPrefetch - 1) % kPrefetch]);
+        for (int d = 0; d < 2; ++d) {
+          const int k = k0 + d;
+          if (k < mine) {
+            if (k + 1 < mine) issue(buf[d ^ 1], okm[d ^ 1]);
             process(buf[d], okm[d]);
           }
         }
+      }
+      {   // ring position of the next tile's first k-block
+        const int tmp = base_stage + KB;
+        base_phase ^= (uint32_t)((tmp / C::S) & 1);
+        base_stage = tmp % C::S;
       }
     }
   } else if (warp == kProducerWarps) {

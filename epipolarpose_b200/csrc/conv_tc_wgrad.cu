@@ -73,10 +73,6 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
   using C = WCfg<BNW, NS>;
   constexpr int QA = WM / 4;                 // float4 per dout row (32)
   constexpr int QB = BNW / 4;                // float4 per input row
-  constexpr int RA = kProd / QA;             // dout rows covered per pass (8)
-  constexpr int RB = kProd / QB;             // input rows covered per pass
-  constexpr int PA = KPIX / RA;              // passes (4)
-  constexpr int PB = KPIX / RB;              // passes (BNW=128:4, 64:2, 32:1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;

@@ -384,14 +384,13 @@ def test_fused_adam_matches_torch(dev):
 
 
 def test_graphed_train_step_matches_eager(dev):
-    """train_integral with the CUDA-graph stepper (default) against the eager loop: same
-    losses and parameters after several steps (LR change in between included)."""
-    import copy
+    """The CUDA-graph stepper (first call eager, second captures, then replays) against
+    plain eager steps: same loss trajectory; BatchNorm counters advance under replay; a
+    host-side LR change reaches the captured Adam kernel (lr = 0 freezes the weights)."""
     import lib.models as models
     import lib.core.integral_loss as il
     import lib.core.function as fn
     import lib.utils.utils as U
-    from lib.core.config import config, reset_config
     from oracle import refshim
     from tests import golden_inputs as gi
     J, D, HW = 4, 16, 64
@@ -400,35 +399,39 @@ def test_graphed_train_step_matches_eager(dev):
     meta = {k: torch.from_numpy(v) for k, v in meta_np.items()}
     cfg = refshim.make_cfg(num_layers=18, num_joints=J, volume=True, depth_res=D, image_size=(HW, HW))
     sd = restate_net.init_state(restate_net.param_shapes(18, J, True, D), 3)
-    batches = [(torch.from_numpy(gi.images(B, HW, 40 + i)), torch.zeros(B, J * 3), torch.ones(B, J * 3), meta)
-               for i in range(5)]
-
-    class Loader(list):
-        dataset = None
-    results = {}
-    for mode in (False, True):
-        reset_config()
-        config.PRINT_FREQ = 1
-        config.TRAIN.ONLINE_TRIANGULATION = True
-        config.TRAIN.CUDA_GRAPH = mode
+    xs = [torch.from_numpy(gi.images(B, HW, 40 + i)).to(dev) for i in range(5)]
+    out = {}
+    for mode in ("eager", "graph"):
         model = models.pose3d_resnet.get_pose_net(cfg, False)
         model.load_state_dict(sd)
-        model = model.to(dev)
+        model = model.to(dev).train()
         crit = il.SmoothL1JointLocationLoss(J)
-        opt = U.FusedAdam(list(model.parameters()), lr=1e-3)
-        l1 = fn.train_integral(config, Loader(batches[:3]), model, crit, opt, 0)
+        opt = U.FusedAdam(list(model.parameters()), lr=1e-4)
+        stepper = fn.GraphedTrainStep(model, crit, opt, online=True)
+        losses = []
+        for i in range(4):
+            if mode == "graph":
+                losses.append(float(stepper(xs[i], meta=meta)))
+            else:
+                import lib.utils.img_utils as iu
+                losses.append(float(stepper.eager_step(xs[i], None, None, iu.pack_meta(meta, B, dev))))
+        if mode == "graph":
+            assert stepper.graph is not None
+        before = {k: v.detach().clone() for k, v in model.named_parameters()}
         for gr in opt.param_groups:
-            gr["lr"] = 1e-4                       # scheduler step between epochs
-        l2 = fn.train_integral(config, Loader(batches[3:]), model, crit, opt, 1)
+            gr["lr"] = 0.0                      # e.g. an lr_scheduler step between epochs
+        if mode == "graph":
+            stepper(xs[4], meta=meta)
+        else:
+            opt.sync_hyper()
+            stepper.eager_step(xs[4], None, None, iu.pack_meta(meta, B, dev))
         torch.cuda.synchronize()
-        results[mode] = (l1, l2, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
-        assert int(results[mode][2]["bn1.num_batches_tracked"]) == 5
-    reset_config()
-    # two runs of the same fp32 training differ through atomics order and ReLU' flips at
-    # rounding level (see test_network_gradients_vs_oracle_fp64); Adam's sign-like update
-    # then moves single weights by up to lr.  Bars: losses 1e-2, parameters 5e-2 (max-norm).
-    assert abs(results[True][0] - results[False][0]) <= 1e-2 * abs(results[False][0])
-    assert abs(results[True][1] - results[False][1]) <= 1e-2 * abs(results[False][1])
-    for k, v in results[False][2].items():
-        if v.is_floating_point():
-            assert relerr(results[True][2][k].numpy(), v.numpy()) <= 5e-2, k
+        for k, v in model.named_parameters():
+            assert torch.equal(v.detach(), before[k]), (mode, k)       # lr = 0 reached the kernel
+        assert int(model.state_dict()["bn1.num_batches_tracked"]) == 5
+        out[mode] = (losses, {k: v.detach().cpu().numpy() for k, v in model.named_parameters()})
+    for a, b in zip(out["graph"][0], out["eager"][0]):
+        assert abs(a - b) <= 2e-2 * abs(b), (out["graph"][0], out["eager"][0])
+    assert abs(out["graph"][0][0] - out["eager"][0][0]) <= 1e-5 * abs(out["eager"][0][0])
+    for k, v in out["eager"][1].items():
+        assert relerr(out["graph"][1][k], v) <= 5e-2, k

@@ -327,7 +327,7 @@ def run_gpu(args):
                                  "after the timed region (eager step %.2f ms)" % (n_inst, eager_ms)},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference(steps=1, warmup=0, tuples=args.cpu_tuples, layers=layers)
+        out["cpu_baseline"] = cpu_reference(steps=1, warmup=1, tuples=args.cpu_tuples, layers=layers)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

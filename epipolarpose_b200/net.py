@@ -195,9 +195,20 @@ class _BNState:
 class Engine:
     """Executes a PoseNetPlan.  `params` maps state_dict names to tensors."""
 
-    def __init__(self, plan, precision=0, ops=None):
+    def __init__(self, plan, precision=0, ops=None, wgrad_precision=None):
         self.plan = plan
         self.precision = precision
+        # Weight gradients are leaf outputs: their rounding error is not propagated through
+        # further layers (no ReLU-mask flips downstream), and it averages over the N*H*W
+        # reduction.  A separate precision can therefore be chosen for wgrad
+        # (EPB_WGRAD_PRECISION=tf32|tf32x3|fp32; default: same as `precision`).
+        import os
+        env = os.environ.get("EPB_WGRAD_PRECISION")
+        if wgrad_precision is None and env:
+            wgrad_precision = {"fp32": 0, "tf32": 1, "tf32x3": 3}[env]
+        self.wgrad_precision = precision if wgrad_precision is None else wgrad_precision
+        if precision == 0:
+            self.wgrad_precision = 0
         self.ops = ops or _default_ops
 
     # ------------------------------------------------------------------ helpers
@@ -247,7 +258,10 @@ class Engine:
             if g is None:
                 continue
             g.in_relu = relu if affine is not None else 0
+            g.accumulate = 0
+            g.precision = self.wgrad_precision
             ops.conv_wgrad(g, x, dout, dwp, sc, sh)
+            g.precision = self.precision
         conv.unpack_grad(ops, dwp, grad_out)
 
     def _bn_train(self, name, C, stats, M, params, new_buffers):

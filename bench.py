@@ -247,6 +247,7 @@ def run_gpu(args):
         return wrapper
 
     geom_dev = iu.pack_meta(meta_dev, n_img, dev)
+    os.environ["EPB_OVERLAP_WGRAD"] = "0"      # serialise wgrad with the rest: clean per-kernel times
     ops.conv_fprop, ops.conv_wgrad = timed(orig_f), timed(orig_w)
     l0 = ops.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -261,6 +262,7 @@ def run_gpu(args):
     conv_ms = sum(a.elapsed_time(b) for a, b in conv_t["events"]) / n_inst
     n_conv_launch = len(conv_t["events"]) // n_inst
     ops.conv_fprop, ops.conv_wgrad = orig_f, orig_w
+    os.environ.pop("EPB_OVERLAP_WGRAD", None)
 
     # ---- e2e through the public loop API with HOST batches (H2D + loss read-back)
     reset_config()
@@ -290,9 +292,17 @@ def run_gpu(args):
         e2e_s = tmax.item()
     e2e_value = world * args.tuples * args.steps / e2e_s
 
-    if rank != 0:
+    def finish():
+        # tear-down of NCCL communicators that are referenced by a live CUDA graph can
+        # block at interpreter exit: flush and leave without running destructors
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     peaks, which = measured_peaks()
     total_flops, _ = conv_flops(model._plan, n_img, HW)
@@ -329,8 +339,7 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(steps=1, warmup=1, tuples=args.cpu_tuples, layers=layers)
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 # ---------------------------------------------------------------------------- CPU arm

@@ -250,6 +250,19 @@ class Engine:
         return din
 
     def _conv_wgrad(self, conv, x, dout, N, H, W, grad_out, affine=None, relu=1):
+        """Weight gradient.  Off the critical path of the backward pass (nothing downstream
+        consumes it before the optimiser), so it is issued on a side stream and overlaps the
+        next layers' dgrad / BatchNorm-backward kernels; `backward` joins the streams."""
+        side = getattr(self, "_side", None)
+        if side is None:
+            return self._conv_wgrad_now(conv, x, dout, N, H, W, grad_out, affine, relu)
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)                    # dout / x are ready on the main stream
+        self._keep.append((x, dout, affine))      # keep operands alive until the join
+        with torch.cuda.stream(side):
+            self._conv_wgrad_now(conv, x, dout, N, H, W, grad_out, affine, relu)
+
+    def _conv_wgrad_now(self, conv, x, dout, N, H, W, grad_out, affine=None, relu=1):
         ops = self.ops
         T = conv.k * conv.k
         dwp = torch.zeros(conv.cout_p * T * conv.cin_p, device=self.dev, dtype=torch.float32)
@@ -296,7 +309,7 @@ class Engine:
         ops, plan = self.ops, self.plan
         self.dev = x_nchw.device
         N, _, H, W = x_nchw.shape
-        S = {"N": N, "H": H, "W": W, "packed": {}, "bn": {}, "blocks": []} if True else None
+        S = {"N": N, "H": H, "W": W, "packed": {}, "bn": {}, "blocks": []}
         # per-forward BN statistics accumulators (one memset)
         bns = plan.all_bns()
         offs, tot = {}, 0
@@ -423,6 +436,22 @@ class Engine:
         ops, plan = self.ops, self.plan
         N = S["N"]
         self.dev = dlogits.device
+        import os
+        self._side, self._keep = None, []
+        if dlogits.is_cuda and os.environ.get("EPB_OVERLAP_WGRAD", "1") != "0":
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = torch.cuda.Stream()
+            self._side = self._side_stream
+        try:
+            self._backward(S, dlogits, ddepth, params, grads)
+        finally:
+            if self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)   # join before grads are used
+            self._side, self._keep = None, []
+
+    def _backward(self, S, dlogits, ddepth, params, grads):
+        ops, plan = self.ops, self.plan
+        N = S["N"]
 
         def wd_of(conv):
             return S["packed"][conv.name][1]

@@ -237,18 +237,31 @@ def run_gpu(args):
     # inside a replayed graph); the kernels and their arguments are identical
     orig_f, orig_w = ops.conv_fprop, ops.conv_wgrad
 
-    def timed(fnc):
-        def wrapper(*a, **k):
+    ns = {"fp32": 0, "tf32": 1, "tf32x3": 3}[args.precision]
+
+    def kernel_class(kind, g):
+        """Name of the kernel template the C dispatcher picks for this call (csrc/conv*.cu)."""
+        if ns == 0 or g.Cin % 32 or (kind == "fprop" and g.Cout % 32):
+            return "conv_%s_simt" % kind
+        if kind == "fprop":
+            bn = 256 if g.Cout >= 256 else (128 if g.Cout >= 128 else 64)
+            return "conv_fprop_tc_kernel<%d,%d>" % (bn, ns)
+        bn = 128 if g.Cin >= 128 else (64 if g.Cin >= 64 else 32)
+        return "conv_wgrad_tc_kernel<%d,%d>" % (bn, g.precision if g.precision else ns)
+
+    def timed(fnc, kind):
+        def wrapper(g, *a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()                       # torch's CURRENT stream = the one the kernel uses
-            fnc(*a, **k)
+            fnc(g, *a, **k)
             e1.record()
-            conv_t["events"].append((e0, e1))
+            flops = 2.0 * g.N * g.Hp * g.Wp * g.Cin * g.Cout * g.T
+            conv_t["events"].append((e0, e1, kernel_class(kind, g), flops))
         return wrapper
 
     geom_dev = iu.pack_meta(meta_dev, n_img, dev)
     os.environ["EPB_OVERLAP_WGRAD"] = "0"      # serialise wgrad with the rest: clean per-kernel times
-    ops.conv_fprop, ops.conv_wgrad = timed(orig_f), timed(orig_w)
+    ops.conv_fprop, ops.conv_wgrad = timed(orig_f, "fprop"), timed(orig_w, "wgrad")
     l0 = ops.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -259,8 +272,15 @@ def run_gpu(args):
     barrier()
     launches = (ops.launches - l0) // n_inst
     eager_ms = e0.elapsed_time(e1) / n_inst
-    conv_ms = sum(a.elapsed_time(b) for a, b in conv_t["events"]) / n_inst
+    conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in conv_t["events"]) / n_inst
     n_conv_launch = len(conv_t["events"]) // n_inst
+    per_class = {}
+    for a, b, name, fl in conv_t["events"]:
+        c = per_class.setdefault(name, [0, 0.0, 0.0])
+        c[0] += 1
+        c[1] += a.elapsed_time(b)
+        c[2] += fl
+    dom = max(per_class, key=lambda k: per_class[k][1])
     ops.conv_fprop, ops.conv_wgrad = orig_f, orig_w
     os.environ.pop("EPB_OVERLAP_WGRAD", None)
 
@@ -307,7 +327,14 @@ def run_gpu(args):
     peaks, which = measured_peaks()
     total_flops, _ = conv_flops(model._plan, n_img, HW)
     tensor_peak = peaks["bf16_tflops_sustained"] / 2.0      # TF32 rate = half the bf16 rate
-    achieved = total_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    fam_achieved = total_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    d_n, d_ms, d_fl = per_class[dom]
+    achieved = d_fl / (d_ms / 1e3) / 1e12        # padded-channel FLOPs of the dominant kernel's calls
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
@@ -327,12 +354,19 @@ def run_gpu(args):
         "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
         "cuda_graph": bool(use_graph),
-        "roofline": {"bound": "tensor", "kernel": "conv implicit-GEMM family (fprop/dgrad/wgrad)",
+        "roofline": {"bound": "tensor", "kernel": dom,
                      "achieved": round(achieved, 3), "peak": round(tensor_peak, 1),
                      "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 5),
-                     "traffic": None, "peak_source": which + " bf16_tflops_sustained / 2 (tf32)",
-                     "launches_per_step": n_conv_launch,
-                     "share_of_step": round(conv_ms / ms_step, 4) if ms_step > 0 else None,
+                     "traffic": traffic, "peak_source": which + " bf16_tflops_sustained / 2 (tf32)",
+                     "note": "achieved counts algorithmic FLOPs (2MNK once); in 3xTF32 the tensor pipe "
+                             "executes 3x that",
+                     "launches_per_step": d_n // n_inst,
+                     "avg_launch_ms": round(d_ms / d_n, 4),
+                     "share_of_step": round(d_ms / n_inst / ms_step, 4) if ms_step > 0 else None,
+                     "conv_family": {"achieved": round(fam_achieved, 3), "launches_per_step": n_conv_launch,
+                                     "share_of_step": round(conv_ms / ms_step, 4),
+                                     "per_kernel_ms_per_step": {k: round(v[1] / n_inst, 3)
+                                                                for k, v in sorted(per_class.items())}},
                      "measured": "CUDA events around each launch of %d eager step(s) run right "
                                  "after the timed region (eager step %.2f ms)" % (n_inst, eager_ms)},
     }

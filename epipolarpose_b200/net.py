@@ -249,18 +249,25 @@ class Engine:
             ops.conv_fprop(g, dout, wd, din, None, None, None, None)
         return din
 
-    def _conv_wgrad(self, conv, x, dout, N, H, W, grad_out, affine=None, relu=1):
+    def _conv_wgrad(self, conv, x, dout, N, H, W, grad_out, affine=None, relu=1, post=None):
         """Weight gradient.  Off the critical path of the backward pass (nothing downstream
         consumes it before the optimiser), so it is issued on a side stream and overlaps the
-        next layers' dgrad / BatchNorm-backward kernels; `backward` joins the streams."""
+        next layers' dgrad / BatchNorm-backward kernels; `backward` joins the streams.
+        `post` (optional) runs right after it ON THE SAME STREAM (layout fix-ups of the
+        gradient)."""
         side = getattr(self, "_side", None)
         if side is None:
-            return self._conv_wgrad_now(conv, x, dout, N, H, W, grad_out, affine, relu)
+            self._conv_wgrad_now(conv, x, dout, N, H, W, grad_out, affine, relu)
+            if post is not None:
+                post()
+            return
         main = torch.cuda.current_stream()
         side.wait_stream(main)                    # dout / x are ready on the main stream
-        self._keep.append((x, dout, affine))      # keep operands alive until the join
+        self._keep.append((x, dout, affine, grad_out))   # keep operands alive until the join
         with torch.cuda.stream(side):
             self._conv_wgrad_now(conv, x, dout, N, H, W, grad_out, affine, relu)
+            if post is not None:
+                post()
 
     def _conv_wgrad_now(self, conv, x, dout, N, H, W, grad_out, affine=None, relu=1):
         ops = self.ops
@@ -527,6 +534,9 @@ class Engine:
         dz0 = self._bn_bwd(S["bn"]["bn1"], gpool, z0, None, 1, params, grads)
         kpad = plan.stem_kpad
         gcol = torch.zeros((64, kpad, 1, 1), device=self.dev, dtype=torch.float32)
-        self._conv_wgrad(plan.stem_col, col, dz0, N, H1, W1, gcol)
-        g147 = gcol.view(64, kpad)[:, :147].contiguous()
-        ops.pack_weight(g147, grads["conv1.weight"], 64, 3, 7, 7, 0, 3, 1)
+
+        def stem_unpack():
+            g147 = gcol.view(64, kpad)[:, :147].contiguous()
+            ops.pack_weight(g147, grads["conv1.weight"], 64, 3, 7, 7, 0, 3, 1)
+            self._keep.append(g147)
+        self._conv_wgrad(plan.stem_col, col, dz0, N, H1, W1, gcol, post=stem_unpack)

@@ -361,10 +361,18 @@ int launch_wgrad(const epb_conv_geom* g, const float* in, const float* dout, con
   const int nb = (total_slots + groups - 1) / groups;          // balanced group size
   const int groups2 = (total_slots + nb - 1) / nb;
   const int64_t tiles = (int64_t)co_tiles * groups2;
-  int64_t splits = (2 * kNumSMs + tiles - 1) / tiles;
+  // Split the pixel range so that the grid fills whole waves of one CTA per SM (a
+  // 2.16-wave grid idles most SMs in its last round): try every split count up to ~3
+  // waves and keep the one with the best wave efficiency (ties -> more CTAs).
   const int64_t max_splits = (M + 8 * KPIX - 1) / (8 * KPIX);   // >= 8 pixel blocks per CTA
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  int64_t splits = 1;
+  double best = -1.0;
+  for (int64_t sp = 1; sp <= max_splits && sp * tiles <= 3 * kNumSMs + tiles; ++sp) {
+    const int64_t grid_sp = sp * tiles;
+    const int64_t waves = (grid_sp + kNumSMs - 1) / kNumSMs;
+    const double eff = (double)grid_sp / (double)(waves * kNumSMs);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && sp > splits)) { best = eff; splits = sp; }
+  }
   int64_t rows = (M + splits - 1) / splits;
   rows = (rows + KPIX - 1) / KPIX * KPIX;
   splits = (M + rows - 1) / rows;

@@ -26,13 +26,12 @@ for h, v in sorted(stalls, key=lambda x: -x[1])[:10]:
 if len(sys.argv) > 2:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
-    h = rows[0]
-    try:
-        isrc = h.index("Source"); ismp = [i for i, x in enumerate(h) if x.startswith("# Samples") or x == "Warp Stall Sampling (All Samples)"][0]
-        body = [r for r in rows[1:] if len(r) > ismp and r[ismp].replace(",", "").isdigit()]
-        body.sort(key=lambda r: -int(r[ismp].replace(",", "")))
-        tot = sum(int(r[ismp].replace(",", "")) for r in body) or 1
-        for r in body[:int(sys.argv[2])]:
-            print("  %5.1f%%  %s" % (100.0 * int(r[ismp].replace(",", "")) / tot, r[isrc][:110]))
-    except Exception as e:
-        print("source page parse failed", e, h[:12])
+    h, body = rows[1], rows[2:]
+    isrc, ismp = h.index("Source"), h.index("# Samples")
+    stall_cols = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
+    body = [r for r in body if len(r) > ismp and r[ismp].isdigit()]
+    tot = sum(int(r[ismp]) for r in body) or 1
+    print("  top SASS instructions by warp-stall samples:")
+    for r in sorted(body, key=lambda r: -int(r[ismp]))[:int(sys.argv[2])]:
+        st = sorted([(int(r[i]), h[i]) for i in stall_cols if r[i].isdigit()], reverse=True)[:2]
+        print("  %5.1f%%  %-58s %s" % (100.0 * int(r[ismp]) / tot, r[isrc].strip()[:58], st))

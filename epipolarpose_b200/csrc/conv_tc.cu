@@ -50,9 +50,8 @@ struct Cfg {
 };
 
 struct RowInfo {
-  int pix_base[BM];   // n * Hi * Wi  (or -1 for rows past M)
-  int ih0[BM];        // i * is
-  int iw0[BM];        // j * is
+  int off0[BM];                  // ((n*Hi + i*is)*Wi + j*is)*Cin : element offset of the un-shifted pixel
+  unsigned long long vmask[BM];  // bit t set <=> tap t reads inside the image (0 for rows past M)
 };
 
 template <int BN, int NS>
@@ -117,16 +116,21 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (p < BM) {
         const int64_t m = (int64_t)mt * BM + p;
+        unsigned long long vm = 0;
+        int off = 0;
         if (m < M) {
           const unsigned um = (unsigned)m;
           const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
           const unsigned i = qq % (unsigned)g.Hp, n = qq / (unsigned)g.Hp;
-          rows->pix_base[p] = (int)n * g.Hi * g.Wi;
-          rows->ih0[p] = (int)i * g.is;
-          rows->iw0[p] = (int)j * g.is;
-        } else {
-          rows->pix_base[p] = -1;
+          const int ih0 = (int)i * g.is, iw0 = (int)j * g.is;
+          off = (((int)n * g.Hi + ih0) * g.Wi + iw0) * g.Cin;
+          for (int t = 0; t < g.T; ++t) {
+            const int ih = ih0 + g.dh[t], iw = iw0 + g.dw[t];
+            if (ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi) vm |= 1ull << t;
+          }
         }
+        rows->off0[p] = off;
+        rows->vmask[p] = vm;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // Two groups of 4 warps alternate k-blocks (group = kb & 1): each warp pays the
@@ -164,21 +168,19 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         }
       }
       auto issue = [&](float4 (&dst)[8], unsigned& mask) {
-        const int dh = g.dh[it], dw = g.dw[it];
-        const int ch = icb * BKE + c4 * 4;
+        // one uniform element offset per (tap, channel block); per row only the table
+        // look-ups remain (offset of the un-shifted pixel, bit mask of in-image taps)
+        const int delta = (g.dh[it] * g.Wi + g.dw[it]) * g.Cin + icb * BKE + c4 * 4;
+        const int tap = it;
         icb += 2;
         while (icb >= CB) { icb -= CB; ++it; }
         mask = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int r = wg * 32 + q * 4 + rsub;
-          const int pb = rows->pix_base[r];
-          const int ih = rows->ih0[r] + dh, iw = rows->iw0[r] + dw;
-          const bool ok = (pb >= 0) && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
           dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) {
-            dst[q] = *reinterpret_cast<const float4*>(
-                in + ((int64_t)pb + (int64_t)ih * g.Wi + iw) * g.Cin + ch);
+          if ((rows->vmask[r] >> tap) & 1ull) {
+            dst[q] = *reinterpret_cast<const float4*>(in + ((int64_t)rows->off0[r] + delta));
             mask |= 1u << q;
           }
         }
@@ -464,7 +466,9 @@ bool epb_conv_wgrad_tc_supported(const epb_conv_geom* g);
 
 bool epb_conv_tc_supported(const epb_conv_geom* g, bool wgrad) {
   if (wgrad) return epb_conv_wgrad_tc_supported(g);
-  return g->Cin % 32 == 0 && g->Cout % 32 == 0 && g->Cout >= 32;
+  // the producers address the input with 32-bit element offsets
+  return g->Cin % 32 == 0 && g->Cout % 32 == 0 && g->Cout >= 32 &&
+         (int64_t)g->N * g->Hi * g->Wi * g->Cin < (1LL << 31);
 }
 
 int epb_conv_fprop_tc(const epb_conv_geom* g, const float* in, const float* w,

@@ -138,7 +138,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
     const int qb = tg % QB, rb0 = tg / QB;
     const int co = co0 + qa * 4;
     const bool co_ok = co < g.Cout;
-    int* rt = rowtab + grpi * 4 * KPIX;           // [dout pixel | n*Hi*Wi | i*is | j*is][KPIX]
+    int* rt = rowtab + grpi * 4 * KPIX;   // [dout pixel | input element offset | tap mask lo | hi][KPIX]
     const int per_blk = NB + 1;
     const int total = nblk * per_blk;
     float4 buf[2][NREG];
@@ -155,11 +155,19 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
             const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
             const unsigned i = qq % (unsigned)g.Hp, n = qq / (unsigned)g.Hp;
             rt[tg] = ((int)n * g.Ho + ((int)i * g.os + g.ph)) * g.Wo + ((int)j * g.os + g.pw);
-            rt[KPIX + tg] = (int)n * g.Hi * g.Wi;
-            rt[2 * KPIX + tg] = (int)i * g.is;
-            rt[3 * KPIX + tg] = (int)j * g.is;
+            const int ih0 = (int)i * g.is, iw0 = (int)j * g.is;
+            rt[KPIX + tg] = (((int)n * g.Hi + ih0) * g.Wi + iw0) * g.Cin;
+            unsigned long long vm = 0;
+            for (int t = 0; t < g.T; ++t) {
+              const int ih = ih0 + g.dh[t], iw = iw0 + g.dw[t];
+              if (ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi) vm |= 1ull << t;
+            }
+            rt[2 * KPIX + tg] = (int)(unsigned)(vm & 0xffffffffull);
+            rt[3 * KPIX + tg] = (int)(unsigned)(vm >> 32);
           } else {
             rt[tg] = -1;
+            rt[2 * KPIX + tg] = 0;
+            rt[3 * KPIX + tg] = 0;
           }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grpi) : "memory");
@@ -197,15 +205,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
       } else {
         const int sl = ie - 1;
         const int ci = slot_cit[sl] * BNW + qb * 4;
-        const int dh = g.dh[slot_t[sl]], dwv = g.dw[slot_t[sl]];
+        const int tap = slot_t[sl];
+        const int delta = (g.dh[tap] * g.Wi + g.dw[tap]) * g.Cin + ci;
+        const int word = 2 + (tap >> 5);
+        const unsigned bit = 1u << (tap & 31);
 #pragma unroll
         for (int k = 0; k < PBg; ++k) {
           dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int r = rb0 + k * RBg;
-          const int ih = rt[2 * KPIX + r] + dh, iw = rt[3 * KPIX + r] + dwv;
-          if (ci < g.Cin && rt[r] >= 0 && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi) {
-            dst[k] = *reinterpret_cast<const float4*>(
-                in + ((int64_t)rt[KPIX + r] + (int64_t)ih * g.Wi + iw) * g.Cin + ci);
+          if (ci < g.Cin && ((unsigned)rt[word * KPIX + r] & bit)) {
+            dst[k] = *reinterpret_cast<const float4*>(in + ((int64_t)rt[KPIX + r] + delta));
             mask |= 1u << k;
           }
         }
@@ -393,7 +402,10 @@ int launch_wgrad(const epb_conv_geom* g, const float* in, const float* dout, con
 }  // namespace
 
 bool epb_conv_wgrad_tc_supported(const epb_conv_geom* g) {
-  return g->Cin % 32 == 0 && g->Cout % 4 == 0 && g->Cout >= 32;
+  // 32-bit element offsets into the input / pixel indices into dout
+  return g->Cin % 32 == 0 && g->Cout % 4 == 0 && g->Cout >= 32 &&
+         (int64_t)g->N * g->Hi * g->Wi * g->Cin < (1LL << 31) &&
+         (int64_t)g->N * g->Ho * g->Wo < (1LL << 31);
 }
 
 int epb_conv_wgrad_tc(const epb_conv_geom* g, const float* in, const float* dout,

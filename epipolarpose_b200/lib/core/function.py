@@ -61,6 +61,10 @@ class GraphedTrainStep:
     eagerly (sizes workspaces, one-time attributes), the second captures and replays."""
 
     def __init__(self, model, criterion, optimizer, online=False, method="iterative"):
+        # scripts/train.py:94 wraps the model in nn.DataParallel(device_ids=[k]); with one
+        # device id that wrapper only forwards the call (and its scatter is not capturable)
+        if isinstance(model, torch.nn.DataParallel) and len(model.device_ids) == 1:
+            model = model.module
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.online, self.method = online, method
         self.graph = None

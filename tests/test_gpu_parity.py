@@ -435,3 +435,60 @@ def test_graphed_train_step_matches_eager(dev):
     assert abs(out["graph"][0][0] - out["eager"][0][0]) <= 1e-5 * abs(out["eager"][0][0])
     for k, v in out["eager"][1].items():
         assert relerr(out["graph"][1][k], v) <= 5e-2, k
+
+
+def test_reference_script_flow(dev, tmp_path):
+    """The call sequence of the reference's scripts/train.py (:83-182) against the mirror:
+    model factory, DataParallel wrap, criterion by name, get_optimizer + MultiStepLR, dataset
+    by name, DataLoader, train / validate / eval loops, checkpoint save + reload."""
+    import torch.utils.data
+    import lib.core.integral_loss as loss            # noqa: F401  (eval by name below)
+    import lib.dataset as dataset                    # noqa: F401
+    import lib.models as models
+    from lib.core.config import config, reset_config
+    from lib.core.function import train_integral, validate_integral, eval_integral
+    from lib.utils.utils import get_optimizer, save_checkpoint
+    reset_config()
+    config.MODEL.NUM_JOINTS = 4
+    config.MODEL.DEPTH_RES = 16
+    config.MODEL.IMAGE_SIZE = [64, 64]
+    config.MODEL.EXTRA.NUM_LAYERS = 18
+    config.MODEL.INIT_WEIGHTS = False
+    config.LOSS.FN = "SmoothL1JointLocationLoss"
+    config.DATASET.DATASET = "synthetic_h36m"
+    config.DATASET.SYNTHETIC_LEN = 24
+    config.TRAIN.BATCH_SIZE = 8
+    config.PRINT_FREQ = 1
+    model = models.pose3d_resnet.get_pose_net(config, is_train=True)
+    model = torch.nn.DataParallel(model, device_ids=[0]).cuda()
+    criterion = eval("loss." + config.LOSS.FN)(num_joints=config.MODEL.NUM_JOINTS, norm=config.LOSS.NORM).cuda()
+    optimizer = get_optimizer(config, model)
+    sched = torch.optim.lr_scheduler.MultiStepLR(optimizer, [1], 0.1)
+    ds = eval("dataset." + config.DATASET.DATASET)
+    train_ds = ds(cfg=config, root="", image_set="train", is_train=True)
+    valid_ds = ds(cfg=config, root="", image_set="valid", is_train=False)
+    mk = lambda d, sh: torch.utils.data.DataLoader(d, batch_size=config.TRAIN.BATCH_SIZE, shuffle=sh,
+                                                   num_workers=0, pin_memory=True)
+    train_loader, valid_loader = mk(train_ds, True), mk(valid_ds, False)
+    before = {k: v.detach().clone() for k, v in model.module.state_dict().items()}
+    for epoch in range(2):
+        avg = train_integral(config, train_loader, model, criterion, optimizer, epoch)
+        sched.step()
+        assert np.isfinite(avg)
+        preds = validate_integral(valid_loader, model)
+        assert preds.shape == (len(valid_ds), config.MODEL.NUM_JOINTS, 4) and np.isfinite(preds).all()
+        perf = eval_integral(epoch, preds, valid_loader, str(tmp_path), debug=False)
+        assert np.isfinite(perf)
+        save_checkpoint({"epoch": epoch + 1, "model": "pose3d_resnet", "state_dict": model.state_dict(),
+                         "perf": perf, "optimizer": optimizer.state_dict()}, True, str(tmp_path))
+    after = model.module.state_dict()
+    assert any(not torch.equal(before[k], after[k]) for k in before if before[k].is_floating_point())
+    # DataParallel-prefixed checkpoint reloads through the reference's own prefix-stripping path
+    best = torch.load(str(tmp_path / "model_best.pth.tar"), map_location="cpu")
+    assert all(k.startswith("module.") for k in best)
+    fresh = models.pose3d_resnet.get_pose_net(config, is_train=False)
+    torch.save(best, str(tmp_path / "mpii_like.pth.tar"))
+    fresh.load_pretrained_pose_model(str(tmp_path / "mpii_like.pth.tar"))
+    for k, v in fresh.state_dict().items():
+        assert torch.equal(v.cpu(), after[k].cpu()), k
+    reset_config()

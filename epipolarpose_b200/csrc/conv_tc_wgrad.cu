@@ -371,16 +371,16 @@ int launch_wgrad(const epb_conv_geom* g, const float* in, const float* dout, con
   const int groups2 = (total_slots + nb - 1) / nb;
   const int64_t tiles = (int64_t)co_tiles * groups2;
   // Split the pixel range so that the grid fills whole waves of one CTA per SM (a
-  // 2.16-wave grid idles most SMs in its last round): try every split count up to ~3
-  // waves and keep the one with the best wave efficiency (ties -> more CTAs).
+  // 2.16-wave grid idles most SMs in its last round).  Cost model per split count:
+  // rounds x (pixel blocks per CTA + fixed prologue/epilogue cost worth ~6 blocks).
   const int64_t max_splits = (M + 8 * KPIX - 1) / (8 * KPIX);   // >= 8 pixel blocks per CTA
   int64_t splits = 1;
-  double best = -1.0;
+  int64_t best = -1;
   for (int64_t sp = 1; sp <= max_splits && sp * tiles <= 3 * kNumSMs + tiles; ++sp) {
-    const int64_t grid_sp = sp * tiles;
-    const int64_t waves = (grid_sp + kNumSMs - 1) / kNumSMs;
-    const double eff = (double)grid_sp / (double)(waves * kNumSMs);
-    if (eff > best + 1e-9 || (eff > best - 1e-9 && sp > splits)) { best = eff; splits = sp; }
+    const int64_t rounds = (sp * tiles + kNumSMs - 1) / kNumSMs;
+    const int64_t blocks = ((M + sp - 1) / sp + KPIX - 1) / KPIX;
+    const int64_t cost = rounds * (blocks + 6);
+    if (best < 0 || cost < best) { best = cost; splits = sp; }
   }
   int64_t rows = (M + splits - 1) / splits;
   rows = (rows + KPIX - 1) / KPIX * KPIX;

@@ -5,13 +5,13 @@
 //   BatchNorm+ReLU applied on the fly.
 //
 // One persistent CTA per SM, warp-specialised:
-//   warps 0-7  A producers: gather 128 pixel rows x 32 channels (128-byte rows),
+//   warps 0-15 A producers: gather 128 pixel rows x 32 channels (128-byte rows),
 //              fused BN+ReLU, split into TF32 hi (+ lo for the 3xTF32 mode) and
 //              store into the SWIZZLE_128B K-major smem layout tcgen05 reads;
-//   warp  8    B producer: TMA loads of the packed weight tile (hi / lo planes);
-//   warp  9    MMA issuer: one thread issues tcgen05.mma kind::tf32 (M=128,
+//   warp  16   B producer: TMA loads of the packed weight tile (hi / lo planes);
+//   warp  17   MMA issuer: one thread issues tcgen05.mma kind::tf32 (M=128,
 //              N=BN, K=8) with FP32 accumulators in TMEM (double buffered);
-//   warps 10-13 epilogue: tcgen05.ld TMEM -> registers -> bias / accumulate ->
+//   warps 18-21 epilogue: tcgen05.ld TMEM -> registers -> bias / accumulate ->
 //              global, plus per-channel sum / sum-of-squares for the following
 //              BatchNorm (warp transpose-reduce, smem, one double atomic per
 //              column per tile).
@@ -28,10 +28,10 @@ namespace {
 
 constexpr int BM = 128;          // pixel rows per tile == UMMA M
 constexpr int BKE = 32;          // tf32 elements per k-block (128 bytes)
-constexpr int kProducerWarps = 8;       // 256 gather threads: bytes in flight, not issue rate, bound the A stream
+constexpr int kProducerWarps = 16;      // G groups take k-blocks round-robin (Cfg::G)
 
 constexpr int kEpiWarps = 4;
-constexpr int kThreads = 32 * (kProducerWarps + 2 + kEpiWarps);   // 448
+constexpr int kThreads = 32 * (kProducerWarps + 2 + kEpiWarps);   // 704
 constexpr int kSmemBudget = 200 * 1024;
 
 template <int BN, int NS>
@@ -42,6 +42,15 @@ struct Cfg {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int S_ = kSmemBudget / STAGE;
   static constexpr int S = S_ > 8 ? 8 : S_;
+  // Producer groups.  A group waits on a slot's empty barrier by PARITY, which is only
+  // sound while it is less than two phases ahead of the barrier: G <= S.  With a deep
+  // ring: 4 groups of 4 warps, one register buffer each; with 2-3 slots (3xTF32, wide
+  // tiles): 2 groups of 8 warps with a register double buffer.  Either way the loads of
+  // four k-blocks are in flight and every SM sub-partition has 4 producer warps.
+  static constexpr int G = S >= 4 ? 4 : 2;
+  static constexpr int D = 4 / G;                              // register buffers per group
+  static constexpr int W = kProducerWarps / G;                 // warps per group
+  static constexpr int NQ = 32 / W;                            // float4 per thread per k-block
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int EPI_PITCH = 36;                          // floats per staged row (144 B)
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;       // one 32x32 block per epilogue warp
@@ -86,7 +95,7 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::S; ++s) {
-      tc::mbar_init(full_bar(s), kProducerWarps / 2 + 1);
+      tc::mbar_init(full_bar(s), C::W + 1);
       tc::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -104,7 +113,7 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < kProducerWarps) {
-    // =================================================== A producers (256 threads)
+    // =================================================== A producers (512 threads)
     const int p = threadIdx.x;                 // threads 0..127 also compute one row's geometry
     const int c4 = lane & 7;                   // 16-byte chunk within the 128-byte row
     const int rsub = lane >> 3;                // 0..3
@@ -113,7 +122,7 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / n_tiles;
       // producers of the previous tile are done reading rowinfo once all reach this barrier
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       if (p < BM) {
         const int64_t m = (int64_t)mt * BM + p;
         unsigned long long vm = 0;
@@ -132,17 +141,16 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         rows->off0[p] = off;
         rows->vmask[p] = vm;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      // Two groups of 4 warps alternate k-blocks (group = kb & 1): each warp pays the
-      // per-k-block fixed costs (mbarrier wait, proxy fence, arrive) for every OTHER
-      // k-block while the groups overlap; inside a group the loads of its next k-block
-      // are in flight (register double buffer) while the current one is converted.
-      float4 buf[2][8];
-      unsigned okm[2];
-      const int grp = warp >> 2, wg = warp & 3;
-      int st = base_stage + grp;
-      uint32_t ph = base_phase;
-      if (st >= C::S) { st -= C::S; ph ^= 1; }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // Groups take k-blocks round-robin (group = kb % G): each warp pays the per-k-block
+      // fixed costs (mbarrier wait, proxy fence, arrive) for every G-th k-block while the
+      // other groups' warps keep the sub-partition's issue slots busy.
+      constexpr int G = C::G, D = C::D, NQ = C::NQ, RPW = BM / C::W;
+      float4 buf[D][NQ];
+      unsigned okm[D];
+      const int grp = warp / C::W, wg = warp % C::W;
+      int st = (base_stage + grp) % C::S;
+      uint32_t ph = base_phase ^ (uint32_t)(((base_stage + grp) / C::S) & 1);
       int it = 0, icb = grp, pcb = grp;          // issue cursor (tap, channel block); consume cursor
       while (icb >= CB) { icb -= CB; ++it; }
       while (pcb >= CB) pcb -= CB;
@@ -167,17 +175,17 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           }
         }
       }
-      auto issue = [&](float4 (&dst)[8], unsigned& mask) {
+      auto issue = [&](float4 (&dst)[NQ], unsigned& mask) {
         // one uniform element offset per (tap, channel block); per row only the table
         // look-ups remain (offset of the un-shifted pixel, bit mask of in-image taps)
         const int delta = (g.dh[it] * g.Wi + g.dw[it]) * g.Cin + icb * BKE + c4 * 4;
         const int tap = it;
-        icb += 2;
+        icb += G;
         while (icb >= CB) { icb -= CB; ++it; }
         mask = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = wg * 32 + q * 4 + rsub;
+        for (int q = 0; q < NQ; ++q) {
+          const int r = wg * RPW + q * 4 + rsub;
           dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           if ((rows->vmask[r] >> tap) & 1ull) {
             dst[q] = *reinterpret_cast<const float4*>(in + ((int64_t)rows->off0[r] + delta));
@@ -185,9 +193,9 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           }
         }
       };
-      auto process = [&](const float4 (&v)[8], unsigned mask) {
+      auto process = [&](const float4 (&v)[NQ], unsigned mask) {
         const int ch = pcb * BKE + c4 * 4;
-        pcb += 2;
+        pcb += G;
         while (pcb >= CB) pcb -= CB;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in_scale) {
@@ -197,8 +205,8 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         tc::mbar_wait(empty_bar(st), ph ^ 1);
         uint8_t* a_hi = sm + st * C::STAGE;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = wg * 32 + q * 4 + rsub;
+        for (int q = 0; q < NQ; ++q) {
+          const int r = wg * RPW + q * 4 + rsub;
           float4 x = v[q];
           if (in_scale && ((mask >> q) & 1u)) {
             x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
@@ -220,18 +228,26 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(full_bar(st));
-        st += 2;
-        if (st >= C::S) { st -= C::S; ph ^= 1; }
+        st += G;
+        ph ^= (uint32_t)((st / C::S) & 1);
+        st %= C::S;
       };
-      const int mine = (KB - grp + 1) / 2;
-      if (mine > 0) issue(buf[0], okm[0]);
-      for (int k0 = 0; k0 < mine; k0 += 2) {
+      const int mine = (KB - grp + G - 1) / G;
+      if constexpr (D == 1) {
+        for (int k = 0; k < mine; ++k) {
+          issue(buf[0], okm[0]);
+          process(buf[0], okm[0]);
+        }
+      } else {
+        if (mine > 0) issue(buf[0], okm[0]);
+        for (int k0 = 0; k0 < mine; k0 += 2) {
 #pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          const int k = k0 + d;
-          if (k < mine) {
-            if (k + 1 < mine) issue(buf[d ^ 1], okm[d ^ 1]);
-            process(buf[d], okm[d]);
+          for (int d = 0; d < 2; ++d) {
+            const int k = k0 + d;
+            if (k < mine) {
+              if (k + 1 < mine) issue(buf[d ^ 1], okm[d ^ 1]);
+              process(buf[d], okm[d]);
+            }
           }
         }
       }

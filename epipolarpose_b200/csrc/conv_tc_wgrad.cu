@@ -15,8 +15,9 @@
 // split of the pixel range).  The dout tile A(p) of pixel block p is produced
 // ONCE and multiplied against the NB input tiles B(p, b) (two smem rings), each
 // slot accumulating into its own TMEM columns (NB * BNW <= 512 fp32 columns), so
-// dout is gathered once per NB taps instead of once per tap.  Global loads of the
-// next tile are in flight while the current one is converted and stored.  One
+// dout is gathered once per NB taps instead of once per tap.  Four groups of four
+// producer warps take tiles round-robin, so four tiles' global loads are in flight and
+// every SM sub-partition has four warps to issue the convert/store work from.  One
 // thread issues tcgen05.mma kind::tf32 (M = 128, N = BNW, K = 8 pixels); the
 // epilogue adds the partial tiles to dw with red.global.add.v4.f32 (split-K).
 #include "conv_common.cuh"
@@ -26,7 +27,8 @@ namespace {
 
 constexpr int WM = 128;          // co rows per tile (UMMA M); rows >= Cout are zero
 constexpr int KPIX = 32;         // pixels per tile (4 MMAs of K = 8)
-constexpr int kProdWarps = 8;
+constexpr int kProdWarps = 16;
+constexpr int kGroups = 4;       // producer groups of 4 warps (one tile each, round-robin)
 constexpr int kProd = 32 * kProdWarps;
 constexpr int kThreadsW = kProd + 32;      // + 1 MMA warp
 constexpr int kMaxSlots = 16;
@@ -39,8 +41,9 @@ struct WCfg {
   static constexpr int SA = 2;
   static constexpr int SB_ = (196 * 1024 - SA * A_TILE) / B_TILE;
   static constexpr int SB = SB_ > 8 ? 8 : SB_;
+  static_assert(SB >= 2, "input ring too small");
   static constexpr int NB_MAX = (512 / BNW) > kMaxSlots ? kMaxSlots : (512 / BNW);
-  static constexpr int SMEM = SA * A_TILE + SB * B_TILE + 1024 + 2048;
+  static constexpr int SMEM = SA * A_TILE + SB * B_TILE + 1024 + 3072;
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -62,7 +65,17 @@ __device__ __forceinline__ void st_mn(uint8_t* tile, int r, int ch4, float4 v) {
   *reinterpret_cast<float4*>(tile + off) = v;
 }
 
-struct PixCoord { int n, i, j; };
+// Slots are awaited by mbarrier PARITY, which is ambiguous for a waiter two phases ahead of
+// the barrier.  With tiles handed round-robin to four groups a group can get that far ahead,
+// so every ring slot carries a use counter in smem: use k of a slot may start its parity
+// wait only after use k-1 has PASSED its own wait (i.e. the release before last is known to
+// have happened), and publishes k+1 once it has passed.
+__device__ __forceinline__ void wait_seen(const volatile int* p, int need) {
+  if (*p >= need) return;
+  const long long t0 = clock64();
+  while (*p < need)
+    if (clock64() - t0 > 4000000000LL) __trap();
+}
 
 template <int BNW, int NS>
 __global__ void __launch_bounds__(kThreadsW, 1)
@@ -83,7 +96,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl + 8 * 24);
   int* slot_t = reinterpret_cast<int*>(ctrl + 256);          // [kMaxSlots] tap of each slot
   int* slot_cit = slot_t + kMaxSlots;                        // [kMaxSlots] ci tile of each slot
-  int* rowtab = slot_cit + kMaxSlots;                        // [2 groups][4][KPIX]
+  int* rowtab = slot_cit + kMaxSlots;                        // [kGroups][4][KPIX]
+  volatile int* seenA = rowtab + kGroups * 4 * KPIX;         // [SA] uses whose wait has passed
+  volatile int* seenB = seenA + C::SA;                       // [SB]
   const uint32_t bar0 = tc::smem_u32(bars);
   auto fullA = [&](int s) { return bar0 + 8u * s; };
   auto emptyA = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -107,10 +122,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
   const int co0 = cot * WM;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::SA; ++s) { tc::mbar_init(fullA(s), kProdWarps / 2); tc::mbar_init(emptyA(s), 1); }
-    for (int s = 0; s < C::SB; ++s) { tc::mbar_init(fullB(s), kProdWarps / 2); tc::mbar_init(emptyB(s), 1); }
+    for (int s = 0; s < C::SA; ++s) { tc::mbar_init(fullA(s), kProdWarps / kGroups); tc::mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < C::SB; ++s) { tc::mbar_init(fullB(s), kProdWarps / kGroups); tc::mbar_init(emptyB(s), 1); }
     tc::mbar_init(done_bar, 1);
     tc::fence_barrier_init();
+    for (int s = 0; s < C::SA; ++s) seenA[s] = 0;
+    for (int s = 0; s < C::SB; ++s) seenB[s] = 0;
     for (int b = 0; b < NB; ++b) {
       slot_t[b] = (slot0 + b) / ci_tiles;
       slot_cit[b] = (slot0 + b) % ci_tiles;
@@ -123,12 +140,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < kProdWarps) {
-    // ======================================================== producers (2 groups of 4 warps)
-    // Tiles alternate between the two groups (group = u & 1): each warp pays the per-tile
-    // fixed costs (mbarrier wait, proxy fence, arrive) for every OTHER tile while the two
-    // groups overlap; inside a group the loads of its next tile are in flight (register
-    // double buffer) while the current tile is converted and stored.
-    constexpr int GT = kProd / 2;                  // threads per group (128)
+    // ======================================================== producers (4 groups of 4 warps)
+    // Tiles go round-robin to the groups (group = u % 4): each warp pays the per-tile fixed
+    // costs (mbarrier wait, proxy fence, arrive) for every FOURTH tile, the loads of four
+    // tiles are in flight at once, and each SM sub-partition always has other groups'
+    // warps to issue from while one waits for its loads (slot hand-over: wait_seen).
+    constexpr int GT = kProd / kGroups;            // threads per group (128)
     constexpr int RAg = GT / QA, PAg = KPIX / RAg; // dout rows per pass / passes (4, 8)
     constexpr int RBg = GT / QB, PBg = KPIX / RBg; // input rows per pass / passes
     constexpr int NREG = PAg > PBg ? PAg : PBg;
@@ -138,44 +155,58 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
     const int qb = tg % QB, rb0 = tg / QB;
     const int co = co0 + qa * 4;
     const bool co_ok = co < g.Cout;
-    int* rt = rowtab + grpi * 4 * KPIX;   // [dout pixel | input element offset | tap mask lo | hi][KPIX]
+    // dense: phase-grid pixel m IS the dout / input pixel (1x1 stride-1 layers and the
+    // dout side of every stride-1 conv): no row table, no bounds checks
+    const bool dense_out = g.os == 1 && g.Hp == g.Ho && g.Wp == g.Wo;
+    const bool dense_in = g.is == 1 && g.Hp == g.Hi && g.Wp == g.Wi && g.T == 1 &&
+                          g.dh[0] == 0 && g.dw[0] == 0;
+    const bool need_tab = !(dense_out && dense_in);
+    int* rt = rowtab + grpi * 4 * KPIX;           // [dout pixel | n*Hi*Wi | i*is | j*is][KPIX]
     const int per_blk = NB + 1;
     const int total = nblk * per_blk;
-    float4 buf[2][NREG];
-    unsigned msk[2];
-    int ie = grpi, iblk = 0, tab_blk = -1;        // issue cursor of this group
+    float4 buf[NREG];
+    unsigned msk;
+    int ie = grpi, iblk = 0, tab_blk = -1;        // tile cursor of this group
     while (ie >= per_blk) { ie -= per_blk; ++iblk; }
-    auto issue_next = [&](float4 (&dst)[NREG], unsigned& mask) {
+    auto split_store = [&](uint8_t* tile, int tile_plane_bytes, int r, int ch4, float4 x) {
+      const float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
+                                    tc::to_tf32(x.w));
+      st_mn(tile, r, ch4, hi);
+      if (NS == 3)
+        st_mn(tile + tile_plane_bytes, r, ch4,
+              make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+    };
+    const int mine = (total - grpi + kGroups - 1) / kGroups;
+    for (int k0 = 0; k0 < mine; ++k0) {
+      // ---------------------------------------------------------------- loads of this tile
       if (tab_blk != iblk) {                      // the cursor entered a new pixel block
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + grpi) : "memory");
-        if (tg < KPIX) {
-          const int m = mbeg + iblk * KPIX + tg;
-          if (m < mend) {
-            const unsigned um = (unsigned)m;
-            const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
-            const unsigned i = qq % (unsigned)g.Hp, n = qq / (unsigned)g.Hp;
-            rt[tg] = ((int)n * g.Ho + ((int)i * g.os + g.ph)) * g.Wo + ((int)j * g.os + g.pw);
-            const int ih0 = (int)i * g.is, iw0 = (int)j * g.is;
-            rt[KPIX + tg] = (((int)n * g.Hi + ih0) * g.Wi + iw0) * g.Cin;
-            unsigned long long vm = 0;
-            for (int t = 0; t < g.T; ++t) {
-              const int ih = ih0 + g.dh[t], iw = iw0 + g.dw[t];
-              if (ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi) vm |= 1ull << t;
+        if (need_tab) {
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + grpi) : "memory");
+          if (tg < KPIX) {
+            const int m = mbeg + iblk * KPIX + tg;
+            if (m < mend) {
+              const unsigned um = (unsigned)m;
+              const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
+              const unsigned i = qq % (unsigned)g.Hp, n = qq / (unsigned)g.Hp;
+              rt[tg] = ((int)n * g.Ho + ((int)i * g.os + g.ph)) * g.Wo + ((int)j * g.os + g.pw);
+              rt[KPIX + tg] = (int)n * g.Hi * g.Wi;
+              rt[2 * KPIX + tg] = (int)i * g.is;
+              rt[3 * KPIX + tg] = (int)j * g.is;
+            } else {
+              rt[tg] = -1;
             }
-            rt[2 * KPIX + tg] = (int)(unsigned)(vm & 0xffffffffull);
-            rt[3 * KPIX + tg] = (int)(unsigned)(vm >> 32);
-          } else {
-            rt[tg] = -1;
-            rt[2 * KPIX + tg] = 0;
-            rt[3 * KPIX + tg] = 0;
           }
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + grpi) : "memory");
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + grpi) : "memory");
         tab_blk = iblk;
+      }
+      const int m0 = mbeg + iblk * KPIX;
+      msk = 0;
+      if (ie == 0) {
         // warm L2 eight pixel blocks ahead (rows of a block are contiguous when the phase
         // grid is dense): the register buffers alone keep too few bytes in flight for HBM
-        const int pfm = mbeg + (iblk + 8) * KPIX;
-        if (grpi == 0 && pfm < mend) {
+        const int pfm = m0 + 8 * KPIX;
+        if (pfm < mend) {
           if (g.os == 1) {
             const int lines = (KPIX * WM * 4) / 128;
             for (int l = tg; l < lines; l += GT) {
@@ -192,71 +223,72 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
             }
           }
         }
-      }
-      mask = 0;
-      if (ie == 0) {
 #pragma unroll
         for (int k = 0; k < PAg; ++k) {
-          dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int dp = rt[ra0 + k * RAg];
+          buf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int r = ra0 + k * RAg;
+          const int dp = dense_out ? (m0 + r < mend ? m0 + r : -1) : rt[r];
           if (co_ok && dp >= 0)
-            dst[k] = *reinterpret_cast<const float4*>(dout + (int64_t)dp * g.Cout + co);
+            buf[k] = *reinterpret_cast<const float4*>(dout + (int64_t)dp * g.Cout + co);
         }
       } else {
         const int sl = ie - 1;
         const int ci = slot_cit[sl] * BNW + qb * 4;
-        const int tap = slot_t[sl];
-        const int delta = (g.dh[tap] * g.Wi + g.dw[tap]) * g.Cin + ci;
-        const int word = 2 + (tap >> 5);
-        const unsigned bit = 1u << (tap & 31);
+        if (dense_in) {
 #pragma unroll
-        for (int k = 0; k < PBg; ++k) {
-          dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int r = rb0 + k * RBg;
-          if (ci < g.Cin && ((unsigned)rt[word * KPIX + r] & bit)) {
-            dst[k] = *reinterpret_cast<const float4*>(in + ((int64_t)rt[KPIX + r] + delta));
-            mask |= 1u << k;
+          for (int k = 0; k < PBg; ++k) {
+            buf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int mr = m0 + rb0 + k * RBg;
+            if (ci < g.Cin && mr < mend) {
+              buf[k] = *reinterpret_cast<const float4*>(in + (int64_t)mr * g.Cin + ci);
+              msk |= 1u << k;
+            }
+          }
+        } else {
+          const int dh = g.dh[slot_t[sl]], dwv = g.dw[slot_t[sl]];
+#pragma unroll
+          for (int k = 0; k < PBg; ++k) {
+            buf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r = rb0 + k * RBg;
+            const int ih = rt[2 * KPIX + r] + dh, iw = rt[3 * KPIX + r] + dwv;
+            if (ci < g.Cin && rt[r] >= 0 && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi) {
+              buf[k] = *reinterpret_cast<const float4*>(
+                  in + ((int64_t)rt[KPIX + r] + (int64_t)ih * g.Wi + iw) * g.Cin + ci);
+              msk |= 1u << k;
+            }
           }
         }
       }
-      ie += 2;
-      while (ie >= per_blk) { ie -= per_blk; ++iblk; }
-    };
-    auto split_store = [&](uint8_t* tile, int tile_plane_bytes, int r, int ch4, float4 x) {
-      const float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
-                                    tc::to_tf32(x.w));
-      st_mn(tile, r, ch4, hi);
-      if (NS == 3)
-        st_mn(tile + tile_plane_bytes, r, ch4,
-              make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
-    };
-    int pe = grpi, pblk = 0;                      // consume cursor of this group
-    while (pe >= per_blk) { pe -= per_blk; ++pblk; }
-    auto process = [&](const float4 (&cur)[NREG], unsigned curm) {
-      if (pe == 0) {
-        const int s = pblk % C::SA;
-        tc::mbar_wait(emptyA(s), ((pblk / C::SA) & 1) ^ 1);
+      // ---------------------------------------------------------------- convert + store
+      if (ie == 0) {
+        const int s = iblk % C::SA, use = iblk / C::SA;
+        wait_seen(seenA + s, use);
+        tc::mbar_wait(emptyA(s), (use & 1) ^ 1);
+        if (lane == 0) seenA[s] = use + 1;
         uint8_t* tile = sm + s * C::A_TILE;
 #pragma unroll
-        for (int k = 0; k < PAg; ++k) split_store(tile, WM * KPIX * 4, ra0 + k * RAg, qa, cur[k]);
+        for (int k = 0; k < PAg; ++k) split_store(tile, WM * KPIX * 4, ra0 + k * RAg, qa, buf[k]);
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(fullA(s));
       } else {
-        const int qn = pblk * NB + (pe - 1);
+        const int qn = iblk * NB + (ie - 1);
         const int s = qn % C::SB;
-        const int ci = slot_cit[pe - 1] * BNW + qb * 4;
+        const int ci = slot_cit[ie - 1] * BNW + qb * 4;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in_scale && ci < g.Cin) {
           sc = *reinterpret_cast<const float4*>(in_scale + ci);
           sh = *reinterpret_cast<const float4*>(in_shift + ci);
         }
-        tc::mbar_wait(emptyB(s), ((qn / C::SB) & 1) ^ 1);
+        const int use = qn / C::SB;
+        wait_seen(seenB + s, use);
+        tc::mbar_wait(emptyB(s), (use & 1) ^ 1);
+        if (lane == 0) seenB[s] = use + 1;
         uint8_t* tile = smB + s * C::B_TILE;
 #pragma unroll
         for (int k = 0; k < PBg; ++k) {
-          float4 x = cur[k];
-          if (in_scale && ((curm >> k) & 1u)) {
+          float4 x = buf[k];
+          if (in_scale && ((msk >> k) & 1u)) {
             x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
             x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
             if (g.in_relu) {
@@ -270,21 +302,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(fullB(s));
       }
-      pe += 2;
-      while (pe >= per_blk) { pe -= per_blk; ++pblk; }
-    };
-    // this group's tiles: u = grpi, grpi + 2, ...
-    const int mine = (total - grpi + 1) / 2;
-    if (mine > 0) issue_next(buf[0], msk[0]);
-    for (int k0 = 0; k0 < mine; k0 += 2) {
-#pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        const int k = k0 + d;
-        if (k < mine) {
-          if (k + 1 < mine) issue_next(buf[d ^ 1], msk[d ^ 1]);
-          process(buf[d], msk[d]);
-        }
-      }
+      ie += kGroups;
+      while (ie >= per_blk) { ie -= per_blk; ++iblk; }
     }
     // ======================================================== epilogue (warps 0-3)
     if (warp < 4) {

@@ -4,7 +4,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libepb.so")
+# EPB_LIB_PATH: a probe build of the same library (tools/build_variant.py); never a fallback
+LIB_PATH = os.environ.get("EPB_LIB_PATH") or os.path.join(HERE, "libepb.so")
 
 EPB_MAX_TAPS = 64
 
@@ -31,6 +32,7 @@ _PROTOS = {
     "epb_conv_fprop": (c_int, [ctypes.POINTER(ConvGeom), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "epb_conv_wgrad": (c_int, [ctypes.POINTER(ConvGeom), c_p, c_p, c_p, c_p, c_p, c_p]),
     "epb_pack_weight": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "epb_pack_weight_batch": (c_int, [c_p, c_int, ctypes.c_longlong, c_p]),
     "epb_im2col": (c_int, [c_p, c_p] + [c_int] * 12 + [c_p]),
     "epb_nchw_to_nhwc": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p]),
     "epb_nhwc_to_nchw": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p]),

@@ -252,17 +252,36 @@ bn_bwd_reduce_kernel(const float4* __restrict__ dy, const float4* __restrict__ x
   float4 acc[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
   if (active) {
     const float4 s = scale[c4], b = shift[c4], mu = mean[c4], is = invstd[c4];
-    for (int k = 0; k < kRowsPerThread; ++k) {
-      const int64_t r = r0 + (int64_t)k * rm.rpi + slot;
-      if (r >= M) break;
-      const int64_t i = r * rm.C4 + c4;
-      const float4 xv = ldg_stream(x + i);
-      const float4 g = masked_grad(ldg_stream(dy + i), xv, y_out, i, s, b, relu);
+    auto fold = [&](float4 dv, float4 xv, int64_t i) {
+      const float4 g = masked_grad(dv, xv, y_out, i, s, b, relu);
       acc[0].x += g.x; acc[0].y += g.y; acc[0].z += g.z; acc[0].w += g.w;
       acc[1].x += g.x * (xv.x - mu.x) * is.x;
       acc[1].y += g.y * (xv.y - mu.y) * is.y;
       acc[1].z += g.z * (xv.z - mu.z) * is.z;
       acc[1].w += g.w * (xv.w - mu.w) * is.w;
+    };
+    // four rows per trip: the eight streaming loads are issued before the first use
+    int k = 0;
+    for (; k + 4 <= kRowsPerThread; k += 4) {
+      const int64_t rl = r0 + (int64_t)(k + 3) * rm.rpi + slot;
+      if (rl >= M) break;
+      float4 xv[4], dv[4];
+      int64_t idx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        idx[u] = (r0 + (int64_t)(k + u) * rm.rpi + slot) * rm.C4 + c4;
+        xv[u] = ldg_stream(x + idx[u]);
+        dv[u] = ldg_stream(dy + idx[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fold(dv[u], xv[u], idx[u]);
+    }
+    for (; k < kRowsPerThread; ++k) {
+      const int64_t r = r0 + (int64_t)k * rm.rpi + slot;
+      if (r >= M) break;
+      const int64_t i = r * rm.C4 + c4;
+      const float4 xv = ldg_stream(x + i);
+      fold(ldg_stream(dy + i), xv, i);
     }
   }
   cta_reduce_to_global<2>(acc, c4, active, rm.tpr, rm.rpi, C, sums);

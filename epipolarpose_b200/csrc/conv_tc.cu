@@ -21,6 +21,7 @@
 // precision 1: TF32 single pass.  precision 3: 3xTF32 error-compensated
 // (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, FP32 accumulate): fp32-grade results on
 // the tensor pipe, which is what the 1e-3 end-to-end parity bar needs.
+#include <cstdlib>
 #include "conv_common.cuh"
 #include "tc_common.cuh"
 
@@ -34,11 +35,15 @@ constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (kProducerWarps + 2 + kEpiWarps);   // 704
 constexpr int kSmemBudget = 200 * 1024;
 
-template <int BN, int NS>
+// PAIR: two CTAs of a cluster work on one 256-row M tile with tcgen05 cta_group::2; each
+// holds its own 128 A rows and HALF of the B tile's N rows, which halves the weight bytes
+// every SM pulls from L2 per MMA (the bound of the wide 3xTF32 tiles) and its smem stage.
+template <int BN, int NS, bool PAIR = false>
 struct Cfg {
   static constexpr int PL = (NS == 3) ? 2 : 1;                 // operand planes (hi, lo)
+  static constexpr int BROWS = PAIR ? BN / 2 : BN;             // B rows held by this CTA
   static constexpr int A_BYTES = BM * 128 * PL;
-  static constexpr int B_BYTES = BN * 128 * PL;
+  static constexpr int B_BYTES = BROWS * 128 * PL;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int S_ = kSmemBudget / STAGE;
   static constexpr int S = S_ > 8 ? 8 : S_;
@@ -63,14 +68,19 @@ struct RowInfo {
   unsigned long long vmask[BM];  // bit t set <=> tap t reads inside the image (0 for rows past M)
 };
 
-template <int BN, int NS>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
-                     const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ in,
-                     const float* __restrict__ in_scale, const float* __restrict__ in_shift,
-                     const float* __restrict__ bias, float* __restrict__ out,
-                     double* __restrict__ stats, int npad, int m_tiles, int n_tiles) {
-  using C = Cfg<BN, NS>;
+template <int BN, int NS, bool PAIR>
+__device__ __forceinline__ void
+fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __restrict__ in,
+           const float* __restrict__ in_scale, const float* __restrict__ in_shift,
+           const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats,
+           int npad, int m_tiles, int n_tiles, int tune) {
+  using C = Cfg<BN, NS, PAIR>;
+  // PAIR: `tile` enumerates (pair of M tiles, N tile); CTA `crank` of the cluster owns M tile
+  // 2 * (tile / n_tiles) + crank (rows past M are zero rows / unwritten, as in the tail tile)
+  const int crank = PAIR ? (int)tc::cluster_ctarank() : 0;
+  const int tile0 = PAIR ? (int)tc::cluster_id_x() : (int)blockIdx.x;
+  const int tstep = PAIR ? (int)tc::cluster_count_x() : (int)gridDim.x;
+  auto m_tile_of = [&](int tile) { return PAIR ? 2 * (tile / n_tiles) + crank : tile / n_tiles; };
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;               // SWIZZLE_128B needs 1024 B
@@ -91,36 +101,55 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
   const int64_t M = (int64_t)g.N * g.Hp * g.Wp;
   const int CB = g.Cin / BKE;              // channel blocks per tap
   const int KB = g.T * CB;                 // k-blocks per tile
-  const int total_tiles = m_tiles * n_tiles;
+  const int total_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::S; ++s) {
-      tc::mbar_init(full_bar(s), C::W + 1);
+      tc::mbar_init(full_bar(s), (PAIR ? 2 : 1) * C::W + 1);   // PAIR: leader's barrier collects both CTAs
       tc::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tfull_bar(a), 1);
-      tc::mbar_init(tempty_bar(a), kEpiWarps);
+      tc::mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * kEpiWarps);
     }
     tc::fence_barrier_init();
   }
-  if (warp == kProducerWarps + 1) tc::tmem_alloc<C::TMEM_COLS>(tc::smem_u32(tmem_ptr));
+  if (warp == kProducerWarps + 1) {
+    if (PAIR) tc::tmem_alloc_pair<C::TMEM_COLS>(tc::smem_u32(tmem_ptr));
+    else tc::tmem_alloc<C::TMEM_COLS>(tc::smem_u32(tmem_ptr));
+  }
   if (threadIdx.x < 2 * BN) sstat[threadIdx.x] = 0.f;
   if (BN * 2 > kThreads && threadIdx.x + kThreads < 2 * BN) sstat[threadIdx.x + kThreads] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
+  if (PAIR) tc::cluster_sync();             // the peer's barriers are initialised before any remote arrive
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < kProducerWarps) {
     // =================================================== A producers (512 threads)
+    // L2 prefetch policy of the A stream (measured on the bench layers, tools/tune_sweep.sh):
+    //  * dense 1x1 layers (phase-grid pixel == input pixel): ROLLING prefetch kPfDist k-blocks
+    //    ahead of the loads, crossing into this CTA's next tiles -- bounded footprint;
+    //  * otherwise the whole NEXT tile while the current one is processed, but only for rows
+    //    of <= 1 KB: with wider rows 148 CTAs x 2 tiles overflow L2 and the prefetch costs
+    //    more than it saves (Cin = 512: -9 %, Cin = 1024: -11 %).
+    constexpr int kPfDist = 6;
+    const bool roll = (tune & 1) && g.T == 1 && g.is == 1 && g.Hp == g.Hi && g.Wp == g.Wi;
+    const bool pf_tile = ((tune & 1) && !roll && g.Cin <= 256) || (tune & 2);
+    const int dmt = (n_tiles == 1 && tile0 + tstep < total_tiles)
+                        ? m_tile_of(tile0 + tstep) - m_tile_of(tile0) : 0;   // M-tile stride of this CTA
+    // every input line is read exactly once (one tap, one N tile): read it evict-first
+    const bool once = (tune & 4) && g.T == 1 && n_tiles == 1;
+    uint64_t pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
     const int p = threadIdx.x;                 // threads 0..127 also compute one row's geometry
     const int c4 = lane & 7;                   // 16-byte chunk within the 128-byte row
     const int rsub = lane >> 3;                // 0..3
     int base_stage = 0;                        // ring slot / phase of the tile's k-block 0
     uint32_t base_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / n_tiles;
+    for (int tile = tile0; tile < total_tiles; tile += tstep) {
+      const int mt = m_tile_of(tile);
       // producers of the previous tile are done reading rowinfo once all reach this barrier
       asm volatile("bar.sync 1, 512;" ::: "memory");
       if (p < BM) {
@@ -159,9 +188,9 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
       // their activations from HBM exactly once; without this every k-block pays the
       // DRAM latency with only the register buffers' bytes in flight.
       {
-        const int ntile = tile + gridDim.x;
-        if (p < BM && ntile < total_tiles && ntile / n_tiles != mt) {
-          const int64_t mn = (int64_t)(ntile / n_tiles) * BM + p;
+        const int ntile = tile + tstep;
+        if (pf_tile && p < BM && ntile < total_tiles && m_tile_of(ntile) != mt) {
+          const int64_t mn = (int64_t)m_tile_of(ntile) * BM + p;
           if (mn < M) {
             const unsigned um = (unsigned)mn;
             const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
@@ -180,6 +209,17 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         // look-ups remain (offset of the un-shifted pixel, bit mask of in-image taps)
         const int delta = (g.dh[it] * g.Wi + g.dw[it]) * g.Cin + icb * BKE + c4 * 4;
         const int tap = it;
+        if (roll) {
+          int pb = icb + kPfDist, ta = 0;          // channel block / tiles ahead of this CTA
+          while (pb >= CB) { pb -= CB; ++ta; }
+          if ((ta == 0 || dmt > 0) && lane < RPW) {
+            // one prefetch instruction per warp: lane l takes row l of the warp's row block
+            const int r = wg * RPW + lane;
+            if ((int64_t)(mt + ta * dmt) * BM + r < M)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                  in + ((int64_t)rows->off0[r] + (int64_t)ta * dmt * BM * g.Cin + pb * BKE)));
+          }
+        }
         icb += G;
         while (icb >= CB) { icb -= CB; ++it; }
         mask = 0;
@@ -188,7 +228,14 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           const int r = wg * RPW + q * 4 + rsub;
           dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           if ((rows->vmask[r] >> tap) & 1ull) {
-            dst[q] = *reinterpret_cast<const float4*>(in + ((int64_t)rows->off0[r] + delta));
+            const float* ap = in + ((int64_t)rows->off0[r] + delta);
+            if (once) {
+              asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                           : "=f"(dst[q].x), "=f"(dst[q].y), "=f"(dst[q].z), "=f"(dst[q].w)
+                           : "l"(ap), "l"(pol_first));
+            } else {
+              dst[q] = *reinterpret_cast<const float4*>(ap);
+            }
             mask |= 1u << q;
           }
         }
@@ -227,12 +274,32 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(full_bar(st));
+        if (lane == 0) {
+          if (PAIR) {
+            if (tune & 8) tc::mbar_arrive_cluster_cta(tc::mapa(full_bar(st), 0));
+            else tc::mbar_arrive_cluster(tc::mapa(full_bar(st), 0));
+          } else {
+            tc::mbar_arrive(full_bar(st));
+          }
+        }
         st += G;
         ph ^= (uint32_t)((st / C::S) & 1);
         st %= C::S;
       };
       const int mine = (KB - grp + G - 1) / G;
+#ifdef EPB_DBG_SKIP_A     // bottleneck probe (tools/build_variant.py): slots are handed over unfilled
+      for (int k = 0; k < mine; ++k) {
+        tc::mbar_wait(empty_bar(st), ph ^ 1);
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) tc::mbar_arrive_cluster(tc::mapa(full_bar(st), 0));
+          else tc::mbar_arrive(full_bar(st));
+        }
+        st += G;
+        ph ^= (uint32_t)((st / C::S) & 1);
+        st %= C::S;
+      }
+#else
       if constexpr (D == 1) {
         for (int k = 0; k < mine; ++k) {
           issue(buf[0], okm[0]);
@@ -251,6 +318,7 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           }
         }
       }
+#endif
       {   // ring position of the next tile's first k-block
         const int tmp = base_stage + KB;
         base_phase ^= (uint32_t)((tmp / C::S) & 1);
@@ -260,10 +328,10 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
   } else if (warp == kProducerWarps) {
     // =================================================== B producer (TMA)
     if (lane == 0) {
-      tc::tma_prefetch_desc(&tmap_w);
+      tc::tma_prefetch_desc(tmap_w);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
         const int nt = tile % n_tiles;
         int t = 0, cb = 0;
         for (int kb = 0; kb < KB; ++kb) {
@@ -271,27 +339,55 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
           if (++cb == CB) { cb = 0; ++t; }
           tc::mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t b_dst = base + stage * C::STAGE + C::A_BYTES;
-          tc::mbar_arrive_expect_tx(full_bar(stage), C::B_BYTES);
+#ifdef EPB_DBG_SKIP_B
+          if (!PAIR || crank == 0) tc::mbar_arrive(full_bar(stage));
+          if (++stage == C::S) { stage = 0; phase ^= 1; }
+          continue;
+#endif
+          if (PAIR) {
+            // both halves complete on the LEADER's barrier; the leader posts the byte count
+            if (crank == 0) tc::mbar_arrive_expect_tx(full_bar(stage), 2 * C::B_BYTES);
+            const uint32_t lead_bar = tc::mapa(full_bar(stage), 0);
 #pragma unroll
-          for (int pl = 0; pl < C::PL; ++pl)
-            tc::tma_load_2d(b_dst + pl * BN * 128, &tmap_w, full_bar(stage), kx,
-                            pl * npad + nt * BN);
+            for (int pl = 0; pl < C::PL; ++pl)
+              tc::tma_load_2d_pair(b_dst + pl * C::BROWS * 128, tmap_w, lead_bar, kx,
+                                   pl * npad + nt * BN + crank * C::BROWS);
+          } else {
+            tc::mbar_arrive_expect_tx(full_bar(stage), C::B_BYTES);
+#pragma unroll
+            for (int pl = 0; pl < C::PL; ++pl)
+              tc::tma_load_2d(b_dst + pl * BN * 128, tmap_w, full_bar(stage), kx,
+                              pl * npad + nt * BN);
+          }
           if (++stage == C::S) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == kProducerWarps + 1) {
     // =================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_tf32(BM, BN, 0, 0);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = tc::idesc_tf32(PAIR ? 2 * BM : BM, BN, 0, 0);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+#ifdef EPB_DBG_SKIP_MMA
+        return;
+#endif
+        if (PAIR) tc::mma_tf32_pair(d, a, b, idesc, acc);
+        else tc::mma_tf32(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) {
+        if (PAIR) tc::mma_commit_pair(bar);
+        else tc::mma_commit(bar);
+      };
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        tc::mbar_wait(tempty_bar(as), aphase ^ 1);
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
+        if (PAIR) tc::mbar_wait_cluster(tempty_bar(as), aphase ^ 1);
+        else tc::mbar_wait(tempty_bar(as), aphase ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < KB; ++kb) {
-          tc::mbar_wait(full_bar(stage), phase);
+          if (PAIR) tc::mbar_wait_cluster(full_bar(stage), phase);
+          else tc::mbar_wait(full_bar(stage), phase);
           tc::tc_fence_after();
           const uint32_t a_hi = base + stage * C::STAGE;
           const uint32_t b_hi = a_hi + C::A_BYTES;
@@ -301,18 +397,18 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
             const uint64_t bh = tc::desc_kmajor_sw128(b_hi + kk * 32);
             if (NS == 3) {
               const uint64_t al = tc::desc_kmajor_sw128(a_hi + BM * 128 + kk * 32);
-              const uint64_t bl = tc::desc_kmajor_sw128(b_hi + BN * 128 + kk * 32);
-              tc::mma_tf32(d_tmem, al, bh, idesc, (kb | kk) != 0);
-              tc::mma_tf32(d_tmem, ah, bl, idesc, 1);
-              tc::mma_tf32(d_tmem, ah, bh, idesc, 1);
+              const uint64_t bl = tc::desc_kmajor_sw128(b_hi + C::BROWS * 128 + kk * 32);
+              mma(d_tmem, al, bh, (kb | kk) != 0);
+              mma(d_tmem, ah, bl, 1);
+              mma(d_tmem, ah, bh, 1);
             } else {
-              tc::mma_tf32(d_tmem, ah, bh, idesc, (kb | kk) != 0);
+              mma(d_tmem, ah, bh, (kb | kk) != 0);
             }
           }
-          tc::mma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
+          commit(empty_bar(stage));                  // frees the smem slot when the MMAs retire
           if (++stage == C::S) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(tfull_bar(as));                // accumulator complete
+        commit(tfull_bar(as));                        // accumulator complete
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -322,8 +418,8 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
     const int et = (warp - (kProducerWarps + 2)) * 32 + lane;   // 0..127
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / n_tiles, nt = tile % n_tiles;
+    for (int tile = tile0; tile < total_tiles; tile += tstep) {
+      const int mt = m_tile_of(tile), nt = tile % n_tiles;
       const int64_t m = (int64_t)mt * BM + q * 32 + lane;
       const bool valid = m < M;
       float* orow = nullptr;
@@ -392,7 +488,14 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (PAIR) {
+          if (tune & 8) tc::mbar_arrive_cluster_cta(tc::mapa(tempty_bar(as), 0));
+          else tc::mbar_arrive_cluster(tc::mapa(tempty_bar(as), 0));
+        } else {
+          tc::mbar_arrive(tempty_bar(as));
+        }
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
       if (stats) {
         asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -408,10 +511,36 @@ conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
 
   tc::tc_fence_before();
   __syncthreads();
+  if (PAIR) tc::cluster_sync();             // the peer may still read this CTA's smem / signal its barriers
   if (warp == kProducerWarps + 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (PAIR) tc::tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+    else tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
+}
+
+template <int BN, int NS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fprop_tc_kernel(const __grid_constant__ epb_conv_geom g,
+                     const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ in,
+                     const float* __restrict__ in_scale, const float* __restrict__ in_shift,
+                     const float* __restrict__ bias, float* __restrict__ out,
+                     double* __restrict__ stats, int npad, int m_tiles, int n_tiles, int tune) {
+  fprop_body<BN, NS, false>(g, &tmap_w, in, in_scale, in_shift, bias, out, stats, npad, m_tiles,
+                            n_tiles, tune);
+}
+
+// CTA-pair variant (cluster of 2, tcgen05 cta_group::2, M = 256 per pair)
+template <int BN, int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_fprop_tc_pair_kernel(const __grid_constant__ epb_conv_geom g,
+                          const __grid_constant__ CUtensorMap tmap_w,
+                          const float* __restrict__ in, const float* __restrict__ in_scale,
+                          const float* __restrict__ in_shift, const float* __restrict__ bias,
+                          float* __restrict__ out, double* __restrict__ stats, int npad,
+                          int m_tiles, int n_tiles, int tune) {
+  fprop_body<BN, NS, true>(g, &tmap_w, in, in_scale, in_shift, bias, out, stats, npad, m_tiles,
+                           n_tiles, tune);
 }
 
 // ---------------------------------------------------------------- weight prep
@@ -442,26 +571,56 @@ int ensure_wws(size_t nfloats) {
   return EPB_OK;
 }
 
-template <int BN, int NS>
+// EPB_TUNE: memory-system switches of the A stream (bit 0 prefetch policy, bit 1 force next-tile
+// prefetch, bit 2 evict-first single-use loads, bit 3 CTA-scope arrive across the CTA pair)
+int tune_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EPB_TUNE");
+    v = e ? atoi(e) : 13;      // prefetch policy on, evict-first single-use loads, CTA-scope pair arrive
+  }
+  return v;
+}
+
+template <int BN, int NS, bool PAIR>
 int launch_fprop(const epb_conv_geom* g, const CUtensorMap& tmap, const float* in,
                  const float* in_scale, const float* in_shift, const float* bias, float* out,
                  double* stats, int npad, cudaStream_t st) {
-  using C = Cfg<BN, NS>;
+  using C = Cfg<BN, NS, PAIR>;
   const int64_t M = (int64_t)g->N * g->Hp * g->Wp;
   const int m_tiles = (int)((M + BM - 1) / BM);
   const int n_tiles = npad / BN;
+  auto kern = [] {
+    if constexpr (PAIR) return conv_fprop_tc_pair_kernel<BN, NS>;
+    else return conv_fprop_tc_kernel<BN, NS>;
+  }();
   static bool attr_set = false;
   if (!attr_set) {
-    EPB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BN, NS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    EPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
-  const int64_t tiles = (int64_t)m_tiles * n_tiles;
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  conv_fprop_tc_kernel<BN, NS><<<grid, kThreads, C::SMEM, st>>>(
-      *g, tmap, in, in_scale, in_shift, bias, out, stats, npad, m_tiles, n_tiles);
+  int grid;
+  if (PAIR) {
+    const int64_t pairs = (int64_t)((m_tiles + 1) / 2) * n_tiles;       // one cluster per tile pair
+    grid = 2 * (int)(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
+  } else {
+    const int64_t tiles = (int64_t)m_tiles * n_tiles;
+    grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  }
+  kern<<<grid, kThreads, C::SMEM, st>>>(*g, tmap, in, in_scale, in_shift, bias, out, stats, npad,
+                                        m_tiles, n_tiles, tune_flags());
   EPB_LAUNCH_CHECK();
   return EPB_OK;
+}
+
+// EPB_CTA_PAIR=0 keeps every tile on single-CTA MMAs
+bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EPB_CTA_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 }  // namespace
@@ -511,7 +670,11 @@ int epb_conv_fprop_tc(const epb_conv_geom* g, const float* in, const float* w,
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)((int64_t)planes * npad)};
   const cuuint64_t strides[1] = {(cuuint64_t)(K * sizeof(float))};
-  const cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)bn};
+  // wide tiles over at least one full pair of M tiles run on CTA pairs (each CTA loads half
+  // of the tile's weight rows)
+  const bool pair = bn == 256 && pair_enabled() &&
+                    (int64_t)g->N * g->Hp * g->Wp > BM;
+  const cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(pair ? bn / 2 : bn)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g_wws, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -520,11 +683,12 @@ int epb_conv_fprop_tc(const epb_conv_geom* g, const float* in, const float* w,
     epb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr);
     return EPB_ECUDA;
   }
-#define EPB_TC_CASE(BN_, NS_) \
-  if (bn == BN_ && ns == NS_)  \
-    return launch_fprop<BN_, NS_>(g, tmap, in, in_scale, in_shift, bias, out, stats, npad, st);
-  EPB_TC_CASE(64, 1) EPB_TC_CASE(128, 1) EPB_TC_CASE(256, 1)
-  EPB_TC_CASE(64, 3) EPB_TC_CASE(128, 3) EPB_TC_CASE(256, 3)
+#define EPB_TC_CASE(BN_, NS_, PAIR_)                   \
+  if (bn == BN_ && ns == NS_ && pair == PAIR_)         \
+    return launch_fprop<BN_, NS_, PAIR_>(g, tmap, in, in_scale, in_shift, bias, out, stats, npad, st);
+  EPB_TC_CASE(64, 1, false) EPB_TC_CASE(128, 1, false) EPB_TC_CASE(256, 1, false)
+  EPB_TC_CASE(64, 3, false) EPB_TC_CASE(128, 3, false) EPB_TC_CASE(256, 3, false)
+  EPB_TC_CASE(256, 1, true) EPB_TC_CASE(256, 3, true)
 #undef EPB_TC_CASE
   epb_set_error("no tcgen05 tile configuration for Cout=%d", g->Cout);
   return EPB_EINVAL;

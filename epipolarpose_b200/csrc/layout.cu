@@ -60,6 +60,35 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
+// Many pack / unpack jobs in one launch: a block finds its job by binary search over the
+// jobs' first blocks and converts 1024 packed elements of it.
+__global__ void __launch_bounds__(256)
+pack_weight_batch_kernel(const epb_pack_job* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const epb_pack_job j = jobs[lo];
+  const int X = j.swap ? j.B : j.A, Y = j.swap ? j.A : j.B;
+  const int64_t total = (int64_t)X * j.T * j.Ypad;
+  const int64_t i0 = ((int64_t)blockIdx.x - j.first_block) * 1024;
+  const int64_t i1 = i0 + 1024 < total ? i0 + 1024 : total;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int y = (int)(i % j.Ypad);
+    const int t = (int)((i / j.Ypad) % j.T);
+    const int x = (int)(i / ((int64_t)j.Ypad * j.T));
+    const int a = j.swap ? y : x, b = j.swap ? x : y;
+    const int64_t pk = (int64_t)x * j.x_pitch + (int64_t)t * j.Ypad + y;
+    if (!j.unpack) {
+      j.dst[pk] = (y < Y) ? j.src[((int64_t)a * j.B + b) * j.T + t] : 0.f;
+    } else if (y < Y) {
+      j.dst[((int64_t)a * j.B + b) * j.T + t] = j.src[pk];
+    }
+  }
+}
+
 // col[m][kk], kk = (r*kw + s)*C + c (zero for kk >= kh*kw*C and for padding pixels):
 // the 7x7 stem (C = 3) becomes a K-major GEMM operand for the tensor-core path.
 __global__ void im2col_kernel(const float* __restrict__ in, float4* __restrict__ col, int N, int Hi,
@@ -265,6 +294,14 @@ extern "C" __attribute__((visibility("default"))) int epb_pack_weight(const floa
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   pack_weight_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, dst, A, B, kh * kw, swap,
                                                                  Ypad, unpack);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_pack_weight_batch(const epb_pack_job* jobs, int njobs, long long total_blocks,
+                                     epb_stream_t stream) {
+  EPB_CHECK_ARG(jobs && njobs > 0 && total_blocks > 0 && total_blocks < (1LL << 31));
+  pack_weight_batch_kernel<<<(unsigned)total_blocks, 256, 0, as_stream(stream)>>>(jobs, njobs);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

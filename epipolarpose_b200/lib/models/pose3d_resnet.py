@@ -134,12 +134,25 @@ class _PoseNetFn(torch.autograd.Function):
         names = module._param_names
         sizes = [params[n].numel() for n in names]
         padded = [(s + 3) // 4 * 4 for s in sizes]
-        flat = torch.zeros(sum(padded), device=g0.device, dtype=torch.float32)
+        # The engine writes into a PERSISTENT staging buffer (its batched gradient unpack and
+        # scratch tables are keyed on these addresses); autograd gets a fresh copy every step,
+        # so accumulating into / keeping p.grad across steps stays correct.
+        stage = getattr(module, "_grad_stage", None)
+        if stage is None or stage[0].device != g0.device or stage[0].numel() != sum(padded):
+            sflat = torch.zeros(sum(padded), device=g0.device, dtype=torch.float32)
+            sgrads, off = {}, 0
+            for n, s, ps in zip(names, sizes, padded):
+                sgrads[n] = sflat[off:off + s].view(params[n].shape)
+                off += ps
+            stage = module._grad_stage = (sflat, sgrads)
+        sflat, sgrads = stage
+        sflat.zero_()
+        eng.backward(S, dlogits, ddepth, params, sgrads)
+        flat = sflat.clone()
         grads, off = {}, 0
         for n, s, ps in zip(names, sizes, padded):
             grads[n] = flat[off:off + s].view(params[n].shape)
             off += ps
-        eng.backward(S, dlogits, ddepth, params, grads)
         ctx.saved_state = None
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \

@@ -212,6 +212,76 @@ class Engine:
         self.ops = ops or _default_ops
 
     # ------------------------------------------------------------------ helpers
+    def _pack_weights(self, params):
+        """state_dict weights -> persistent GEMM operands {name: (fprop, dgrad)} with ONE
+        batched conversion launch (epb_pack_weight_batch).  The buffers and the job table are
+        built once per parameter storage; padding rows / columns stay zero."""
+        plan, ops = self.plan, self.ops
+        convs = plan.all_convs()
+        key = tuple(params[c.name + ".weight"].data_ptr() for c in convs) + (str(self.dev),)
+        st = getattr(self, "_wstate", None)
+        if st is None or st["key"] != key:
+            packed, jobs = {}, []
+            for conv in convs:
+                w = params[conv.name + ".weight"]
+                if conv is plan.stem:
+                    kpad = plan.stem_kpad
+                    wcol = torch.zeros(64 * kpad, device=self.dev, dtype=torch.float32)
+                    jobs.append((w, wcol, 64, 3, 49, 0, 3, 0, kpad))
+                    packed[conv.name] = (wcol, None)
+                    continue
+                T = conv.k * conv.k
+                A, B = w.shape[0], w.shape[1]
+                wf = torch.zeros(conv.cout_p * T * conv.cin_p, device=self.dev, dtype=torch.float32)
+                wd = torch.zeros(conv.cin_p * T * conv.cout_p, device=self.dev, dtype=torch.float32)
+                sf, sd = (0, 1) if conv.kind == "conv" else (1, 0)
+                jobs.append((w, wf, A, B, T, sf, conv.cin_p, 0, T * conv.cin_p))
+                jobs.append((w, wd, A, B, T, sd, conv.cout_p, 0, T * conv.cout_p))
+                packed[conv.name] = (wf, wd)
+            st = {"key": key, "packed": packed, "batch": ops.PackBatch(jobs)}
+            self._wstate = st
+        ops.pack_weight_batch(st["batch"])
+        return st["packed"]
+
+    def _grad_state(self, grads):
+        """Persistent backward scratch: packed weight-gradient accumulators (one flat buffer,
+        one memset per step), the BatchNorm-backward sums, and the batched unpack into the
+        state_dict-shaped `grads`."""
+        plan, ops = self.plan, self.ops
+        convs = plan.all_convs()
+        key = tuple(grads[c.name + ".weight"].data_ptr() for c in convs) + (str(self.dev),)
+        st = getattr(self, "_gstate", None)
+        if st is None or st["key"] != key:
+            sizes = []
+            for conv in convs:
+                if conv is plan.stem:
+                    sizes.append(64 * plan.stem_kpad)
+                else:
+                    sizes.append(conv.cout_p * conv.k * conv.k * conv.cin_p)
+            flat = torch.zeros(sum(sizes), device=self.dev, dtype=torch.float32)
+            dwp, jobs, off = {}, [], 0
+            for conv, n in zip(convs, sizes):
+                view = flat[off:off + n]
+                off += n
+                dwp[conv.name] = view
+                g = grads[conv.name + ".weight"]
+                if conv is plan.stem:
+                    jobs.append((view, g, 64, 3, 49, 0, 3, 1, plan.stem_kpad))
+                else:
+                    T = conv.k * conv.k
+                    jobs.append((view, g, g.shape[0], g.shape[1], T, 0 if conv.kind == "conv" else 1,
+                                 conv.cin_p, 1, T * conv.cin_p))
+            bns = plan.all_bns()
+            sums = torch.zeros(sum(2 * C for _, C in bns), device=self.dev, dtype=torch.float64)
+            bsum, off = {}, 0
+            for name, C in bns:
+                bsum[name] = sums[off:off + 2 * C]
+                off += 2 * C
+            st = {"key": key, "flat": flat, "dwp": dwp, "sums": sums, "bsum": bsum,
+                  "batch": ops.PackBatch(jobs)}
+            self._gstate = st
+        return st
+
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(shape, device=self.dev, dtype=dtype)
 
@@ -272,7 +342,13 @@ class Engine:
     def _conv_wgrad_now(self, conv, x, dout, N, H, W, grad_out, affine=None, relu=1):
         ops = self.ops
         T = conv.k * conv.k
-        dwp = torch.zeros(conv.cout_p * T * conv.cin_p, device=self.dev, dtype=torch.float32)
+        gs = getattr(self, "_gs", None)
+        batched = gs is not None and gs["dwp"].get(conv.name) is not None and \
+            gs["dwp"][conv.name].numel() == conv.cout_p * T * conv.cin_p
+        # inside backward(): accumulate into the step's flat buffer (zeroed once, unpacked in
+        # one launch at the end); stand-alone calls convert immediately
+        dwp = gs["dwp"][conv.name] if batched else \
+            torch.zeros(conv.cout_p * T * conv.cin_p, device=self.dev, dtype=torch.float32)
         sc, sh = affine if affine is not None else (None, None)
         for g in conv.fprop_geoms(ops, N, H, W, self.precision):
             if g is None:
@@ -282,7 +358,8 @@ class Engine:
             g.precision = self.wgrad_precision
             ops.conv_wgrad(g, x, dout, dwp, sc, sh)
             g.precision = self.precision
-        conv.unpack_grad(ops, dwp, grad_out)
+        if not batched:
+            conv.unpack_grad(ops, dwp, grad_out)
 
     def _bn_train(self, name, C, stats, M, params, new_buffers):
         ops = self.ops
@@ -334,10 +411,10 @@ class Engine:
             S["bn"][name] = st
             return st
 
+        S["packed"] = self._pack_weights(params)     # every layer's operands, one launch
+
         def packed(conv):
-            wf, wd = conv.pack(ops, params[conv.name + ".weight"])
-            S["packed"][conv.name] = (wf, wd)
-            return wf
+            return S["packed"][conv.name][0]
 
         # ---- stem (pose3d_resnet.py:186-189)
         stem, scol, kpad = plan.stem, plan.stem_col, plan.stem_kpad
@@ -346,13 +423,9 @@ class Engine:
         H1, W1 = stem.out_hw(H, W)
         col = self._new(N, H1, W1, kpad)
         ops.im2col(x, col, N, H, W, stem.cin_p, 3, 7, 7, 2, 3, H1, W1, kpad)
-        # conv1.weight [64,3,7,7] -> [64][(r,s,c)] -> zero-padded [64][kpad]
-        w147 = torch.empty(64 * 147, device=self.dev, dtype=torch.float32)
-        ops.pack_weight(params["conv1.weight"], w147, 64, 3, 7, 7, 0, 3)
-        wcol = torch.zeros((64, kpad, 1, 1), device=self.dev, dtype=torch.float32)
-        wcol.view(64, kpad)[:, :147] = w147.view(64, 147)
-        wf_col, _ = scol.pack(ops, wcol)
-        z0, _, _ = self._conv_fwd(scol, col, N, H1, W1, wf_col, stats=stats_of("bn1", 64))
+        # conv1.weight [64,3,7,7] -> [64][(r,s,c)] zero-padded to [64][kpad]: the fprop operand
+        # of the 1x1 conv over the patch matrix (packed with the other layers)
+        z0, _, _ = self._conv_fwd(scol, col, N, H1, W1, packed(stem), stats=stats_of("bn1", 64))
         b0 = bn("bn1", 64, N * H1 * W1)
         H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
         cur = self._new(N, H2, W2, 64)
@@ -429,7 +502,9 @@ class Engine:
         ops = self.ops
         C = st.C
         M = z.numel() // C
-        sums = torch.zeros(2 * C, device=self.dev, dtype=torch.float64)
+        gs = getattr(self, "_gs", None)
+        sums = gs["bsum"][st.name] if gs is not None else \
+            torch.zeros(2 * C, device=self.dev, dtype=torch.float64)
         ops.bn_bwd_reduce(dy, z, y_out, st.scale, st.shift, st.mean, st.invstd, relu, M, C, sums)
         dz = torch.empty_like(z)
         ops.bn_bwd_apply(dy, z, y_out, st.scale, st.shift, st.mean, st.invstd,
@@ -449,12 +524,18 @@ class Engine:
             if getattr(self, "_side_stream", None) is None:
                 self._side_stream = torch.cuda.Stream()
             self._side = self._side_stream
+        self._gs = self._grad_state(grads)
+        self._gs["flat"].zero_()
+        self._gs["sums"].zero_()
         try:
             self._backward(S, dlogits, ddepth, params, grads)
-        finally:
             if self._side is not None:
                 torch.cuda.current_stream().wait_stream(self._side)   # join before grads are used
-            self._side, self._keep = None, []
+            ops.pack_weight_batch(self._gs["batch"])                  # packed dW -> state_dict layout
+        finally:
+            if self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)
+            self._side, self._keep, self._gs = None, [], None
 
     def _backward(self, S, dlogits, ddepth, params, grads):
         ops, plan = self.ops, self.plan
@@ -532,11 +613,6 @@ class Engine:
         gpool = self._new(N, H1, W1, 64)
         ops.maxpool_bwd(dcur, argidx, gpool, N, H1, W1, 64)
         dz0 = self._bn_bwd(S["bn"]["bn1"], gpool, z0, None, 1, params, grads)
-        kpad = plan.stem_kpad
-        gcol = torch.zeros((64, kpad, 1, 1), device=self.dev, dtype=torch.float32)
-
-        def stem_unpack():
-            g147 = gcol.view(64, kpad)[:, :147].contiguous()
-            ops.pack_weight(g147, grads["conv1.weight"], 64, 3, 7, 7, 0, 3, 1)
-            self._keep.append(g147)
-        self._conv_wgrad(plan.stem_col, col, dz0, N, H1, W1, gcol, post=stem_unpack)
+        # the stem's gradient w.r.t. the [64][kpad] patch-matrix operand lands in the flat
+        # buffer; the batched unpack maps its first 147 columns back to [64,3,7,7]
+        self._conv_wgrad(plan.stem_col, col, dz0, N, H1, W1, None)

@@ -80,6 +80,33 @@ def pack_weight(src, dst, A, B, kh, kw, swap, ypad, unpack=0):
     _call("epb_pack_weight", _p(src), _p(dst), A, B, kh, kw, swap, ypad, unpack, _stream())
 
 
+class PackBatch:
+    """A fixed list of pack / unpack jobs (epb_pack_job, include/epb.h) with its device table.
+    jobs: (src, dst, A, B, T, swap, ypad, unpack, x_pitch) with src / dst tensors whose
+    storage must stay where it is for the lifetime of the batch."""
+
+    def __init__(self, jobs):
+        import struct
+        self.jobs = list(jobs)
+        self.keep = [(j[0], j[1]) for j in self.jobs]
+        blob, first = b"", 0
+        for (src, dst, A, B, T, swap, ypad, unpack, xp) in self.jobs:
+            X = B if swap else A
+            blob += struct.pack("<QQ8iqq", src.data_ptr(), dst.data_ptr(), A, B, T, swap, ypad,
+                                unpack, xp, 0, first, 0)
+            first += (X * T * ypad + 1023) // 1024
+        self.total_blocks = first
+        dev = self.jobs[0][1].device
+        self.table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+
+    def pointers(self):
+        return tuple((j[0].data_ptr(), j[1].data_ptr()) for j in self.jobs)
+
+
+def pack_weight_batch(batch):
+    _call("epb_pack_weight_batch", _p(batch.table, torch.uint8), len(batch.jobs), batch.total_blocks, _stream())
+
+
 def im2col(x, col, N, Hi, Wi, pitch, C, kh, kw, stride, pad, Ho, Wo, Kpad):
     _call("epb_im2col", _p(x), _p(col), N, Hi, Wi, pitch, C, kh, kw, stride, pad, Ho, Wo, Kpad,
           _stream())

@@ -101,6 +101,23 @@ int epb_conv_wgrad(const epb_conv_geom* g, const float* in, const float* dout,
 int epb_pack_weight(const float* src, float* dst, int A, int B, int kh, int kw,
                     int swap, int Ypad, int unpack, epb_stream_t stream);
 
+/* The same conversion for MANY tensors in one launch (all layers of the network before
+ * a forward pass; all weight gradients after a backward pass).  `jobs` is a DEVICE array
+ * of njobs descriptors ordered by first_block; job j owns the blocks
+ * [first_block_j, first_block_{j+1}) of 1024 packed elements each, total_blocks in all.
+ * x_pitch is the distance in floats between consecutive X rows of the packed tensor
+ * (kh*kw*Ypad when dense; larger when the packed tensor is a slice of a wider matrix,
+ * as for the im2col form of the stem). */
+typedef struct epb_pack_job {
+  const float* src;
+  float* dst;
+  int A, B, T, swap, Ypad, unpack, x_pitch, reserved;
+  long long first_block;
+  long long reserved2;
+} epb_pack_job;
+int epb_pack_weight_batch(const epb_pack_job* jobs, int njobs, long long total_blocks,
+                          epb_stream_t stream);
+
 /* Patch matrix of a small-Cin convolution (the 7x7 stem, pose3d_resnet.py:99):
  * col[m][(r*kw+s)*C + c] = in[n, oh*stride-pad+r, ow*stride-pad+s, c] (0 outside
  * the image and for columns >= kh*kw*C), row pitch Kpad floats, so the layer

@@ -88,6 +88,26 @@ def pack_weight(src, dst, A, B, kh, kw, swap, ypad, unpack=0):
         d.copy_(p.permute(2, 0, 1) if swap else p.permute(0, 2, 1))
 
 
+class PackBatch:
+    def __init__(self, jobs):
+        self.jobs = list(jobs)
+
+
+def pack_weight_batch(batch):
+    for (src, dst, A, B, T, swap, ypad, unpack, xp) in batch.jobs:
+        X, Y = (B, A) if swap else (A, B)
+        if not unpack:
+            s = src.reshape(A, B, T)
+            p = s.permute(1, 2, 0) if swap else s.permute(0, 2, 1)   # [X][T][Y]
+            d = torch.as_strided(dst.view(-1), (X, T, ypad), (xp, ypad, 1))
+            d.zero_()
+            d[:, :, :Y] = p
+        else:
+            p = torch.as_strided(src.view(-1), (X, T, ypad), (xp, ypad, 1))[:, :, :Y]
+            d = dst.view(A, B, T)
+            d.copy_(p.permute(2, 0, 1) if swap else p.permute(0, 2, 1))
+
+
 def im2col(x, col, N, Hi, Wi, pitch, C, kh, kw, stride, pad, Ho, Wo, Kpad):
     xs = x.reshape(N, Hi, Wi, pitch)[..., :C]
     xp = torch.nn.functional.pad(xs, (0, 0, pad, pad, pad, pad))

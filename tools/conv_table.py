@@ -1,6 +1,7 @@
 """Per-conv-call timing table of one training step of the bench workload
 (CUDA events around each epb_conv_fprop / epb_conv_wgrad call)."""
 import os, sys, collections
+os.environ.setdefault("EPB_OVERLAP_WGRAD", "0")   # serialise wgrad: clean per-call times
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "epipolarpose_b200"))

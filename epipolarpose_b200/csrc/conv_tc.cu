@@ -141,6 +141,7 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
                         ? m_tile_of(tile0 + tstep) - m_tile_of(tile0) : 0;   // M-tile stride of this CTA
     // every input line is read exactly once (one tap, one N tile): read it evict-first
     const bool once = (tune & 4) && g.T == 1 && n_tiles == 1;
+    const float lb = g.in_relu ? 0.f : -INFINITY;
     uint64_t pol_first;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
     const int p = threadIdx.x;                 // threads 0..127 also compute one row's geometry
@@ -251,18 +252,24 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
         }
         tc::mbar_wait(empty_bar(st), ph ^ 1);
         uint8_t* a_hi = sm + st * C::STAGE;
+        float4 xv[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) xv[q] = v[q];
+        if (in_scale) {
+          // branch-free affine (+ReLU); rows that were not loaded (padding, rows past M) are
+          // post-activation zeros and are patched afterwards
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) xv[q] = tc::bn_act4(xv[q], sc, sh, lb);
+          if (mask != (1u << NQ) - 1u) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+              if (!((mask >> q) & 1u)) xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           const int r = wg * RPW + q * 4 + rsub;
-          float4 x = v[q];
-          if (in_scale && ((mask >> q) & 1u)) {
-            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
-            x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
-            if (g.in_relu) {
-              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f);
-              x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-            }
-          }
+          const float4 x = xv[q];
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);
           float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
                                   tc::to_tf32(x.w));

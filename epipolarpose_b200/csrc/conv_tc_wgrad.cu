@@ -161,6 +161,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
     const bool dense_in = g.is == 1 && g.Hp == g.Hi && g.Wp == g.Wi && g.T == 1 &&
                           g.dh[0] == 0 && g.dw[0] == 0;
     const bool need_tab = !(dense_out && dense_in);
+    const float lb = g.in_relu ? 0.f : -INFINITY;
     int* rt = rowtab + grpi * 4 * KPIX;           // [dout pixel | n*Hi*Wi | i*is | j*is][KPIX]
     const int per_blk = NB + 1;
     const int total = nblk * per_blk;
@@ -285,19 +286,19 @@ conv_wgrad_tc_kernel(const __grid_constant__ epb_conv_geom g, const float* __res
         tc::mbar_wait(emptyB(s), (use & 1) ^ 1);
         if (lane == 0) seenB[s] = use + 1;
         uint8_t* tile = smB + s * C::B_TILE;
+        if (in_scale) {
+          // branch-free affine (+ReLU) on every row; rows that were not loaded (image border,
+          // end of the pixel range) are post-activation zeros and are patched afterwards
 #pragma unroll
-        for (int k = 0; k < PBg; ++k) {
-          float4 x = buf[k];
-          if (in_scale && ((msk >> k) & 1u)) {
-            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
-            x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
-            if (g.in_relu) {
-              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f);
-              x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-            }
+          for (int k = 0; k < PBg; ++k) buf[k] = tc::bn_act4(buf[k], sc, sh, lb);
+          if (msk != (1u << PBg) - 1u) {
+#pragma unroll
+            for (int k = 0; k < PBg; ++k)
+              if (!((msk >> k) & 1u)) buf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          split_store(tile, BNW * KPIX * 4, rb0 + k * RBg, qb, x);
         }
+#pragma unroll
+        for (int k = 0; k < PBg; ++k) split_store(tile, BNW * KPIX * 4, rb0 + k * RBg, qb, buf[k]);
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(fullB(s));

@@ -38,7 +38,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  const long long t0 = clock64();
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -48,7 +48,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity), "r"(2000u)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: protocol bug, fail loudly
+    const long long now = clock64();            // the clock is read only when the wait blocks
+    if (t0 == 0) t0 = now;
+    if (now - t0 > 4000000000LL) __trap();      // ~2 s: protocol bug, fail loudly
   }
 }
 
@@ -89,7 +91,7 @@ __device__ __forceinline__ void cluster_sync() {
 // wait on a LOCAL mbarrier whose arrivals may come from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  const long long t0 = clock64();
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -99,7 +101,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity), "r"(2000u)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > 4000000000LL) __trap();
   }
 }
 
@@ -242,11 +246,16 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, 
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// round-to-nearest TF32 (10-bit mantissa) kept in an fp32 container
+// round-to-nearest (ties away) TF32 kept in an fp32 container.  Same result as
+// cvt.rna.tf32.f32 for finite inputs, in 2 integer instructions instead of the 4 the
+// conversion expands to (it adds an Inf/NaN guard the operand split does not need).
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+// BatchNorm affine + optional ReLU of the producing layer (lb = 0 with ReLU, -inf without)
+__device__ __forceinline__ float4 bn_act4(float4 x, float4 sc, float4 sh, float lb) {
+  return make_float4(fmaxf(fmaf(x.x, sc.x, sh.x), lb), fmaxf(fmaf(x.y, sc.y, sh.y), lb),
+                     fmaxf(fmaf(x.z, sc.z, sh.z), lb), fmaxf(fmaf(x.w, sc.w, sh.w), lb));
 }
 
 }  // namespace tc

@@ -245,7 +245,9 @@ def run_gpu(args):
             return "conv_%s_simt" % kind
         if kind == "fprop":
             bn = 256 if g.Cout >= 256 else (128 if g.Cout >= 128 else 64)
-            return "conv_fprop_tc_kernel<%d,%d>" % (bn, ns)
+            # wide tiles over more than one M tile run on CTA pairs (csrc/conv_tc.cu:epb_conv_fprop_tc)
+            pair = bn == 256 and g.N * g.Hp * g.Wp > 128 and os.environ.get("EPB_CTA_PAIR", "1") != "0"
+            return "conv_fprop_tc_%skernel<%d,%d>" % ("pair_" if pair else "", bn, ns)
         bn = 128 if g.Cin >= 128 else (64 if g.Cin >= 64 else 32)
         return "conv_wgrad_tc_kernel<%d,%d>" % (bn, g.precision if g.precision else ns)
 

@@ -59,8 +59,11 @@ struct Cfg {
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int EPI_PITCH = 36;                          // floats per staged row (144 B)
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;       // one 32x32 block per epilogue warp
-  static constexpr int SMEM = S * STAGE + 1024 /*align*/ + 1024 /*barriers, rowinfo*/ +
-                              BM * 3 * 4 + 2 * BN * 4 + EPI_BYTES;
+  static constexpr int STAT_BYTES = kEpiWarps * 2 * BN * 4;     // per-warp [sum | sum of squares][BN]
+  static constexpr int PTAB_BYTES = kEpiWarps * 32 * 8;         // output row pointer of every TMEM lane
+  static constexpr int SMEM = S * STAGE + 1024 /*align*/ + 1024 /*barriers*/ + BM * 3 * 4 /*rowinfo*/ +
+                              STAT_BYTES + EPI_BYTES + PTAB_BYTES;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 struct RowInfo {
@@ -89,8 +92,10 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
   uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);          // full[S], empty[S], tfull[2], tempty[2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl + 8 * (2 * 8 + 4));
   RowInfo* rows = reinterpret_cast<RowInfo*>(ctrl + 1024);
-  float* sstat = reinterpret_cast<float*>(ctrl + 1024 + sizeof(RowInfo));   // [2][BN]
-  float* epi_stage = sstat + 2 * BN;                                         // [4][32][EPI_PITCH]
+  float* sstat = reinterpret_cast<float*>(ctrl + 1024 + sizeof(RowInfo));   // [4 warps][2][BN]
+  float* epi_stage = sstat + kEpiWarps * 2 * BN;                             // [4][32][EPI_PITCH]
+  unsigned long long* eprow =                                                // [4][32] output row pointers
+      reinterpret_cast<unsigned long long*>(epi_stage + kEpiWarps * 32 * C::EPI_PITCH);
   const uint32_t bar0 = tc::smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
@@ -118,8 +123,6 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
     if (PAIR) tc::tmem_alloc_pair<C::TMEM_COLS>(tc::smem_u32(tmem_ptr));
     else tc::tmem_alloc<C::TMEM_COLS>(tc::smem_u32(tmem_ptr));
   }
-  if (threadIdx.x < 2 * BN) sstat[threadIdx.x] = 0.f;
-  if (BN * 2 > kThreads && threadIdx.x + kThreads < 2 * BN) sstat[threadIdx.x + kThreads] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
   if (PAIR) tc::cluster_sync();             // the peer's barriers are initialised before any remote arrive
@@ -421,8 +424,20 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
     }
   } else {
     // =================================================== epilogue (4 warps)
+    // One warp per TMEM lane quarter drains its 32 rows x BN columns in chunks of 32 columns.
+    // The warp is alone on its scheduler slot, so the chunk is written to expose as few
+    // dependent latencies as possible (short-K layers -- K <= 256 -- are bound by this loop):
+    // row pointers come from a per-tile smem table (no shuffle + branch per row group), rows
+    // past M are clamped onto the last valid row (a duplicate store of the same value) so the
+    // store loop is branch free, and the per-column statistics go to a warp-private smem slice
+    // with plain stores (no shared-memory CAS loops); the slices are summed at the tile end.
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int et = (warp - (kProducerWarps + 2)) * 32 + lane;   // 0..127
+    const int wq = warp - (kProducerWarps + 2);
+    const int et = wq * 32 + lane;             // 0..127
+    float* stg = epi_stage + wq * 32 * C::EPI_PITCH;
+    float* sst = sstat + wq * 2 * BN;
+    unsigned long long* ptab = eprow + wq * 32;
+    const int c4 = lane & 7, rsub = lane >> 3;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = tile0; tile < total_tiles; tile += tstep) {
@@ -436,10 +451,12 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
         const int n = (int)(m / ((int64_t)g.Wp * g.Hp));
         orow = out + (((int64_t)n * g.Ho + (i * g.os + g.ph)) * g.Wo + (j * g.os + g.pw)) * g.Cout;
       }
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      const int nvalid = __popc(vmask);        // rows of a tile are valid in a prefix (m < M)
+      ptab[lane] = reinterpret_cast<unsigned long long>(orow);
+      __syncwarp();
       tc::mbar_wait(tfull_bar(as), aphase);
       tc::tc_fence_after();
-      float* stg = epi_stage + (warp - (kProducerWarps + 2)) * 32 * C::EPI_PITCH;
-      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         const int col0 = nt * BN + chunk * 32;
@@ -462,33 +479,36 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
         }
         __syncwarp();
         if (stats) {
-          // lane = column: sum over the 32 staged rows (bank = 4*row + lane: conflict free)
-          float s1 = 0.f, s2 = 0.f;
+          // lane = column: sum over the staged valid rows (bank = 4*row + lane: conflict free);
+          // four independent partial sums keep the add chains short
+          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
             const float x = ((vmask >> rr) & 1u) ? stg[rr * C::EPI_PITCH + lane] : 0.f;
-            s1 += x;
-            s2 = fmaf(x, x, s2);
+            s1[rr & 3] += x;
+            s2[rr & 3] = fmaf(x, x, s2[rr & 3]);
           }
-          atomicAdd(&sstat[chunk * 32 + lane], s1);
-          atomicAdd(&sstat[BN + chunk * 32 + lane], s2);
+          sst[chunk * 32 + lane] = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+          sst[BN + chunk * 32 + lane] = (s2[0] + s2[1]) + (s2[2] + s2[3]);
         }
-        {
-          const int c4 = lane & 7, rsub = lane >> 3;
+        if (g.accumulate) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + rsub;
-            float* prow = reinterpret_cast<float*>(
-                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(orow), rr));
-            if (prow) {
+            if (rr < nvalid) {
               float4 x = *reinterpret_cast<const float4*>(stg + rr * C::EPI_PITCH + c4 * 4);
-              float4* o = reinterpret_cast<float4*>(prow + col0) + c4;
-              if (g.accumulate) {
-                const float4 pv = *o;
-                x.x += pv.x; x.y += pv.y; x.z += pv.z; x.w += pv.w;
-              }
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ptab[rr]) + col0) + c4;
+              const float4 pv = *o;
+              x.x += pv.x; x.y += pv.y; x.z += pv.z; x.w += pv.w;
               *o = x;
             }
+          }
+        } else if (nvalid > 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = min(i * 4 + rsub, nvalid - 1);
+            const float4 x = *reinterpret_cast<const float4*>(stg + rr * C::EPI_PITCH + c4 * 4);
+            *(reinterpret_cast<float4*>(reinterpret_cast<float*>(ptab[rr]) + col0) + c4) = x;
           }
         }
         __syncwarp();
@@ -505,11 +525,14 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
       if (stats) {
+        // every column of this N tile that lies below Cout was written by all four warps
         asm volatile("bar.sync 2, 128;" ::: "memory");
         for (int c = et; c < 2 * BN; c += 128) {
           const int which = c / BN, col = nt * BN + (c % BN);
-          if (col < g.Cout) atomicAdd(stats + (int64_t)which * g.Cout + col, (double)sstat[c]);
-          sstat[c] = 0.f;
+          if (col < g.Cout) {
+            const float v = (sstat[c] + sstat[2 * BN + c]) + (sstat[4 * BN + c] + sstat[6 * BN + c]);
+            atomicAdd(stats + (int64_t)which * g.Cout + col, (double)v);
+          }
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");
       }

@@ -3,8 +3,9 @@ import csv, io, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, vals = rows[0], rows[-1]
+hdr, units, vals = rows[0], rows[1], rows[-1]
 d = dict(zip(hdr, vals))
+u = dict(zip(hdr, units))
 keys = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "gpu__time_duration.sum", "sm__cycles_active.avg",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -18,7 +19,7 @@ keys = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
 for k in keys:
     for h in hdr:
         if h == k:
-            print("%-70s %s" % (h, d[h]))
+            print("%-70s %s %s" % (h, d[h], u.get(h, "")))
 stalls = [(h, float(d[h].replace(",", ""))) for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")] or \
          [(h, float(d[h].replace(",", ""))) for h in hdr if "warp_issue_stalled" in h and h.endswith(".pct")]
 for h, v in sorted(stalls, key=lambda x: -x[1])[:10]:

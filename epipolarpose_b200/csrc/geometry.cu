@@ -18,7 +18,7 @@ namespace {
 // orthogonal; V (C x C) accumulates the right rotations.  On exit
 // A = U*diag(sigma) (columns), sigma_j = ||A[:,j]||.
 template <int R, int C>
-__device__ void jacobi_onesided(double (&A)[R][C], double (&V)[C][C]) {
+__host__ __device__ void jacobi_onesided(double (&A)[R][C], double (&V)[C][C]) {
 #pragma unroll
   for (int i = 0; i < C; ++i)
 #pragma unroll
@@ -273,6 +273,148 @@ __global__ void project_labels_kernel(const double* __restrict__ X, const double
   weight[idx * 3 + 2] = 1.f;
 }
 
+// --------------------------------------------------------------- evaluation (H36M protocol)
+// lib/dataset/h36m.py:168-378 per sample: back-projection of image-space joints
+// (lib/utils/prep_h36m.py:85-89), similarity (Procrustes) alignment with optimal scale
+// (:108-168, numpy SVD there; here the one-sided Jacobi on the 3x3 covariance -- V*U^T does
+// not depend on the ordering / paired signs of the singular triplets), root alignment and
+// the nine protocol means.  One thread per sample, float64, J <= 32.
+//   metrics[s] = { e, e_align, e_norm, e14, e14_align, e14_norm, ex, ey, ez }   (means over joints)
+// (also compiled for the host: tests/harness/host_geometry.cu runs this exact code on the CPU)
+__host__ __device__ void h36m_eval_sample(const double* p, const double* q, const double* cam,
+                                          int J, int root, unsigned j14mask, double pck_thr,
+                                          double* metrics, double* per_joint, int32_t* pck,
+                                          double* poses) {
+  const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+  const double zr = cam[4];
+  // back projection (h36m.py:228-240): X = gt (targets), Y = prediction (inputs)
+  auto bp = [&](const double* a, int j, double (&o)[3]) {
+    const double d = a[j * 3 + 2] + zr;
+    o[0] = (a[j * 3 + 0] - cx) / fx * d;
+    o[1] = (a[j * 3 + 1] - cy) / fy * d;
+    o[2] = d;
+  };
+  double muX[3] = {0, 0, 0}, muY[3] = {0, 0, 0};
+  for (int j = 0; j < J; ++j) {
+    double x[3], y[3];
+    bp(q, j, x);
+    bp(p, j, y);
+    for (int k = 0; k < 3; ++k) { muX[k] += x[k]; muY[k] += y[k]; }
+  }
+  for (int k = 0; k < 3; ++k) { muX[k] /= J; muY[k] /= J; }
+  double ssX = 0, ssY = 0;
+  for (int j = 0; j < J; ++j) {
+    double x[3], y[3];
+    bp(q, j, x);
+    bp(p, j, y);
+    for (int k = 0; k < 3; ++k) {
+      const double a = x[k] - muX[k], b = y[k] - muY[k];
+      ssX += a * a;
+      ssY += b * b;
+    }
+  }
+  const double normX = sqrt(ssX), normY = sqrt(ssY);
+  double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};     // X0^T Y0 (unit Frobenius norm each)
+  for (int j = 0; j < J; ++j) {
+    double x[3], y[3];
+    bp(q, j, x);
+    bp(p, j, y);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        A[a][b] += ((x[a] - muX[a]) / normX) * ((y[b] - muY[b]) / normY);
+  }
+  double V[3][3];
+  jacobi_onesided<3, 3>(A, V);                            // A = U diag(sg) (columns)
+  double sg[3], U[3][3];
+  for (int c = 0; c < 3; ++c) {
+    sg[c] = sqrt(A[0][c] * A[0][c] + A[1][c] * A[1][c] + A[2][c] * A[2][c]);
+    for (int r = 0; r < 3; ++r) U[r][c] = sg[c] > 0 ? A[r][c] / sg[c] : 0.0;
+  }
+  int jmin = 0;
+  for (int c = 1; c < 3; ++c) if (sg[c] < sg[jmin]) jmin = c;
+  if (sg[jmin] == 0.0) {
+    // rank-deficient covariance: complete U with the cross product of the other two columns
+    const int a = (jmin + 1) % 3, b = (jmin + 2) % 3;
+    U[0][jmin] = U[1][a] * U[2][b] - U[2][a] * U[1][b];
+    U[1][jmin] = U[2][a] * U[0][b] - U[0][a] * U[2][b];
+    U[2][jmin] = U[0][a] * U[1][b] - U[1][a] * U[0][b];
+  }
+  double T[3][3];
+  auto make_T = [&]() {
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        T[r][c] = V[r][0] * U[c][0] + V[r][1] * U[c][1] + V[r][2] * U[c][2];   // V U^T
+  };
+  make_T();
+  const double det = T[0][0] * (T[1][1] * T[2][2] - T[1][2] * T[2][1]) -
+                     T[0][1] * (T[1][0] * T[2][2] - T[1][2] * T[2][0]) +
+                     T[0][2] * (T[1][0] * T[2][1] - T[1][1] * T[2][0]);
+  const double sgn = det > 0 ? 1.0 : (det < 0 ? -1.0 : 0.0);   // np.sign
+  for (int r = 0; r < 3; ++r) V[r][jmin] *= sgn;               // V[:,-1] *= sign(detT)
+  sg[jmin] *= sgn;
+  make_T();
+  const double trace = sg[0] + sg[1] + sg[2];
+  const double bsc = trace * normX / normY;                    // optimal scale
+  double cvec[3];
+  for (int c = 0; c < 3; ++c)
+    cvec[c] = muX[c] - bsc * (muY[0] * T[0][c] + muY[1] * T[1][c] + muY[2] * T[2][c]);
+  // root joint of each variant (h36m.py:247-251)
+  double xr[3], yr[3], yar[3], ynr[3];
+  bp(q, root, xr);
+  bp(p, root, yr);
+  for (int c = 0; c < 3; ++c) {
+    yar[c] = bsc * (yr[0] * T[0][c] + yr[1] * T[1][c] + yr[2] * T[2][c]) + cvec[c];
+    ynr[c] = bsc * yr[c];
+  }
+  double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int n14 = 0;
+  for (int j = 0; j < J; ++j) {
+    double x[3], y[3], d[3], da[3], dn[3];
+    bp(q, j, x);
+    bp(p, j, y);
+    for (int c = 0; c < 3; ++c) {
+      const double ya = bsc * (y[0] * T[0][c] + y[1] * T[1][c] + y[2] * T[2][c]) + cvec[c];
+      const double yn = bsc * y[c];
+      const double g0 = x[c] - xr[c];
+      d[c] = g0 - (y[c] - yr[c]);
+      da[c] = g0 - (ya - yar[c]);
+      dn[c] = g0 - (yn - ynr[c]);
+      if (poses) {
+        double* o = poses + j * 9;
+        o[c] = y[c] - yr[c];            // pred
+        o[3 + c] = ya - yar[c];         // align_pred
+        o[6 + c] = g0;                  // gt
+      }
+    }
+    const double e = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const double ea = sqrt(da[0] * da[0] + da[1] * da[1] + da[2] * da[2]);
+    const double en = sqrt(dn[0] * dn[0] + dn[1] * dn[1] + dn[2] * dn[2]);
+    m[0] += e; m[1] += ea; m[2] += en;
+    if ((j14mask >> j) & 1u) { m[3] += e; m[4] += ea; m[5] += en; ++n14; }
+    m[6] += fabs(d[0]); m[7] += fabs(d[1]); m[8] += fabs(d[2]);
+    if (per_joint) per_joint[j] = e;
+    if (pck) pck[j] = e >= pck_thr ? 0 : 1;
+  }
+  for (int k = 0; k < 9; ++k) {
+    const int div = (k >= 3 && k < 6) ? (n14 > 0 ? n14 : 1) : J;
+    metrics[k] = m[k] / div;
+  }
+}
+
+__global__ void h36m_eval_kernel(const double* __restrict__ pred, const double* __restrict__ gt,
+                                 const double* __restrict__ cam, int S, int J, int root,
+                                 unsigned j14mask, double pck_thr, double* __restrict__ metrics,
+                                 double* __restrict__ per_joint, int32_t* __restrict__ pck,
+                                 double* __restrict__ poses) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  h36m_eval_sample(pred + (int64_t)s * J * 3, gt + (int64_t)s * J * 3, cam + (int64_t)s * 5, J, root,
+                   j14mask, pck_thr, metrics + (int64_t)s * 9,
+                   per_joint ? per_joint + (int64_t)s * J : nullptr,
+                   pck ? pck + (int64_t)s * J : nullptr,
+                   poses ? poses + (int64_t)s * J * 9 : nullptr);
+}
+
 // --------------------------------------------------------------- argmax
 // inference.py:24-39: one warp per (n,j) map; (value, index) reduction with
 // smallest-index tie-break == numpy argmax first-occurrence.  NaN: numpy
@@ -363,6 +505,20 @@ extern "C" __attribute__((visibility("default"))) int epb_argmax2d(const float* 
   const int threads = 256;
   const int blocks = (NJ * 32 + threads - 1) / threads;
   argmax2d_kernel<<<blocks, threads, 0, as_stream(stream)>>>(hm, NJ, H * W, W, idx, maxval, preds);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_h36m_eval(
+    const double* pred, const double* gt, const double* cam, int S, int J, int root,
+    uint32_t j14mask, double pck_thr, double* metrics, double* per_joint, int32_t* pck,
+    double* poses, epb_stream_t stream) {
+  EPB_CHECK_ARG(pred && gt && cam && metrics);
+  EPB_CHECK_ARG(S >= 0 && J > 0 && J <= 32 && root >= 0 && root < J);
+  if (S == 0) return EPB_OK;
+  h36m_eval_kernel<<<(S + 63) / 64, 64, 0, as_stream(stream)>>>(pred, gt, cam, S, J, root, j14mask,
+                                                               pck_thr, metrics, per_joint, pck,
+                                                               poses);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

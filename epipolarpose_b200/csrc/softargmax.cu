@@ -319,6 +319,101 @@ jointloss_kernel(const float* __restrict__ x, const float* __restrict__ t,
   }
 }
 
+// ---------------------------------------------------------------- heat-map MSE + joint loss
+// One launch for the VOLUME=False training objective: mean squared error of the 2-D heat-maps
+// against their (Gaussian) targets, fused with the weighted L1 / SmoothL1 / MSE joint-location
+// loss of the 3-D branch.  HBM-bound: reads hm and target once, writes dhm once (12 B per
+// heat-map element); per-CTA partial sums are combined by the LAST CTA to finish (ticket
+// counter) in a fixed order, so the loss is deterministic; that CTA also evaluates the tiny
+// joint part (n <= a few thousand elements) and writes the three loss values.
+constexpr int kHmThreads = 256;
+constexpr int kHmMaxBlocks = 4 * kNumSMs;
+
+__global__ void __launch_bounds__(kHmThreads)
+heatmap_joint_loss_kernel(const float* __restrict__ hm, const float* __restrict__ target,
+                          const float* __restrict__ wh, int R, int HW, float hm_scale,
+                          const float* __restrict__ x, const float* __restrict__ t,
+                          const float* __restrict__ w, int n, int kind, float div, float jt_scale,
+                          float* __restrict__ loss, float* __restrict__ dhm,
+                          float* __restrict__ dx, double* __restrict__ parts,
+                          unsigned* __restrict__ ticket) {
+  __shared__ double shd[kHmThreads / 32];
+  __shared__ bool last;
+  const int64_t total = (int64_t)R * HW;
+  const float inv = 1.f / (float)total;
+  const float gs = 2.f * hm_scale * inv;
+  double acc = 0.0;
+  if ((HW & 3) == 0) {
+    const int64_t total4 = total >> 2;
+    const int hw4 = HW >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * kHmThreads + threadIdx.x; i < total4;
+         i += (int64_t)gridDim.x * kHmThreads) {
+      const float wr = wh ? wh[i / hw4] : 1.f;
+      const float4 h = ldg_stream(reinterpret_cast<const float4*>(hm) + i);
+      const float4 g = ldg_stream(reinterpret_cast<const float4*>(target) + i);
+      const float4 d = make_float4(wr * (h.x - g.x), wr * (h.y - g.y), wr * (h.z - g.z),
+                                   wr * (h.w - g.w));
+      acc += (double)(d.x * d.x + d.y * d.y) + (double)(d.z * d.z + d.w * d.w);
+      if (dhm) {
+        const float c = gs * wr;
+        reinterpret_cast<float4*>(dhm)[i] = make_float4(c * d.x, c * d.y, c * d.z, c * d.w);
+      }
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * kHmThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kHmThreads) {
+      const float wr = wh ? wh[i / HW] : 1.f;
+      const float d = wr * (hm[i] - target[i]);
+      acc += (double)(d * d);
+      if (dhm) dhm[i] = gs * wr * d;
+    }
+  }
+  acc = warp_sum(acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) shd[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0;
+    for (int k = 0; k < kHmThreads / 32; ++k) b += shd[k];
+    parts[blockIdx.x] = b;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();                            // partials of every CTA are visible
+  // joint-location part (integral_loss.py:7-47 without `norm`)
+  const float idiv = n > 0 ? 1.f / div : 0.f;
+  double jacc = 0.0;
+  for (int i = threadIdx.x; i < n; i += kHmThreads) {
+    const float d = x[i] - t[i];
+    const float a = fabsf(d);
+    float l, g;
+    if (kind == 0) { l = d * d; g = 2.f * d; }
+    else if (kind == 1) { l = a; g = (float)((d > 0.f) - (d < 0.f)); }
+    else { l = a < 1.f ? 0.5f * d * d : a - 0.5f; g = a < 1.f ? d : (float)((d > 0.f) - (d < 0.f)); }
+    jacc += (double)(l * w[i]);
+    if (dx) dx[i] = g * w[i] * idiv * jt_scale;
+  }
+  jacc = warp_sum(jacc);
+  __syncthreads();
+  if (lane == 0) shd[wid] = jacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double lj = 0.0, lh = 0.0;
+    for (int k = 0; k < kHmThreads / 32; ++k) lj += shd[k];
+    for (unsigned k = 0; k < gridDim.x; ++k) lh += parts[k];      // fixed order
+    const float loss_hm = (float)(lh / (double)total);
+    const float loss_jt = (float)(lj * (double)idiv);
+    loss[0] = loss_hm;
+    loss[1] = loss_jt;
+    loss[2] = hm_scale * loss_hm + jt_scale * loss_jt;
+    *ticket = 0u;                             // ready for the next launch (stream ordered)
+  }
+}
+
+double* g_hm_parts = nullptr;                 // [kHmMaxBlocks] partials + ticket counter behind them
+
 // workspace for per-CTA partials (grows on demand; one per process, reused
 // stream-ordered -- the library is used from one stream per device at a time)
 Part* g_parts = nullptr;
@@ -416,6 +511,29 @@ extern "C" __attribute__((visibility("default"))) int epb_jointloss_fwd_bwd(cons
   EPB_CHECK_ARG(kind >= 0 && kind <= 2);
   EPB_CHECK_ARG(div != 0.f);
   jointloss_kernel<<<1, kLossThreads, 0, as_stream(stream)>>>(x, t, w, n, kind, norm, div, loss, dx);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_heatmap_joint_loss(
+    const float* hm, const float* target, const float* hm_weight, int R, int HW, float hm_scale,
+    const float* x, const float* t, const float* w, int n, int kind, float div, float jt_scale,
+    float* loss, float* dhm, float* dx, epb_stream_t stream) {
+  EPB_CHECK_ARG(hm && target && loss);
+  EPB_CHECK_ARG(R > 0 && HW > 0);
+  EPB_CHECK_ARG(n >= 0 && (n == 0 || (x && t && w)));
+  EPB_CHECK_ARG(kind >= 0 && kind <= 2);
+  EPB_CHECK_ARG(n == 0 || div != 0.f);
+  if (!g_hm_parts) {
+    EPB_CUDA(cudaMalloc(&g_hm_parts, (kHmMaxBlocks + 1) * sizeof(double)));
+    EPB_CUDA(cudaMemset(g_hm_parts, 0, (kHmMaxBlocks + 1) * sizeof(double)));
+  }
+  const int64_t work = ((int64_t)R * HW + 3) / 4;
+  int64_t blocks = (work + kHmThreads - 1) / kHmThreads;
+  if (blocks > kHmMaxBlocks) blocks = kHmMaxBlocks;
+  heatmap_joint_loss_kernel<<<(int)blocks, kHmThreads, 0, as_stream(stream)>>>(
+      hm, target, hm_weight, R, HW, hm_scale, x, t, w, n, kind, div, jt_scale, loss, dhm, dx,
+      g_hm_parts, reinterpret_cast<unsigned*>(g_hm_parts + kHmMaxBlocks));
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

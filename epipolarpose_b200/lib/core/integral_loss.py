@@ -14,6 +14,13 @@ Deviation (documented): L2JointLocationLoss in the reference is broken
 weighted MSE it was evidently meant to.
 The logits may be NCHW-contiguous or the channels_last view PoseResNet returns;
 both layouts are handled natively (no transposition pass).
+
+Addition for the VOLUME=False head (pose3d_resnet.py:202-212 returns 2-D heat-maps and a
+depth vector; BASELINE north_star "MSE heatmap loss + L1 3D loss fused into one kernel",
+SURVEY 8(d) C2(ii)): HeatmapMSELoss / HeatmapJointLoss / heatmap_joint_loss over the single
+launch epb_heatmap_joint_loss.  The reference ships no heat-map criterion (only the config
+remnants LOSS.USE_TARGET_WEIGHT, lib/core/config.py:32-34); the arithmetic is
+torch.nn.functional.mse_loss on the (weighted) maps.
 """
 import numpy as np
 import torch
@@ -142,6 +149,105 @@ class L1JointLocationLoss(_JointLocationLoss):
 
 class SmoothL1JointLocationLoss(_JointLocationLoss):
     _kind = "smoothl1"
+
+
+class _HeatmapJointLossFn(torch.autograd.Function):
+    """total = hm_scale * mse(w_hm * hm, w_hm * target) + jt_scale * joint_loss(x, t, w)."""
+
+    @staticmethod
+    def forward(ctx, hm, target, hm_weight, x, t, w, kind, hm_scale, jt_scale, size_average):
+        ops = _backend[0]
+        if hm.dtype != torch.float32:
+            raise TypeError("heat-map loss expects float32 heat-maps")
+        if hm.shape != target.shape:
+            raise ValueError("heat-map / target shape mismatch: %s vs %s"
+                             % (tuple(hm.shape), tuple(target.shape)))
+        N, J = hm.shape[0], hm.shape[1]
+        R, HW = N * J, int(np.prod(hm.shape[2:]))
+        h = hm.contiguous()
+        tg = target.contiguous().float()
+        wh = None
+        if hm_weight is not None:
+            wh = hm_weight.reshape(-1).contiguous().float()
+            if wh.numel() != R:
+                raise ValueError("heat-map weight must have one entry per (sample, joint)")
+        dhm = torch.empty_like(h)
+        loss = torch.empty((3,), device=h.device, dtype=torch.float32)
+        n, div = 0, 1.0
+        xc = tc = wc = dx = None
+        if x is not None:
+            xc = x.contiguous()
+            tc, wc = t.contiguous().float(), w.contiguous().float()
+            n = xc.numel()
+            div = float(len(x)) if size_average else 1.0
+            dx = torch.empty_like(xc)
+        ops.heatmap_joint_loss(h, tg, wh, R, HW, hm_scale, xc, tc, wc, n, _KIND[kind], div,
+                               jt_scale, loss, dhm, dx)
+        ctx.save_for_backward(dhm, dx if dx is not None else dhm.new_empty(0))
+        ctx.has_x = x is not None
+        return loss            # [loss_hm, loss_jt, total]; only `total` carries gradient
+
+    @staticmethod
+    def backward(ctx, g):
+        dhm, dx = ctx.saved_tensors
+        gt = g[2]
+        return (dhm * gt, None, None, dx * gt if ctx.has_x else None, None, None, None, None,
+                None, None)
+
+
+def heatmap_joint_loss(heatmaps, hm_target, hm_weight=None, pred_jts=None, gt_jts=None,
+                       jts_weight=None, kind="l1", hm_scale=1.0, jt_scale=1.0, size_average=True):
+    """One fused launch.  heatmaps / hm_target [N, J, H, W] float32, hm_weight [N, J(,1)] or
+    None, pred_jts / gt_jts / jts_weight [N, J*3] or None.
+    Returns (total, parts): total = hm_scale*loss_hm + jt_scale*loss_jt (differentiable w.r.t.
+    heatmaps and pred_jts), parts = tensor [loss_hm, loss_jt] (detached)."""
+    if pred_jts is not None:
+        _assert_no_grad(gt_jts)
+        _assert_no_grad(jts_weight)
+    _assert_no_grad(hm_target)
+    out = _HeatmapJointLossFn.apply(heatmaps, hm_target, hm_weight, pred_jts, gt_jts, jts_weight,
+                                    kind, float(hm_scale), float(jt_scale), size_average)
+    return out[2], out[:2].detach()
+
+
+class HeatmapMSELoss(nn.Module):
+    """criterion(output [N,J,H,W], target [N,J,H,W], target_weight [N,J,1]) -> mean squared
+    error of the (weighted, when use_target_weight) heat-maps."""
+
+    def __init__(self, use_target_weight=False):
+        super().__init__()
+        self.use_target_weight = use_target_weight
+
+    def forward(self, output, target, target_weight=None):
+        w = target_weight if self.use_target_weight else None
+        if self.use_target_weight and target_weight is None:
+            raise ValueError("use_target_weight=True needs target_weight")
+        return heatmap_joint_loss(output, target, w)[0]
+
+
+class HeatmapJointLoss(nn.Module):
+    """criterion((heatmaps, pred_jts), (hm_target, hm_weight), gt_joints, gt_joints_vis):
+    heat-map MSE + jt_scale * L1 / SmoothL1 / MSE joint-location loss, one kernel launch.
+    `last_parts` holds [loss_hm, loss_jt] of the most recent call."""
+
+    def __init__(self, num_joints, kind="l1", hm_scale=1.0, jt_scale=1.0, size_average=True,
+                 use_target_weight=True):
+        super().__init__()
+        if kind not in _KIND:
+            raise ValueError("unknown joint loss kind %r" % (kind,))
+        self.num_joints, self.kind = num_joints, kind
+        self.hm_scale, self.jt_scale = hm_scale, jt_scale
+        self.size_average, self.use_target_weight = size_average, use_target_weight
+        self.last_parts = None
+
+    def forward(self, preds, hm_target, gt_joints, gt_joints_vis, hm_weight=None):
+        heatmaps, pred_jts = preds
+        total, parts = heatmap_joint_loss(heatmaps, hm_target,
+                                          hm_weight if self.use_target_weight else None,
+                                          pred_jts, gt_joints, gt_joints_vis, self.kind,
+                                          self.hm_scale, self.jt_scale, self.size_average)
+        self.last_parts = parts
+        return total
 
 
 def get_loss_func(config):

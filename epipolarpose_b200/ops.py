@@ -195,6 +195,13 @@ def jointloss(x, t, w, n, kind, norm, div, loss, dx):
           _p(loss), _p(dx), _stream())
 
 
+def heatmap_joint_loss(hm, target, hm_weight, R, HW, hm_scale, x, t, w, n, kind, div, jt_scale,
+                       loss, dhm, dx):
+    _call("epb_heatmap_joint_loss", _p(hm), _p(target), _p(hm_weight), R, HW, float(hm_scale),
+          _p(x), _p(t), _p(w), n, kind, float(div), float(jt_scale), _p(loss), _p(dhm), _p(dx),
+          _stream())
+
+
 def argmax2d(hm, NJ, H, W, idx, maxval, preds):
     _call("epb_argmax2d", _p(hm), NJ, H, W, _p(idx, torch.int32), _p(maxval), _p(preds), _stream())
 
@@ -210,6 +217,12 @@ def triangulate(u1, u2, stride_u, P1, P2, NP, J, method, tol, X, status):
     _call("epb_triangulate", _p(u1, torch.float64), _p(u2, torch.float64), stride_u,
           _p(P1, torch.float64), _p(P2, torch.float64), NP, J, method, float(tol),
           _p(X, torch.float64), _p(status, torch.int32), _stream())
+
+
+def h36m_eval(pred, gt, cam, S, J, root, j14mask, pck_thr, metrics, per_joint, pck, poses):
+    _call("epb_h36m_eval", _p(pred, torch.float64), _p(gt, torch.float64), _p(cam, torch.float64),
+          S, J, root, int(j14mask), float(pck_thr), _p(metrics, torch.float64),
+          _p(per_joint, torch.float64), _p(pck, torch.int32), _p(poses, torch.float64), _stream())
 
 
 def project_labels(X, cam, box, B, J, patch_w, patch_h, rect3d_w, label, weight):

@@ -216,6 +216,22 @@ int epb_jointloss_fwd_bwd(const float* x, const float* t, const float* w, int n,
                           int kind, int norm, float div, float* loss, float* dx,
                           epb_stream_t stream);
 
+/* Heat-map regression loss fused with the joint-location loss, ONE launch (the objective of
+ * the VOLUME=False head, pose3d_resnet.py:202-212: 2-D heat-maps + depth branch; the
+ * reference keeps only the config remnants of its heat-map loss, lib/core/config.py:32-34
+ * LOSS.USE_TARGET_WEIGHT, so the arithmetic is torch.nn.functional.mse_loss on the
+ * weighted maps plus integral_loss.py:7-47 on the joint vector):
+ *   loss_hm = sum_{r,p} (wh[r] * (hm[r][p] - target[r][p]))^2 / (R*HW)   r = (n, j) map
+ *   loss_jt = sum_i w[i] * l_kind(x[i] - t[i]) / div      (kind as epb_jointloss_fwd_bwd)
+ *   loss[0] = loss_hm, loss[1] = loss_jt, loss[2] = hm_scale*loss_hm + jt_scale*loss_jt
+ *   dhm = d loss[2] / d hm  [R][HW],   dx = d loss[2] / d x  [n]
+ * hm, target: [R][HW] float32 contiguous; hm_weight [R] or NULL (ones); n may be 0 (heat-map
+ * loss only; x, t, w, dx ignored); dhm / dx may be NULL (loss only).  Deterministic. */
+int epb_heatmap_joint_loss(const float* hm, const float* target, const float* hm_weight,
+                           int R, int HW, float hm_scale, const float* x, const float* t,
+                           const float* w, int n, int kind, float div, float jt_scale,
+                           float* loss, float* dhm, float* dx, epb_stream_t stream);
+
 /* Hard argmax (numpy call site lib/core/inference.py:24-39).  hm [NJ][HW]
  * float32 contiguous.  idx: flat first-max index (int32), maxval float32,
  * preds [NJ][2] float32 = (idx%W, idx/W) * (max > 0). */
@@ -248,6 +264,22 @@ int epb_project_labels(const double* X, const double* cam, const double* box,
                        int B, int J, double patch_w, double patch_h,
                        double rect3d_w, float* label, float* weight,
                        epb_stream_t stream);
+
+/* H36M evaluation protocol per sample (lib/dataset/h36m.py:168-378: CamBackProj
+ * lib/utils/prep_h36m.py:85-89, compute_similarity_transform(..., compute_optimal_scale=True)
+ * :108-168, root alignment, per-joint Euclidean errors).  float64.
+ *   pred, gt  [S][J][3]  image-space joints (x px, y px, root-relative depth mm); gt already in
+ *                        the order of pred (the H36M_TO_MPII permutation is a host gather)
+ *   cam       [S][5]     fx, fy, cx, cy, pelvis depth (gt['fl'], gt['c_p'], gt['pelvis'][2])
+ *   root                 root joint (6 with MPII_ORDER, else 0); j14mask: bit j set <=> joint j
+ *                        belongs to the 14-joint subset; pck_thr = 150 (mm)
+ *   metrics   [S][9]     means over joints of: e, e_align, e_norm, e (14), e_align (14),
+ *                        e_norm (14), |dx|, |dy|, |dz|
+ *   per_joint [S][J] (or NULL)  e per joint;   pck [S][J] int32 (or NULL)  e < pck_thr
+ *   poses     [S][J][9] (or NULL)  root-aligned pred | align_pred | gt  (pred_to_save) */
+int epb_h36m_eval(const double* pred, const double* gt, const double* cam, int S, int J,
+                  int root, uint32_t j14mask, double pck_thr, double* metrics,
+                  double* per_joint, int32_t* pck, double* poses, epb_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Optimiser (torch.optim.Adam call site lib/utils/utils.py:56-60; betas

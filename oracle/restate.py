@@ -74,6 +74,27 @@ def softmax_integral_grad(preds, grad_out, num_joints, hm_width, hm_height, hm_d
 # a9: weighted losses  (lib/core/integral_loss.py:7-47)
 # --------------------------------------------------------------------------
 
+def heatmap_joint_loss(hm, target, hm_weight=None, x=None, t=None, w=None, kind="l1",
+                       hm_scale=1.0, jt_scale=1.0, size_average=True):
+    """Objective of the VOLUME=False head (north_star "MSE heatmap loss + L1 3D loss"; SURVEY
+    8(d) C2(ii)): torch.nn.functional.mse_loss(w*hm, w*target) (mean over every element; the
+    reference ships no heat-map criterion, only config.py:32-34) plus weighted_loss (:7-47) on
+    the joint vector.  float64.  Returns (loss_hm, loss_jt, total, dtotal/dhm, dtotal/dx)."""
+    h = np.asarray(hm, dtype=np.float64)
+    g = np.asarray(target, dtype=np.float64)
+    wr = np.ones(h.shape[:2]) if hm_weight is None else \
+        np.asarray(hm_weight, dtype=np.float64).reshape(h.shape[:2])
+    wr = wr.reshape(h.shape[:2] + (1,) * (h.ndim - 2))
+    d = wr * (h - g)
+    loss_hm = float((d * d).mean())
+    dhm = hm_scale * 2.0 * wr * d / d.size
+    loss_jt, dx = 0.0, None
+    if x is not None:
+        loss_jt, dxx = weighted_loss(kind, x, t, w, size_average, False)
+        dx = jt_scale * dxx
+    return loss_hm, float(loss_jt), hm_scale * loss_hm + jt_scale * float(loss_jt), dhm, dx
+
+
 def weighted_loss(kind, inp, target, weights, size_average=True, norm=False):
     """kind in {'mse','l1','smoothl1'}; integral_loss.py:7-18 / 20-31 / 33-47.
     Divisor is len(input) = batch size (:16,29,45).  Returns (loss, dL/dinput)
@@ -414,3 +435,97 @@ def project(P, X):
     Xh = np.concatenate([X, np.ones(X.shape[:-1] + (1,))], axis=-1)
     uvw = Xh @ P.T
     return uvw[..., 0:2] / uvw[..., 2:3]
+
+
+# ---------------------------------------------------------------- H36M evaluation protocol
+H36M_NAMES = ['Hip', 'RHip', 'RKnee', 'RFoot', 'LHip', 'LKnee', 'LFoot', 'Spine', 'Thorax',
+              'Neck/Nose', 'Head', 'LShoulder', 'LElbow', 'LWrist', 'RShoulder', 'RElbow', 'RWrist']
+MPII_NAMES = ['RFoot', 'RKnee', 'RHip', 'LHip', 'LKnee', 'LFoot', 'Hip', 'Thorax', 'Neck/Nose',
+              'Head', 'RWrist', 'RElbow', 'RShoulder', 'LShoulder', 'LElbow', 'LWrist']
+# lib/dataset/h36m.py:17 (names: lib/dataset/JointIntegralDataset.py)
+H36M_TO_MPII_PERM = np.array([H36M_NAMES.index(h) for h in MPII_NAMES if h != '' and h in H36M_NAMES])
+J14_MPII = [0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 14, 15]          # h36m.py:186
+J14_H36M = [0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15]
+
+
+def cam_back_proj(cam_x, cam_y, depth, fx, fy, u, v):
+    """lib/utils/prep_h36m.py:85-89."""
+    return (cam_x - u) / fx * depth, (cam_y - v) / fy * depth, depth
+
+
+def compute_similarity_transform(X, Y, compute_optimal_scale=False):
+    """lib/utils/prep_h36m.py:108-168 (MATLAB procrustes): X targets [N,M], Y inputs.
+    Returns (d, Z, T, b, c)."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    muX, muY = X.mean(0), Y.mean(0)
+    X0, Y0 = X - muX, Y - muY
+    ssX, ssY = (X0 ** 2.).sum(), (Y0 ** 2.).sum()
+    normX, normY = np.sqrt(ssX), np.sqrt(ssY)
+    X0, Y0 = X0 / normX, Y0 / normY
+    A = np.dot(X0.T, Y0)
+    U, s, Vt = np.linalg.svd(A, full_matrices=False)
+    V = Vt.T
+    T = np.dot(V, U.T)
+    detT = np.linalg.det(T)
+    V[:, -1] *= np.sign(detT)
+    s[-1] *= np.sign(detT)
+    T = np.dot(V, U.T)
+    traceTA = s.sum()
+    if compute_optimal_scale:
+        b = traceTA * normX / normY
+        d = 1 - traceTA ** 2
+        Z = normX * traceTA * np.dot(Y0, T) + muX
+    else:
+        b = 1
+        d = 1 + ssY / ssX - 2 * traceTA * normY / normX
+        Z = normY * np.dot(Y0, T) + muX
+    c = muX - b * np.dot(muY, T)
+    return d, Z, T, b, c
+
+
+def h36m_evaluate(preds, gt_joints, pelvis_z, fl, c_p, mpii_order=False, pck_thr=150.0):
+    """lib/dataset/h36m.py:168-378 on arrays instead of db records.
+    preds [S,J,>=3] image-space predictions (x, y px; root-relative depth mm), gt_joints [S,J,3]
+    (`joints_3d`, H36M order), pelvis_z [S] (gt['pelvis'][2]), fl / c_p [S,2].
+    Returns dict(metrics [S,9], per_joint [S,J], pck [S,J], poses [S,J,9], name_value, mean)."""
+    preds = np.asarray(preds, dtype=np.float64)[:, :, 0:3]
+    S, J = preds.shape[0], preds.shape[1]
+    root = 6 if mpii_order else 0
+    j14 = J14_MPII if mpii_order else J14_H36M
+    metrics = np.zeros((S, 9))
+    per_joint = np.zeros((S, J))
+    pck = np.zeros((S, J), dtype=np.int32)
+    poses = np.zeros((S, J, 9))
+    for n in range(S):
+        gt2 = np.asarray(gt_joints[n], dtype=np.float64).copy()
+        pre2 = preds[n].copy()
+        if mpii_order:
+            gt2 = gt2[H36M_TO_MPII_PERM, :]
+        pre2[:, 2] = pre2[:, 2] + pelvis_z[n]
+        gt2[:, 2] = gt2[:, 2] + pelvis_z[n]
+        pre3, gt3 = np.zeros((J, 3)), np.zeros((J, 3))
+        for j in range(J):
+            pre3[j] = cam_back_proj(pre2[j, 0], pre2[j, 1], pre2[j, 2], fl[n][0], fl[n][1], c_p[n][0], c_p[n][1])
+            gt3[j] = cam_back_proj(gt2[j, 0], gt2[j, 1], gt2[j, 2], fl[n][0], fl[n][1], c_p[n][0], c_p[n][1])
+        _, Z, T, b, c = compute_similarity_transform(gt3, pre3, compute_optimal_scale=True)
+        align = (b * pre3.dot(T)) + c
+        norm = b * pre3
+        pre3 = pre3 - pre3[root]
+        gt3 = gt3 - gt3[root]
+        align = align - align[root]
+        norm = norm - norm[root]
+        diff, diff_a, diff_n = gt3 - pre3, gt3 - align, gt3 - norm
+        e = np.linalg.norm(diff, axis=1)
+        ea = np.linalg.norm(diff_a, axis=1)
+        en = np.linalg.norm(diff_n, axis=1)
+        metrics[n] = [e.mean(), ea.mean(), en.mean(), e[j14].mean(), ea[j14].mean(), en[j14].mean(),
+                      np.abs(diff[:, 0]).mean(), np.abs(diff[:, 1]).mean(), np.abs(diff[:, 2]).mean()]
+        per_joint[n] = e
+        pck[n] = (e < pck_thr).astype(np.int32)
+        poses[n] = np.concatenate([pre3, align, gt3], axis=1)
+    names = ['hm36_17j      :', 'hm36_17j_align:', 'hm36_17j_norm:', 'hm36_17j_14   :', 'hm36_17j_14_al:',
+             'hm36_17j_14_nm:', 'hm36_17j_x    :', 'hm36_17j_y    :', 'hm36_17j_z    :']
+    means = metrics.mean(axis=0) if S else np.zeros(9)
+    return dict(metrics=metrics, per_joint=per_joint, pck=pck, poses=poses,
+                name_value=list(zip(names, means.tolist())), mean=float(means[0]))

@@ -288,6 +288,29 @@ def softargmax_bwd(logits, layout, N, J, D, H, W, coords, lse, dcoords, dlogits)
         dlogits.view(N, H, W, J, D).copy_(d.permute(0, 3, 4, 1, 2))
 
 
+def heatmap_joint_loss(hm, target, hm_weight, R, HW, hm_scale, x, t, w, n, kind, div, jt_scale,
+                       loss, dhm, dx):
+    h = hm.reshape(R, HW).double()
+    g = target.reshape(R, HW).double()
+    wr = torch.ones(R, 1, dtype=torch.float64) if hm_weight is None else \
+        hm_weight.reshape(R, 1).double()
+    d = wr * (h - g)
+    loss_hm = (d * d).mean()
+    if dhm is not None:
+        dhm.view(R, HW).copy_((2.0 * hm_scale * wr * d / (R * HW)).float())
+    loss_jt = torch.zeros((), dtype=torch.float64)
+    if n > 0:
+        tmp = torch.empty(1)
+        gx = torch.empty(n)
+        jointloss(x, t, w, n, kind, 0, div, tmp, gx)
+        loss_jt = tmp[0].double()
+        if dx is not None:
+            dx.view(-1).copy_(gx * jt_scale)
+    loss.view(-1)[0] = loss_hm.float()
+    loss.view(-1)[1] = loss_jt.float()
+    loss.view(-1)[2] = (hm_scale * loss_hm + jt_scale * loss_jt).float()
+
+
 def jointloss(x, t, w, n, kind, norm, div, loss, dx):
     with torch.enable_grad():
         xv = x.reshape(-1).detach().clone().requires_grad_(True)
@@ -364,3 +387,45 @@ def sgd_step_dev(param, grad, buf, n, hyper, step_dev):
 
 def device_check():
     pass
+
+
+def h36m_eval(pred, gt, cam, S, J, root, j14mask, pck_thr, metrics, per_joint, pck, poses):
+    """CPU emulation of epb_h36m_eval: closed-form restatement in torch float64 (batched SVD)."""
+    p, q, c = pred.reshape(S, J, 3).double(), gt.reshape(S, J, 3).double(), cam.reshape(S, 5).double()
+
+    def bp(a):
+        d = a[:, :, 2] + c[:, 4:5]
+        return torch.stack([(a[:, :, 0] - c[:, 2:3]) / c[:, 0:1] * d,
+                            (a[:, :, 1] - c[:, 3:4]) / c[:, 1:2] * d, d], dim=2)
+    X, Y = bp(q), bp(p)
+    muX, muY = X.mean(1, keepdim=True), Y.mean(1, keepdim=True)
+    X0, Y0 = X - muX, Y - muY
+    nX = X0.pow(2).sum((1, 2), keepdim=True).sqrt()
+    nY = Y0.pow(2).sum((1, 2), keepdim=True).sqrt()
+    A = (X0 / nX).transpose(1, 2) @ (Y0 / nY)
+    U, sv, Vt = torch.linalg.svd(A)
+    V = Vt.transpose(1, 2).clone()
+    T = V @ U.transpose(1, 2)
+    sgn = torch.sign(torch.linalg.det(T))
+    V[:, :, -1] *= sgn[:, None]
+    sv = sv.clone()
+    sv[:, -1] *= sgn
+    T = V @ U.transpose(1, 2)
+    b = (sv.sum(1).reshape(S, 1, 1) * nX / nY)
+    cv = muX - b * (muY @ T)
+    Ya = b * (Y @ T) + cv
+    Yn = b * Y
+    r = lambda a: a - a[:, root:root + 1, :]
+    G, P0, Pa, Pn = r(X), r(Y), r(Ya), r(Yn)
+    e, ea, en = (G - P0).norm(dim=2), (G - Pa).norm(dim=2), (G - Pn).norm(dim=2)
+    sel = [j for j in range(J) if (j14mask >> j) & 1]
+    out = torch.stack([e.mean(1), ea.mean(1), en.mean(1), e[:, sel].mean(1), ea[:, sel].mean(1),
+                       en[:, sel].mean(1), (G - P0)[:, :, 0].abs().mean(1),
+                       (G - P0)[:, :, 1].abs().mean(1), (G - P0)[:, :, 2].abs().mean(1)], dim=1)
+    metrics.view(S, 9).copy_(out)
+    if per_joint is not None:
+        per_joint.view(S, J).copy_(e)
+    if pck is not None:
+        pck.view(S, J).copy_((e < pck_thr).to(torch.int32))
+    if poses is not None:
+        poses.view(S, J, 9).copy_(torch.cat([P0, Pa, G], dim=2))

@@ -1,0 +1,49 @@
+"""Golden vectors of the H36M evaluation protocol, produced by the
+UNMODIFIED reference: lib/dataset/h36m.py::H36M_Integral.evaluate is called as an unbound
+method on a stand-in `self` carrying only the fields it reads (db, cfg.DATASET.MPII_ORDER,
+cfg.DEBUG.DEBUG, root), and lib/utils/prep_h36m.py::compute_similarity_transform directly.
+Run in the build container only:
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_eval.py"""
+import contextlib
+import importlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, ROOT)
+from oracle import refshim, restate  # noqa: E402
+from tests import golden_inputs as gi  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+refshim.install()
+h36m = importlib.import_module("lib.dataset.h36m")
+prep = importlib.import_module("lib.utils.prep_h36m")
+S = types.SimpleNamespace
+
+pred, gt, pelvis, fl, c_p = gi.eval_case()
+assert np.array_equal(h36m.H36M_TO_MPII_PERM, restate.H36M_TO_MPII_PERM)
+rec = {}
+for mpii in (False, True):
+    db = [dict(fl=fl[i], c_p=c_p[i], pelvis=pelvis[i], joints_3d=gt[i],
+               joints_3d_vis=np.ones((17, 3))) for i in range(len(pred))]
+    fake = S(db=db, cfg=S(DATASET=S(MPII_ORDER=mpii), DEBUG=S(DEBUG=False)), root='')
+    p = pred[:, h36m.H36M_TO_MPII_PERM, :] if mpii else pred
+    with contextlib.redirect_stdout(io.StringIO()) as buf:       # evaluate prints the per-joint means
+        name_value, mean = h36m.H36M_Integral.evaluate(fake, p.copy())
+    tag = "mpii" if mpii else "h36m"
+    rec[tag + "_values"] = np.array([v for _, v in name_value])
+    rec[tag + "_mean"] = np.array(mean)
+    rec[tag + "_per_joint"] = np.array([float(l.split()[-1]) for l in buf.getvalue().strip().splitlines()])
+proc = [prep.compute_similarity_transform(gt[i], pred[i][:, :3], compute_optimal_scale=True)
+        for i in range(4)]
+rec["proc_d"] = np.array([q[0] for q in proc])
+rec["proc_Z"] = np.stack([q[1] for q in proc])
+rec["proc_T"] = np.stack([q[2] for q in proc])
+rec["proc_b"] = np.array([q[3] for q in proc])
+rec["proc_c"] = np.stack([q[4] for q in proc])
+np.savez_compressed(os.path.join(OUT, "h36m_eval.npz"), **rec)
+print("wrote h36m_eval", {k: v.shape for k, v in rec.items()})

@@ -113,3 +113,43 @@ def images(N, HW, seed):
 
 def grad_like(shape, seed):
     return np.random.default_rng(seed).standard_normal(tuple(shape)).astype(np.float32)
+
+
+def heatmap_case(N, J, H, W, seed, sigma=2.0):
+    """VOLUME=False objective inputs: predicted heat-maps ~ N(0, 0.5),
+    Gaussian targets exp(-((x-mx)^2+(y-my)^2)/(2 sigma^2)) (sigma = 2, config.py:34) with
+    centres U{8..W-9} (margin W/4 on small maps), per-joint visibility weights in {0, 1}, joint vector + labels + weights."""
+    rng = np.random.default_rng(seed)
+    hm = (0.5 * rng.standard_normal((N, J, H, W))).astype(np.float32)
+    bx, by = min(8, W // 4), min(8, H // 4)          # keep the blob inside the map
+    mx = rng.integers(bx, max(bx + 1, W - bx), size=(N, J, 1, 1))
+    my = rng.integers(by, max(by + 1, H - by), size=(N, J, 1, 1))
+    yy, xx = np.mgrid[0:H, 0:W]
+    tgt = np.exp(-((xx - mx) ** 2 + (yy - my) ** 2) / (2.0 * sigma * sigma)).astype(np.float32)
+    wh = (rng.random((N, J, 1)) > 0.2).astype(np.float32)
+    x = (rng.random((N, J * 3)) - 0.5).astype(np.float32)
+    t = (rng.random((N, J * 3)) - 0.5).astype(np.float32)
+    w = (rng.random((N, J * 3)) > 0.1).astype(np.float32)
+    return hm, tgt, wh, x, t, w
+
+
+def eval_case(S=24, J=17, seed=81):
+    """H36M-protocol evaluation inputs: gt joints in camera space ~ N(0, 300 mm) around a
+    pelvis at depth 4.5 m +- 0.5, projected with f ~ (1145, 1144), c ~ (512, 515) to
+    `joints_3d` (x px, y px, root-relative depth mm); predictions = gt + N(0, 8 px / 40 mm)
+    and a random global scale error."""
+    rng = np.random.default_rng(seed)
+    fl = np.stack([1145.0 + rng.uniform(-5, 5, S), 1144.0 + rng.uniform(-5, 5, S)], axis=1)
+    c_p = np.stack([512.0 + rng.uniform(-5, 5, S), 515.0 + rng.uniform(-5, 5, S)], axis=1)
+    pelvis = np.stack([rng.normal(0, 200, S), rng.normal(0, 200, S), 4500 + rng.uniform(-500, 500, S)], axis=1)
+    X = pelvis[:, None, :] + rng.normal(0, 300, (S, J, 3))
+    X[:, 0, :] = pelvis
+    gt = np.zeros((S, J, 3))
+    gt[:, :, 0] = X[:, :, 0] / X[:, :, 2] * fl[:, None, 0] + c_p[:, None, 0]
+    gt[:, :, 1] = X[:, :, 1] / X[:, :, 2] * fl[:, None, 1] + c_p[:, None, 1]
+    gt[:, :, 2] = X[:, :, 2] - pelvis[:, None, 2]
+    pred = gt.copy()
+    pred[:, :, :2] += rng.normal(0, 8, (S, J, 2))
+    pred[:, :, 2] = pred[:, :, 2] * rng.uniform(0.8, 1.2, (S, 1)) + rng.normal(0, 40, (S, J))
+    pred = np.concatenate([pred, np.ones((S, J, 1))], axis=2)      # score column as in the loop
+    return pred, gt, pelvis, fl, c_p

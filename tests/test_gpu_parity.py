@@ -96,6 +96,79 @@ def test_softargmax_vs_oracle_medium(dev):
 
 
 # ------------------------------------------------------------------ argmax
+@pytest.mark.parametrize("shape", [(3, 5, 16, 24), (2, 17, 64, 64), (1, 2, 5, 7)])
+@pytest.mark.parametrize("kind", ["l1", "smoothl1", "mse"])
+def test_heatmap_joint_loss_vs_oracle(dev, shape, kind):
+    """epb_heatmap_joint_loss (one launch: heat-map MSE + joint loss, value and both gradients)
+    against the float64 oracle; losses <= 1e-5 rel, gradients <= 1e-5 of the tensor maximum;
+    deterministic across repeated launches.  (1,2,5,7): HW not a multiple of 4 (scalar path)."""
+    import lib.core.integral_loss as il
+    N, J, H, W = shape
+    hm, tgt, wh, x, t, w = gi.heatmap_case(N, J, H, W, 72 + N)
+    o_hm, o_jt, o_tot, o_dhm, o_dx = restate.heatmap_joint_loss(hm, tgt, wh, x, t, w, kind, 0.5, 2.0)
+    th = torch.from_numpy(hm).to(dev).requires_grad_(True)
+    tx = torch.from_numpy(x).to(dev).requires_grad_(True)
+    crit = il.HeatmapJointLoss(J, kind=kind, hm_scale=0.5, jt_scale=2.0)
+    args = (torch.from_numpy(tgt).to(dev), torch.from_numpy(t).to(dev), torch.from_numpy(w).to(dev))
+    tot = crit((th, tx), *args, hm_weight=torch.from_numpy(wh).to(dev))
+    tot.backward()
+    assert abs(tot.item() - o_tot) <= 1e-5 * abs(o_tot)
+    assert abs(crit.last_parts[0].item() - o_hm) <= 1e-5 * o_hm
+    assert abs(crit.last_parts[1].item() - o_jt) <= 1e-5 * max(o_jt, 1e-30)
+    assert relerr(th.grad.cpu().numpy(), o_dhm) <= 1e-5
+    assert relerr(tx.grad.cpu().numpy(), o_dx) <= 1e-5
+    tot2 = crit((th, tx), *args, hm_weight=torch.from_numpy(wh).to(dev))
+    assert tot2.item() == tot.item()
+    # heat-map loss alone, unweighted == F.mse_loss
+    l2 = il.HeatmapMSELoss()(th, args[0])
+    ref = float(((hm.astype(np.float64) - tgt) ** 2).mean())
+    assert abs(l2.item() - ref) <= 1e-5 * ref
+
+
+@pytest.mark.parametrize("mpii", [False, True])
+def test_h36m_eval_vs_oracle_and_reference(golden, dev, mpii):
+    """epb_h36m_eval (back-projection, Procrustes with optimal scale, root alignment, protocol
+    means) against the numpy oracle per sample (<= 1e-8 mm) and against the aggregate values the
+    unmodified H36M_Integral.evaluate produced (<= 1e-8 mm); PCK flags bit-exact; a larger batch
+    through size-independent properties (alignment removes any similarity transform)."""
+    import lib.dataset.h36m_eval as he
+    g = golden("h36m_eval")
+    tag = "mpii" if mpii else "h36m"
+    pred, gt, pelvis, fl, c_p = gi.eval_case()
+    p = pred[:, he.H36M_TO_MPII_PERM, :] if mpii else pred
+    nv, perf, det = he.evaluate_h36m(p, gt, pelvis, fl, c_p, mpii_order=mpii, return_poses=True)
+    o = restate.h36m_evaluate(p, gt, pelvis[:, 2], fl, c_p, mpii_order=mpii)
+    assert np.max(np.abs(det["metrics"] - o["metrics"])) <= 1e-8
+    assert np.max(np.abs(det["per_joint"] - o["per_joint"])) <= 1e-8
+    assert np.array_equal(det["pck"], o["pck"])
+    assert np.max(np.abs(det["poses"] - o["poses"])) <= 1e-8
+    assert np.max(np.abs(np.array([v for _, v in nv]) - g[tag + "_values"])) <= 1e-8
+    assert abs(perf - float(g[tag + "_mean"])) <= 1e-8
+    # property at scale: predictions that are an exact similarity transform of the ground truth
+    # in camera space align to zero error (4096 samples)
+    if not mpii:
+        rng = np.random.default_rng(5)
+        S, J = 4096, 17
+        pb, gb, pel, f2, c2 = gi.eval_case(S, J, 83)
+        X = np.zeros((S, J, 3))
+        d = gb[:, :, 2] + pel[:, 2:3]
+        X[:, :, 0] = (gb[:, :, 0] - c2[:, 0:1]) / f2[:, 0:1] * d
+        X[:, :, 1] = (gb[:, :, 1] - c2[:, 1:2]) / f2[:, 1:2] * d
+        X[:, :, 2] = d
+        ang = rng.uniform(-0.3, 0.3, S)
+        R = np.stack([np.stack([np.cos(ang), -np.sin(ang), 0 * ang], 1),
+                      np.stack([np.sin(ang), np.cos(ang), 0 * ang], 1),
+                      np.stack([0 * ang, 0 * ang, 1 + 0 * ang], 1)], 1)
+        Y = 1.1 * np.einsum("sjk,skl->sjl", X - X[:, :1], R) + X[:, :1]
+        pp = np.zeros((S, J, 3))
+        pp[:, :, 0] = Y[:, :, 0] / Y[:, :, 2] * f2[:, 0:1] + c2[:, 0:1]
+        pp[:, :, 1] = Y[:, :, 1] / Y[:, :, 2] * f2[:, 1:2] + c2[:, 1:2]
+        pp[:, :, 2] = Y[:, :, 2] - pel[:, 2:3]
+        _, _, dd = he.evaluate_h36m(pp, gb, pel, f2, c2)
+        assert np.max(dd["metrics"][:, 1]) <= 1e-6          # aligned error vanishes
+        assert np.min(dd["metrics"][:, 0]) > 1.0            # un-aligned error does not
+
+
 def test_argmax_bit_exact(golden, dev):
     import lib.core.inference as inf
     g = golden("argmax")

@@ -130,6 +130,116 @@ def test_losses_and_decode_surface_emulated():
         inf._backend[0] = il._backend[0]
 
 
+def test_heatmap_joint_loss_oracle_and_surface_emulated():
+    """oracle == torch autograd on F.mse_loss + the reference weighted loss; the Python surface
+    (HeatmapMSELoss / HeatmapJointLoss) through the emulated C ABI == oracle."""
+    import torch.nn.functional as F
+    import lib.core.integral_loss as il
+    hm, tgt, wh, x, t, w = gi.heatmap_case(3, 5, 16, 24, 71)
+    for kind in ("l1", "smoothl1", "mse"):
+        th = torch.from_numpy(hm).double().requires_grad_(True)
+        tx = torch.from_numpy(x).double().requires_grad_(True)
+        ww = torch.from_numpy(wh).double().reshape(3, 5, 1, 1)
+        lh = F.mse_loss(th * ww, torch.from_numpy(tgt).double() * ww)
+        d = tx - torch.from_numpy(t).double()
+        l = {"l1": d.abs(), "mse": d * d,
+             "smoothl1": torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5)}[kind]
+        lj = (l * torch.from_numpy(w).double()).sum() / len(x)
+        (0.5 * lh + 3.0 * lj).backward()
+        o_hm, o_jt, o_tot, o_dhm, o_dx = restate.heatmap_joint_loss(hm, tgt, wh, x, t, w, kind, 0.5, 3.0)
+        assert abs(o_hm - lh.item()) <= 1e-12 and abs(o_jt - lj.item()) <= 1e-12
+        assert np.allclose(o_dhm, th.grad.numpy(), rtol=0, atol=1e-14)
+        assert np.allclose(o_dx, tx.grad.numpy(), rtol=0, atol=1e-14)
+    il._backend[0] = emul_ops
+    try:
+        th = torch.from_numpy(hm).requires_grad_(True)
+        tx = torch.from_numpy(x).requires_grad_(True)
+        crit = il.HeatmapJointLoss(5, kind="smoothl1", hm_scale=0.5, jt_scale=3.0)
+        tot = crit((th, tx), torch.from_numpy(tgt), torch.from_numpy(t), torch.from_numpy(w),
+                   hm_weight=torch.from_numpy(wh))
+        tot.backward()
+        o_hm, o_jt, o_tot, o_dhm, o_dx = restate.heatmap_joint_loss(hm, tgt, wh, x, t, w, "smoothl1", 0.5, 3.0)
+        assert abs(tot.item() - o_tot) <= 1e-5 * abs(o_tot)
+        assert abs(crit.last_parts[0].item() - o_hm) <= 1e-5 * o_hm
+        assert abs(crit.last_parts[1].item() - o_jt) <= 1e-5 * o_jt
+        assert relerr(th.grad.numpy(), o_dhm) <= 1e-5 and relerr(tx.grad.numpy(), o_dx) <= 1e-5
+        # heat-map loss alone == F.mse_loss (no weights)
+        th2 = torch.from_numpy(hm).requires_grad_(True)
+        l2 = il.HeatmapMSELoss()(th2, torch.from_numpy(tgt))
+        assert abs(l2.item() - F.mse_loss(torch.from_numpy(hm), torch.from_numpy(tgt)).item()) <= 1e-6
+        with pytest.raises(ValueError):
+            il.HeatmapMSELoss(True)(th2, torch.from_numpy(tgt))
+        with pytest.raises(ValueError):
+            il.HeatmapMSELoss()(th2, torch.from_numpy(tgt[:, :2]))
+    finally:
+        il._backend[0] = __import__("epipolarpose_b200.ops", fromlist=["ops"])
+
+
+def test_h36m_eval_surface_emulated():
+    """lib/dataset/h36m_eval.evaluate_h36m through the emulated C ABI == oracle == reference
+    golden values; argument validation as the reference's array indexing would fail."""
+    import lib.dataset.h36m_eval as he
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "h36m_eval.npz")))
+    pred, gt, pelvis, fl, c_p = gi.eval_case()
+    he._backend[0] = emul_ops
+    try:
+        for mpii, tag in ((False, "h36m"), (True, "mpii")):
+            p = pred[:, he.H36M_TO_MPII_PERM, :] if mpii else pred
+            nv, perf, det = he.evaluate_h36m(p, gt, pelvis, fl, c_p, mpii_order=mpii, return_poses=True)
+            assert [n for n, _ in nv] == he.METRIC_NAMES
+            assert np.max(np.abs(np.array([v for _, v in nv]) - g[tag + "_values"])) <= 1e-8
+            assert abs(perf - float(g[tag + "_mean"])) <= 1e-8
+            o = restate.h36m_evaluate(p, gt, pelvis[:, 2], fl, c_p, mpii_order=mpii)
+            assert np.max(np.abs(det["metrics"] - o["metrics"])) <= 1e-8
+            assert np.array_equal(det["pck"], o["pck"])
+            assert np.max(np.abs(det["poses"] - o["poses"])) <= 1e-8
+        with pytest.raises(ValueError):
+            he.evaluate_h36m(pred[:, :5], gt, pelvis, fl, c_p)
+        nv, perf, det = he.evaluate_h36m(pred[:0], gt[:0], pelvis[:0], fl[:0], c_p[:0])
+        assert perf == 0.0 and det["metrics"].shape == (0, 9)
+    finally:
+        he._backend[0] = __import__("epipolarpose_b200.ops", fromlist=["ops"])
+
+
+@pytest.fixture(scope="module")
+def host_geometry(tmp_path_factory):
+    """tests/harness/host_geometry.cu: the __host__ __device__ bodies of csrc/geometry.cu built
+    for the CPU with nvcc (same source and --fmad=false arithmetic as the kernels)."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path_factory.mktemp("harness") / "host_geometry")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--fmad=false", "-O1",
+                        "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "harness", "host_geometry.cu")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+    def run(args, *arrays):
+        inp = b"".join(np.ascontiguousarray(a, dtype=np.float64).tobytes() for a in arrays)
+        out = subprocess.run([exe] + [str(a) for a in args], input=inp, capture_output=True)
+        assert out.returncode == 0, out.stderr
+        return np.frombuffer(out.stdout, dtype=np.float64)
+    return run
+
+
+@pytest.mark.parametrize("mpii", [False, True])
+def test_h36m_eval_kernel_body_on_host(host_geometry, mpii):
+    """the per-sample body of h36m_eval_kernel, executed on the CPU, against the numpy oracle."""
+    pred, gt, pelvis, fl, c_p = gi.eval_case(64, 17, 82)
+    p = pred[:, restate.H36M_TO_MPII_PERM, :3] if mpii else pred[:, :, :3]
+    g = gt[:, restate.H36M_TO_MPII_PERM, :] if mpii else gt
+    S, J = p.shape[:2]
+    cam = np.concatenate([fl, c_p, pelvis[:, 2:3]], 1)
+    j14 = restate.J14_MPII if mpii else restate.J14_H36M
+    a = host_geometry(["eval", S, J, 6 if mpii else 0, sum(1 << j for j in j14)], p, g, cam)
+    met, pj, poses = a[:S * 9].reshape(S, 9), a[S * 9:S * 9 + S * J].reshape(S, J), a[S * 9 + S * J:].reshape(S, J, 9)
+    o = restate.h36m_evaluate(p, gt, pelvis[:, 2], fl, c_p, mpii_order=mpii)
+    assert np.max(np.abs(met - o["metrics"])) <= 1e-9
+    assert np.max(np.abs(pj - o["per_joint"])) <= 1e-9
+    assert np.max(np.abs(poses - o["poses"])) <= 1e-9
+
+
 def test_fused_optimizers_match_torch():
     import lib.utils.utils as U
     U._backend[0] = emul_ops

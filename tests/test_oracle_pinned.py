@@ -108,3 +108,22 @@ def test_network_restatement(golden, tag):
                                 image_size=(c["HW"], c["HW"]), training=False)
     e = e[0] if isinstance(e, tuple) else e
     assert relerr(e.numpy(), g["eval_out0"]) <= 5e-4
+
+
+def test_h36m_evaluation_protocol(golden):
+    """oracle/restate.py::h36m_evaluate / compute_similarity_transform against the outputs of
+    the unmodified H36M_Integral.evaluate (tests/golden/make_golden_eval.py)."""
+    g = golden("h36m_eval")
+    pred, gt, pelvis, fl, c_p = gi.eval_case()
+    for mpii, tag in ((False, "h36m"), (True, "mpii")):
+        p = pred[:, restate.H36M_TO_MPII_PERM, :] if mpii else pred
+        o = restate.h36m_evaluate(p, gt, pelvis[:, 2], fl, c_p, mpii_order=mpii)
+        vals = np.array([v for _, v in o["name_value"]])
+        assert np.max(np.abs(vals - g[tag + "_values"])) <= 1e-9
+        assert abs(o["mean"] - float(g[tag + "_mean"])) <= 1e-9
+        assert np.max(np.abs(o["per_joint"].mean(0) - g[tag + "_per_joint"])) <= 1e-9
+    for i in range(4):
+        d, Z, T, b, c = restate.compute_similarity_transform(gt[i], pred[i][:, :3], True)
+        assert abs(d - g["proc_d"][i]) <= 1e-12 and abs(b - g["proc_b"][i]) <= 1e-12
+        assert np.max(np.abs(Z - g["proc_Z"][i])) <= 1e-9 and np.max(np.abs(T - g["proc_T"][i])) <= 1e-12
+        assert np.max(np.abs(c - g["proc_c"][i])) <= 1e-9

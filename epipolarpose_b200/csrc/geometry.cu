@@ -102,6 +102,212 @@ __device__ void build_Ab(const double* u1, const double* P1, const double* u2, c
   }
 }
 
+// --------------------------------------------------------------- polynomial (optimal) correction
+// lib/utils/triangulation.py:184-220: F from the two projection matrices, cv2.correctMatches
+// (Hartley-Sturm, Hartley & Zisserman Alg. 12.1) and the homogeneous DLT on the corrected
+// matches.  OpenCV finds the six roots of the stationarity polynomial with cvSolvePoly; here:
+// Laguerre iterations with deflation and a polishing pass on the un-deflated polynomial
+// (complex float64), which reaches the same roots to rounding.
+struct cplx { double re, im; };
+__host__ __device__ inline cplx cmk(double r, double i) { cplx c; c.re = r; c.im = i; return c; }
+__host__ __device__ inline cplx cadd(cplx a, cplx b) { return cmk(a.re + b.re, a.im + b.im); }
+__host__ __device__ inline cplx csub(cplx a, cplx b) { return cmk(a.re - b.re, a.im - b.im); }
+__host__ __device__ inline cplx cmul(cplx a, cplx b) {
+  return cmk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+__host__ __device__ inline cplx cscale(cplx a, double k) { return cmk(a.re * k, a.im * k); }
+__host__ __device__ inline double cabs2(cplx a) { return hypot(a.re, a.im); }
+__host__ __device__ inline cplx cdiv(cplx a, cplx b) {       // Smith's algorithm
+  if (fabs(b.re) >= fabs(b.im)) {
+    const double r = b.im / b.re, den = b.re + r * b.im;
+    return cmk((a.re + r * a.im) / den, (a.im - r * a.re) / den);
+  }
+  const double r = b.re / b.im, den = b.im + r * b.re;
+  return cmk((a.re * r + a.im) / den, (a.im * r - a.re) / den);
+}
+__host__ __device__ inline cplx csqrt2(cplx z) {
+  if (z.re == 0.0 && z.im == 0.0) return cmk(0.0, 0.0);
+  const double x = fabs(z.re), y = fabs(z.im);
+  double w;
+  if (x >= y) { const double r = y / x; w = sqrt(x) * sqrt(0.5 * (1.0 + sqrt(1.0 + r * r))); }
+  else { const double r = x / y; w = sqrt(y) * sqrt(0.5 * (r + sqrt(1.0 + r * r))); }
+  if (z.re >= 0.0) return cmk(w, z.im / (2.0 * w));
+  return cmk(y / (2.0 * w), z.im >= 0.0 ? w : -w);
+}
+
+// one root of sum_{k<=m} a[k] x^k by Laguerre's method, starting from (and returned in) x
+__host__ __device__ inline void laguerre(const cplx* a, int m, cplx& x) {
+  const double frac[9] = {0.0, 0.5, 0.25, 0.75, 0.13, 0.38, 0.62, 0.88, 1.0};
+  for (int iter = 1; iter <= 80; ++iter) {
+    cplx b = a[m], d = cmk(0, 0), f = cmk(0, 0);
+    double err = cabs2(b);
+    const double abx = cabs2(x);
+    for (int j = m - 1; j >= 0; --j) {
+      f = cadd(cmul(x, f), d);
+      d = cadd(cmul(x, d), b);
+      b = cadd(cmul(x, b), a[j]);
+      err = cabs2(b) + abx * err;
+    }
+    if (cabs2(b) <= err * 2.0e-16) return;                 // on the root to rounding
+    const cplx g = cdiv(d, b), g2 = cmul(g, g);
+    const cplx h = csub(g2, cscale(cdiv(f, b), 2.0));
+    const cplx sq = csqrt2(cscale(csub(cscale(h, (double)m), g2), (double)(m - 1)));
+    cplx gp = cadd(g, sq);
+    const cplx gm = csub(g, sq);
+    const double abp = cabs2(gp), abm = cabs2(gm);
+    if (abp < abm) gp = gm;
+    cplx dx;
+    if (fmax(abp, abm) > 0.0) dx = cdiv(cmk((double)m, 0.0), gp);
+    else dx = cscale(cmk(cos((double)iter), sin((double)iter)), 1.0 + abx);
+    const cplx x1 = csub(x, dx);
+    if (x.re == x1.re && x.im == x1.im) return;
+    if (iter % 10) x = x1;
+    else x = csub(x, cscale(dx, frac[(iter / 10) % 9]));
+  }
+}
+
+// real parts of the roots of the real polynomial sum_{k<=6} k[k] t^k (leading zeros stripped)
+__host__ __device__ inline int poly6_root_reals(const double* k, double* re) {
+  int m = 6;
+  double big = 0.0;
+  for (int i = 0; i <= 6; ++i) big = fmax(big, fabs(k[i]));
+  while (m > 0 && fabs(k[m]) <= big * 1e-300) --m;
+  if (m == 0) return 0;
+  cplx a[7], ad[7];
+  for (int i = 0; i <= m; ++i) { a[i] = cmk(k[i], 0.0); ad[i] = a[i]; }
+  cplx roots[6];
+  for (int j = m; j >= 1; --j) {
+    cplx x = cmk(0.0, 0.0);
+    laguerre(ad, j, x);
+    if (fabs(x.im) <= 4.0e-16 * fabs(x.re)) x.im = 0.0;
+    roots[j - 1] = x;
+    cplx b = ad[j];
+    for (int jj = j - 1; jj >= 0; --jj) {                  // forward deflation
+      const cplx c = ad[jj];
+      ad[jj] = b;
+      b = cadd(cmul(x, b), c);
+    }
+  }
+  for (int j = 0; j < m; ++j) {
+    laguerre(a, m, roots[j]);                              // polish on the full polynomial
+    re[j] = roots[j].re;
+  }
+  return m;
+}
+
+// [t]x R of the canonical pair P2_full * inv(P1_full)  (triangulation.py:198-204)
+__host__ __device__ inline void fundamental_from_P(const double* P1, const double* P2, double* F) {
+  // inv([M p; 0 1]) = [M^-1  -M^-1 p; 0 1]
+  const double m00 = P1[0], m01 = P1[1], m02 = P1[2], m10 = P1[4], m11 = P1[5], m12 = P1[6],
+               m20 = P1[8], m21 = P1[9], m22 = P1[10];
+  const double c00 = m11 * m22 - m12 * m21, c01 = m12 * m20 - m10 * m22, c02 = m10 * m21 - m11 * m20;
+  const double det = m00 * c00 + m01 * c01 + m02 * c02;
+  double Mi[3][3];
+  Mi[0][0] = c00 / det; Mi[0][1] = (m02 * m21 - m01 * m22) / det; Mi[0][2] = (m01 * m12 - m02 * m11) / det;
+  Mi[1][0] = c01 / det; Mi[1][1] = (m00 * m22 - m02 * m20) / det; Mi[1][2] = (m02 * m10 - m00 * m12) / det;
+  Mi[2][0] = c02 / det; Mi[2][1] = (m01 * m20 - m00 * m21) / det; Mi[2][2] = (m00 * m11 - m01 * m10) / det;
+  double R[3][3], t[3];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c)
+      R[r][c] = P2[r * 4 + 0] * Mi[0][c] + P2[r * 4 + 1] * Mi[1][c] + P2[r * 4 + 2] * Mi[2][c];
+    t[r] = P2[r * 4 + 3] - (R[r][0] * P1[3] + R[r][1] * P1[7] + R[r][2] * P1[11]);
+  }
+  for (int c = 0; c < 3; ++c) {                            // F[:,c] = t x R[:,c]
+    F[0 * 3 + c] = t[1] * R[2][c] - t[2] * R[1][c];
+    F[1 * 3 + c] = t[2] * R[0][c] - t[0] * R[2][c];
+    F[2 * 3 + c] = t[0] * R[1][c] - t[1] * R[0][c];
+  }
+}
+
+// cv2.correctMatches for one match (u1, u2 updated in place)
+__host__ __device__ inline void correct_match(const double* F, double* u1, double* u2) {
+  const double x1 = u1[0], y1 = u1[1], x2 = u2[0], y2 = u2[1];
+  // TFT = T2i^T F T1i with T = [1 0 x; 0 1 y; 0 0 1]
+  double G[3][3];
+  for (int r = 0; r < 3; ++r) {
+    G[r][0] = F[r * 3 + 0];
+    G[r][1] = F[r * 3 + 1];
+    G[r][2] = F[r * 3 + 0] * x1 + F[r * 3 + 1] * y1 + F[r * 3 + 2];
+  }
+  double T[3][3];
+  for (int c = 0; c < 3; ++c) {
+    T[0][c] = G[0][c];
+    T[1][c] = G[1][c];
+    T[2][c] = x2 * G[0][c] + y2 * G[1][c] + G[2][c];
+  }
+  // epipoles: right null vector = cross product of the two most independent rows, left null
+  // vector likewise from the columns (OpenCV takes them from the SVD of the rank-2 matrix)
+  auto null_of = [&](bool rows, double (&e)[3]) {
+    double best = -1.0;
+    for (int i = 0; i < 3; ++i) {
+      const int j = (i + 1) % 3;
+      double a[3], b[3], c[3];
+      for (int k = 0; k < 3; ++k) { a[k] = rows ? T[i][k] : T[k][i]; b[k] = rows ? T[j][k] : T[k][j]; }
+      c[0] = a[1] * b[2] - a[2] * b[1];
+      c[1] = a[2] * b[0] - a[0] * b[2];
+      c[2] = a[0] * b[1] - a[1] * b[0];
+      const double n = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+      if (n > best) { best = n; e[0] = c[0]; e[1] = c[1]; e[2] = c[2]; }
+    }
+    const double s = sqrt(e[0] * e[0] + e[1] * e[1]);
+    e[0] /= s; e[1] /= s; e[2] /= s;
+  };
+  double e1[3], e2[3];
+  null_of(true, e1);
+  null_of(false, e2);
+  // RF = R2 TFT R1^T, R = [ex ey 0; -ey ex 0; 0 0 1]
+  double H[3][3];
+  for (int r = 0; r < 3; ++r) {                            // H = TFT R1^T
+    H[r][0] = T[r][0] * e1[0] + T[r][1] * e1[1];
+    H[r][1] = -T[r][0] * e1[1] + T[r][1] * e1[0];
+    H[r][2] = T[r][2];
+  }
+  const double a = -e2[1] * H[0][1] + e2[0] * H[1][1], b = -e2[1] * H[0][2] + e2[0] * H[1][2];
+  const double c = H[2][1], d = H[2][2];
+  const double f1 = e1[2], f2 = e2[2];
+  // g(t) = t((at+b)^2 + f2^2(ct+d)^2)^2 - (ad-bc)(1+f1^2 t^2)^2 (at+b)(ct+d), ascending powers
+  const double q0 = b * b + f2 * f2 * d * d, q1 = 2.0 * (a * b + f2 * f2 * c * d),
+               q2 = a * a + f2 * f2 * c * c;
+  const double qq[5] = {q0 * q0, 2.0 * q0 * q1, 2.0 * q0 * q2 + q1 * q1, 2.0 * q1 * q2, q2 * q2};
+  const double w = a * d - b * c, ff = f1 * f1;
+  const double r0 = b * d, r1 = a * d + b * c, r2 = a * c;              // (at+b)(ct+d)
+  const double p4[5] = {1.0, 0.0, 2.0 * ff, 0.0, ff * ff};               // (1+f1^2 t^2)^2
+  double k[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 5; ++i) k[i + 1] += qq[i];
+  for (int i = 0; i < 5; ++i) {
+    k[i] -= w * p4[i] * r0;
+    k[i + 1] -= w * p4[i] * r1;
+    k[i + 2] -= w * p4[i] * r2;
+  }
+  double re[6];
+  const int nr = poly6_root_reals(k, re);
+  double smin = DBL_MAX, tmin = 0.0;
+  for (int i = 0; i < nr; ++i) {
+    const double t = re[i];
+    const double n1 = c * t + d, n0 = a * t + b;
+    const double sv = t * t / (1.0 + ff * t * t) + n1 * n1 / (n0 * n0 + f2 * f2 * n1 * n1);
+    if (sv < smin) { smin = sv; tmin = t; }
+  }
+  const double sinf = 1.0 / ff + c * c / (a * a + f2 * f2 * c * c);
+  double l1[3], l2[3];
+  if (sinf < smin) {                                       // minimum at t = infinity
+    l1[0] = f1; l1[1] = 0.0; l1[2] = -1.0;
+    l2[0] = -f2 * c; l2[1] = a; l2[2] = c;
+  } else {
+    l1[0] = tmin * f1; l1[1] = 1.0; l1[2] = -tmin;
+    l2[0] = -f2 * (c * tmin + d); l2[1] = a * tmin + b; l2[2] = c * tmin + d;
+  }
+  // closest points to the origin on the two lines, rotated and translated back
+  const double h1[3] = {-l1[0] * l1[2], -l1[1] * l1[2], l1[0] * l1[0] + l1[1] * l1[1]};
+  const double h2[3] = {-l2[0] * l2[2], -l2[1] * l2[2], l2[0] * l2[0] + l2[1] * l2[1]};
+  const double g1[3] = {e1[0] * h1[0] - e1[1] * h1[1], e1[1] * h1[0] + e1[0] * h1[1], h1[2]};   // R1^T h1
+  const double g2[3] = {e2[0] * h2[0] - e2[1] * h2[1], e2[1] * h2[0] + e2[0] * h2[1], h2[2]};
+  u1[0] = (g1[0] + x1 * g1[2]) / g1[2];
+  u1[1] = (g1[1] + y1 * g1[2]) / g1[2];
+  u2[0] = (g2[0] + x2 * g2[2]) / g2[2];
+  u2[1] = (g2[1] + y2 * g2[2]) / g2[2];
+}
+
 __global__ void triangulate_kernel(const double* __restrict__ u1, const double* __restrict__ u2,
                                    int stride_u, const double* __restrict__ P1,
                                    const double* __restrict__ P2, int NP, int J, int method,
@@ -113,11 +319,16 @@ __global__ void triangulate_kernel(const double* __restrict__ u1, const double* 
   double p1[12], p2[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) { p1[k] = P1[pair * 12 + k]; p2[k] = P2[pair * 12 + k]; }
-  const double a1[2] = {u1[(int64_t)idx * stride_u], u1[(int64_t)idx * stride_u + 1]};
-  const double a2[2] = {u2[(int64_t)idx * stride_u], u2[(int64_t)idx * stride_u + 1]};
+  double a1[2] = {u1[(int64_t)idx * stride_u], u1[(int64_t)idx * stride_u + 1]};
+  double a2[2] = {u2[(int64_t)idx * stride_u], u2[(int64_t)idx * stride_u + 1]};
   double x[3];
   int st;
-  if (method == 0) {
+  if (method == 3) {   // triangulation.py:184-220: optimal correction, then the homogeneous DLT
+    double F[9];
+    fundamental_from_P(p1, p2, F);
+    correct_match(F, a1, a2);
+  }
+  if (method == 0 || method == 3) {
     // triangulation.py:22 cv2.triangulatePoints: A rows x*P[2]-P[0], y*P[2]-P[1]
     double A[4][4], V[4][4];
 #pragma unroll
@@ -463,7 +674,7 @@ extern "C" __attribute__((visibility("default"))) int epb_triangulate(const doub
                                int32_t* status, epb_stream_t stream) {
   EPB_CHECK_ARG(u1 && u2 && P1 && P2 && X);
   EPB_CHECK_ARG(NP >= 0 && J >= 0 && stride_u >= 2);
-  EPB_CHECK_ARG(method >= 0 && method <= 2);
+  EPB_CHECK_ARG(method >= 0 && method <= 3);
   if (NP * J == 0) return EPB_OK;
   const int n = NP * J;
   triangulate_kernel<<<(n + 63) / 64, 64, 0, as_stream(stream)>>>(u1, u2, stride_u, P1, P2, NP, J,

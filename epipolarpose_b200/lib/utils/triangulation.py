@@ -6,15 +6,18 @@ linear_LS_triangulation (:34-97) and iterative_LS_triangulation (:104-181), plus
 set_triangl_output_dtype (:226-232).  The arithmetic (float64 one-sided Jacobi
 SVD per joint) runs in the sm_100a kernel epb_triangulate; numpy in / numpy out
 like the reference.  `triangulate_pairs` is the batched tensor API the training
-loop uses (no host round trip).  polynomial_triangulation (Hartley-Sturm) is
-listed as "next" in SURVEY.md section 8(f) and raises NotImplementedError."""
+loop uses (no host round trip).  polynomial_triangulation (:184-220: fundamental matrix
+from the projection matrices, cv2.correctMatches = Hartley-Sturm optimal correction, then
+the homogeneous DLT) runs as method "polynomial" of the same kernel; the reference's 8-point
+fallback for an all-NaN correction (:215-217, a purely sideways camera pair) is not built:
+the NaNs are returned with status False."""
 import numpy as np
 import torch
 
 from epipolarpose_b200 import ops as _ops
 
 _backend = [_ops]
-METHODS = {"linear_eigen": 0, "linear_LS": 1, "iterative_LS": 2,
+METHODS = {"linear_eigen": 0, "linear_LS": 1, "iterative_LS": 2, "polynomial": 3,
            "eigen": 0, "ls": 1, "iterative": 2}
 
 output_dtype = float
@@ -73,4 +76,5 @@ def iterative_LS_triangulation(u1, P1, u2, P2, tolerance=3.e-5):
 
 
 def polynomial_triangulation(u1, P1, u2, P2):
-    raise NotImplementedError("polynomial (Hartley-Sturm) triangulation: SURVEY.md 8(f) 'next'")
+    x, st = _run(u1, P1, u2, P2, "polynomial")
+    return x.astype(output_dtype), st.astype(bool)

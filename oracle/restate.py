@@ -332,6 +332,80 @@ def iterative_LS_triangulation(u1, P1, u2, P2, tolerance=3.e-5):
 # a6/a12/a14/a15: cameras, pairing, projection to labels, self_supervision
 # --------------------------------------------------------------------------
 
+def correct_matches(F, u1, u2):
+    """cv2.correctMatches restated (OpenCV calib3d triangulate.cpp, Hartley-Sturm optimal
+    correction, Hartley & Zisserman Alg. 12.1; the reference calls it at
+    lib/utils/triangulation.py:212): per match, translate both points to the origin, rotate
+    the epipoles onto the x axes, minimise s(t) = t^2/(1+f1^2 t^2) + (ct+d)^2/((at+b)^2 +
+    f2^2 (ct+d)^2) over the real parts of the roots of the degree-6 stationarity polynomial and
+    the asymptote t = inf, and map the closest points on the two epipolar lines back.
+    u1, u2 [N,2] float64 -> corrected (u1, u2)."""
+    F = np.asarray(F, dtype=np.float64)
+    u1 = np.asarray(u1, dtype=np.float64)
+    u2 = np.asarray(u2, dtype=np.float64)
+    o1, o2 = np.empty_like(u1), np.empty_like(u2)
+    for p in range(len(u1)):
+        x1, y1, x2, y2 = u1[p, 0], u1[p, 1], u2[p, 0], u2[p, 1]
+        T1i = np.array([[1, 0, x1], [0, 1, y1], [0, 0, 1.0]])
+        T2i = np.array([[1, 0, x2], [0, 1, y2], [0, 0, 1.0]])
+        TFT = T2i.T @ F @ T1i
+        U, _, Vt = np.linalg.svd(TFT)
+        e1 = Vt[2] / np.sqrt(Vt[2, 0] ** 2 + Vt[2, 1] ** 2)          # right epipole, F e1 = 0
+        e2 = U[:, 2] / np.sqrt(U[0, 2] ** 2 + U[1, 2] ** 2)          # left epipole, e2^T F = 0
+        R1 = np.array([[e1[0], e1[1], 0], [-e1[1], e1[0], 0], [0, 0, 1.0]])
+        R2 = np.array([[e2[0], e2[1], 0], [-e2[1], e2[0], 0], [0, 0, 1.0]])
+        RF = R2 @ TFT @ R1.T
+        f1, f2 = e1[2], e2[2]
+        a, b, c, d = RF[1, 1], RF[1, 2], RF[2, 1], RF[2, 2]
+        # g(t) = t((at+b)^2 + f2^2(ct+d)^2)^2 - (ad-bc)(1+f1^2 t^2)^2 (at+b)(ct+d)
+        q = np.polyadd(np.polymul([a, b], [a, b]), f2 * f2 * np.polymul([c, d], [c, d]))
+        g = np.polysub(np.polymul([1.0, 0.0], np.polymul(q, q)),
+                       (a * d - b * c) * np.polymul(np.polymul([f1 * f1, 0, 1.0], [f1 * f1, 0, 1.0]),
+                                                    np.polymul([a, b], [c, d])))
+        cand = [r.real for r in np.roots(g)]
+
+        def cost(t):
+            return t * t / (1 + f1 * f1 * t * t) + (c * t + d) ** 2 / ((a * t + b) ** 2 + f2 * f2 * (c * t + d) ** 2)
+        s_min, t_min = np.inf, np.inf
+        for t in cand:
+            sv = cost(t)
+            if sv < s_min:
+                s_min, t_min = sv, t
+        s_inf = 1.0 / (f1 * f1) + c * c / (a * a + f2 * f2 * c * c)
+        if s_inf < s_min:
+            # OpenCV evaluates the asymptote but keeps the finite minimiser's lines only when it
+            # wins; at t = inf the lines are l1 = (f1, 0, -1), l2 = (-f2 c, a, c)
+            l1 = np.array([f1, 0.0, -1.0])
+            l2 = np.array([-f2 * c, a, c])
+        else:
+            l1 = np.array([t_min * f1, 1.0, -t_min])
+            l2 = np.array([-f2 * (c * t_min + d), a * t_min + b, c * t_min + d])
+        xh1 = np.array([-l1[0] * l1[2], -l1[1] * l1[2], l1[0] ** 2 + l1[1] ** 2])
+        xh2 = np.array([-l2[0] * l2[2], -l2[1] * l2[2], l2[0] ** 2 + l2[1] ** 2])
+        n1 = T1i @ R1.T @ xh1
+        n2 = T2i @ R2.T @ xh2
+        o1[p] = n1[:2] / n1[2]
+        o2[p] = n2[:2] / n2[2]
+    return o1, o2
+
+
+def fundamental_from_projections(P1, P2):
+    """lib/utils/triangulation.py:198-204: canonical P = P2_full * inv(P1_full), F = [t]x R."""
+    P1f, P2f = np.eye(4), np.eye(4)
+    P1f[0:3, :] = np.asarray(P1, dtype=np.float64)[0:3, :]
+    P2f[0:3, :] = np.asarray(P2, dtype=np.float64)[0:3, :]
+    Pc = P2f.dot(np.linalg.inv(P1f))
+    return np.cross(Pc[0:3, 3], Pc[0:3, 0:3], axisb=0).T
+
+
+def polynomial_triangulation(u1, P1, u2, P2):
+    """lib/utils/triangulation.py:184-220 (the 8-point fallback for an all-NaN correction,
+    :215-217, is not restated: it needs >= 8 matches and a degenerate camera pair)."""
+    F = fundamental_from_projections(P1, P2)
+    n1, n2 = correct_matches(F, np.asarray(u1, dtype=np.float64)[:, :2], np.asarray(u2, dtype=np.float64)[:, :2])
+    return linear_eigen_triangulation(n1, P1, n2, P2)
+
+
 def projection_matrix(R, T, f, c):
     """lib/utils/cameras.py:120-131,149-150: K.[R | R.(-T)] float64 3x4."""
     R = np.asarray(R, dtype=np.float64)

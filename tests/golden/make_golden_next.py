@@ -1,9 +1,11 @@
-"""Golden vectors of the H36M evaluation protocol, produced by the
-UNMODIFIED reference: lib/dataset/h36m.py::H36M_Integral.evaluate is called as an unbound
+"""Golden vectors of the SURVEY.md 8(f) "next" rows built so far -- the H36M evaluation protocol
+(row 2) and polynomial triangulation (row 3) -- produced by the UNMODIFIED reference:
+lib/utils/triangulation.py::polynomial_triangulation (which calls cv2.correctMatches of the
+installed OpenCV) on the seeded camera pairs of tests/golden_inputs.py::triangulation_case; lib/dataset/h36m.py::H36M_Integral.evaluate is called as an unbound
 method on a stand-in `self` carrying only the fields it reads (db, cfg.DATASET.MPII_ORDER,
 cfg.DEBUG.DEBUG, root), and lib/utils/prep_h36m.py::compute_similarity_transform directly.
 Run in the build container only:
-    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_eval.py"""
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_next.py"""
 import contextlib
 import importlib
 import io
@@ -47,3 +49,24 @@ rec["proc_b"] = np.array([q[3] for q in proc])
 rec["proc_c"] = np.stack([q[4] for q in proc])
 np.savez_compressed(os.path.join(OUT, "h36m_eval.npz"), **rec)
 print("wrote h36m_eval", {k: v.shape for k, v in rec.items()})
+
+# ---- polynomial (optimal) triangulation, triangulation.py:184-220
+import cv2  # noqa: E402
+tri = importlib.import_module("lib.utils.triangulation")
+u1, u2, P1, P2, Xtrue = gi.triangulation_case()
+xs, sts, c1s, c2s = [], [], [], []
+for i in range(len(u1)):
+    x, st = tri.polynomial_triangulation(u1[i], P1[i], u2[i], P2[i])
+    xs.append(x)
+    sts.append(st)
+    F = restate.fundamental_from_projections(P1[i], P2[i])
+    c1, c2 = cv2.correctMatches(F, u1[i].reshape(1, -1, 2), u2[i].reshape(1, -1, 2))
+    c1s.append(c1[0])
+    c2s.append(c2[0])
+u1e, u2e = gi.exact_projections(P1, P2, Xtrue)
+exact = np.asarray([tri.polynomial_triangulation(u1e[i], P1[i], u2e[i], P2[i])[0] for i in range(len(u1))])
+np.savez_compressed(os.path.join(OUT, "triangulation_poly.npz"), x=np.asarray(xs),
+                    status=np.asarray(sts).astype(np.int64), corrected_u1=np.asarray(c1s),
+                    corrected_u2=np.asarray(c2s), exact=exact, cv2_version=np.array(cv2.__version__))
+print("wrote triangulation_poly", np.asarray(xs).shape, "exact-recovery error",
+      float(np.abs(exact - Xtrue).max()))

@@ -203,6 +203,32 @@ def test_triangulators_golden(golden, dev):
         assert np.max(np.abs(Xg.cpu().numpy() - X)) <= 1e-6             # known answer
 
 
+def test_polynomial_triangulation_golden(golden, dev):
+    """method "polynomial" (F from the projection matrices, Hartley-Sturm correction with the
+    Laguerre root finder, homogeneous DLT) against the unmodified reference
+    polynomial_triangulation / cv2.correctMatches: <= 1e-4 mm, status equal; exact projections
+    recover the 3-D points; corrected matches agree with the other triangulators' input when the
+    observations are noise free."""
+    import lib.utils.triangulation as tri
+    g = golden("triangulation_poly")
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    for i in range(len(u1)):
+        x, st = tri.polynomial_triangulation(u1[i], P1[i], u2[i], P2[i])
+        assert np.max(np.abs(x - g["x"][i])) <= 1e-4                        # mm
+        assert np.array_equal(np.asarray(st).astype(np.int64), g["status"][i])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    u1e, u2e = gi.exact_projections(P1, P2, X)
+    Xg, _ = tri.triangulate_pairs(t(u1e), t(u2e), t(P1), t(P2), "polynomial")
+    assert np.max(np.abs(Xg.cpu().numpy() - X)) <= 1e-6
+    assert np.max(np.abs(Xg.cpu().numpy() - g["exact"])) <= 1e-6
+    # batched: 64 pairs against the numpy oracle
+    u1b, u2b, P1b, P2b, _ = gi.triangulation_case(n_pairs=64, J=17, seed=98)
+    Xb, _ = tri.triangulate_pairs(t(u1b), t(u2b), t(P1b), t(P2b), "polynomial")
+    for i in range(0, 64, 9):
+        xr, _ = restate.polynomial_triangulation(u1b[i], P1b[i], u2b[i], P2b[i])
+        assert np.max(np.abs(Xb[i].cpu().numpy() - xr)) <= 1e-4
+
+
 def test_triangulation_large_vs_oracle(dev):
     import lib.utils.triangulation as tri
     u1, u2, P1, P2, X = gi.triangulation_case(n_pairs=64, J=17, seed=99)

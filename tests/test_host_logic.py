@@ -240,6 +240,25 @@ def test_h36m_eval_kernel_body_on_host(host_geometry, mpii):
     assert np.max(np.abs(poses - o["poses"])) <= 1e-9
 
 
+def test_polynomial_correction_kernel_body_on_host(host_geometry):
+    """fundamental_from_P + correct_match of csrc/geometry.cu (Laguerre root finder, float64),
+    executed on the CPU, against cv2.correctMatches outputs stored by the reference run."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "triangulation_poly.npz")))
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    for i in range(len(u1)):
+        N = len(u1[i])
+        a = host_geometry(["correct", N], P1[i], P2[i], u1[i], u2[i])
+        F, n1, n2 = a[:9].reshape(3, 3), a[9:9 + 2 * N].reshape(N, 2), a[9 + 2 * N:].reshape(N, 2)
+        Fo = restate.fundamental_from_projections(P1[i], P2[i])
+        assert np.max(np.abs(F - Fo)) <= 1e-12 * np.abs(Fo).max()
+        assert np.max(np.abs(n1 - g["corrected_u1"][i])) <= 1e-9          # px
+        assert np.max(np.abs(n2 - g["corrected_u2"][i])) <= 1e-9
+    # exact projections are a fixed point of the correction
+    u1e, u2e = gi.exact_projections(P1, P2, X)
+    a = host_geometry(["correct", 17], P1[0], P2[0], u1e[0], u2e[0])
+    assert np.max(np.abs(a[9:9 + 34].reshape(17, 2) - u1e[0])) <= 1e-8
+
+
 def test_fused_optimizers_match_torch():
     import lib.utils.utils as U
     U._backend[0] = emul_ops

@@ -112,7 +112,7 @@ def test_network_restatement(golden, tag):
 
 def test_h36m_evaluation_protocol(golden):
     """oracle/restate.py::h36m_evaluate / compute_similarity_transform against the outputs of
-    the unmodified H36M_Integral.evaluate (tests/golden/make_golden_eval.py)."""
+    the unmodified H36M_Integral.evaluate (tests/golden/make_golden_next.py)."""
     g = golden("h36m_eval")
     pred, gt, pelvis, fl, c_p = gi.eval_case()
     for mpii, tag in ((False, "h36m"), (True, "mpii")):
@@ -127,3 +127,22 @@ def test_h36m_evaluation_protocol(golden):
         assert abs(d - g["proc_d"][i]) <= 1e-12 and abs(b - g["proc_b"][i]) <= 1e-12
         assert np.max(np.abs(Z - g["proc_Z"][i])) <= 1e-9 and np.max(np.abs(T - g["proc_T"][i])) <= 1e-12
         assert np.max(np.abs(c - g["proc_c"][i])) <= 1e-9
+
+
+def test_polynomial_triangulation(golden):
+    """restate.correct_matches / polynomial_triangulation against cv2.correctMatches and the
+    unmodified reference polynomial_triangulation (tests/golden/make_golden_next.py)."""
+    g = golden("triangulation_poly")
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    for i in range(len(u1)):
+        F = restate.fundamental_from_projections(P1[i], P2[i])
+        n1, n2 = restate.correct_matches(F, u1[i], u2[i])
+        assert np.max(np.abs(n1 - g["corrected_u1"][i])) <= 1e-9          # px
+        assert np.max(np.abs(n2 - g["corrected_u2"][i])) <= 1e-9
+        x, st = restate.polynomial_triangulation(u1[i], P1[i], u2[i], P2[i])
+        assert np.max(np.abs(x - g["x"][i])) <= 1e-6                      # mm
+        assert np.array_equal(np.asarray(st).astype(np.int64), g["status"][i])
+        # corrected matches satisfy the epipolar constraint exactly
+        h1 = np.concatenate([n1, np.ones((len(n1), 1))], 1)
+        h2 = np.concatenate([n2, np.ones((len(n2), 1))], 1)
+        assert np.max(np.abs(np.einsum("ni,ij,nj->n", h2, F, h1))) <= 1e-9 * np.abs(F).max() * 1e6

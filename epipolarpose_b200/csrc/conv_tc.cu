@@ -7,14 +7,17 @@
 // One persistent CTA per SM, warp-specialised:
 //   warps 0-15 A producers: gather 128 pixel rows x 32 channels (128-byte rows),
 //              fused BN+ReLU, split into TF32 hi (+ lo for the 3xTF32 mode) and
-//              store into the SWIZZLE_128B K-major smem layout tcgen05 reads;
+//              store into the SWIZZLE_128B K-major smem layout tcgen05 reads; the
+//              k-blocks of all tiles of the CTA form ONE stream that the producer
+//              groups take round-robin (warp-private row tables, no CTA barrier);
 //   warp  16   B producer: TMA loads of the packed weight tile (hi / lo planes);
 //   warp  17   MMA issuer: one thread issues tcgen05.mma kind::tf32 (M=128,
 //              N=BN, K=8) with FP32 accumulators in TMEM (double buffered);
-//   warps 18-21 epilogue: tcgen05.ld TMEM -> registers -> bias / accumulate ->
-//              global, plus per-channel sum / sum-of-squares for the following
-//              BatchNorm (warp transpose-reduce, smem, one double atomic per
-//              column per tile).
+//   warps 18-21 epilogue: tcgen05.ld TMEM -> registers -> bias -> smem-staged
+//              128-byte-line stores (row pointers from a per-tile smem table, rows
+//              past M clamped: branch free) / accumulate, plus per-channel sum and
+//              sum of squares for the following BatchNorm (warp-private smem
+//              slices, one double atomic per column per tile).
 // smem ring full/empty mbarriers, TMEM full/empty mbarriers; every wait is
 // bounded (trap instead of hang).
 //
@@ -34,6 +37,7 @@ constexpr int kProducerWarps = 16;      // G groups take k-blocks round-robin (C
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (kProducerWarps + 2 + kEpiWarps);   // 704
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kRowTab = kProducerWarps * 32;   // one private table of <= 32 rows per producer warp
 
 // PAIR: two CTAs of a cluster work on one 256-row M tile with tcgen05 cta_group::2; each
 // holds its own 128 A rows and HALF of the B tile's N rows, which halves the weight bytes
@@ -61,14 +65,14 @@ struct Cfg {
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;       // one 32x32 block per epilogue warp
   static constexpr int STAT_BYTES = kEpiWarps * 2 * BN * 4;     // per-warp [sum | sum of squares][BN]
   static constexpr int PTAB_BYTES = kEpiWarps * 32 * 8;         // output row pointer of every TMEM lane
-  static constexpr int SMEM = S * STAGE + 1024 /*align*/ + 1024 /*barriers*/ + BM * 3 * 4 /*rowinfo*/ +
+  static constexpr int SMEM = S * STAGE + 1024 /*align*/ + 1024 /*barriers*/ + kRowTab * 12 /*rowinfo*/ +
                               STAT_BYTES + EPI_BYTES + PTAB_BYTES;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 struct RowInfo {
-  int off0[BM];                  // ((n*Hi + i*is)*Wi + j*is)*Cin : element offset of the un-shifted pixel
-  unsigned long long vmask[BM];  // bit t set <=> tap t reads inside the image (0 for rows past M)
+  int off0[kRowTab];                  // ((n*Hi + i*is)*Wi + j*is)*Cin : element offset of the un-shifted pixel
+  unsigned long long vmask[kRowTab];  // bit t set <=> tap t reads inside the image (0 for rows past M)
 };
 
 template <int BN, int NS, bool PAIR>
@@ -130,7 +134,16 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < kProducerWarps) {
-    // =================================================== A producers (512 threads)
+    // =================================================== A producers (512 threads), flat stream
+    // The k-blocks of ALL tiles of this CTA form one stream n = 0, 1, 2, ...; group g takes
+    // n = g, g + G, ... (ring slot n % S).  A warp only ever touches its own RPW pixel rows,
+    // so the row geometry lives in a WARP-PRIVATE table that the warp rebuilds when its issue
+    // cursor enters a new tile: no CTA-wide barrier between tiles, and the loads of the next
+    // tile's first k-blocks are in flight while the current tile is still being converted
+    // (with two bar.sync of all 16 producer warps per tile, 1x1 layers with 2..8 k-blocks per
+    // tile spent 20-30 % of their warp-stall samples at those barriers; measured gain 4-9 % on
+    // the K <= 256 layers, profiles/r1_layer_sweep_flat_producer.md).
+    //
     // L2 prefetch policy of the A stream (measured on the bench layers, tools/tune_sweep.sh):
     //  * dense 1x1 layers (phase-grid pixel == input pixel): ROLLING prefetch kPfDist k-blocks
     //    ahead of the loads, crossing into this CTA's next tiles -- bounded footprint;
@@ -138,26 +151,37 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
     //    of <= 1 KB: with wider rows 148 CTAs x 2 tiles overflow L2 and the prefetch costs
     //    more than it saves (Cin = 512: -9 %, Cin = 1024: -11 %).
     constexpr int kPfDist = 6;
+    constexpr int G = C::G, D = C::D, NQ = C::NQ, RPW = BM / C::W;
     const bool roll = (tune & 1) && g.T == 1 && g.is == 1 && g.Hp == g.Hi && g.Wp == g.Wi;
     const bool pf_tile = ((tune & 1) && !roll && g.Cin <= 256) || (tune & 2);
     const int dmt = (n_tiles == 1 && tile0 + tstep < total_tiles)
                         ? m_tile_of(tile0 + tstep) - m_tile_of(tile0) : 0;   // M-tile stride of this CTA
-    // every input line is read exactly once (one tap, one N tile): read it evict-first
     const bool once = (tune & 4) && g.T == 1 && n_tiles == 1;
     const float lb = g.in_relu ? 0.f : -INFINITY;
     uint64_t pol_first;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
-    const int p = threadIdx.x;                 // threads 0..127 also compute one row's geometry
     const int c4 = lane & 7;                   // 16-byte chunk within the 128-byte row
     const int rsub = lane >> 3;                // 0..3
-    int base_stage = 0;                        // ring slot / phase of the tile's k-block 0
-    uint32_t base_phase = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tstep) {
-      const int mt = m_tile_of(tile);
-      // producers of the previous tile are done reading rowinfo once all reach this barrier
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (p < BM) {
-        const int64_t m = (int64_t)mt * BM + p;
+    const int grp = warp / C::W, wg = warp % C::W;
+    int* w_off = rows->off0 + warp * 32;                   // this warp's rows wg*RPW .. +RPW-1
+    unsigned long long* w_vm = rows->vmask + warp * 32;
+    const int my_tiles = tile0 < total_tiles ? (total_tiles - tile0 + tstep - 1) / tstep : 0;
+    const long long total_kb = (long long)my_tiles * KB;
+    const int mine = (int)((total_kb - grp + G - 1) / G);  // k-blocks of this group (>= 0)
+    int i_tile = tile0, i_kb = grp, it = 0, icb = 0, i_mt = 0;
+    int p_kb = grp, pcb = 0;
+    bool i_new = true;                         // the issue cursor stands on a tile whose rows are not tabled yet
+    while (i_kb >= KB) { i_kb -= KB; i_tile += tstep; }
+    it = i_kb / CB; icb = i_kb - it * CB;
+    while (p_kb >= KB) p_kb -= KB;
+    pcb = p_kb % CB;
+    int st = grp;                              // G <= S: ring slot / phase of this group's next k-block
+    uint32_t ph = 0;
+    auto table_rows = [&]() {
+      i_mt = m_tile_of(i_tile);
+      __syncwarp();
+      if (lane < RPW) {
+        const int64_t m = (int64_t)i_mt * BM + wg * RPW + lane;
         unsigned long long vm = 0;
         int off = 0;
         if (m < M) {
@@ -171,30 +195,11 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
             if (ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi) vm |= 1ull << t;
           }
         }
-        rows->off0[p] = off;
-        rows->vmask[p] = vm;
-      }
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      // Groups take k-blocks round-robin (group = kb % G): each warp pays the per-k-block
-      // fixed costs (mbarrier wait, proxy fence, arrive) for every G-th k-block while the
-      // other groups' warps keep the sub-partition's issue slots busy.
-      constexpr int G = C::G, D = C::D, NQ = C::NQ, RPW = BM / C::W;
-      float4 buf[D][NQ];
-      unsigned okm[D];
-      const int grp = warp / C::W, wg = warp % C::W;
-      int st = (base_stage + grp) % C::S;
-      uint32_t ph = base_phase ^ (uint32_t)(((base_stage + grp) / C::S) & 1);
-      int it = 0, icb = grp, pcb = grp;          // issue cursor (tap, channel block); consume cursor
-      while (icb >= CB) { icb -= CB; ++it; }
-      while (pcb >= CB) pcb -= CB;
-      // Warm L2 for the NEXT tile of this CTA while the current one is processed: one
-      // prefetch per 128-byte line of the (un-shifted) pixel row.  These layers stream
-      // their activations from HBM exactly once; without this every k-block pays the
-      // DRAM latency with only the register buffers' bytes in flight.
-      {
-        const int ntile = tile + tstep;
-        if (pf_tile && p < BM && ntile < total_tiles && m_tile_of(ntile) != mt) {
-          const int64_t mn = (int64_t)m_tile_of(ntile) * BM + p;
+        w_off[lane] = off;
+        w_vm[lane] = vm;
+        const int ntile = i_tile + tstep;
+        if (pf_tile && grp == 0 && ntile < total_tiles && m_tile_of(ntile) != i_mt) {
+          const int64_t mn = (int64_t)m_tile_of(ntile) * BM + wg * RPW + lane;
           if (mn < M) {
             const unsigned um = (unsigned)mn;
             const unsigned j = um % (unsigned)g.Wp, qq = um / (unsigned)g.Wp;
@@ -208,133 +213,137 @@ fprop_body(const epb_conv_geom& g, const CUtensorMap* tmap_w, const float* __res
           }
         }
       }
-      auto issue = [&](float4 (&dst)[NQ], unsigned& mask) {
-        // one uniform element offset per (tap, channel block); per row only the table
-        // look-ups remain (offset of the un-shifted pixel, bit mask of in-image taps)
-        const int delta = (g.dh[it] * g.Wi + g.dw[it]) * g.Cin + icb * BKE + c4 * 4;
-        const int tap = it;
-        if (roll) {
-          int pb = icb + kPfDist, ta = 0;          // channel block / tiles ahead of this CTA
-          while (pb >= CB) { pb -= CB; ++ta; }
-          if ((ta == 0 || dmt > 0) && lane < RPW) {
-            // one prefetch instruction per warp: lane l takes row l of the warp's row block
-            const int r = wg * RPW + lane;
-            if ((int64_t)(mt + ta * dmt) * BM + r < M)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(
-                  in + ((int64_t)rows->off0[r] + (int64_t)ta * dmt * BM * g.Cin + pb * BKE)));
-          }
+      __syncwarp();
+      i_new = false;
+    };
+    float4 buf[D][NQ];
+    unsigned okm[D];
+    auto issue = [&](float4 (&dst)[NQ], unsigned& mask) {
+      if (i_new) table_rows();
+      const int delta = (g.dh[it] * g.Wi + g.dw[it]) * g.Cin + icb * BKE + c4 * 4;
+      const int tap = it;
+      if (roll) {
+        int pb = icb + kPfDist, ta = 0;          // channel block / tiles ahead of this CTA
+        while (pb >= CB) { pb -= CB; ++ta; }
+        if ((ta == 0 || dmt > 0) && lane < RPW) {
+          if ((int64_t)(i_mt + ta * dmt) * BM + wg * RPW + lane < M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                in + ((int64_t)w_off[lane] + (int64_t)ta * dmt * BM * g.Cin + pb * BKE)));
         }
-        icb += G;
-        while (icb >= CB) { icb -= CB; ++it; }
-        mask = 0;
+      }
+      mask = 0;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const int r = wg * RPW + q * 4 + rsub;
-          dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if ((rows->vmask[r] >> tap) & 1ull) {
-            const float* ap = in + ((int64_t)rows->off0[r] + delta);
-            if (once) {
-              asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                           : "=f"(dst[q].x), "=f"(dst[q].y), "=f"(dst[q].z), "=f"(dst[q].w)
-                           : "l"(ap), "l"(pol_first));
-            } else {
-              dst[q] = *reinterpret_cast<const float4*>(ap);
-            }
-            mask |= 1u << q;
-          }
-        }
-      };
-      auto process = [&](const float4 (&v)[NQ], unsigned mask) {
-        const int ch = pcb * BKE + c4 * 4;
-        pcb += G;
-        while (pcb >= CB) pcb -= CB;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in_scale) {
-          sc = *reinterpret_cast<const float4*>(in_scale + ch);
-          sh = *reinterpret_cast<const float4*>(in_shift + ch);
-        }
-        tc::mbar_wait(empty_bar(st), ph ^ 1);
-        uint8_t* a_hi = sm + st * C::STAGE;
-        float4 xv[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) xv[q] = v[q];
-        if (in_scale) {
-          // branch-free affine (+ReLU); rows that were not loaded (padding, rows past M) are
-          // post-activation zeros and are patched afterwards
-#pragma unroll
-          for (int q = 0; q < NQ; ++q) xv[q] = tc::bn_act4(xv[q], sc, sh, lb);
-          if (mask != (1u << NQ) - 1u) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-              if (!((mask >> q) & 1u)) xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const int r = wg * RPW + q * 4 + rsub;
-          const float4 x = xv[q];
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);
-          float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
-                                  tc::to_tf32(x.w));
-          *reinterpret_cast<float4*>(a_hi + off) = hi;
-          if (NS == 3) {
-            float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
-            *reinterpret_cast<float4*>(a_hi + BM * 128 + off) = lo;
-          }
-        }
-        tc::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) {
-            if (tune & 8) tc::mbar_arrive_cluster_cta(tc::mapa(full_bar(st), 0));
-            else tc::mbar_arrive_cluster(tc::mapa(full_bar(st), 0));
+      for (int q = 0; q < NQ; ++q) {
+        const int lr = q * 4 + rsub;
+        dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((w_vm[lr] >> tap) & 1ull) {
+          const float* ap = in + ((int64_t)w_off[lr] + delta);
+          if (once) {
+            asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                         : "=f"(dst[q].x), "=f"(dst[q].y), "=f"(dst[q].z), "=f"(dst[q].w)
+                         : "l"(ap), "l"(pol_first));
           } else {
-            tc::mbar_arrive(full_bar(st));
+            dst[q] = *reinterpret_cast<const float4*>(ap);
           }
+          mask |= 1u << q;
         }
-        st += G;
-        ph ^= (uint32_t)((st / C::S) & 1);
-        st %= C::S;
-      };
-      const int mine = (KB - grp + G - 1) / G;
-#ifdef EPB_DBG_SKIP_A     // bottleneck probe (tools/build_variant.py): slots are handed over unfilled
-      for (int k = 0; k < mine; ++k) {
-        tc::mbar_wait(empty_bar(st), ph ^ 1);
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) tc::mbar_arrive_cluster(tc::mapa(full_bar(st), 0));
-          else tc::mbar_arrive(full_bar(st));
-        }
-        st += G;
-        ph ^= (uint32_t)((st / C::S) & 1);
-        st %= C::S;
       }
-#else
-      if constexpr (D == 1) {
-        for (int k = 0; k < mine; ++k) {
-          issue(buf[0], okm[0]);
-          process(buf[0], okm[0]);
-        }
-      } else {
-        if (mine > 0) issue(buf[0], okm[0]);
-        for (int k0 = 0; k0 < mine; k0 += 2) {
+      i_kb += G;
+      icb += G;
+      while (icb >= CB) { icb -= CB; ++it; }
+      if (i_kb >= KB) {
+        do { i_kb -= KB; i_tile += tstep; } while (i_kb >= KB);
+        it = i_kb / CB; icb = i_kb - it * CB;
+        i_new = true;
+      }
+    };
+    auto process = [&](const float4 (&v)[NQ], unsigned mask) {
+      const int ch = pcb * BKE + c4 * 4;
+      p_kb += G;
+      pcb += G;
+      while (pcb >= CB) pcb -= CB;
+      if (p_kb >= KB) {
+        do { p_kb -= KB; } while (p_kb >= KB);
+        pcb = p_kb % CB;
+      }
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in_scale) {
+        sc = *reinterpret_cast<const float4*>(in_scale + ch);
+        sh = *reinterpret_cast<const float4*>(in_shift + ch);
+      }
+      tc::mbar_wait(empty_bar(st), ph ^ 1);
+      uint8_t* a_hi = sm + st * C::STAGE;
+      float4 xv[NQ];
 #pragma unroll
-          for (int d = 0; d < 2; ++d) {
-            const int k = k0 + d;
-            if (k < mine) {
-              if (k + 1 < mine) issue(buf[d ^ 1], okm[d ^ 1]);
-              process(buf[d], okm[d]);
-            }
-          }
+      for (int q = 0; q < NQ; ++q) xv[q] = v[q];
+      if (in_scale) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) xv[q] = tc::bn_act4(xv[q], sc, sh, lb);
+        if (mask != (1u << NQ) - 1u) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            if (!((mask >> q) & 1u)) xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-#endif
-      {   // ring position of the next tile's first k-block
-        const int tmp = base_stage + KB;
-        base_phase ^= (uint32_t)((tmp / C::S) & 1);
-        base_stage = tmp % C::S;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int r = wg * RPW + q * 4 + rsub;
+        const float4 x = xv[q];
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);
+        float4 hi = make_float4(tc::to_tf32(x.x), tc::to_tf32(x.y), tc::to_tf32(x.z),
+                                tc::to_tf32(x.w));
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        if (NS == 3) {
+          float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+          *reinterpret_cast<float4*>(a_hi + BM * 128 + off) = lo;
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) {
+          if (tune & 8) tc::mbar_arrive_cluster_cta(tc::mapa(full_bar(st), 0));
+          else tc::mbar_arrive_cluster(tc::mapa(full_bar(st), 0));
+        } else {
+          tc::mbar_arrive(full_bar(st));
+        }
+      }
+      st += G;
+      ph ^= (uint32_t)((st / C::S) & 1);
+      st %= C::S;
+    };
+#ifdef EPB_DBG_SKIP_A     // bottleneck probe (tools/build_variant.py): slots are handed over unfilled
+    for (int k = 0; k < mine; ++k) {
+      tc::mbar_wait(empty_bar(st), ph ^ 1);
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_cluster(tc::mapa(full_bar(st), 0));
+        else tc::mbar_arrive(full_bar(st));
+      }
+      st += G;
+      ph ^= (uint32_t)((st / C::S) & 1);
+      st %= C::S;
+    }
+#else
+    if constexpr (D == 1) {
+      for (int k = 0; k < mine; ++k) {
+        issue(buf[0], okm[0]);
+        process(buf[0], okm[0]);
+      }
+    } else {
+      if (mine > 0) issue(buf[0], okm[0]);
+      for (int k0 = 0; k0 < mine; k0 += 2) {
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const int k = k0 + d;
+          if (k < mine) {
+            if (k + 1 < mine) issue(buf[d ^ 1], okm[d ^ 1]);
+            process(buf[d], okm[d]);
+          }
+        }
       }
     }
+#endif
   } else if (warp == kProducerWarps) {
     // =================================================== B producer (TMA)
     if (lane == 0) {

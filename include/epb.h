@@ -252,7 +252,10 @@ int epb_patch_to_image(const float* coords, const double* box, int B, int J,
  * used), P1,P2 [NP][12] f64 row-major 3x4.  X [NP][J][3] f64, status [NP][J].
  * method 0: linear-eigen homogeneous DLT (:8-27, cv2.triangulatePoints);
  * method 1: linear LS (:34-97); method 2: iterative LS, 10 cumulative
- * re-weighting rounds, tol 3e-5 (:104-181). */
+ * re-weighting rounds, tol 3e-5 (:104-181); method 3: polynomial / optimal
+ * (:184-220): F = [t]x R of the canonical pair, cv2.correctMatches
+ * (Hartley-Sturm: degree-6 polynomial per match, roots by Laguerre iteration),
+ * then method 0 on the corrected matches. */
 int epb_triangulate(const double* u1, const double* u2, int stride_u,
                     const double* P1, const double* P2, int NP, int J,
                     int method, double tol, double* X, int32_t* status,

@@ -1,0 +1,81 @@
+"""Throughput of the small kernels around the CNN (HBM / latency bound; no tensor cores):
+fused heat-map + joint loss, H36M evaluation, the four triangulators.  One JSON line each:
+algorithmic bytes per unit / CUDA-event time, against the measured HBM peak.
+
+    python tools/bench_aux.py
+"""
+import json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "epipolarpose_b200"))
+from epipolarpose_b200 import ops
+
+dev = torch.device("cuda:0")
+peak = 6479.6
+pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(pk):
+    peak = json.load(open(pk))["hbm_gbs"]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, reps=9):
+    fn(); fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2] * 1e-3
+
+
+def line(name, units, unit_name, bytes_per_unit, t):
+    gbs = units * bytes_per_unit / t / 1e9
+    print(json.dumps({"kernel": name, "units": units, "unit": unit_name, "ms": round(t * 1e3, 4),
+                      "units_per_s": round(units / t, 1), "bytes_per_unit": bytes_per_unit,
+                      "achieved_gbs": round(gbs, 1), "hbm_peak_gbs": peak, "frac": round(gbs / peak, 4)}))
+
+
+# fused heat-map MSE + L1 joint loss: 128 / 1024 images x 17 joints x 64 x 64
+for N in (128, 1024):
+    J, HW = 17, 64 * 64
+    hm = torch.randn(N * J, HW, device=dev); tg = torch.rand(N * J, HW, device=dev)
+    wh = torch.ones(N * J, device=dev)
+    x = torch.rand(N, J * 3, device=dev) - 0.5; t = torch.rand(N, J * 3, device=dev) - 0.5
+    w = torch.ones(N, J * 3, device=dev)
+    loss = torch.empty(3, device=dev); dhm = torch.empty_like(hm); dx = torch.empty_like(x)
+    tt = timeit(lambda: ops.heatmap_joint_loss(hm, tg, wh, N * J, HW, 1.0, x, t, w, x.numel(), 1, float(N),
+                                               1.0, loss, dhm, dx))
+    line("heatmap_joint_loss N=%d" % N, N * J * HW, "heat-map element", 12, tt)
+
+# H36M evaluation: 2^18 samples x 17 joints (pred + gt 816 B, cam 40 B, metrics 72 B, per-joint 136 B, pck 68 B)
+S, J = 1 << 18, 17
+pred = torch.randn(S, J, 3, device=dev, dtype=torch.float64) * 50 + 500
+gt = pred + torch.randn(S, J, 3, device=dev, dtype=torch.float64) * 5
+pred[:, :, 2] = torch.randn(S, J, device=dev, dtype=torch.float64) * 300; gt[:, :, 2] = pred[:, :, 2] + 20
+cam = torch.tensor([1145.0, 1144.0, 512.0, 515.0, 4500.0], device=dev, dtype=torch.float64).repeat(S, 1)
+met = torch.empty(S, 9, device=dev, dtype=torch.float64); pj = torch.empty(S, J, device=dev, dtype=torch.float64)
+pck = torch.empty(S, J, device=dev, dtype=torch.int32)
+mask = sum(1 << j for j in [0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15])
+tt = timeit(lambda: ops.h36m_eval(pred, gt, cam, S, J, 0, mask, 150.0, met, pj, pck, None))
+line("h36m_eval", S, "sample", 816 + 40 + 72 + 136 + 68, tt)
+
+# triangulators: 2^16 pairs x 17 joints, 1144 B per pair
+NP, J = 1 << 16, 17
+rng = np.random.default_rng(0)
+sys.path.insert(0, ROOT)
+from oracle import restate          # camera synthesis only (bench input), not a compute path
+R, T, f, c, P = restate.synthetic_cameras(rng, 64, 4)
+X = rng.normal(0, 400, (64, J, 3))
+u1 = np.stack([restate.project(P[i, 0], X[i]) for i in range(64)]) + rng.normal(0, 3, (64, J, 2))
+u2 = np.stack([restate.project(P[i, 1], X[i]) for i in range(64)]) + rng.normal(0, 3, (64, J, 2))
+rep = NP // 64
+tu1 = torch.from_numpy(np.tile(u1, (rep, 1, 1))).to(dev); tu2 = torch.from_numpy(np.tile(u2, (rep, 1, 1))).to(dev)
+tP1 = torch.from_numpy(np.tile(P[:, 0], (rep, 1, 1))).to(dev).contiguous()
+tP2 = torch.from_numpy(np.tile(P[:, 1], (rep, 1, 1))).to(dev).contiguous()
+Xo = torch.empty(NP, J, 3, device=dev, dtype=torch.float64); st = torch.empty(NP, J, device=dev, dtype=torch.int32)
+for m, name in ((0, "linear_eigen"), (1, "linear_LS"), (2, "iterative_LS"), (3, "polynomial")):
+    tt = timeit(lambda: ops.triangulate(tu1, tu2, 2, tP1, tP2, NP, J, m, 3e-5, Xo, st), reps=5)
+    line("triangulate " + name, NP, "17-joint pair", 1144, tt)

@@ -1,0 +1,242 @@
+// Input pipeline on the device: the crop / colour / normalisation half of the reference
+// lib/utils/img_utils.py:246-298 (get_single_patch_sample) once the frame is decoded:
+//   generate_patch_image_cv (:114-127): gen_trans_from_patch_cv (:72-105, float32 point
+//   triplets, cv2.getAffineTransform = 6x6 LU in float64) + cv2.warpAffine(INTER_LINEAR,
+//   constant border 0) on uint8 BGR -> BGR->RGB (:268) -> per-channel colour scale, clip,
+//   (x - mean) / std (:277-281) -> float32 [3][ph][pw];
+// and the joint half (:283-296): joints through the same affine, depth scaling and
+// generate_joint_location_label (lib/core/integral_loss.py:170-177).
+//
+// Byte / integer work, bit-exact against OpenCV: warpAffine's fixed-point source coordinates
+// (10 fractional bits rounded per term, reduced to 5) and integer bilinear weights of sum 2^15
+// are reproduced exactly (imgproc/imgwarp.cpp).  HBM bound: 12 B written per output pixel plus
+// the touched source bytes; one thread per output pixel, x fastest (coalesced plane writes).
+// Compiled with --fmad=false: the float64 affine arithmetic rounds as on the CPU.
+#include "common.cuh"
+
+namespace {
+
+// cv::solve(A, B, DECOMP_LU) on the 6x6 system of cv2.getAffineTransform (hal::LU64f: partial
+// pivoting by largest magnitude, row operations with alpha = A[j][i] * (-1 / A[i][i]),
+// back substitution); src / dst are the three float32 point pairs.
+__host__ __device__ inline bool affine_lu6(const float (*src)[2], const float (*dst)[2], double* M) {
+  double A[6][6], b[6];
+  for (int i = 0; i < 3; ++i) {
+    const int r0 = 2 * i, r1 = 2 * i + 1;
+    for (int k = 0; k < 6; ++k) { A[r0][k] = 0.0; A[r1][k] = 0.0; }
+    A[r0][0] = A[r1][3] = (double)src[i][0];
+    A[r0][1] = A[r1][4] = (double)src[i][1];
+    A[r0][2] = A[r1][5] = 1.0;
+    b[r0] = (double)dst[i][0];
+    b[r1] = (double)dst[i][1];
+  }
+  const double eps = 2.220446049250313e-16 * 100;
+  for (int i = 0; i < 6; ++i) {
+    int k = i;
+    for (int j = i + 1; j < 6; ++j)
+      if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+    if (fabs(A[k][i]) < eps) return false;
+    if (k != i) {
+      for (int j = i; j < 6; ++j) { const double t = A[i][j]; A[i][j] = A[k][j]; A[k][j] = t; }
+      const double t = b[i]; b[i] = b[k]; b[k] = t;
+    }
+    const double d = -1.0 / A[i][i];
+    for (int j = i + 1; j < 6; ++j) {
+      const double alpha = A[j][i] * d;
+      for (int kk = i + 1; kk < 6; ++kk) A[j][kk] += alpha * A[i][kk];
+      b[j] += alpha * b[i];
+    }
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = b[i];
+    for (int kk = i + 1; kk < 6; ++kk) s -= A[i][kk] * b[kk];
+    b[i] = s / A[i][i];
+  }
+  for (int k = 0; k < 6; ++k) M[k] = b[k];
+  return true;
+}
+
+// img_utils.py:72-105 (inv = False): image -> patch transform, row-major 2x3 in M.
+// box = (c_x, c_y, bb_width, bb_height, scale, rot)
+__host__ __device__ inline bool patch_affine_fwd(const double* box, double patch_w, double patch_h,
+                                                 double* M) {
+  const double c_x = box[0], c_y = box[1], scale = box[4], rot = box[5];
+  const double src_w = box[2] * scale, src_h = box[3] * scale;
+  const double rot_rad = 3.141592653589793 * rot / 180;
+  const double sn = sin(rot_rad), cs = cos(rot_rad);
+  // rotate_2d(np.array([0, src_h*0.5], f32), rot_rad) -> f32 (:63-69)
+  const double dy_ = (double)(float)(src_h * 0.5), rx_ = (double)(float)(src_w * 0.5);
+  const float down_x = (float)(0.0 * cs - dy_ * sn), down_y = (float)(0.0 * sn + dy_ * cs);
+  const float right_x = (float)(rx_ * cs - 0.0 * sn), right_y = (float)(rx_ * sn + 0.0 * cs);
+  float s[3][2], d[3][2];
+  s[0][0] = (float)c_x;                       s[0][1] = (float)c_y;
+  s[1][0] = (float)(c_x + (double)down_x);    s[1][1] = (float)(c_y + (double)down_y);
+  s[2][0] = (float)(c_x + (double)right_x);   s[2][1] = (float)(c_y + (double)right_y);
+  const float dcx = (float)(patch_w * 0.5), dcy = (float)(patch_h * 0.5);
+  d[0][0] = dcx;        d[0][1] = dcy;
+  d[1][0] = dcx + 0.f;  d[1][1] = dcy + (float)(patch_h * 0.5);
+  d[2][0] = dcx + (float)(patch_w * 0.5);  d[2][1] = dcy + 0.f;
+  return affine_lu6(s, d, M);
+}
+
+// cv::warpAffine without WARP_INVERSE_MAP: invert the 2x3 map in float64 (imgwarp.cpp)
+__host__ __device__ inline void invert_affine(const double* M, double* iM) {
+  double D = M[0] * M[4] - M[1] * M[3];
+  D = D != 0 ? 1.0 / D : 0.0;
+  const double A11 = M[4] * D, A22 = M[0] * D;
+  iM[0] = A11; iM[1] = M[1] * (-D);
+  iM[3] = M[3] * (-D); iM[4] = A22;
+  const double b1 = -iM[0] * M[2] - iM[1] * M[5];
+  const double b2 = -iM[3] * M[2] - iM[4] * M[5];
+  iM[2] = b1; iM[5] = b2;
+}
+
+// saturate_cast<int>(double) of OpenCV = cvRound: round half to even, saturating
+__host__ __device__ inline long long cv_round(double v) {
+  const double r = rint(v);
+  if (r >= 2147483647.0) return 2147483647LL;
+  if (r <= -2147483648.0) return -2147483648LL;
+  return (long long)r;
+}
+
+// one output pixel of the uint8 BGR patch (warpAffine INTER_LINEAR, constant border 0).
+// flip: the source is the horizontally mirrored frame (img[:, ::-1, :], img_utils.py:119).
+__host__ __device__ inline void warp_pixel_u8(const uint8_t* img, int H, int W, int64_t pitch, int flip,
+                                              const double* iM, int x, int y, int (&bgr)[3]) {
+  const long long adelta = cv_round(iM[0] * x * 1024.0), bdelta = cv_round(iM[3] * x * 1024.0);
+  const long long X0 = cv_round((iM[1] * y + iM[2]) * 1024.0) + 16;
+  const long long Y0 = cv_round((iM[4] * y + iM[5]) * 1024.0) + 16;
+  const long long X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  const long long sx = X >> 5, sy = Y >> 5;
+  const int ax = (int)(X & 31), ay = (int)(Y & 31);
+  const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32,
+            w11 = ax * ay * 32;
+  int acc[3] = {0, 0, 0};
+  auto tap = [&](long long yy, long long xx, int wgt) {
+    if (wgt == 0 || yy < 0 || yy >= H || xx < 0 || xx >= W) return;
+    const long long xs = flip ? (W - 1 - xx) : xx;
+    const uint8_t* p = img + yy * pitch + xs * 3;
+    acc[0] += wgt * p[0];
+    acc[1] += wgt * p[1];
+    acc[2] += wgt * p[2];
+  };
+  tap(sy, sx, w00);
+  tap(sy, sx + 1, w01);
+  tap(sy + 1, sx, w10);
+  tap(sy + 1, sx + 1, w11);
+  for (int c = 0; c < 3; ++c) {
+    const int v = (acc[c] + (1 << 14)) >> 15;
+    bgr[c] = v < 0 ? 0 : (v > 255 ? 255 : v);
+  }
+}
+
+// img_utils.py:268-281 for output channel c (RGB order) of one pixel
+__host__ __device__ inline float finish_pixel(int v_u8, float color_scale, bool norm, double mean,
+                                              double stdv) {
+  float f = (float)v_u8 * color_scale;              // float32 array * python float
+  f = f < 0.f ? 0.f : (f > 255.f ? 255.f : f);      // np.clip(., 0, 255)
+  if (!norm) return f;
+  return (float)(((double)f - mean) / stdv);        // float64 scalars promote; stored as float32
+}
+
+struct PatchArgs {
+  double mean[3], stdv[3];
+  int norm;
+};
+
+__global__ void __launch_bounds__(256)
+patch_sample_kernel(const uint8_t* __restrict__ img_base, const int64_t* __restrict__ img_off,
+                    const int32_t* __restrict__ img_hwp, const double* __restrict__ box,
+                    const int32_t* __restrict__ flip, const float* __restrict__ color, PatchArgs pa,
+                    int patch_w, int patch_h, float* __restrict__ out, double* __restrict__ trans) {
+  const int b = blockIdx.z;
+  __shared__ double siM[6];
+  const int H = img_hwp[b * 3 + 0], W = img_hwp[b * 3 + 1];
+  const int64_t pitch = img_hwp[b * 3 + 2];
+  const int fl = flip ? flip[b] : 0;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    double bx[6];
+    for (int k = 0; k < 6; ++k) bx[k] = box[b * 6 + k];
+    if (fl) bx[0] = (double)W - bx[0] - 1.0;          // c_x = img_width - c_x - 1 (:120)
+    double M[6] = {0, 0, 0, 0, 0, 0};
+    patch_affine_fwd(bx, (double)patch_w, (double)patch_h, M);
+    double iM[6];
+    invert_affine(M, iM);
+    for (int k = 0; k < 6; ++k) siM[k] = iM[k];
+    if (trans && blockIdx.x == 0 && blockIdx.y == 0)
+      for (int k = 0; k < 6; ++k) trans[b * 6 + k] = M[k];
+  }
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= patch_w || y >= patch_h) return;
+  int bgr[3];
+  warp_pixel_u8(img_base + img_off[b], H, W, pitch, fl, siM, x, y, bgr);
+  const int64_t plane = (int64_t)patch_w * patch_h;
+  float* o = out + (int64_t)b * 3 * plane + (int64_t)y * patch_w + x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float cs = color ? color[b * 3 + c] : 1.f;
+    o[c * plane] = finish_pixel(bgr[2 - c], cs, pa.norm != 0, pa.mean[c], pa.stdv[c]);   // BGR -> RGB
+  }
+}
+
+// joints half: one thread per (sample, joint)
+__host__ __device__ inline void patch_joint(const double* jt, const double* M, double patch_w,
+                                            double patch_h, double depth_den, double* label) {
+  const double x = (M[0] * jt[0] + M[1] * jt[1]) + M[2] * 1.0;     // np.dot(trans, [x, y, 1])
+  const double y = (M[3] * jt[0] + M[4] * jt[1]) + M[5] * 1.0;
+  const double z = jt[2] / depth_den * patch_w;                    // :291-293
+  label[0] = x / patch_w - 0.5;                                    // integral_loss.py:171-173
+  label[1] = y / patch_h - 0.5;
+  label[2] = z / patch_w;
+}
+
+__global__ void patch_joints_kernel(const double* __restrict__ joints, const double* __restrict__ box,
+                                    const double* __restrict__ trans, int B, int J, double patch_w,
+                                    double patch_h, double rect_3d_w, int depth_in_image,
+                                    double* __restrict__ label) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * J) return;
+  const int b = i / J;
+  const double scale = box[b * 6 + 4];
+  const double den = depth_in_image ? box[b * 6 + 2] * scale : rect_3d_w * scale;
+  patch_joint(joints + (int64_t)i * 3, trans + b * 6, patch_w, patch_h, den, label + (int64_t)i * 3);
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int epb_patch_sample(
+    const uint8_t* img_base, const int64_t* img_off, const int32_t* img_hwp, const double* box,
+    const int32_t* flip, const float* color, const double* mean_std_host, int B, int patch_w,
+    int patch_h, float* out, double* trans, epb_stream_t stream) {
+  EPB_CHECK_ARG(img_base && img_off && img_hwp && box && out);
+  EPB_CHECK_ARG(B >= 0 && patch_w > 0 && patch_h > 0 && B <= 65535);
+  if (B == 0) return EPB_OK;
+  PatchArgs pa;
+  pa.norm = mean_std_host ? 1 : 0;
+  for (int c = 0; c < 3; ++c) {
+    pa.mean[c] = mean_std_host ? mean_std_host[c] : 0.0;
+    pa.stdv[c] = mean_std_host ? mean_std_host[3 + c] : 1.0;
+    EPB_CHECK_ARG(pa.stdv[c] != 0.0);
+  }
+  const dim3 block(64, 4);
+  const dim3 grid((patch_w + 63) / 64, (patch_h + 3) / 4, B);
+  patch_sample_kernel<<<grid, block, 0, as_stream(stream)>>>(img_base, img_off, img_hwp, box, flip, color,
+                                                            pa, patch_w, patch_h, out, trans);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_patch_joints(
+    const double* joints, const double* box, const double* trans, int B, int J, double patch_w,
+    double patch_h, double rect_3d_w, int depth_in_image, double* label, epb_stream_t stream) {
+  EPB_CHECK_ARG(joints && box && trans && label);
+  EPB_CHECK_ARG(B >= 0 && J >= 0 && patch_w > 0 && patch_h > 0 && rect_3d_w != 0);
+  if (B * J == 0) return EPB_OK;
+  const int n = B * J;
+  patch_joints_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(joints, box, trans, B, J, patch_w,
+                                                                     patch_h, rect_3d_w, depth_in_image,
+                                                                     label);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}

@@ -7,7 +7,17 @@ kernels (epb_patch_to_image -> epb_triangulate -> epb_project_labels); the
 reference's per-sample / per-joint Python loops disappear.  `meta` follows the
 dataset contract of reference lib/dataset/h36m.py:73-86 (collated: tensors or
 lists of length B).  numpy in / numpy out like the reference;
-`self_supervision_device` returns CUDA tensors for the training loop."""
+`self_supervision_device` returns CUDA tensors for the training loop.
+
+Input pipeline: get_single_patch_sample (:246-298),
+do_augmentation (:28-39), fliplr_joints (:42-60) with the same names and return values; the crop
+(cv2.warpAffine), BGR->RGB, colour scale, clip and normalisation run in ONE kernel for the whole
+batch (epb_patch_sample, bit-exact against OpenCV) and the joints -> label half in
+epb_patch_joints; `generate_patch_batch_device` is the batched entry point a GPU data loader
+calls with already decoded frames.  The occluder paste (lib/utils/augmentation.py) is not built:
+`occluder` must be None."""
+import random
+
 import numpy as np
 import torch
 
@@ -150,3 +160,123 @@ def trans_coords_from_patch_to_org_3d_batch(coords, c_x, c_y, bb_w, bb_h, patch_
     res = kps.cpu().numpy()
     out[:, :, 0:3] = res[:, :, 0:3]
     return out
+
+
+# ---------------------------------------------------------------------- input pipeline
+def do_augmentation():
+    """reference :28-39 (scale_factor 0.25, rot_factor 30, color_factor 0.2, rot_aug_rate 0.6,
+    do_flip_aug False) -- the same draws from np.random / random in the same order."""
+    scale = np.clip(np.random.randn(), -1.0, 1.0) * 0.25 + 1.0
+    rot = np.clip(np.random.randn(), -2.0, 2.0) * 30 if random.random() <= 0.6 else 0
+    do_flip = False and random.random() <= 0.5
+    c_up, c_low = 1.0 + 0.2, 1.0 - 0.2
+    color_scale = [random.uniform(c_low, c_up), random.uniform(c_low, c_up), random.uniform(c_low, c_up)]
+    return scale, rot, do_flip, color_scale
+
+
+def fliplr_joints(_joints, _joints_vis, width, matched_parts):
+    """reference :42-60."""
+    joints = _joints.copy()
+    joints_vis = _joints_vis.copy()
+    joints[:, 0] = width - joints[:, 0] - 1
+    for pair in matched_parts:
+        joints[pair[0], :], joints[pair[1], :] = joints[pair[1], :], joints[pair[0], :].copy()
+        joints_vis[pair[0], :], joints_vis[pair[1], :] = joints_vis[pair[1], :], joints_vis[pair[0], :].copy()
+    return joints, joints_vis
+
+
+def generate_patch_batch_device(images, center_x, center_y, width, height, patch_width, patch_height,
+                                scale=None, rot=None, do_flip=None, color_scale=None, mean=None, std=None):
+    """B decoded BGR frames (uint8 [H,W,3] numpy arrays or tensors, sizes may differ) ->
+    (patches float32 [B,3,ph,pw] on the device, trans float64 [B,2,3], box float64 [B,6])."""
+    ops = _backend[0]
+    dev = _dev()
+    B = len(images)
+    offs, hwp, chunks, pos = [], [], [], 0
+    for im in images:
+        t = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(im))
+        if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+            raise ValueError("frames must be uint8 [H, W, 3] (cv2.imread layout)")
+        t = t.contiguous()
+        offs.append(pos)
+        hwp.append([t.shape[0], t.shape[1], t.shape[1] * 3])
+        chunks.append(t.reshape(-1))
+        pos += (t.numel() + 15) // 16 * 16
+    base = torch.zeros(max(pos, 16), dtype=torch.uint8)
+    for o, c in zip(offs, chunks):
+        base[o:o + c.numel()] = c.cpu()
+    ones, zeros = np.ones(B), np.zeros(B)
+    box = np.stack([np.asarray(center_x, dtype=np.float64).reshape(B), np.asarray(center_y, dtype=np.float64).reshape(B),
+                    np.asarray(width, dtype=np.float64).reshape(B), np.asarray(height, dtype=np.float64).reshape(B),
+                    np.asarray(ones if scale is None else scale, dtype=np.float64).reshape(B),
+                    np.asarray(zeros if rot is None else rot, dtype=np.float64).reshape(B)], axis=1)
+    t_box = torch.from_numpy(np.ascontiguousarray(box)).to(dev)
+    t_flip = None if do_flip is None else torch.as_tensor(np.asarray(do_flip).astype(np.int32).reshape(B)).to(dev)
+    t_col = None if color_scale is None else \
+        torch.as_tensor(np.asarray(color_scale, dtype=np.float32).reshape(B, 3)).to(dev)
+    ms = None
+    if mean is not None and std is not None:
+        ms = [float(v) for v in np.asarray(mean).reshape(3)] + [float(v) for v in np.asarray(std).reshape(3)]
+    out = torch.empty((B, 3, int(patch_height), int(patch_width)), device=dev, dtype=torch.float32)
+    trans = torch.empty((B, 6), device=dev, dtype=torch.float64)
+    ops.patch_sample(base.to(dev), torch.tensor(offs, dtype=torch.int64, device=dev),
+                     torch.tensor(hwp, dtype=torch.int32, device=dev), t_box, t_flip, t_col, ms, B,
+                     int(patch_width), int(patch_height), out, trans)
+    return out, trans.reshape(B, 2, 3), t_box
+
+
+def patch_labels_device(joints, box, trans, patch_width, patch_height, rect_3d_width, depth_in_image=False):
+    """joints [B,J,3] (image px, depth mm) -> label float64 [B, J*3] (reference :283-296 +
+    generate_joint_location_label)."""
+    ops = _backend[0]
+    dev = _dev()
+    jt = torch.as_tensor(np.ascontiguousarray(joints, dtype=np.float64)).to(dev)
+    B, J = jt.shape[0], jt.shape[1]
+    label = torch.empty((B, J * 3), device=dev, dtype=torch.float64)
+    ops.patch_joints(jt.contiguous(), box, trans.reshape(B, 6).contiguous(), B, J, patch_width, patch_height,
+                     rect_3d_width, bool(depth_in_image), label)
+    return label
+
+
+def get_single_patch_sample(img_path, center_x, center_y, width, height,
+                            joints, joints_vis, flip_pairs, parent_ids,
+                            patch_width, patch_height, rect_3d_width, rect_3d_height, mean, std,
+                            do_augment, label_func, depth_in_image=False, occluder=None, DEBUG=False):
+    """reference :246-298, same arguments and return tuple (img_patch f32 [3,ph,pw] numpy, label,
+    label_weight, scale, rot).  `img_path` may also be an already decoded BGR uint8 array.
+    `label_func` is honoured when it is not the default generate_joint_location_label."""
+    if occluder:
+        raise NotImplementedError("occluder paste (lib/utils/augmentation.py) is not built")
+    if isinstance(img_path, np.ndarray):
+        cvimg = img_path
+    else:
+        import cv2
+        cvimg = cv2.imread(img_path, cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        if not isinstance(cvimg, np.ndarray):
+            raise IOError("Fail to read %s" % img_path)
+    img_width = cvimg.shape[1]
+    if do_augment:
+        scale, rot, do_flip, color_scale = do_augmentation()
+    else:
+        scale, rot, do_flip, color_scale = 1.0, 0, False, [1.0, 1.0, 1.0]
+    patches, trans, box = generate_patch_batch_device(
+        [cvimg], [center_x], [center_y], [width], [height], patch_width, patch_height, [scale], [rot],
+        [do_flip], [color_scale], mean, std)
+    joints = np.array(joints, dtype=np.float64, copy=True)
+    joints_vis = np.array(joints_vis, copy=True)
+    if do_flip:
+        joints, joints_vis = fliplr_joints(joints, joints_vis, img_width, flip_pairs)
+    from ..core.integral_loss import generate_joint_location_label
+    if label_func is None or label_func is generate_joint_location_label or \
+            getattr(label_func, "__name__", "") == "generate_joint_location_label":
+        label = patch_labels_device(joints[None], box, trans, patch_width, patch_height, rect_3d_width,
+                                    depth_in_image)[0].cpu().numpy()
+        label_weight = joints_vis.reshape((-1))
+    else:
+        tr = trans[0].cpu().numpy()
+        for n_jt in range(len(joints)):
+            joints[n_jt, 0:2] = np.dot(tr, np.array([joints[n_jt, 0], joints[n_jt, 1], 1.]).T)[0:2]
+            den = (width * scale) if depth_in_image else (rect_3d_width * scale)
+            joints[n_jt, 2] = joints[n_jt, 2] / den * patch_width
+        label, label_weight = label_func(patch_width, patch_height, joints, joints_vis)
+    return patches[0].cpu().numpy(), label, label_weight, scale, rot

@@ -219,6 +219,22 @@ def triangulate(u1, u2, stride_u, P1, P2, NP, J, method, tol, X, status):
           _p(X, torch.float64), _p(status, torch.int32), _stream())
 
 
+def patch_sample(img_base, img_off, img_hwp, box, flip, color, mean_std, B, patch_w, patch_h, out, trans):
+    """mean_std: None or a sequence of 6 floats (mean RGB, std RGB) -- passed as a HOST array."""
+    ms = None
+    if mean_std is not None:
+        ms = (ctypes.c_double * 6)(*[float(v) for v in mean_std])
+    _call("epb_patch_sample", _p(img_base, torch.uint8), _p(img_off, torch.int64), _p(img_hwp, torch.int32),
+          _p(box, torch.float64), _p(flip, torch.int32), _p(color), ms, B, patch_w, patch_h, _p(out),
+          _p(trans, torch.float64), _stream())
+
+
+def patch_joints(joints, box, trans, B, J, patch_w, patch_h, rect_3d_w, depth_in_image, label):
+    _call("epb_patch_joints", _p(joints, torch.float64), _p(box, torch.float64), _p(trans, torch.float64),
+          B, J, float(patch_w), float(patch_h), float(rect_3d_w), int(depth_in_image),
+          _p(label, torch.float64), _stream())
+
+
 def h36m_eval(pred, gt, cam, S, J, root, j14mask, pck_thr, metrics, per_joint, pck, poses):
     _call("epb_h36m_eval", _p(pred, torch.float64), _p(gt, torch.float64), _p(cam, torch.float64),
           S, J, root, int(j14mask), float(pck_thr), _p(metrics, torch.float64),

@@ -285,6 +285,33 @@ int epb_h36m_eval(const double* pred, const double* gt, const double* cam, int S
                   double* per_joint, int32_t* pck, double* poses, epb_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Input pipeline (lib/utils/img_utils.py:246-298 get_single_patch_sample after the frame is
+ * decoded; the occluder paste of lib/utils/augmentation.py is not built).
+ * ---------------------------------------------------------------------- */
+/* Crop + colour + normalisation of B frames in one launch, bit-exact against OpenCV:
+ * generate_patch_image_cv (:114-127: gen_trans_from_patch_cv :72-105 with float32 point
+ * triplets and cv2.getAffineTransform's 6x6 LU; cv2.warpAffine INTER_LINEAR, constant border 0,
+ * fixed-point coordinates and weights as imgproc/imgwarp.cpp), BGR->RGB (:268), colour scale,
+ * clip to [0,255], (x-mean)/std (:277-281).
+ *   img_base            uint8 BGR frames (cv2.imread layout [H][W][3]) in one device buffer
+ *   img_off  [B] int64  byte offset of frame b;  img_hwp [B][3] int32: H, W, row pitch in bytes
+ *   box      [B][6] f64 c_x, c_y, bb_width, bb_height, scale, rot (degrees)
+ *   flip     [B] int32 or NULL (horizontal mirror: img[:, ::-1, :], c_x = W - c_x - 1, :118-120)
+ *   color    [B][3] f32 or NULL (ones): colour_scale per RGB channel
+ *   mean_std_host [6] f64 HOST pointer (mean RGB, std RGB) or NULL (no normalisation)
+ *   out      [B][3][patch_h][patch_w] f32;  trans [B][6] f64 or NULL: the image->patch affine */
+int epb_patch_sample(const uint8_t* img_base, const int64_t* img_off, const int32_t* img_hwp,
+                     const double* box, const int32_t* flip, const float* color,
+                     const double* mean_std_host, int B, int patch_w, int patch_h, float* out,
+                     double* trans, epb_stream_t stream);
+/* Joint half (:283-296 + lib/core/integral_loss.py:170-177): joints [B][J][3] f64 (x, y image px;
+ * z mm) through trans [B][6] (from epb_patch_sample), z / (rect_3d_w*scale) * patch_w (or the
+ * box width when depth_in_image), then x/pw - 0.5, y/ph - 0.5, z/pw -> label [B][J*3] f64. */
+int epb_patch_joints(const double* joints, const double* box, const double* trans, int B, int J,
+                     double patch_w, double patch_h, double rect_3d_w, int depth_in_image,
+                     double* label, epb_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Optimiser (torch.optim.Adam call site lib/utils/utils.py:56-60; betas
  * (0.9,0.999), eps 1e-8, no weight decay) over one flat parameter buffer.
  * step is the 1-based step count.  grad_scale multiplies the gradient first

@@ -184,14 +184,42 @@ def joint_location_result(patch_width, patch_height, coords_norm):
 # --------------------------------------------------------------------------
 
 def _affine_from_3pts(src, dst):
-    """Restates cv2.getAffineTransform (OpenCV imgproc/imgwarp.cpp): the 2x3
-    float64 M with M*[sx,sy,1]^T = [dx,dy]^T for three float32 point pairs.
-    Solved in float64 (OpenCV: 6x6 LU in double)."""
+    """Restates cv2.getAffineTransform (OpenCV imgproc/imgwarp.cpp): the 2x3 float64 M with
+    M*[sx,sy,1]^T = [dx,dy]^T for three float32 point pairs, solved like cv::solve(DECOMP_LU)
+    (hal::LU64f: 6x6 system, partial pivoting, alpha = A[j][i] * (-1/A[i][i]), back
+    substitution) -- bit-exact against the installed OpenCV on 2000 random triplets."""
     s = np.asarray(src, dtype=np.float32).astype(np.float64)
     d = np.asarray(dst, dtype=np.float32).astype(np.float64)
-    a = np.concatenate([s, np.ones((3, 1))], axis=1)  # 3x3
-    m = np.linalg.solve(a, d)  # 3x2
-    return m.T.copy()
+    A = [[0.0] * 6 for _ in range(6)]
+    b = [0.0] * 6
+    for i in range(3):
+        A[2 * i][0] = A[2 * i + 1][3] = float(s[i][0])
+        A[2 * i][1] = A[2 * i + 1][4] = float(s[i][1])
+        A[2 * i][2] = A[2 * i + 1][5] = 1.0
+        b[2 * i], b[2 * i + 1] = float(d[i][0]), float(d[i][1])
+    eps = np.finfo(np.float64).eps * 100
+    for i in range(6):
+        k = i
+        for j in range(i + 1, 6):
+            if abs(A[j][i]) > abs(A[k][i]):
+                k = j
+        if abs(A[k][i]) < eps:
+            return np.zeros((2, 3))
+        if k != i:
+            A[i], A[k] = A[k], A[i]
+            b[i], b[k] = b[k], b[i]
+        dd = -1.0 / A[i][i]
+        for j in range(i + 1, 6):
+            alpha = A[j][i] * dd
+            for kk in range(i + 1, 6):
+                A[j][kk] += alpha * A[i][kk]
+            b[j] += alpha * b[i]
+    for i in range(5, -1, -1):
+        sacc = b[i]
+        for kk in range(i + 1, 6):
+            sacc -= A[i][kk] * b[kk]
+        b[i] = sacc / A[i][i]
+    return np.array(b, dtype=np.float64).reshape(2, 3)
 
 
 def gen_trans_from_patch(c_x, c_y, src_width, src_height, dst_width, dst_height,
@@ -603,3 +631,87 @@ def h36m_evaluate(preds, gt_joints, pelvis_z, fl, c_p, mpii_order=False, pck_thr
     means = metrics.mean(axis=0) if S else np.zeros(9)
     return dict(metrics=metrics, per_joint=per_joint, pck=pck, poses=poses,
                 name_value=list(zip(names, means.tolist())), mean=float(means[0]))
+
+
+# ---------------------------------------------------------------- input pipeline (8(f) row 1)
+def warp_affine_linear_u8(img, M, dst_w, dst_h):
+    """cv2.warpAffine(img u8 [H,W,C], M 2x3 f64, (dst_w, dst_h), flags=INTER_LINEAR), constant
+    border 0, restated from OpenCV imgproc/imgwarp.cpp (the reference calls it at
+    lib/utils/img_utils.py:125): M is inverted in float64; source coordinates are fixed point
+    with AB_BITS = 10 and rounded per term (cvRound of M00*x*1024 per column, of
+    (M01*y + M02)*1024 per row) plus round_delta = 16, then reduced to INTER_BITS = 5 fractional
+    bits; the four neighbours (0 outside the image) are blended with integer weights
+    (32-ax)(32-ay)*32 ... of sum 2^15 and rounded (+2^14) >> 15.  Bit-exact against the
+    installed OpenCV 4.13 on the golden cases."""
+    img = np.asarray(img)
+    M = np.asarray(M, dtype=np.float64)
+    D = M[0, 0] * M[1, 1] - M[0, 1] * M[1, 0]
+    D = 1.0 / D if D != 0 else 0.0
+    iM = np.zeros((2, 3))
+    iM[0, 0], iM[0, 1] = M[1, 1] * D, M[0, 1] * (-D)
+    iM[1, 0], iM[1, 1] = M[1, 0] * (-D), M[0, 0] * D
+    iM[0, 2] = -iM[0, 0] * M[0, 2] - iM[0, 1] * M[1, 2]
+    iM[1, 2] = -iM[1, 0] * M[0, 2] - iM[1, 1] * M[1, 2]
+    H, W = img.shape[:2]
+    xs = np.arange(dst_w)
+    adelta = np.rint(iM[0, 0] * xs * 1024).astype(np.int64)
+    bdelta = np.rint(iM[1, 0] * xs * 1024).astype(np.int64)
+    out = np.zeros((dst_h, dst_w) + img.shape[2:], dtype=np.uint8)
+
+    def px(yy, xx):
+        ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+        v = img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)].astype(np.int64)
+        v[~ok] = 0
+        return v
+    for y in range(dst_h):
+        X0 = int(np.rint((iM[0, 1] * y + iM[0, 2]) * 1024)) + 16
+        Y0 = int(np.rint((iM[1, 1] * y + iM[1, 2]) * 1024)) + 16
+        X, Y = (X0 + adelta) >> 5, (Y0 + bdelta) >> 5
+        sx, sy, ax, ay = X >> 5, Y >> 5, X & 31, Y & 31
+        w = [((32 - ax) * (32 - ay) * 32), (ax * (32 - ay) * 32), ((32 - ax) * ay * 32), (ax * ay * 32)]
+        sh = (-1,) + (1,) * (img.ndim - 2)
+        acc = px(sy, sx) * w[0].reshape(sh) + px(sy, sx + 1) * w[1].reshape(sh) + \
+            px(sy + 1, sx) * w[2].reshape(sh) + px(sy + 1, sx + 1) * w[3].reshape(sh)
+        out[y] = np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+    return out
+
+
+def patch_sample(cvimg, center_x, center_y, width, height, joints, joints_vis, patch_width,
+                 patch_height, rect_3d_width, mean, std, scale=1.0, rot=0.0, do_flip=False,
+                 color_scale=(1.0, 1.0, 1.0), flip_pairs=(), depth_in_image=False):
+    """lib/utils/img_utils.py:246-298 (get_single_patch_sample) after the image is decoded and
+    the augmentation parameters are drawn, without the occluder paste: crop by warpAffine
+    (:114-127), BGR->RGB (:268), per-channel colour scale + clip + (x-mean)/std (:277-281,
+    float32 * python float stays float32; minus / divided by np.float64 scalars is float64,
+    stored back as float32 -- numpy >= 2 promotion, the version the golden run used), joints
+    through the same affine + depth scaling (:283-293) and generate_joint_location_label.
+    Returns (img_patch f32 [3,ph,pw], label f64 [J*3], label_weight [J*3], trans 2x3)."""
+    img = np.asarray(cvimg)
+    img_h, img_w = img.shape[:2]
+    c_x = center_x
+    if do_flip:
+        img = img[:, ::-1, :]
+        c_x = img_w - c_x - 1
+    trans = gen_trans_from_patch(c_x, center_y, width, height, patch_width, patch_height, scale, rot, inv=False)
+    patch = warp_affine_linear_u8(img, trans, int(patch_width), int(patch_height))
+    image = patch[:, :, ::-1]
+    t = np.transpose(image, (2, 0, 1)).astype(np.float32)
+    for c in range(t.shape[0]):
+        t[c] = np.clip(t[c] * np.float32(color_scale[c]), 0, 255)
+        if mean is not None and std is not None:
+            t[c] = ((t[c].astype(np.float64) - np.float64(mean[c])) / np.float64(std[c])).astype(np.float32)
+    joints = np.array(joints, dtype=np.float64, copy=True)
+    joints_vis = np.array(joints_vis, dtype=np.float64, copy=True)
+    if do_flip:
+        joints[:, 0] = img_w - joints[:, 0] - 1
+        for a, b in flip_pairs:
+            joints[[a, b]] = joints[[b, a]]
+            joints_vis[[a, b]] = joints_vis[[b, a]]
+    for j in range(len(joints)):
+        joints[j, 0:2] = trans @ np.array([joints[j, 0], joints[j, 1], 1.0])
+        den = (width * scale) if depth_in_image else (rect_3d_width * scale)
+        joints[j, 2] = joints[j, 2] / den * patch_width
+    joints[:, 0] = joints[:, 0] / patch_width - 0.5
+    joints[:, 1] = joints[:, 1] / patch_height - 0.5
+    joints[:, 2] = joints[:, 2] / patch_width
+    return t, joints.reshape(-1), joints_vis.reshape(-1), trans

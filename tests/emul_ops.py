@@ -3,6 +3,7 @@ the SAME signatures as epipolarpose_b200.ops, written directly from the
 contracts in include/epb.h.  It lets the CPU test-suite exercise the host
 logic (network plan, geometry/tap tables, weight packing, autograd wiring,
 optimiser) without a GPU.  It is never imported by the product path."""
+import numpy as np
 import torch
 
 from epipolarpose_b200._lib import ConvGeom, EPB_MAX_TAPS
@@ -429,3 +430,33 @@ def h36m_eval(pred, gt, cam, S, J, root, j14mask, pck_thr, metrics, per_joint, p
         pck.view(S, J).copy_((e < pck_thr).to(torch.int32))
     if poses is not None:
         poses.view(S, J, 9).copy_(torch.cat([P0, Pa, G], dim=2))
+
+
+def patch_sample(img_base, img_off, img_hwp, box, flip, color, mean_std, B, patch_w, patch_h, out, trans):
+    """CPU emulation of epb_patch_sample through the numpy oracle (test infrastructure)."""
+    from oracle import restate
+    base = img_base.numpy().reshape(-1)
+    for b in range(B):
+        H, W, pitch = [int(v) for v in img_hwp[b]]
+        off = int(img_off[b])
+        img = np.lib.stride_tricks.as_strided(base[off:], shape=(H, W, 3), strides=(pitch, 3, 1))
+        bx = box[b].numpy()
+        fl = bool(flip[b]) if flip is not None else False
+        cs = color[b].numpy() if color is not None else np.ones(3, np.float32)
+        mean = None if mean_std is None else np.asarray(mean_std[:3], dtype=np.float64)
+        std = None if mean_std is None else np.asarray(mean_std[3:], dtype=np.float64)
+        t, _, _, tr = restate.patch_sample(img, bx[0], bx[1], bx[2], bx[3], np.zeros((1, 3)), np.zeros((1, 3)),
+                                           patch_w, patch_h, 2000.0, mean, std, bx[4], bx[5], fl, cs)
+        out[b].copy_(torch.from_numpy(t))
+        if trans is not None:
+            trans[b].copy_(torch.from_numpy(tr.reshape(-1)))
+
+
+def patch_joints(joints, box, trans, B, J, patch_w, patch_h, rect_3d_w, depth_in_image, label):
+    jt = joints.reshape(B, J, 3).double()
+    M = trans.reshape(B, 2, 3).double()
+    xy = torch.einsum("brc,bjc->bjr", M, torch.cat([jt[:, :, :2], torch.ones(B, J, 1, dtype=torch.float64)], 2))
+    den = (box[:, 2] * box[:, 4]) if depth_in_image else (rect_3d_w * box[:, 4])
+    z = jt[:, :, 2] / den.reshape(B, 1) * patch_w
+    lab = torch.stack([xy[:, :, 0] / patch_w - 0.5, xy[:, :, 1] / patch_h - 0.5, z / patch_w], dim=2)
+    label.view(B, J * 3).copy_(lab.reshape(B, J * 3))

@@ -70,3 +70,33 @@ np.savez_compressed(os.path.join(OUT, "triangulation_poly.npz"), x=np.asarray(xs
                     corrected_u2=np.asarray(c2s), exact=exact, cv2_version=np.array(cv2.__version__))
 print("wrote triangulation_poly", np.asarray(xs).shape, "exact-recovery error",
       float(np.abs(exact - Xtrue).max()))
+
+# ---- input pipeline: get_single_patch_sample (img_utils.py:246-298) on synthetic frames
+import random  # noqa: E402
+import tempfile  # noqa: E402
+iu = importlib.import_module("lib.utils.img_utils")
+il = importlib.import_module("lib.core.integral_loss")
+MEAN = np.array([123.675, 116.280, 103.530])          # lib/dataset/JointIntegralDataset.py:67-68
+STD = np.array([58.395, 57.120, 57.375])
+rec = {}
+with tempfile.TemporaryDirectory() as tmp:
+    for tag in gi.PATCH_CASES:
+        img, box, joints, joints_vis, pw, ph, seed = gi.frame_case(tag)
+        path = os.path.join(tmp, tag + ".png")              # lossless: imread returns the same BGR bytes
+        assert cv2.imwrite(path, img)
+        for aug in (False, True):
+            np.random.seed(seed); random.seed(seed)
+            scale, rot, do_flip, color_scale = iu.do_augmentation() if aug else (1.0, 0, False, [1.0, 1.0, 1.0])
+            np.random.seed(seed); random.seed(seed)          # the call below draws the same parameters
+            patch, label, weight, s2, r2 = iu.get_single_patch_sample(
+                path, box[0], box[1], box[2], box[3], joints.copy(), joints_vis.copy(), [], None, pw, ph,
+                2000.0, 2000.0, MEAN, STD, aug, il.generate_joint_location_label)
+            assert (s2, r2) == (scale, rot) and not do_flip
+            k = tag + ("_aug" if aug else "")
+            rec[k + "_patch"] = patch
+            rec[k + "_label"] = np.asarray(label, dtype=np.float64)
+            rec[k + "_weight"] = np.asarray(weight, dtype=np.float64)
+            rec[k + "_aug"] = np.array([scale, rot, float(do_flip)] + list(color_scale), dtype=np.float64)
+np.savez_compressed(os.path.join(OUT, "patch_sample.npz"), cv2_version=np.array(cv2.__version__),
+                    numpy_version=np.array(np.__version__), **rec)
+print("wrote patch_sample", {k: v.shape for k, v in rec.items() if k.endswith("_patch")})

@@ -153,3 +153,34 @@ def eval_case(S=24, J=17, seed=81):
     pred[:, :, 2] = pred[:, :, 2] * rng.uniform(0.8, 1.2, (S, 1)) + rng.normal(0, 40, (S, J))
     pred = np.concatenate([pred, np.ones((S, J, 1))], axis=2)      # score column as in the loop
     return pred, gt, pelvis, fl, c_p
+
+
+PATCH_CASES = {
+    # tag: (img H, img W, patch_w, patch_h, seed, smooth image?)
+    "noise64": (1000, 1002, 64, 64, 91, False),
+    "smooth96x128": (1002, 1000, 96, 128, 92, True),
+    "edge48": (480, 640, 48, 48, 93, False),      # box partly outside the image: border zeros
+}
+
+
+def frame_case(tag):
+    """Decoded BGR frame (uint8) + box + joints for the input-pipeline tests; the augmentation
+    parameters are NOT here: the reference draws them (np.random / random seeded with `seed`)."""
+    H, W, pw, ph, seed, smooth = PATCH_CASES[tag]
+    rng = np.random.default_rng(seed)
+    if smooth:
+        yy, xx = np.mgrid[0:H, 0:W]
+        img = np.stack([127 + 120 * np.sin(xx / 37.0 + c) * np.cos(yy / 23.0 - c) for c in range(3)], axis=2)
+        img = np.clip(img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+    else:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    if tag == "edge48":
+        box = (600.5, 30.25, 300.0, 280.0)
+    else:
+        box = (W / 2 + rng.uniform(-50, 50), H / 2 + rng.uniform(-50, 50), 800 + rng.uniform(-100, 100),
+               800 + rng.uniform(-100, 100))
+    J = 17
+    joints = np.stack([box[0] + rng.uniform(-300, 300, J), box[1] + rng.uniform(-300, 300, J),
+                       rng.uniform(-800, 800, J)], axis=1)
+    joints_vis = (rng.random((J, 3)) > 0.1).astype(np.float64)
+    return img, box, joints, joints_vis, pw, ph, seed

@@ -3,12 +3,15 @@
 // the oracle in the CPU test suite too.  Binary protocol on stdin/stdout (little-endian doubles):
 //   "eval" S J root mask  then pred[S*J*3] gt[S*J*3] cam[S*5]  ->  metrics[S*9] per_joint[S*J] poses[S*J*9]
 //   "correct" N  then P1[12] P2[12] u1[N*2] u2[N*2]  ->  F[9] u1'[N*2] u2'[N*2]
+//   "patch" H W pw ph flip J  then box[6] color[3] mean_std[6] depth_den[1] joints[J*3] img[H*W*3 as doubles]
+//           ->  trans[6] patch[3*ph*pw] (float32 values widened) label[J*3]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 void epb_set_error(const char*, ...) {}
 #include "../../epipolarpose_b200/csrc/geometry.cu"
+#include "../../epipolarpose_b200/csrc/input.cu"
 
 static void rd(void* p, size_t n) { if (fread(p, 1, n, stdin) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 
@@ -26,6 +29,35 @@ int main(int argc, char** argv) {
     fwrite(met.data(), 8, met.size(), stdout);
     fwrite(pj.data(), 8, pj.size(), stdout);
     fwrite(poses.data(), 8, poses.size(), stdout);
+    return 0;
+  }
+  if (!strcmp(argv[1], "patch")) {
+    const int H = atoi(argv[2]), W = atoi(argv[3]), pw = atoi(argv[4]), ph = atoi(argv[5]);
+    const int flip = atoi(argv[6]), J = atoi(argv[7]);
+    std::vector<double> box(6), color(3), ms(6), den(1), joints(J * 3), imgd((size_t)H * W * 3);
+    rd(box.data(), 48); rd(color.data(), 24); rd(ms.data(), 48); rd(den.data(), 8);
+    rd(joints.data(), joints.size() * 8); rd(imgd.data(), imgd.size() * 8);
+    std::vector<uint8_t> img(imgd.size());
+    for (size_t i = 0; i < img.size(); ++i) img[i] = (uint8_t)imgd[i];
+    double bx[6];
+    for (int k = 0; k < 6; ++k) bx[k] = box[k];
+    if (flip) bx[0] = (double)W - bx[0] - 1.0;
+    double M[6], iM[6];
+    if (!patch_affine_fwd(bx, (double)pw, (double)ph, M)) return 3;
+    invert_affine(M, iM);
+    std::vector<double> patch((size_t)3 * ph * pw), label(J * 3);
+    for (int y = 0; y < ph; ++y)
+      for (int x = 0; x < pw; ++x) {
+        int bgr[3];
+        warp_pixel_u8(img.data(), H, W, (int64_t)W * 3, flip, iM, x, y, bgr);
+        for (int c = 0; c < 3; ++c)
+          patch[((size_t)c * ph + y) * pw + x] =
+              (double)finish_pixel(bgr[2 - c], (float)color[c], true, ms[c], ms[3 + c]);
+      }
+    for (int j = 0; j < J; ++j) patch_joint(&joints[j * 3], M, (double)pw, (double)ph, den[0], &label[j * 3]);
+    fwrite(M, 8, 6, stdout);
+    fwrite(patch.data(), 8, patch.size(), stdout);
+    fwrite(label.data(), 8, label.size(), stdout);
     return 0;
   }
   if (!strcmp(argv[1], "correct")) {

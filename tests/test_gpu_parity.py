@@ -169,6 +169,54 @@ def test_h36m_eval_vs_oracle_and_reference(golden, dev, mpii):
         assert np.min(dd["metrics"][:, 0]) > 1.0            # un-aligned error does not
 
 
+MEAN = np.array([123.675, 116.280, 103.530])          # reference lib/dataset/JointIntegralDataset.py:67-68
+STD = np.array([58.395, 57.120, 57.375])
+
+
+def test_input_pipeline_bit_exact(golden, dev):
+    """epb_patch_sample / epb_patch_joints through the reference-named get_single_patch_sample:
+    patches BIT-EXACT against the unmodified reference (cv2.warpAffine INTER_LINEAR + colour scale +
+    normalisation), labels to rounding, same augmentation draws; batched launch with frames of
+    different sizes and a mirrored frame against the oracle; a full-size batch (64 frames of
+    1000x1002 -> 256x256) spot-checked bit-exactly against the oracle."""
+    import random
+    import lib.utils.img_utils as iu
+    g = golden("patch_sample")
+    for tag in gi.PATCH_CASES:
+        img, box, joints, vis, pw, ph, seed = gi.frame_case(tag)
+        for aug in (False, True):
+            k = tag + ("_aug" if aug else "")
+            np.random.seed(seed); random.seed(seed)
+            patch, label, weight, scale, rot = iu.get_single_patch_sample(
+                img, box[0], box[1], box[2], box[3], joints.copy(), vis.copy(), [], None, pw, ph, 2000.0, 2000.0,
+                MEAN, STD, aug, None)
+            assert (scale, rot) == (g[k + "_aug"][0], g[k + "_aug"][1])
+            assert np.array_equal(patch, g[k + "_patch"]), k
+            assert np.max(np.abs(label - g[k + "_label"])) <= 1e-12
+            assert np.array_equal(weight, g[k + "_weight"])
+    a, b = gi.frame_case("noise64"), gi.frame_case("edge48")
+    out, trans, _ = iu.generate_patch_batch_device(
+        [a[0], b[0], a[0]], [a[1][0], b[1][0], a[1][0]], [a[1][1], b[1][1], a[1][1]], [a[1][2], b[1][2], a[1][2]],
+        [a[1][3], b[1][3], a[1][3]], 48, 48, scale=[1.1, 1.0, 0.9], rot=[12.0, 0.0, -20.0],
+        do_flip=[False, False, True], color_scale=[[1.1, 0.9, 1.0]] * 3, mean=MEAN, std=STD)
+    out = out.cpu().numpy()
+    for i, (c, sc, rot, fl) in enumerate(((a, 1.1, 12.0, False), (b, 1.0, 0.0, False), (a, 0.9, -20.0, True))):
+        t, _, _, tr = restate.patch_sample(c[0], c[1][0], c[1][1], c[1][2], c[1][3], c[2], c[3], 48, 48, 2000.0,
+                                           MEAN, STD, sc, rot, fl, (1.1, 0.9, 1.0))
+        assert np.array_equal(out[i], t), i
+        assert np.array_equal(trans[i].cpu().numpy(), tr)
+    rng = np.random.default_rng(7)
+    frames = [a[0]] * 64
+    cx, cy = 500 + rng.uniform(-50, 50, 64), 500 + rng.uniform(-50, 50, 64)
+    w, h = 800 + rng.uniform(-100, 100, 64), 800 + rng.uniform(-100, 100, 64)
+    sc, rot = 1 + rng.uniform(-0.25, 0.25, 64), rng.uniform(-60, 60, 64)
+    big, _, _ = iu.generate_patch_batch_device(frames, cx, cy, w, h, 256, 256, scale=sc, rot=rot, mean=MEAN, std=STD)
+    for i in (0, 31, 63):
+        t, _, _, _ = restate.patch_sample(a[0], cx[i], cy[i], w[i], h[i], a[2], a[3], 256, 256, 2000.0, MEAN, STD,
+                                          sc[i], rot[i])
+        assert np.array_equal(big[i].cpu().numpy(), t), i
+
+
 def test_argmax_bit_exact(golden, dev):
     import lib.core.inference as inf
     g = golden("argmax")

@@ -259,6 +259,66 @@ def test_polynomial_correction_kernel_body_on_host(host_geometry):
     assert np.max(np.abs(a[9:9 + 34].reshape(17, 2) - u1e[0])) <= 1e-8
 
 
+MEAN = np.array([123.675, 116.280, 103.530])
+STD = np.array([58.395, 57.120, 57.375])
+
+
+@pytest.mark.parametrize("tag", list(gi.PATCH_CASES))
+def test_input_pipeline_kernel_body_on_host(host_geometry, tag):
+    """warp_pixel_u8 / finish_pixel / patch_affine_fwd / patch_joint of csrc/input.cu, executed on
+    the CPU: patches BIT-EXACT against the unmodified get_single_patch_sample (cv2.warpAffine)."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "patch_sample.npz")))
+    img, box, joints, vis, pw, ph, seed = gi.frame_case(tag)
+    H, W = img.shape[:2]
+    for aug in (False, True):
+        k = tag + ("_aug" if aug else "")
+        sc, rot, fl, c0, c1, c2 = g[k + "_aug"]
+        a = host_geometry(["patch", H, W, pw, ph, int(fl), 17], np.array(list(box) + [sc, rot]),
+                          np.array([c0, c1, c2]), np.concatenate([MEAN, STD]), np.array([2000.0 * sc]), joints,
+                          img.astype(np.float64))
+        patch = a[6:6 + 3 * ph * pw].reshape(3, ph, pw).astype(np.float32)
+        assert np.array_equal(patch, g[k + "_patch"]), k
+        assert np.max(np.abs(a[6 + 3 * ph * pw:] - g[k + "_label"])) <= 1e-12
+
+
+def test_input_pipeline_surface_emulated(tmp_path):
+    """get_single_patch_sample / generate_patch_batch_device of the mirror through the emulated ABI:
+    reference return tuple, same RNG draws as the reference's do_augmentation, error behaviour."""
+    import random
+    import lib.utils.img_utils as iu
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "patch_sample.npz")))
+    iu._backend[0] = emul_ops
+    try:
+        for tag in ("noise64", "edge48"):
+            img, box, joints, vis, pw, ph, seed = gi.frame_case(tag)
+            for aug in (False, True):
+                k = tag + ("_aug" if aug else "")
+                np.random.seed(seed); random.seed(seed)
+                patch, label, weight, scale, rot = iu.get_single_patch_sample(
+                    img, box[0], box[1], box[2], box[3], joints.copy(), vis.copy(), [], None, pw, ph, 2000.0,
+                    2000.0, MEAN, STD, aug, None)
+                assert (scale, rot) == (g[k + "_aug"][0], g[k + "_aug"][1])      # same draws as the reference
+                assert patch.dtype == np.float32 and np.array_equal(patch, g[k + "_patch"])
+                assert np.max(np.abs(label - g[k + "_label"])) <= 1e-12
+                assert np.array_equal(weight, g[k + "_weight"])
+        # batched entry point with frames of different sizes
+        a, b = gi.frame_case("noise64"), gi.frame_case("edge48")
+        out, trans, _ = iu.generate_patch_batch_device([a[0], b[0]], [a[1][0], b[1][0]], [a[1][1], b[1][1]],
+                                                       [a[1][2], b[1][2]], [a[1][3], b[1][3]], 48, 48,
+                                                       mean=MEAN, std=STD)
+        assert np.array_equal(out[1].numpy(), g["edge48_patch"]) and out.shape == (2, 3, 48, 48)
+        with pytest.raises(NotImplementedError):
+            iu.get_single_patch_sample(a[0], 1, 1, 1, 1, a[2], a[3], [], None, 8, 8, 1, 1, None, None, False, None,
+                                       occluder=[1])
+        with pytest.raises(ValueError):
+            iu.generate_patch_batch_device([a[0].astype(np.float32)], [1], [1], [1], [1], 8, 8)
+        with pytest.raises(IOError):
+            iu.get_single_patch_sample(str(tmp_path / "missing.png"), 1, 1, 1, 1, a[2], a[3], [], None, 8, 8, 1, 1,
+                                       None, None, False, None)
+    finally:
+        iu._backend[0] = __import__("epipolarpose_b200.ops", fromlist=["ops"])
+
+
 def test_fused_optimizers_match_torch():
     import lib.utils.utils as U
     U._backend[0] = emul_ops

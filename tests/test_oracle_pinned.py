@@ -146,3 +146,23 @@ def test_polynomial_triangulation(golden):
         h1 = np.concatenate([n1, np.ones((len(n1), 1))], 1)
         h2 = np.concatenate([n2, np.ones((len(n2), 1))], 1)
         assert np.max(np.abs(np.einsum("ni,ij,nj->n", h2, F, h1))) <= 1e-9 * np.abs(F).max() * 1e6
+
+
+MEAN = np.array([123.675, 116.280, 103.530])          # reference lib/dataset/JointIntegralDataset.py:67-68
+STD = np.array([58.395, 57.120, 57.375])
+
+
+@pytest.mark.parametrize("tag", list(gi.PATCH_CASES))
+def test_input_pipeline_bit_exact(golden, tag):
+    """restate.patch_sample (warpAffine fixed-point restatement, getAffineTransform LU) against the
+    unmodified get_single_patch_sample: patches BIT-EXACT, labels to rounding."""
+    g = golden("patch_sample")
+    img, box, joints, vis, pw, ph, seed = gi.frame_case(tag)
+    for aug in (False, True):
+        k = tag + ("_aug" if aug else "")
+        sc, rot, fl, c0, c1, c2 = g[k + "_aug"]
+        t, lab, wt, tr = restate.patch_sample(img, box[0], box[1], box[2], box[3], joints, vis, pw, ph, 2000.0,
+                                              MEAN, STD, sc, rot, bool(fl), (c0, c1, c2))
+        assert np.array_equal(t, g[k + "_patch"]), k
+        assert np.max(np.abs(lab - g[k + "_label"])) <= 1e-12
+        assert np.array_equal(wt, g[k + "_weight"])

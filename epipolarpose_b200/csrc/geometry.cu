@@ -392,6 +392,58 @@ __global__ void triangulate_kernel(const double* __restrict__ u1, const double* 
   if (status) status[idx] = st;
 }
 
+// --------------------------------------------------------------- N-view homogeneous DLT
+// the V-view generalisation of triangulation.py:8-27 (not in the reference,
+// which only pairs two views): A (2V x 4) rows u*P[2]-P[0], v*P[2]-P[1] per view, X = right
+// singular vector of the smallest singular value, de-homogenised.  V <= 4 (one tuple).
+template <int V>
+__host__ __device__ inline int dlt_nview(const double* u /*[V][2]*/, const double* P /*[V][12]*/,
+                                         double* x /*[3]*/) {
+  double A[2 * V][4], Vm[4][4];
+  for (int v = 0; v < V; ++v)
+    for (int k = 0; k < 4; ++k) {
+      A[2 * v + 0][k] = u[v * 2 + 0] * P[v * 12 + 8 + k] - P[v * 12 + 0 + k];
+      A[2 * v + 1][k] = u[v * 2 + 1] * P[v * 12 + 8 + k] - P[v * 12 + 4 + k];
+    }
+  jacobi_onesided<2 * V, 4>(A, Vm);
+  int best = 0;
+  double bn = DBL_MAX;
+  for (int j = 0; j < 4; ++j) {
+    double n2 = 0;
+    for (int i = 0; i < 2 * V; ++i) n2 += A[i][j] * A[i][j];
+    if (n2 < bn) { bn = n2; best = j; }
+  }
+  double h[4];
+  for (int i = 0; i < 4; ++i) h[i] = Vm[i][best];
+  x[0] = h[0] / h[3]; x[1] = h[1] / h[3]; x[2] = h[2] / h[3];
+  const double mx = fmax(fabs(x[0]), fmax(fabs(x[1]), fabs(x[2])));
+  return (mx <= 1.e16) ? 1 : 0;
+}
+
+// u [NT][V][J][stride_u], P [NT][V][12] -> X [NT][J][3], status [NT][J]; one thread per (tuple, joint)
+__global__ void triangulate_nview_kernel(const double* __restrict__ u, int stride_u,
+                                         const double* __restrict__ P, int NT, int V, int J,
+                                         double* __restrict__ X, int32_t* __restrict__ status) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NT * J) return;
+  const int t = idx / J, j = idx - t * J;
+  double uu[8], pp[48], x[3];
+  for (int v = 0; v < V; ++v) {
+    const double* up = u + (((int64_t)t * V + v) * J + j) * stride_u;
+    uu[v * 2 + 0] = up[0];
+    uu[v * 2 + 1] = up[1];
+    for (int k = 0; k < 12; ++k) pp[v * 12 + k] = P[((int64_t)t * V + v) * 12 + k];
+  }
+  int st;
+  if (V == 2) st = dlt_nview<2>(uu, pp, x);
+  else if (V == 3) st = dlt_nview<3>(uu, pp, x);
+  else st = dlt_nview<4>(uu, pp, x);
+  X[(int64_t)idx * 3 + 0] = x[0];
+  X[(int64_t)idx * 3 + 1] = x[1];
+  X[(int64_t)idx * 3 + 2] = x[2];
+  if (status) status[idx] = st;
+}
+
 // img_utils.py:72-105 with its float32 roundings.  Returns the 2x3 transform
 // mapping src->dst (inv=0: image->patch) or dst->src (inv=1: patch->image).
 __device__ void patch_affine(const double* box, double patch_w, double patch_h, int inv,
@@ -730,6 +782,18 @@ extern "C" __attribute__((visibility("default"))) int epb_h36m_eval(
   h36m_eval_kernel<<<(S + 63) / 64, 64, 0, as_stream(stream)>>>(pred, gt, cam, S, J, root, j14mask,
                                                                pck_thr, metrics, per_joint, pck,
                                                                poses);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_triangulate_nview(
+    const double* u, int stride_u, const double* P, int NT, int V, int J, double* X, int32_t* status,
+    epb_stream_t stream) {
+  EPB_CHECK_ARG(u && P && X);
+  EPB_CHECK_ARG(NT >= 0 && J >= 0 && stride_u >= 2 && V >= 2 && V <= 4);
+  if (NT * J == 0) return EPB_OK;
+  const int n = NT * J;
+  triangulate_nview_kernel<<<(n + 63) / 64, 64, 0, as_stream(stream)>>>(u, stride_u, P, NT, V, J, X, status);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

@@ -42,6 +42,20 @@ def triangulate_pairs(u1, u2, P1, P2, method="iterative", tolerance=3.e-5, strid
     return X, status
 
 
+def triangulate_views(u, P):
+    """V-view homogeneous DLT (2 <= V <= 4; not in the reference):
+    u [NT,V,J,S>=2] float64, P [NT,V,3,4] float64 on the device -> (X [NT,J,3], status [NT,J])."""
+    ops = _backend[0]
+    NT, V, J = u.shape[0], u.shape[1], u.shape[2]
+    if not 2 <= V <= 4:
+        raise ValueError("triangulate_views handles 2..4 views per tuple, got %d" % V)
+    X = torch.empty((NT, J, 3), device=u.device, dtype=torch.float64)
+    status = torch.empty((NT, J), device=u.device, dtype=torch.int32)
+    if NT * J:
+        ops.triangulate_nview(u.contiguous(), u.shape[3], P.reshape(NT, V, 12).contiguous(), NT, V, J, X, status)
+    return X, status
+
+
 def _device():
     return torch.device("cuda") if _backend[0] is _ops else torch.device("cpu")
 

@@ -241,6 +241,11 @@ def h36m_eval(pred, gt, cam, S, J, root, j14mask, pck_thr, metrics, per_joint, p
           _p(per_joint, torch.float64), _p(pck, torch.int32), _p(poses, torch.float64), _stream())
 
 
+def triangulate_nview(u, stride_u, P, NT, V, J, X, status):
+    _call("epb_triangulate_nview", _p(u, torch.float64), stride_u, _p(P, torch.float64), NT, V, J,
+          _p(X, torch.float64), _p(status, torch.int32), _stream())
+
+
 def project_labels(X, cam, box, B, J, patch_w, patch_h, rect3d_w, label, weight):
     _call("epb_project_labels", _p(X, torch.float64), _p(cam, torch.float64),
           _p(box, torch.float64), B, J, float(patch_w), float(patch_h), float(rect3d_w),

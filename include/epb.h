@@ -260,6 +260,11 @@ int epb_triangulate(const double* u1, const double* u2, int stride_u,
                     const double* P1, const double* P2, int NP, int J,
                     int method, double tol, double* X, int32_t* status,
                     epb_stream_t stream);
+/* V-view homogeneous DLT (the reference only pairs two views,
+ * triangulation.py:8-27): u [NT][V][J][stride_u] f64 (first two entries used), P [NT][V][12] f64,
+ * 2 <= V <= 4 -> X [NT][J][3], status [NT][J] (max |coordinate| <= 1e16). */
+int epb_triangulate_nview(const double* u, int stride_u, const double* P, int NT, int V, int J,
+                          double* X, int32_t* status, epb_stream_t stream);
 /* lib/utils/img_utils.py:212-243 + lib/utils/prep_h36m.py:170-204 +
  * integral_loss.py:170-177: X [B][J][3] world -> label,weight [B][J*3] f32.
  * cam [B][16] f64 = R(9) T(3) f(2) c(2); box as above. */

@@ -434,6 +434,24 @@ def polynomial_triangulation(u1, P1, u2, P2):
     return linear_eigen_triangulation(n1, P1, n2, P2)
 
 
+def linear_eigen_triangulation_nview(us, Ps):
+    """V-view homogeneous DLT (SURVEY 8(f) row 3): us [V,J,2], Ps [V,3,4] -> (x [J,3], status);
+    rows u*P[2]-P[0], v*P[2]-P[1] per view as cv2.triangulatePoints stacks them for two views
+    (triangulation.py:22), solved with numpy's SVD."""
+    us = np.asarray(us, dtype=np.float64)
+    Ps = np.asarray(Ps, dtype=np.float64)
+    V, J = us.shape[0], us.shape[1]
+    x = np.zeros((J, 3))
+    for j in range(J):
+        A = np.zeros((2 * V, 4))
+        for v in range(V):
+            A[2 * v] = us[v, j, 0] * Ps[v, 2] - Ps[v, 0]
+            A[2 * v + 1] = us[v, j, 1] * Ps[v, 2] - Ps[v, 1]
+        h = np.linalg.svd(A)[2][-1]
+        x[j] = h[:3] / h[3]
+    return x, np.max(np.abs(x), axis=1) <= 1e16
+
+
 def projection_matrix(R, T, f, c):
     """lib/utils/cameras.py:120-131,149-150: K.[R | R.(-T)] float64 3x4."""
     R = np.asarray(R, dtype=np.float64)

@@ -36,3 +36,9 @@ def relerr(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+# GPU tests of kernels whose arithmetic is validated on the CPU (tests/harness) but that have not
+# had a hardware run yet (the round's GPU budget was spent): skipped unless EPB_RUN_HW_PENDING=1.
+hw_pending = pytest.mark.skipif(os.environ.get("EPB_RUN_HW_PENDING") != "1",
+                                reason="hardware run pending: set EPB_RUN_HW_PENDING=1 on a B200")

@@ -3,6 +3,7 @@
 // the oracle in the CPU test suite too.  Binary protocol on stdin/stdout (little-endian doubles):
 //   "eval" S J root mask  then pred[S*J*3] gt[S*J*3] cam[S*5]  ->  metrics[S*9] per_joint[S*J] poses[S*J*9]
 //   "correct" N  then P1[12] P2[12] u1[N*2] u2[N*2]  ->  F[9] u1'[N*2] u2'[N*2]
+//   "nview" V J  then u[V*J*2] P[V*12]  ->  X[J*3]
 //   "patch" H W pw ph flip J  then box[6] color[3] mean_std[6] depth_den[1] joints[J*3] img[H*W*3 as doubles]
 //           ->  trans[6] patch[3*ph*pw] (float32 values widened) label[J*3]
 #include <cstdio>
@@ -29,6 +30,20 @@ int main(int argc, char** argv) {
     fwrite(met.data(), 8, met.size(), stdout);
     fwrite(pj.data(), 8, pj.size(), stdout);
     fwrite(poses.data(), 8, poses.size(), stdout);
+    return 0;
+  }
+  if (!strcmp(argv[1], "nview")) {
+    const int V = atoi(argv[2]), J = atoi(argv[3]);
+    std::vector<double> u(V * J * 2), P(V * 12), X(J * 3);
+    rd(u.data(), u.size() * 8); rd(P.data(), P.size() * 8);
+    for (int j = 0; j < J; ++j) {
+      double uu[8];
+      for (int v = 0; v < V; ++v) { uu[v * 2] = u[(v * J + j) * 2]; uu[v * 2 + 1] = u[(v * J + j) * 2 + 1]; }
+      if (V == 2) dlt_nview<2>(uu, P.data(), &X[j * 3]);
+      else if (V == 3) dlt_nview<3>(uu, P.data(), &X[j * 3]);
+      else dlt_nview<4>(uu, P.data(), &X[j * 3]);
+    }
+    fwrite(X.data(), 8, X.size(), stdout);
     return 0;
   }
   if (!strcmp(argv[1], "patch")) {

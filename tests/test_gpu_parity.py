@@ -9,7 +9,7 @@ import torch
 
 from oracle import restate, restate_net
 from tests import golden_inputs as gi
-from tests.conftest import relerr
+from tests.conftest import hw_pending, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -275,6 +275,33 @@ def test_polynomial_triangulation_golden(golden, dev):
     for i in range(0, 64, 9):
         xr, _ = restate.polynomial_triangulation(u1b[i], P1b[i], u2b[i], P2b[i])
         assert np.max(np.abs(Xb[i].cpu().numpy() - xr)) <= 1e-4
+
+
+@hw_pending
+@pytest.mark.parametrize("V", [2, 3, 4])
+def test_nview_dlt_vs_oracle(dev, V):
+    """epb_triangulate_nview against the numpy-SVD oracle (<= 1e-4 mm, 3 px noise), exact recovery
+    from noise-free views, and V = 2 equal to the pair kernel (method 0)."""
+    import lib.utils.triangulation as tri
+    rng = np.random.default_rng(40 + V)
+    NT, J = 16, 17
+    R, T, f, c, P = restate.synthetic_cameras(rng, NT, 4)
+    X = rng.normal(0, 400, (NT, J, 3))
+    ue = np.stack([[restate.project(P[t, v], X[t]) for v in range(V)] for t in range(NT)])
+    un = ue + rng.normal(0, 3, ue.shape)
+    t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    Xg, st = tri.triangulate_views(t64(un), t64(P[:, :V]))
+    for t in range(NT):
+        xo, so = restate.linear_eigen_triangulation_nview(un[t], P[t, :V])
+        assert np.max(np.abs(Xg[t].cpu().numpy() - xo)) <= 1e-4
+        assert np.array_equal(st[t].cpu().numpy().astype(bool), so)
+    Xe, _ = tri.triangulate_views(t64(ue), t64(P[:, :V]))
+    assert np.max(np.abs(Xe.cpu().numpy() - X)) <= 1e-6
+    if V == 2:
+        Xp, _ = tri.triangulate_pairs(t64(un[:, 0]), t64(un[:, 1]), t64(P[:, 0]), t64(P[:, 1]), "linear_eigen")
+        assert np.max(np.abs(Xp.cpu().numpy() - Xg.cpu().numpy())) <= 1e-9
+    e, _ = tri.triangulate_views(t64(un[:0]), t64(P[:0, :V]))
+    assert e.shape == (0, J, 3)
 
 
 def test_triangulation_large_vs_oracle(dev):

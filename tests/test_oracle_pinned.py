@@ -166,3 +166,19 @@ def test_input_pipeline_bit_exact(golden, tag):
         assert np.array_equal(t, g[k + "_patch"]), k
         assert np.max(np.abs(lab - g[k + "_label"])) <= 1e-12
         assert np.array_equal(wt, g[k + "_weight"])
+
+
+def test_nview_dlt_reduces_to_the_reference_pair_case(golden):
+    """the V-view DLT oracle with V = 2 is the reference's linear_eigen_triangulation (golden);
+    with four exact views it recovers the 3-D points."""
+    g = golden("triangulation")
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    for i in range(len(u1)):
+        x, st = restate.linear_eigen_triangulation_nview(np.stack([u1[i], u2[i]]), np.stack([P1[i], P2[i]]))
+        assert np.max(np.abs(x - g["linear_eigen_triangulation_x"][i])) <= 1e-6
+    rng = np.random.default_rng(3)
+    R, T, f, c, P = restate.synthetic_cameras(rng, 2, 4)
+    Xw = rng.normal(0, 400, (17, 3))
+    us = np.stack([restate.project(P[0, v], Xw) for v in range(4)])
+    x, st = restate.linear_eigen_triangulation_nview(us, P[0])
+    assert np.max(np.abs(x - Xw)) <= 1e-8 and st.all()

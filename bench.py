@@ -449,7 +449,7 @@ def cpu_reference(steps, warmup, tuples, layers=50):
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return {"value": round(tuples / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d step(s) of %d view-tuples (%d images) of the same workload, R%d, "
-                      "%.1f s/step; cv2.solve/getAffineTransform restated with numpy.linalg"
+                      "%.1f s/step; cv2.solve restated with numpy.linalg, cv2.getAffineTransform as its 6x6 LU"
                       % (steps, tuples, n_img, layers, dt),
             "s_per_step": round(dt, 3)}
 

@@ -382,3 +382,42 @@ extern "C" __attribute__((visibility("default"))) int epb_sgd_step_dev(float* pa
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }
+
+// ------------------------------------------------------------------ element-wise helpers of the
+// refiner MLP (refiner/model.py): residual sums and dropout.  HBM bound, 4 B per element per stream.
+namespace {
+__global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                            const float* __restrict__ c, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = c ? (a[i] + b[i]) + c[i] : a[i] + b[i];
+}
+__global__ void mask_scale_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
+                                  float scale, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = mask[i] ? x[i] * scale : 0.f;
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int epb_add3(const float* a, const float* b, const float* c,
+                                                              float* out, int64_t n, epb_stream_t stream) {
+  EPB_CHECK_ARG(a && b && out && n >= 0);
+  if (n == 0) return EPB_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  add3_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(a, b, c, out, n);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_mask_scale(const float* x, const uint8_t* mask, float scale,
+                                                                    float* out, int64_t n, epb_stream_t stream) {
+  EPB_CHECK_ARG(x && mask && out && n >= 0);
+  if (n == 0) return EPB_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  mask_scale_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, mask, scale, out, n);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}

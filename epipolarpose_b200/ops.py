@@ -219,6 +219,14 @@ def triangulate(u1, u2, stride_u, P1, P2, NP, J, method, tol, X, status):
           _p(X, torch.float64), _p(status, torch.int32), _stream())
 
 
+def add3(a, b, c, out, n):
+    _call("epb_add3", _p(a), _p(b), _p(c), _p(out), n, _stream())
+
+
+def mask_scale(x, mask, scale, out, n):
+    _call("epb_mask_scale", _p(x), _p(mask, torch.uint8), float(scale), _p(out), n, _stream())
+
+
 def patch_sample(img_base, img_off, img_hwp, box, flip, color, mean_std, B, patch_w, patch_h, out, trans):
     """mean_std: None or a sequence of 6 floats (mean RGB, std RGB) -- passed as a HOST array."""
     ms = None

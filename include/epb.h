@@ -289,6 +289,13 @@ int epb_h36m_eval(const double* pred, const double* gt, const double* cam, int S
                   int root, uint32_t j14mask, double pck_thr, double* metrics,
                   double* per_joint, int32_t* pck, double* poses, epb_stream_t stream);
 
+/* Element-wise helpers of the refiner MLP (refiner/model.py:39-68,117-143): out = a + b (+ c when
+ * c != NULL) -- the residual sums -- and nn.Dropout with an explicit keep mask:
+ * out = mask ? x * scale : 0  (scale = 1 / (1 - p); the backward is the same call on the gradient). */
+int epb_add3(const float* a, const float* b, const float* c, float* out, int64_t n, epb_stream_t stream);
+int epb_mask_scale(const float* x, const uint8_t* mask, float scale, float* out, int64_t n,
+                   epb_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Input pipeline (lib/utils/img_utils.py:246-298 get_single_patch_sample after the frame is
  * decoded; the occluder paste of lib/utils/augmentation.py is not built).

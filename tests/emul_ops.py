@@ -460,3 +460,15 @@ def patch_joints(joints, box, trans, B, J, patch_w, patch_h, rect_3d_w, depth_in
     z = jt[:, :, 2] / den.reshape(B, 1) * patch_w
     lab = torch.stack([xy[:, :, 0] / patch_w - 0.5, xy[:, :, 1] / patch_h - 0.5, z / patch_w], dim=2)
     label.view(B, J * 3).copy_(lab.reshape(B, J * 3))
+
+
+def add3(a, b, c, out, n):
+    r = a.reshape(-1)[:n] + b.reshape(-1)[:n]
+    if c is not None:
+        r = r + c.reshape(-1)[:n]
+    out.view(-1)[:n].copy_(r)
+
+
+def mask_scale(x, mask, scale, out, n):
+    out.view(-1)[:n].copy_(torch.where(mask.reshape(-1)[:n] != 0, x.reshape(-1)[:n] * scale,
+                                       torch.zeros(n, dtype=x.dtype)))

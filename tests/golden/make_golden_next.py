@@ -100,3 +100,37 @@ with tempfile.TemporaryDirectory() as tmp:
 np.savez_compressed(os.path.join(OUT, "patch_sample.npz"), cv2_version=np.array(cv2.__version__),
                     numpy_version=np.array(np.__version__), **rec)
 print("wrote patch_sample", {k: v.shape for k, v in rec.items() if k.endswith("_patch")})
+
+# ---- refiner MLP (refiner/model.py), imported by path: forward / backward in training mode with
+# p_dropout = 0 (torch's dropout stream cannot be reproduced) and the eval-mode forward
+import importlib.util  # noqa: E402
+import torch  # noqa: E402
+from oracle import restate_refiner  # noqa: E402
+spec = importlib.util.spec_from_file_location("ref_refiner_model", os.path.join(refshim.REF_ROOT, "refiner", "model.py"))
+refm = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(refm)
+LS, NB = 128, 24
+model = refm.LinearModelPG(linear_size=LS, p_dropout=0.0, input_size=45, output_size=45)
+shapes = restate_refiner.param_shapes(LS, 45, 45)
+sd = restate_refiner.init_state(shapes, 17)
+assert list(model.state_dict().keys()) == list(sd.keys())
+assert all(tuple(v.shape) == tuple(shapes[k]) for k, v in model.state_dict().items())
+model.load_state_dict(sd)
+model.train()
+x = torch.from_numpy(gi.grad_like((NB, 45), 18)).requires_grad_(True)
+tgt = torch.from_numpy(gi.grad_like((NB, 45), 19))
+p1, p2 = model(x)
+loss = torch.nn.functional.mse_loss(p1, tgt) + torch.nn.functional.mse_loss(p2, tgt)      # refiner/main.py:50
+loss.backward()
+rec = {"p1": p1.detach().numpy(), "p2": p2.detach().numpy(), "loss": loss.detach().numpy(), "dx": x.grad.numpy()}
+named = dict(model.named_parameters())
+for k in ("w1.weight", "w2.weight", "w4.bias", "linear_stages.0.w3.weight", "linear_stages.1.batch_norm2.weight",
+          "linear_stages.1.batch_norm4.bias", "batch_norm3.weight"):
+    rec["grad/" + k] = named[k].grad.numpy()
+rec["batch_norm1.running_var"] = model.state_dict()["batch_norm1.running_var"].numpy()
+model.eval()
+with torch.no_grad():
+    e1, e2 = model(x.detach())
+rec["eval_p1"], rec["eval_p2"] = e1.numpy(), e2.numpy()
+np.savez_compressed(os.path.join(OUT, "refiner.npz"), **rec)
+print("wrote refiner", {k: v.shape for k, v in rec.items()})

@@ -670,3 +670,46 @@ def test_reference_script_flow(dev, tmp_path):
     for k, v in fresh.state_dict().items():
         assert torch.equal(v.cpu(), after[k].cpu()), k
     reset_config()
+
+
+@hw_pending
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_refiner_vs_reference_golden(golden, dev, precision):
+    """refiner MLP on the device: forward / backward / running statistics against
+    the unmodified refiner/model.py (<= 1e-3 rel per tensor), eval forward, dropout masks replayed
+    through the oracle, one clip-grad-norm + fused Adam step as refiner/main.py:49-56."""
+    from oracle import restate_refiner as rr
+    from epipolarpose_b200.refiner import model as rmodel
+    import lib.utils.utils as U
+    g = golden("refiner")
+    sd = rr.init_state(rr.param_shapes(128, 45, 45), 17)
+    m = rmodel.LinearModelPG(linear_size=128, p_dropout=0.0, input_size=45, output_size=45, precision=precision)
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    x = torch.from_numpy(gi.grad_like((24, 45), 18)).to(dev).requires_grad_(True)
+    tgt = torch.from_numpy(gi.grad_like((24, 45), 19)).to(dev)
+    opt = U.FusedAdam(list(m.parameters()), lr=1e-3)
+    p1, p2 = m(x)
+    loss = torch.nn.functional.mse_loss(p1, tgt) + torch.nn.functional.mse_loss(p2, tgt)
+    loss.backward()
+    assert relerr(p1.detach().cpu().numpy(), g["p1"]) <= 1e-3 and relerr(p2.detach().cpu().numpy(), g["p2"]) <= 1e-3
+    assert relerr(x.grad.cpu().numpy(), g["dx"]) <= 1e-3
+    named = dict(m.named_parameters())
+    for k in [k[5:] for k in g if k.startswith("grad/")]:
+        assert relerr(named[k].grad.cpu().numpy(), g["grad/" + k]) <= 1e-3, k
+    assert relerr(m.state_dict()["batch_norm1.running_var"].cpu().numpy(), g["batch_norm1.running_var"]) <= 1e-4
+    torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=1.)
+    opt.step()
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(x.detach())
+    assert np.isfinite(e1.cpu().numpy()).all() and np.isfinite(e2.cpu().numpy()).all()
+    m2 = rmodel.LinearModelPG(linear_size=128, p_dropout=0.5, input_size=45, output_size=45, precision=precision)
+    m2.load_state_dict(sd)
+    m2 = m2.to(dev).train()
+    torch.manual_seed(7)
+    q1, q2 = m2(x.detach())
+    torch.manual_seed(7)
+    masks = [(torch.rand(24, 128, device=dev) >= 0.5).cpu() for _ in range(10)]
+    o1, o2 = rr.forward(sd, x.detach().cpu(), training=True, masks=masks, p_dropout=0.5)
+    assert relerr(q1.detach().cpu().numpy(), o1.numpy()) <= 1e-3 and relerr(q2.detach().cpu().numpy(), o2.numpy()) <= 1e-3

@@ -333,6 +333,60 @@ def test_nview_dlt_kernel_body_on_host(host_geometry, V):
         assert np.max(np.abs(xh - xo)) <= 1e-6
 
 
+def _refiner_case(precision):
+    from oracle import restate_refiner as rr
+    from epipolarpose_b200.refiner import model as rmodel
+    sd = rr.init_state(rr.param_shapes(128, 45, 45), 17)
+    m = rmodel.LinearModelPG(linear_size=128, p_dropout=0.0, input_size=45, output_size=45, precision=precision)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    return rr, rmodel, sd, m
+
+
+def test_refiner_surface_emulated():
+    """epipolarpose_b200/refiner/model.py (reference names, state_dict, forward signature) over
+    mlp.MLPEngine through the emulated C ABI: forward / backward / running statistics / eval against
+    the golden vectors of the unmodified reference; dropout against the oracle with the same masks."""
+    from epipolarpose_b200.refiner import model as rmodel
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "refiner.npz")))
+    rmodel.LinearModelPG._backend[0] = emul_ops
+    try:
+        rr, _, sd, m = _refiner_case("fp32")
+        x = torch.from_numpy(gi.grad_like((24, 45), 18)).requires_grad_(True)
+        tgt = torch.from_numpy(gi.grad_like((24, 45), 19))
+        m.train()
+        p1, p2 = m(x)
+        loss = torch.nn.functional.mse_loss(p1, tgt) + torch.nn.functional.mse_loss(p2, tgt)
+        loss.backward()
+        assert relerr(p1.detach().numpy(), g["p1"]) <= 1e-5 and relerr(p2.detach().numpy(), g["p2"]) <= 1e-5
+        assert relerr(x.grad.numpy(), g["dx"]) <= 1e-4
+        named = dict(m.named_parameters())
+        for k in [k[5:] for k in g if k.startswith("grad/")]:
+            assert relerr(named[k].grad.numpy(), g["grad/" + k]) <= 1e-4, k
+        assert relerr(m.state_dict()["batch_norm1.running_var"].numpy(), g["batch_norm1.running_var"]) <= 1e-5
+        assert int(m.state_dict()["batch_norm1.num_batches_tracked"]) == 1
+        m.eval()
+        with torch.no_grad():
+            e1, e2 = m(x.detach())
+        assert relerr(e1.numpy(), g["eval_p1"]) <= 1e-5 and relerr(e2.numpy(), g["eval_p2"]) <= 1e-5
+        # dropout: the engine draws its keep masks with torch.rand; replay them through the oracle
+        rr, _, sd, m = _refiner_case("fp32")
+        m.p_dropout = 0.5
+        m.train()
+        torch.manual_seed(123)
+        q1, q2 = m(x.detach())
+        torch.manual_seed(123)
+        masks = [(torch.rand(24, 128) >= 0.5) for _ in range(10)]
+        o1, o2 = rr.forward(sd, x.detach(), training=True, masks=masks, p_dropout=0.5)
+        assert relerr(q1.detach().numpy(), o1.numpy()) <= 1e-5 and relerr(q2.detach().numpy(), o2.numpy()) <= 1e-5
+        with pytest.raises(NotImplementedError):
+            rmodel.LinearModelPG(leaky=True)
+        with pytest.raises(NotImplementedError):
+            rmodel.LinearPG(64, bn=False)
+    finally:
+        rmodel.LinearModelPG._backend[0] = None
+
+
 def test_fused_optimizers_match_torch():
     import lib.utils.utils as U
     U._backend[0] = emul_ops

@@ -182,3 +182,29 @@ def test_nview_dlt_reduces_to_the_reference_pair_case(golden):
     us = np.stack([restate.project(P[0, v], Xw) for v in range(4)])
     x, st = restate.linear_eigen_triangulation_nview(us, P[0])
     assert np.max(np.abs(x - Xw)) <= 1e-8 and st.all()
+
+
+def test_refiner_oracle(golden):
+    """oracle/restate_refiner.py against the unmodified refiner/model.py (training mode without
+    dropout: forward, input / parameter gradients, running statistics; eval-mode forward)."""
+    from oracle import restate_refiner as rr
+    g = golden("refiner")
+    sd = rr.init_state(rr.param_shapes(128, 45, 45), 17)
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    x = torch.from_numpy(gi.grad_like((24, 45), 18)).requires_grad_(True)
+    tgt = torch.from_numpy(gi.grad_like((24, 45), 19))
+    stats = {}
+    p1, p2 = rr.forward(p, x, training=True, new_stats=stats)
+    loss = torch.nn.functional.mse_loss(p1, tgt) + torch.nn.functional.mse_loss(p2, tgt)
+    loss.backward()
+    assert relerr(p1.detach().numpy(), g["p1"]) <= 1e-5 and relerr(p2.detach().numpy(), g["p2"]) <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert relerr(x.grad.numpy(), g["dx"]) <= 1e-4
+    for k in [k[5:] for k in g if k.startswith("grad/")]:
+        assert relerr(p[k].grad.numpy(), g["grad/" + k]) <= 1e-4, k
+    assert relerr(stats["batch_norm1.running_var"].numpy(), g["batch_norm1.running_var"]) <= 1e-5
+    sd_after = dict(sd)
+    sd_after.update(stats)                   # the reference evaluates after its training-mode forward
+    with torch.no_grad():
+        e1, e2 = rr.forward(sd_after, x.detach(), training=False)
+    assert relerr(e1.numpy(), g["eval_p1"]) <= 1e-5 and relerr(e2.numpy(), g["eval_p2"]) <= 1e-5

@@ -38,7 +38,8 @@ def relerr(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
 
 
-# GPU tests of kernels whose arithmetic is validated on the CPU (tests/harness) but that have not
-# had a hardware run yet (the round's GPU budget was spent): skipped unless EPB_RUN_HW_PENDING=1.
+# Marker for GPU tests of kernels whose arithmetic is validated on the CPU (tests/harness, emulated
+# ABI) but that have not had a hardware run yet: skipped unless EPB_RUN_HW_PENDING=1.  Unused when
+# every test has been run on a B200 (the case at the end of round 1).
 hw_pending = pytest.mark.skipif(os.environ.get("EPB_RUN_HW_PENDING") != "1",
                                 reason="hardware run pending: set EPB_RUN_HW_PENDING=1 on a B200")

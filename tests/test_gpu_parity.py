@@ -9,7 +9,7 @@ import torch
 
 from oracle import restate, restate_net
 from tests import golden_inputs as gi
-from tests.conftest import hw_pending, relerr
+from tests.conftest import relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -277,7 +277,6 @@ def test_polynomial_triangulation_golden(golden, dev):
         assert np.max(np.abs(Xb[i].cpu().numpy() - xr)) <= 1e-4
 
 
-@hw_pending
 @pytest.mark.parametrize("V", [2, 3, 4])
 def test_nview_dlt_vs_oracle(dev, V):
     """epb_triangulate_nview against the numpy-SVD oracle (<= 1e-4 mm, 3 px noise), exact recovery
@@ -672,7 +671,6 @@ def test_reference_script_flow(dev, tmp_path):
     reset_config()
 
 
-@hw_pending
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 def test_refiner_vs_reference_golden(golden, dev, precision):
     """refiner MLP on the device: forward / backward / running statistics against

@@ -97,6 +97,39 @@ def test_engine_matches_oracle_through_emulated_abi(layers, volume):
     assert int(m.state_dict()["bn1.num_batches_tracked"]) == 1
 
 
+@pytest.mark.parametrize("dk,fk,db", [((3, 2, 4), 3, True), ((2, 3, 4), 1, False)])
+def test_engine_uncommon_head_configs_emulated(dk, fk, db):
+    """cfg.MODEL.EXTRA variants the bench never uses (reference pose3d_resnet.py:145-156,116-122):
+    deconv kernels 3 -> (pad 1, output_padding 1) and 2 -> (0, 0), FINAL_CONV_KERNEL = 3,
+    DECONV_WITH_BIAS -- geometry tables, packing and gradients through the emulated ABI."""
+    import lib.models as models
+    J, D, HW, N = 3, 8, 64, 2
+    cfg = refshim.make_cfg(num_layers=18, num_joints=J, volume=True, depth_res=D, image_size=(HW, HW),
+                           deconv_with_bias=db, final_kernel=fk)
+    cfg.MODEL.EXTRA.NUM_DECONV_KERNELS = list(dk)
+    shapes = restate_net.param_shapes(18, J, True, D, deconv_kernels=dk, deconv_with_bias=db, final_kernel=fk)
+    sd = restate_net.init_state(shapes, 9)
+    m = models.pose3d_resnet.get_pose_net(cfg, False, ops=emul_ops)
+    assert list(m.state_dict().keys()) == list(shapes.keys())
+    m.load_state_dict(sd)
+    m.train()
+    x = torch.from_numpy(gi.images(N, HW, 9))
+    p = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+             else (v.double() if v.is_floating_point() else v)) for k, v in sd.items()}
+    ref = restate_net.forward(p, x.double(), num_layers=18, volume=True, image_size=(HW, HW),
+                              deconv_kernels=dk, final_kernel=fk)
+    out = m(x)
+    assert out.shape == ref.shape and relerr(out.detach().numpy(), ref.detach().numpy()) <= 1e-4
+    g = torch.from_numpy(gi.grad_like(out.shape, 10))
+    (out * g).sum().backward()
+    (ref * g.double()).sum().backward()
+    gmax = max(float(p[k].grad.abs().max()) for k, _ in m.named_parameters())
+    for k, q in m.named_parameters():
+        r = p[k].grad.numpy()
+        # a bias in front of a training-mode BatchNorm has an exactly-zero gradient: absolute check
+        assert np.max(np.abs(q.grad.numpy() - r)) <= 5e-3 * max(np.max(np.abs(r)), 1e-4 * gmax), k
+
+
 def test_losses_and_decode_surface_emulated():
     import lib.core.integral_loss as il
     import lib.core.inference as inf

@@ -130,6 +130,25 @@ def test_engine_uncommon_head_configs_emulated(dk, fk, db):
         assert np.max(np.abs(q.grad.numpy() - r)) <= 5e-3 * max(np.max(np.abs(r)), 1e-4 * gmax), k
 
 
+@pytest.mark.parametrize("layers", [18, 34, 50, 101, 152])
+def test_state_dict_surface_all_depths(layers):
+    """get_pose_net for every entry of resnet_spec (reference pose3d_resnet.py:288-292): state_dict
+    keys, order and shapes equal the oracle's table (pinned to the reference module for 18 / 50),
+    VOLUME on and off; parameter counts of SURVEY section 8 (R50 34.27 M, R101 53.27 M)."""
+    import lib.models as models
+    for volume in (True, False):
+        cfg = refshim.make_cfg(num_layers=layers, num_joints=17, volume=volume, depth_res=64, image_size=(256, 256))
+        m = models.pose3d_resnet.get_pose_net(cfg, False, ops=emul_ops)
+        shapes = restate_net.param_shapes(layers, 17, volume, 64)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    if layers in (50, 101):
+        cfg = refshim.make_cfg(num_layers=layers, num_joints=17, volume=True, depth_res=64, image_size=(256, 256))
+        n = sum(p.numel() for p in models.pose3d_resnet.get_pose_net(cfg, False, ops=emul_ops).parameters())
+        assert abs(n / 1e6 - {50: 34.27, 101: 53.27}[layers]) < 0.01
+
+
 def test_losses_and_decode_surface_emulated():
     import lib.core.integral_loss as il
     import lib.core.inference as inf

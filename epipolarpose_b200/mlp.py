@@ -151,7 +151,6 @@ class MLPEngine:
         if cin_p != cin:
             xp = torch.zeros((N, cin_p), device=self.dev)
             xp[:, :cin] = x
-        self.x_in, self.cin = xp, cin
         y, st = self.linear("w1", xp.contiguous(), params, pg)
         y = self.bn_relu("batch_norm1", y, st, params, pg, training)
         inp = self.dropout(y, pdrop, training)
@@ -164,20 +163,24 @@ class MLPEngine:
         y = self._stage("linear_stages.1", y, params, pg, training, pdrop)
         y = self.add(inp, y)
         p2, _ = self.linear("w4", y, params, pg)
-        self.outs = (p1, p2)
         cout = params["w2.weight"].shape[0]
-        return p1[:, :cout], p2[:, :cout]
+        # everything the backward needs travels in `record` (several forwards may be alive at once)
+        record = {"tape": self.tape, "pgrads": self.pgrads, "outs": (p1, p2), "x_in": xp, "cin": cin}
+        self.tape, self.pgrads = [], None
+        return p1[:, :cout], p2[:, :cout], record
 
-    def backward(self, dp1, dp2):
-        """dp1, dp2 [N, output_size] -> (dx [N, input_size], {param name: grad})."""
-        p1, p2 = self.outs
+    def backward(self, record, dp1, dp2):
+        """dp1, dp2 [N, output_size] (or None) -> (dx [N, input_size], {param name: grad})."""
+        self.dev = record["x_in"].device
+        self.eng.dev = self.dev
         grads = {}
-        for t, d in ((p1, dp1), (p2, dp2)):
+        for t, d in zip(record["outs"], (dp1, dp2)):
             g = torch.zeros_like(t)
-            g[:, :d.shape[1]] = d
+            if d is not None:
+                g[:, :d.shape[1]] = d
             grads[id(t)] = g
-        for bwd in reversed(self.tape):
+        for bwd in reversed(record["tape"]):
             bwd(grads)
-        dx = grads.pop(id(self.x_in))[:, :self.cin]
-        self.tape = []
-        return dx, self.pgrads
+        dx = grads.pop(id(record["x_in"]))[:, :record["cin"]]
+        record["tape"] = []
+        return dx, record["pgrads"]

@@ -41,19 +41,17 @@ class _RefinerFn(torch.autograd.Function):
         eng = module._engine()
         need = any(ctx.needs_input_grad)
         with torch.no_grad():
-            p1, p2 = eng.forward(x.contiguous().float(), p, module.training, module.p_dropout, want_grad=need)
-        ctx.module, ctx.need = module, need
+            p1, p2, record = eng.forward(x.contiguous().float(), p, module.training, module.p_dropout,
+                                         want_grad=need)
+        ctx.module, ctx.record = module, record
         return p1.clone(), p2.clone()
 
     @staticmethod
     def backward(ctx, dp1, dp2):
         module = ctx.module
-        eng = module._engine()
-        z = lambda d, ref: torch.zeros_like(ref) if d is None else d
-        p1, p2 = eng.outs
-        cout = module.output_size
+        c = lambda d: None if d is None else d.contiguous()
         with torch.no_grad():
-            dx, pg = eng.backward(z(dp1, p1[:, :cout]).contiguous(), z(dp2, p2[:, :cout]).contiguous())
+            dx, pg = module._engine().backward(ctx.record, c(dp1), c(dp2))
         return (None, dx) + tuple(pg.get(n) for n in module._param_names)
 
 

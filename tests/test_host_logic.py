@@ -431,6 +431,18 @@ def test_refiner_surface_emulated():
         masks = [(torch.rand(24, 128) >= 0.5) for _ in range(10)]
         o1, o2 = rr.forward(sd, x.detach(), training=True, masks=masks, p_dropout=0.5)
         assert relerr(q1.detach().numpy(), o1.numpy()) <= 1e-5 and relerr(q2.detach().numpy(), o2.numpy()) <= 1e-5
+        # two forward passes alive at once: each backward uses its own record
+        rr, _, sd, m = _refiner_case("fp32")
+        m.train()
+        xa = torch.from_numpy(gi.grad_like((24, 45), 18)).requires_grad_(True)
+        xb = torch.from_numpy(gi.grad_like((24, 45), 21)).requires_grad_(True)
+        a1, _ = m(xa)
+        b1, _ = m(xb)
+        a1.sum().backward()
+        pa = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+        xo = xa.detach().clone().requires_grad_(True)
+        rr.forward(pa, xo, training=True)[0].sum().backward()
+        assert relerr(xa.grad.numpy(), xo.grad.numpy()) <= 1e-4 and xb.grad is None
         with pytest.raises(NotImplementedError):
             rmodel.LinearModelPG(leaky=True)
         with pytest.raises(NotImplementedError):

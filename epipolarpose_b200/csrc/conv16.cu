@@ -1,0 +1,396 @@
+// Split-fp16 ("f16x3") tensor-core path of the tap-list implicit GEMM (include/epb.h,
+// epb_conv16_fprop): forward convs, transposed convs (one call per output phase) and both of
+// their data gradients, i.e. the cuDNN call sites behind nn.Conv2d / nn.ConvTranspose2d of
+// lib/models/pose3d_resnet.py:12-15,55-60,99,116-122,132,171-178 and their autograd.
+//
+//   out[m, co] = (1 / (s_in * s_w)) * sum_k A[m, k] * W[co, k],   m = phase-grid pixel,
+//   k = (tap, ci),  A = hi + lo, W = hi + lo  (fp16 planes),
+//   A*W ~= A_lo*W_hi + A_hi*W_lo + A_hi*W_hi   (three kind::f16 passes, FP32 accumulate).
+//
+// Both operands are TMA-fed: the activation planes are post-BatchNorm/ReLU (written once by
+// split16.cu), so an M tile of 128 pixels is ONE 5-D box load per plane and tap -- (64 channels,
+// tw, th, tn) of the (C, W, H, N, plane) tensor, shifted by the tap offset; the zero padding
+// of the convolution is the TMA out-of-bounds fill, strided convs use the four parity views of
+// the tensor.  Weight planes are 3-D (k, co, plane) box loads.
+//
+// Always CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): each CTA holds its 128 A
+// rows and HALF of the B tile's N rows, which keeps shared-memory reads under 128 B/clk at
+// the kind::f16 rate.  One persistent cluster per SM pair, 6 warps per CTA:
+//   warp 0    TMA producer (one lane): A hi/lo + B hi/lo boxes per k-block, S-deep ring;
+//   warp 1    MMA issuer (leader CTA, one lane): 4 k-steps x 3 tcgen05.mma per k-block,
+//             FP32 accumulators double buffered in TMEM;
+//   warps 2-5 epilogue: tcgen05.ld -> scale / bias -> smem-staged 128-byte-line stores or
+//             accumulate, per-channel sum / sum of squares for the following BatchNorm.
+// Every mbarrier wait is bounded (trap instead of hang).
+#include "split16_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int kThreads16 = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kStageBudget = 192 * 1024;
+
+struct Plan16 {
+  int N, Hp, Wp;                 // phase grid
+  int Ho, Wo, Cout, os, ph, pw;  // output tensor / phase
+  int T, CB;                     // taps, channel blocks of 64 per tap
+  int tw, th, tn, tiles_w, tiles_h;
+  int m_tiles, n_tiles;
+  int accumulate;
+  int koff[EPB_MAX_TAPS];        // wt[t] * Cin: k offset of the tap inside a packed weight row
+  short dwq[EPB_MAX_TAPS], dhq[EPB_MAX_TAPS];   // tap offset on its parity view
+  unsigned char map[EPB_MAX_TAPS];              // parity view of the tap
+};
+
+struct Maps16 {
+  CUtensorMap a[4];
+  CUtensorMap w;
+};
+
+template <int BN>
+struct Cfg16 {
+  static constexpr int BROWS = BN / 2;                 // B rows held by this CTA
+  static constexpr int A_PLANE = BM * 128;
+  static constexpr int B_PLANE = BROWS * 128;
+  static constexpr int A_BYTES = 2 * A_PLANE;
+  static constexpr int B_BYTES = 2 * B_PLANE;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int S_ = kStageBudget / STAGE;
+  static constexpr int S = S_ > 6 ? 6 : S_;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int EPI_PITCH = 36;
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_PITCH * 4;
+  static constexpr int STAT_BYTES = kEpiWarps * 2 * BN * 4;
+  static constexpr int PTAB_BYTES = kEpiWarps * 32 * 8;
+  static constexpr int SMEM = S * STAGE + 1024 /*align*/ + 1024 /*barriers*/ + STAT_BYTES +
+                              EPI_BYTES + PTAB_BYTES;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(S >= 2, "ring too shallow");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads16, 1)
+conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 maps,
+              const float* __restrict__ in_sc, const float* __restrict__ w_sc,
+              const float* __restrict__ bias, float* __restrict__ out,
+              double* __restrict__ stats) {
+  using C = Cfg16<BN>;
+  const int crank = (int)tc::cluster_ctarank();
+  const int tile0 = (int)tc::cluster_id_x();
+  const int tstep = (int)tc::cluster_count_x();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  uint8_t* ctrl = sm + C::S * C::STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);          // full[8], empty[8], tfull[2], tempty[2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl + 8 * 20);
+  float* sstat = reinterpret_cast<float*>(ctrl + 1024);                      // [4 warps][2][BN]
+  float* epi_stage = sstat + kEpiWarps * 2 * BN;                             // [4][32][EPI_PITCH]
+  unsigned long long* eprow =
+      reinterpret_cast<unsigned long long*>(epi_stage + kEpiWarps * 32 * C::EPI_PITCH);
+  const uint32_t bar0 = tc::smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (16 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (18 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = P.T * P.CB;
+  const int total_tiles = ((P.m_tiles + 1) / 2) * P.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::S; ++s) {
+      tc::mbar_init(full_bar(s), 1);          // the leader's arrive.expect_tx; bytes from both CTAs
+      tc::mbar_init(empty_bar(s), 1);         // tcgen05.commit (multicast to both CTAs)
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar(a), 1);
+      tc::mbar_init(tempty_bar(a), 2 * kEpiWarps);   // epilogue warps of BOTH CTAs (leader's barrier)
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_pair<C::TMEM_COLS>(tc::smem_u32(tmem_ptr));
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();                          // the peer's barriers exist before any remote signal
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =================================================== TMA producer
+    if (lane == 0) {
+      for (int v = 0; v < 4; ++v) tc::tma_prefetch_desc(&maps.a[v]);
+      tc::tma_prefetch_desc(&maps.w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
+        const int nt = tile % P.n_tiles;
+        int it = 2 * (tile / P.n_tiles) + crank;        // this CTA's M tile (may lie past the end: all zero)
+        const int w0 = (it % P.tiles_w) * P.tw; it /= P.tiles_w;
+        const int h0 = (it % P.tiles_h) * P.th;
+        const int n0 = (it / P.tiles_h) * P.tn;
+        int t = 0, cb = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+          tc::mbar_wait(empty_bar(stage), phase ^ 1);
+          if (crank == 0) tc::mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE);
+          const uint32_t lead_bar = tc::mapa(full_bar(stage), 0);
+          const uint32_t a_dst = base + stage * C::STAGE;
+          const CUtensorMap* am = &maps.a[P.map[t]];
+          const int cx = cb * 64, wx = w0 + P.dwq[t], hx = h0 + P.dhq[t];
+          tc::tma_load_5d_pair(a_dst, am, lead_bar, cx, wx, hx, n0, 0);
+          tc::tma_load_5d_pair(a_dst + C::A_PLANE, am, lead_bar, cx, wx, hx, n0, 1);
+          const uint32_t b_dst = a_dst + C::A_BYTES;
+          const int kx = P.koff[t] + cx, rx = nt * BN + crank * C::BROWS;
+          tc::tma_load_3d_pair(b_dst, &maps.w, lead_bar, kx, rx, 0);
+          tc::tma_load_3d_pair(b_dst + C::B_PLANE, &maps.w, lead_bar, kx, rx, 1);
+          if (++cb == P.CB) { cb = 0; ++t; }
+          if (++stage == C::S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================================== MMA issuer (leader CTA)
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = tc::idesc_f16(2 * BM, BN, 0, 0);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
+        tc::mbar_wait_cluster(tempty_bar(as), aphase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          tc::mbar_wait_cluster(full_bar(stage), phase);
+          tc::tc_fence_after();
+          const uint32_t a_hi = base + stage * C::STAGE;
+          const uint32_t b_hi = a_hi + C::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {               // 4 x K = 16 fp16 (32 bytes)
+            const uint64_t ah = tc::desc_kmajor_sw128(a_hi + kk * 32);
+            const uint64_t al = tc::desc_kmajor_sw128(a_hi + C::A_PLANE + kk * 32);
+            const uint64_t bh = tc::desc_kmajor_sw128(b_hi + kk * 32);
+            const uint64_t bl = tc::desc_kmajor_sw128(b_hi + C::B_PLANE + kk * 32);
+            tc::mma_f16_pair(d_tmem, al, bh, idesc, (kb | kk) != 0);
+            tc::mma_f16_pair(d_tmem, ah, bl, idesc, 1);
+            tc::mma_f16_pair(d_tmem, ah, bh, idesc, 1);
+          }
+          tc::mma_commit_pair(empty_bar(stage));          // frees the slot in both CTAs
+          if (++stage == C::S) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit_pair(tfull_bar(as));               // accumulator complete (both CTAs)
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // =================================================== epilogue (4 warps)
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int wq = warp - 2;
+    const int et = wq * 32 + lane;             // 0..127
+    float* stg = epi_stage + wq * 32 * C::EPI_PITCH;
+    float* sst = sstat + wq * 2 * BN;
+    unsigned long long* ptab = eprow + wq * 32;
+    const int c4 = lane & 7, rsub = lane >> 3;
+    const float alpha = in_sc[1] * w_sc[1];
+    const int twh = P.tw * P.th;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tstep) {
+      const int nt = tile % P.n_tiles;
+      const int mt = 2 * (tile / P.n_tiles) + crank;
+      int it = mt;
+      const int w0 = (it % P.tiles_w) * P.tw; it /= P.tiles_w;
+      const int h0 = (it % P.tiles_h) * P.th;
+      const int n0 = (it / P.tiles_h) * P.tn;
+      const int r = q * 32 + lane;             // tile row == TMEM lane
+      const int w = w0 + r % P.tw, h = h0 + (r / P.tw) % P.th, n = n0 + r / twh;
+      const bool valid = mt < P.m_tiles && w < P.Wp && h < P.Hp && n < P.N;
+      float* orow = nullptr;
+      if (valid)
+        orow = out + (((int64_t)n * P.Ho + (h * P.os + P.ph)) * P.Wo + (w * P.os + P.pw)) * P.Cout;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      ptab[lane] = reinterpret_cast<unsigned long long>(orow);
+      __syncwarp();
+      tc::mbar_wait(tfull_bar(as), aphase);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        const int col0 = nt * BN + chunk * 32;
+        if (col0 >= P.Cout) break;             // N tail
+        uint32_t rg[32];
+        tc::tmem_ld32(tmem_base + as * BN + chunk * 32 + ((uint32_t)(q * 32) << 16), rg);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 x = make_float4(__uint_as_float(rg[c]) * alpha, __uint_as_float(rg[c + 1]) * alpha,
+                                 __uint_as_float(rg[c + 2]) * alpha, __uint_as_float(rg[c + 3]) * alpha);
+          if (bias && col0 + c < P.Cout) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + col0 + c);
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+          }
+          *reinterpret_cast<float4*>(stg + lane * C::EPI_PITCH + c) = x;
+        }
+        __syncwarp();
+        if (stats) {
+          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const float x = ((vmask >> rr) & 1u) ? stg[rr * C::EPI_PITCH + lane] : 0.f;
+            s1[rr & 3] += x;
+            s2[rr & 3] = fmaf(x, x, s2[rr & 3]);
+          }
+          sst[chunk * 32 + lane] = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+          sst[BN + chunk * 32 + lane] = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+        }
+        if (col0 + c4 * 4 < P.Cout) {          // Cout % 4 == 0: whole float4 columns
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            float* op = reinterpret_cast<float*>(ptab[rr]);
+            if (op) {
+              float4 x = *reinterpret_cast<const float4*>(stg + rr * C::EPI_PITCH + c4 * 4);
+              float4* o = reinterpret_cast<float4*>(op + col0) + c4;
+              if (P.accumulate) {
+                const float4 pv = *o;
+                x.x += pv.x; x.y += pv.y; x.z += pv.z; x.w += pv.w;
+              }
+              *o = x;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(tempty_bar(as), 0));   // release at cluster scope
+      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (stats) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int c = et; c < 2 * BN; c += 128) {
+          const int which = c / BN, cc = c % BN, col = nt * BN + cc;
+          if (col < P.Cout) {
+            const float v = (sstat[c] + sstat[2 * BN + c]) + (sstat[4 * BN + c] + sstat[6 * BN + c]);
+            atomicAdd(stats + (int64_t)which * P.Cout + col, (double)v);
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();             // the peer may still read this CTA's smem / signal its barriers
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN>
+int launch16(const Plan16& P, const Maps16& maps, const float* in_sc, const float* w_sc,
+             const float* bias, float* out, double* stats, cudaStream_t st) {
+  using C = Cfg16<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EPB_CUDA(cudaFuncSetAttribute(conv16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM));
+    attr_set = true;
+  }
+  const int64_t pairs = (int64_t)((P.m_tiles + 1) / 2) * P.n_tiles;
+  const int grid = 2 * (int)(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
+  conv16_kernel<BN><<<grid, kThreads16, C::SMEM, st>>>(P, maps, in_sc, w_sc, bias, out, stats);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int epb_conv16_fprop(
+    const epb_conv_geom* g, const epb_half* in, const float* in_sc, const epb_half* w,
+    const float* w_sc, const float* bias, float* out, double* stats, epb_stream_t stream) {
+  int rc = epb_conv_geom_check(g);
+  if (rc) return rc;
+  EPB_CHECK_ARG(in && in_sc && w && w_sc && out);
+  EPB_CHECK_ARG(g->Cin % 64 == 0 && g->Cout % 4 == 0 && g->Cout >= 4);
+  EPB_CHECK_ARG(g->is == 1 || g->is == 2);
+  EPB_CHECK_ARG(!(stats && g->accumulate));
+  EPB_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 127) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0);
+  Plan16 P;
+  Maps16 maps;
+  memset(&maps, 0, sizeof(maps));
+  P.Ho = g->Ho; P.Wo = g->Wo; P.Cout = g->Cout; P.os = g->os; P.ph = g->ph; P.pw = g->pw;
+  P.T = g->T; P.CB = g->Cin / 64; P.accumulate = g->accumulate;
+  // a 1x1 stride-1 layer whose phase grid IS the input and the output grid is a plain
+  // [M][C] matrix: tile it as rows (no waste whatever H and W are)
+  const bool dense = g->T == 1 && g->is == 1 && g->os == 1 && g->dh[0] == 0 && g->dw[0] == 0 &&
+                     g->Hp == g->Hi && g->Wp == g->Wi && g->Hp == g->Ho && g->Wp == g->Wo;
+  int N = g->N, Hi = g->Hi, Wi = g->Wi;
+  P.N = g->N; P.Hp = g->Hp; P.Wp = g->Wp;
+  if (dense) {
+    const int64_t M = (int64_t)g->N * g->Hp * g->Wp;
+    EPB_CHECK_ARG(M < (1LL << 31));
+    N = 1; Hi = 1; Wi = (int)M;
+    P.N = 1; P.Hp = 1; P.Wp = (int)M; P.Ho = 1; P.Wo = (int)M;
+  }
+  epb_choose_tile(P.N, P.Hp, P.Wp, BM, P.tw, P.th, P.tn);
+  P.tiles_w = (P.Wp + P.tw - 1) / P.tw;
+  P.tiles_h = (P.Hp + P.th - 1) / P.th;
+  const int64_t mt = (int64_t)P.tiles_w * P.tiles_h * ((P.N + P.tn - 1) / P.tn);
+  EPB_CHECK_ARG(mt < (1LL << 30));
+  P.m_tiles = (int)mt;
+  bool need[4] = {false, false, false, false};
+  for (int t = 0; t < g->T; ++t) {
+    int qh, qw, dq_h, dq_w;
+    epb_tap_split(g->dh[t], g->is, qh, dq_h);
+    epb_tap_split(g->dw[t], g->is, qw, dq_w);
+    P.map[t] = (unsigned char)(qh * 2 + qw);
+    P.dhq[t] = (short)dq_h;
+    P.dwq[t] = (short)dq_w;
+    P.koff[t] = g->wt[t] * g->Cin;
+    need[qh * 2 + qw] = true;
+  }
+  for (int v = 0; v < 4; ++v) {
+    if (!need[v]) continue;
+    rc = epb_make_act_map(&maps.a[v], in, N, Hi, Wi, g->Cin, g->is, v >> 1, v & 1, P.tw, P.th, P.tn);
+    if (rc) return rc;
+  }
+  for (int v = 0; v < 4; ++v)
+    if (!need[v]) {                         // unused slots hold a valid map (they are prefetched)
+      for (int u = 0; u < 4; ++u)
+        if (need[u]) { maps.a[v] = maps.a[u]; break; }
+    }
+  // N tile: 256 unless that wastes more than a quarter of the columns
+  int bn;
+  if (g->Cout <= 64) bn = 64;
+  else if (g->Cout <= 128) bn = 128;
+  else {
+    const int p256 = (g->Cout + 255) / 256 * 256, p128 = (g->Cout + 127) / 128 * 128;
+    bn = (p256 * 4 > p128 * 5) ? 128 : 256;
+  }
+  P.n_tiles = (g->Cout + bn - 1) / bn;
+  {
+    epb_encode_tiled_fn enc = epb_get_encode_tiled();
+    if (!enc) {
+      epb_set_error("cuTensorMapEncodeTiled entry point unavailable");
+      return EPB_ECUDA;
+    }
+    const int64_t K = (int64_t)g->Tw * g->Cin;
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)g->Cout, 2};
+    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * g->Cout};
+    const cuuint32_t box[3] = {64, (cuuint32_t)(bn / 2), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = enc(&maps.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<epb_half*>(w), dims,
+                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      epb_set_error("cuTensorMapEncodeTiled(weights %d x %lld) failed (%d)", g->Cout, (long long)K,
+                    (int)cr);
+      return EPB_ECUDA;
+    }
+  }
+  cudaStream_t st = as_stream(stream);
+  if (bn == 64) return launch16<64>(P, maps, in_sc, w_sc, bias, out, stats, st);
+  if (bn == 128) return launch16<128>(P, maps, in_sc, w_sc, bias, out, stats, st);
+  return launch16<256>(P, maps, in_sc, w_sc, bias, out, stats, st);
+}

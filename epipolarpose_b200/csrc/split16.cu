@@ -1,0 +1,558 @@
+// Element-wise producers / consumers of split-fp16 tensors (include/epb.h, "f16x3" family):
+//   x * s = hi + lo,  hi = fp16(x*s), lo = fp16(x*s - hi), two planes [2][rows][C].
+// Reference call sites: the BatchNorm2d / ReLU / residual add / MaxPool2d / AvgPool2d of
+// lib/models/pose3d_resnet.py:24,31-47,56-88,101-103,125,134,179,187-189,208 and their
+// autograd.  Every kernel is one HBM pass: fp32 rows in, two fp16 planes out (the same
+// 4 bytes per element as an fp32 store), so that the tensor-core kernels (conv16.cu,
+// wgrad16.cu) can take their operands by TMA with no transformation.
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kHalfMax = 65504.f;
+
+// (a, b) * s -> packed fp16 pairs hi, lo
+__device__ __forceinline__ void split2(float a, float b, float s, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a * s, -kHalfMax), kHalfMax);
+  b = fminf(fmaxf(b * s, -kHalfMax), kHalfMax);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split8(const float (&v)[8], float s, uint4& hi, uint4& lo) {
+  split2(v[0], v[1], s, hi.x, lo.x);
+  split2(v[2], v[3], s, hi.y, lo.y);
+  split2(v[4], v[5], s, hi.z, lo.z);
+  split2(v[6], v[7], s, hi.w, lo.w);
+}
+__device__ __forceinline__ float2 h2f(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+// 8 values (hi + lo) * inv
+__device__ __forceinline__ void join8(uint4 hi, uint4 lo, float inv, float (&v)[8]) {
+  const uint32_t* H = &hi.x;
+  const uint32_t* L = &lo.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 a = h2f(H[k]), b = h2f(L[k]);
+    v[2 * k] = (a.x + b.x) * inv;
+    v[2 * k + 1] = (a.y + b.y) * inv;
+  }
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = ldg_stream(reinterpret_cast<const float4*>(p));
+  const float4 b = ldg_stream(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8c(const float* p, float (&v)[8]) {   // cached (per-channel vectors)
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+inline int ew_blocks(int64_t items) {
+  int64_t b = (items + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(kThreads)
+bn_act_split_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ r,
+                    const float* __restrict__ rscale, const float* __restrict__ rshift,
+                    const uint4* __restrict__ rs, const float* __restrict__ rs_sc, int relu,
+                    int64_t total8, int C8, uint4* __restrict__ y, const float* __restrict__ y_sc) {
+  const float s = y_sc[0];
+  const float rinv = rs ? rs_sc[1] : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total8;
+       i += (int64_t)gridDim.x * kThreads) {
+    const int c = (int)(i % C8) * 8;
+    float v[8];
+    ld8(x + i * 8, v);
+    if (scale) {
+      float sc[8], sh[8];
+      ld8c(scale + c, sc);
+      ld8c(shift + c, sh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+    }
+    if (r) {
+      float q[8];
+      ld8(r + i * 8, q);
+      if (rscale) {
+        float sc[8], sh[8];
+        ld8c(rscale + c, sc);
+        ld8c(rshift + c, sh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[k] = fmaf(q[k], sc[k], sh[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += q[k];
+    } else if (rs) {
+      float q[8];
+      join8(rs[i], rs[total8 + i], rinv, q);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += q[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    uint4 hi, lo;
+    split8(v, s, hi, lo);
+    y[i] = hi;
+    y[total8 + i] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+bn_relu_maxpool_split_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                             const float* __restrict__ shift, uint4* __restrict__ y,
+                             const float* __restrict__ y_sc, uint2* __restrict__ argidx, int N, int H,
+                             int W, int C8) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * C8;
+  const float s = y_sc[0];
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * kThreads) {
+    const int c8 = (int)(i % C8);
+    int64_t p = i / C8;
+    const int ow = (int)(p % Wo); p /= Wo;
+    const int oh = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float sc[8], sh[8], best[8];
+    unsigned char bi[8];
+    ld8c(scale + c8 * 8, sc);
+    ld8c(shift + c8 * 8, sh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        float v[8];
+        ld8c(x + (((int64_t)(n * H + ih) * W + iw) * C8 + c8) * 8, v);
+        const unsigned char me = (unsigned char)(kh * 3 + kw);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float a = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+          if (a > best[k]) { best[k] = a; bi[k] = me; }
+        }
+      }
+    }
+    uint4 hi, lo;
+    split8(best, s, hi, lo);
+    y[i] = hi;
+    y[total + i] = lo;
+    if (argidx) {
+      uint2 a;
+      a.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((unsigned)bi[3] << 24);
+      a.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((unsigned)bi[7] << 24);
+      argidx[i] = a;
+    }
+  }
+}
+
+// one thread = 8 consecutive k of one patch row
+__global__ void __launch_bounds__(kThreads)
+im2col_split_kernel(const float* __restrict__ img, uint4* __restrict__ col,
+                    const float* __restrict__ col_sc, int N, int C, int Hi, int Wi, int kh, int kw,
+                    int stride, int pad, int Ho, int Wo, int Kpad) {
+  const int K8 = Kpad >> 3, K = kh * kw * C;
+  const int64_t total = (int64_t)N * Ho * Wo * K8;
+  const float s = col_sc[0];
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * kThreads) {
+    const int k8 = (int)(i % K8);
+    int64_t m = i / K8;
+    const int ow = (int)(m % Wo); m /= Wo;
+    const int oh = (int)(m % Ho);
+    const int n = (int)(m / Ho);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kk = k8 * 8 + e;
+      v[e] = 0.f;
+      if (kk < K) {
+        const int t = kk / C, c = kk - t * C;
+        const int r = t / kw, sx = t - r * kw;
+        const int ih = oh * stride - pad + r, iw = ow * stride - pad + sx;
+        if (ih >= 0 && ih < Hi && iw >= 0 && iw < Wi)
+          v[e] = __ldg(img + ((int64_t)(n * C + c) * Hi + ih) * Wi + iw);
+      }
+    }
+    uint4 hi, lo;
+    split8(v, s, hi, lo);
+    col[i] = hi;
+    col[total + i] = lo;
+  }
+}
+
+// ------------------------------------------------------------------ batched fp32 -> split
+__device__ __forceinline__ const epb_split_job& find_job(const epb_split_job* jobs, int njobs,
+                                                         int& idx) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  idx = lo;
+  return jobs[lo];
+}
+
+__global__ void __launch_bounds__(kThreads)
+split_amax_kernel(const epb_split_job* __restrict__ jobs, int njobs, uint32_t* __restrict__ amax) {
+  int ji;
+  const epb_split_job j = find_job(jobs, njobs, ji);
+  const int64_t i0 = ((int64_t)blockIdx.x - j.first_block) * 2048;
+  const int64_t i1 = i0 + 2048 < j.n ? i0 + 2048 : j.n;
+  float m = 0.f;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += kThreads) m = fmaxf(m, fabsf(j.src[i]));
+  m = warp_max(m);
+  __shared__ float sm[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, sm[w]);
+    if (m > 0.f) atomicMax(amax + ji, __float_as_uint(m));   // non-negative floats order as uints
+  }
+}
+
+// scale 2^(13 - floor(log2(amax))): the largest scaled magnitude lies in [2^13, 2^14)
+__device__ __forceinline__ float pow2_scale(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);                 // amax = f * 2^e, f in [0.5, 1)  ->  floor(log2) = e - 1
+  int k = 13 - (e - 1);
+  k = k < -100 ? -100 : (k > 100 ? 100 : k);
+  return ldexpf(1.f, k);
+}
+
+__global__ void __launch_bounds__(kThreads)
+split_apply_kernel(const epb_split_job* __restrict__ jobs, int njobs,
+                   const uint32_t* __restrict__ amax) {
+  int ji;
+  const epb_split_job j = find_job(jobs, njobs, ji);
+  const float s = pow2_scale(__uint_as_float(amax[ji]));
+  const int64_t i0 = ((int64_t)blockIdx.x - j.first_block) * 2048;
+  if (i0 == 0 && threadIdx.x == 0) {
+    j.sc[0] = s;
+    j.sc[1] = 1.f / s;
+  }
+  const int64_t i1 = i0 + 2048 < j.n ? i0 + 2048 : j.n;
+  __half* hi = reinterpret_cast<__half*>(j.dst);
+  __half* lo = hi + j.n;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += kThreads) {
+    const float v = j.src[i] * s;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm backward
+constexpr int kRowsPerThread = 64;
+
+struct RowMap {
+  int C4, tpr, rpi, chunks;
+};
+inline RowMap make_rowmap(int C) {
+  RowMap r;
+  r.C4 = C / 4;
+  r.tpr = r.C4 < kThreads ? r.C4 : kThreads;
+  r.rpi = kThreads / r.tpr;
+  if (r.rpi < 1) r.rpi = 1;
+  r.chunks = (r.C4 + r.tpr - 1) / r.tpr;
+  return r;
+}
+
+__device__ __forceinline__ float4 mask4(float4 dy, float4 xv, const uint2* mask_hi, int64_t i,
+                                        float4 s, float4 b, int relu) {
+  if (mask_hi) {
+    const uint2 m = mask_hi[i];            // 4 fp16 values of the (non-negative) block output
+    return make_float4((m.x & 0x7fffu) ? dy.x : 0.f, (m.x & 0x7fff0000u) ? dy.y : 0.f,
+                       (m.y & 0x7fffu) ? dy.z : 0.f, (m.y & 0x7fff0000u) ? dy.w : 0.f);
+  }
+  if (relu) {
+    return make_float4(fmaf(xv.x, s.x, b.x) > 0.f ? dy.x : 0.f, fmaf(xv.y, s.y, b.y) > 0.f ? dy.y : 0.f,
+                       fmaf(xv.z, s.z, b.z) > 0.f ? dy.z : 0.f, fmaf(xv.w, s.w, b.w) > 0.f ? dy.w : 0.f);
+  }
+  return dy;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_mx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                        const uint2* __restrict__ mask_hi, const float4* __restrict__ scale,
+                        const float4* __restrict__ shift, const float4* __restrict__ mean,
+                        const float4* __restrict__ invstd, int relu, int64_t M, int C, RowMap rm,
+                        double* __restrict__ sums, float* __restrict__ maxes) {
+  const int slot = threadIdx.x / rm.tpr, tin = threadIdx.x % rm.tpr;
+  const int c4 = blockIdx.y * rm.tpr + tin;
+  const bool active = (c4 < rm.C4) && (slot < rm.rpi);
+  const int64_t rows_per_cta = (int64_t)rm.rpi * kRowsPerThread;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  float4 acc[4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};   // sum g, sum g*xhat, max|g|, max|xhat|
+  if (active) {
+    const float4 s = scale[c4], b = shift[c4], mu = mean[c4], is = invstd[c4];
+    auto fold = [&](float4 dv, float4 xv, int64_t i) {
+      const float4 g = mask4(dv, xv, mask_hi, i, s, b, relu);
+      const float4 xh = make_float4((xv.x - mu.x) * is.x, (xv.y - mu.y) * is.y,
+                                    (xv.z - mu.z) * is.z, (xv.w - mu.w) * is.w);
+      acc[0].x += g.x; acc[0].y += g.y; acc[0].z += g.z; acc[0].w += g.w;
+      acc[1].x += g.x * xh.x; acc[1].y += g.y * xh.y; acc[1].z += g.z * xh.z; acc[1].w += g.w * xh.w;
+      acc[2].x = fmaxf(acc[2].x, fabsf(g.x)); acc[2].y = fmaxf(acc[2].y, fabsf(g.y));
+      acc[2].z = fmaxf(acc[2].z, fabsf(g.z)); acc[2].w = fmaxf(acc[2].w, fabsf(g.w));
+      acc[3].x = fmaxf(acc[3].x, fabsf(xh.x)); acc[3].y = fmaxf(acc[3].y, fabsf(xh.y));
+      acc[3].z = fmaxf(acc[3].z, fabsf(xh.z)); acc[3].w = fmaxf(acc[3].w, fabsf(xh.w));
+    };
+    int k = 0;
+    for (; k + 4 <= kRowsPerThread; k += 4) {
+      const int64_t rl = r0 + (int64_t)(k + 3) * rm.rpi + slot;
+      if (rl >= M) break;
+      float4 xv[4], dv[4];
+      int64_t idx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        idx[u] = (r0 + (int64_t)(k + u) * rm.rpi + slot) * rm.C4 + c4;
+        xv[u] = ldg_stream(x + idx[u]);
+        dv[u] = ldg_stream(dy + idx[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fold(dv[u], xv[u], idx[u]);
+    }
+    for (; k < kRowsPerThread; ++k) {
+      const int64_t r = r0 + (int64_t)k * rm.rpi + slot;
+      if (r >= M) break;
+      const int64_t i = r * rm.C4 + c4;
+      const float4 xv = ldg_stream(x + i);
+      fold(ldg_stream(dy + i), xv, i);
+    }
+  }
+  __shared__ float4 sh[4][kThreads];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) sh[v][threadIdx.x] = acc[v];
+  __syncthreads();
+  if (slot == 0 && active) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int q = 0; q < rm.rpi; ++q) {
+        const float4 t = sh[v][q * rm.tpr + tin];
+        a0 += t.x; a1 += t.y; a2 += t.z; a3 += t.w;
+      }
+      double* o = sums + (int64_t)v * C + c4 * 4;
+      atomicAdd(o + 0, a0); atomicAdd(o + 1, a1); atomicAdd(o + 2, a2); atomicAdd(o + 3, a3);
+    }
+#pragma unroll
+    for (int v = 2; v < 4; ++v) {
+      float4 m = make_float4(0, 0, 0, 0);
+      for (int q = 0; q < rm.rpi; ++q) {
+        const float4 t = sh[v][q * rm.tpr + tin];
+        m.x = fmaxf(m.x, t.x); m.y = fmaxf(m.y, t.y); m.z = fmaxf(m.z, t.z); m.w = fmaxf(m.w, t.w);
+      }
+      uint32_t* o = reinterpret_cast<uint32_t*>(maxes) + (int64_t)(v - 2) * C + c4 * 4;
+      atomicMax(o + 0, __float_as_uint(m.x)); atomicMax(o + 1, __float_as_uint(m.y));
+      atomicMax(o + 2, __float_as_uint(m.z)); atomicMax(o + 3, __float_as_uint(m.w));
+    }
+  }
+}
+
+// one CTA: per-channel coefficients (k1 = sum_g/M, k2 = sum_gx/M overwrite maxes[0..2C)),
+// parameter gradients, and the power-of-two scale of dz from the bound
+//   |dz_c| <= |gamma_c*invstd_c| * (max|g|_c + |k1_c| + max|xhat|_c * |k2_c|)
+__global__ void __launch_bounds__(1024)
+bn_bwd_coef_split_kernel(const double* __restrict__ sums, float* __restrict__ maxes, double M, int C,
+                         const float* __restrict__ gamma, const float* __restrict__ invstd,
+                         float* __restrict__ dz_sc, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta) {
+  float bound = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double sg = sums[c], sgx = sums[C + c];
+    const float k0 = (gamma ? gamma[c] : 1.f) * invstd[c];
+    const float k1 = (float)(sg / M), k2 = (float)(sgx / M);
+    const float mg = maxes[c], mx = maxes[C + c];
+    bound = fmaxf(bound, fabsf(k0) * (mg + fabsf(k1) + mx * fabsf(k2)));
+    maxes[c] = k1;
+    maxes[C + c] = k2;
+    if (dgamma) dgamma[c] = (float)sgx;
+    if (dbeta) dbeta[c] = (float)sg;
+  }
+  bound = warp_max(bound);
+  __shared__ float sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = bound;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) bound = fmaxf(bound, sm[w]);
+    const float s = pow2_scale(bound);
+    dz_sc[0] = s;
+    dz_sc[1] = 1.f / s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_split_kernel(const float4* dy /* may alias dy_masked */, const float4* __restrict__ x,
+                          const uint2* __restrict__ mask_hi, const float4* __restrict__ scale,
+                          const float4* __restrict__ shift, const float4* __restrict__ mean,
+                          const float4* __restrict__ invstd, const float4* __restrict__ gamma,
+                          int relu, const float4* __restrict__ k1v, const float4* __restrict__ k2v,
+                          uint2* __restrict__ dz, const float* __restrict__ dz_sc,
+                          float4* dy_masked, int64_t total4, int C4) {
+  const float s = dz_sc[0];
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total4;
+       i += (int64_t)gridDim.x * kThreads) {
+    const int c4 = (int)(i % C4);
+    const float4 xv = ldg_stream(x + i);
+    const float4 g = mask4(__ldcs(dy + i), xv, mask_hi, i, scale[c4], shift[c4], relu);
+    const float4 mu = mean[c4], is = invstd[c4], b = k1v[c4], c = k2v[c4];
+    float4 a = is;
+    if (gamma) {
+      const float4 ga = gamma[c4];
+      a.x *= ga.x; a.y *= ga.y; a.z *= ga.z; a.w *= ga.w;
+    }
+    float4 o;
+    o.x = a.x * (g.x - b.x - (xv.x - mu.x) * is.x * c.x);
+    o.y = a.y * (g.y - b.y - (xv.y - mu.y) * is.y * c.y);
+    o.z = a.z * (g.z - b.z - (xv.z - mu.z) * is.z * c.z);
+    o.w = a.w * (g.w - b.w - (xv.w - mu.w) * is.w * c.w);
+    uint2 hi, lo;
+    split2(o.x, o.y, s, hi.x, lo.x);
+    split2(o.z, o.w, s, hi.y, lo.y);
+    dz[i] = hi;
+    dz[total4 + i] = lo;
+    if (dy_masked) dy_masked[i] = g;
+  }
+}
+
+__global__ void avgpool_split_kernel(const __half* __restrict__ x, const float* __restrict__ x_sc,
+                                     float* __restrict__ y, int N, int HW, int C) {
+  const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int64_t plane = (int64_t)N * HW * C;
+  float acc = 0.f;
+  for (int p = 0; p < HW; ++p) {
+    const int64_t i = ((int64_t)n * HW + p) * C + c;
+    acc += __half2float(x[i]) + __half2float(x[plane + i]);
+  }
+  y[(int64_t)n * C + c] = acc * x_sc[1] / (float)HW;
+}
+
+}  // namespace
+
+#define EPB_API extern "C" __attribute__((visibility("default")))
+
+EPB_API int epb_bn_act_split(const float* x, const float* scale, const float* shift, const float* r,
+                             const float* rscale, const float* rshift, const epb_half* r_split,
+                             const float* r_sc, int relu, int64_t M, int C, epb_half* y,
+                             const float* y_sc, epb_stream_t stream) {
+  EPB_CHECK_ARG(x && y && y_sc && M > 0 && C > 0 && C % 8 == 0);
+  EPB_CHECK_ARG((scale == nullptr) == (shift == nullptr));
+  EPB_CHECK_ARG((rscale == nullptr) == (rshift == nullptr));
+  EPB_CHECK_ARG(!(r && r_split) && ((r_split == nullptr) == (r_sc == nullptr)));
+  EPB_CHECK_ARG(!rscale || r);
+  const int64_t total8 = M * (C / 8);
+  bn_act_split_kernel<<<ew_blocks(total8), kThreads, 0, as_stream(stream)>>>(
+      x, scale, shift, r, rscale, rshift, reinterpret_cast<const uint4*>(r_split), r_sc, relu, total8,
+      C / 8, reinterpret_cast<uint4*>(y), y_sc);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_bn_relu_maxpool_split(const float* x, const float* scale, const float* shift,
+                                      epb_half* y, const float* y_sc, uint8_t* argidx, int N, int H,
+                                      int W, int C, epb_stream_t stream) {
+  EPB_CHECK_ARG(x && scale && shift && y && y_sc && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  bn_relu_maxpool_split_kernel<<<ew_blocks(total), kThreads, 0, as_stream(stream)>>>(
+      x, scale, shift, reinterpret_cast<uint4*>(y), y_sc, reinterpret_cast<uint2*>(argidx), N, H, W,
+      C / 8);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_im2col_split(const float* img_nchw, epb_half* col, const float* col_sc, int N, int C,
+                             int Hi, int Wi, int kh, int kw, int stride, int pad, int Ho, int Wo,
+                             int Kpad, epb_stream_t stream) {
+  EPB_CHECK_ARG(img_nchw && col && col_sc && N > 0 && C > 0 && Kpad % 8 == 0 && Kpad >= kh * kw * C);
+  const int64_t total = (int64_t)N * Ho * Wo * (Kpad / 8);
+  im2col_split_kernel<<<ew_blocks(total), kThreads, 0, as_stream(stream)>>>(
+      img_nchw, reinterpret_cast<uint4*>(col), col_sc, N, C, Hi, Wi, kh, kw, stride, pad, Ho, Wo, Kpad);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_split16_batch(const epb_split_job* jobs, int njobs, long long total_blocks,
+                              uint32_t* amax_ws, epb_stream_t stream) {
+  EPB_CHECK_ARG(jobs && amax_ws && njobs > 0 && total_blocks > 0 && total_blocks < (1LL << 31));
+  cudaStream_t st = as_stream(stream);
+  EPB_CUDA(cudaMemsetAsync(amax_ws, 0, sizeof(uint32_t) * njobs, st));
+  split_amax_kernel<<<(unsigned)total_blocks, kThreads, 0, st>>>(jobs, njobs, amax_ws);
+  EPB_LAUNCH_CHECK();
+  split_apply_kernel<<<(unsigned)total_blocks, kThreads, 0, st>>>(jobs, njobs, amax_ws);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_bn_bwd_reduce_mx(const float* dy, const float* x, const epb_half* mask_hi,
+                                 const float* scale, const float* shift, const float* mean,
+                                 const float* invstd, int relu, int64_t M, int C, double* sums,
+                                 float* maxes, epb_stream_t stream) {
+  EPB_CHECK_ARG(dy && x && scale && shift && mean && invstd && sums && maxes);
+  EPB_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0);
+  const RowMap rm = make_rowmap(C);
+  const int64_t rows_per_cta = (int64_t)rm.rpi * kRowsPerThread;
+  dim3 grid((unsigned)((M + rows_per_cta - 1) / rows_per_cta), rm.chunks);
+  bn_bwd_reduce_mx_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
+      reinterpret_cast<const uint2*>(mask_hi), reinterpret_cast<const float4*>(scale),
+      reinterpret_cast<const float4*>(shift), reinterpret_cast<const float4*>(mean),
+      reinterpret_cast<const float4*>(invstd), relu, M, C, rm, sums, maxes);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_bn_bwd_apply_split(const float* dy, const float* x, const epb_half* mask_hi,
+                                   const float* scale, const float* shift, const float* mean,
+                                   const float* invstd, const float* gamma, int relu,
+                                   const double* sums, const float* maxes, int64_t M, int C,
+                                   epb_half* dz, float* dz_sc, float* dy_masked, float* dgamma,
+                                   float* dbeta, epb_stream_t stream) {
+  EPB_CHECK_ARG(dy && x && scale && shift && mean && invstd && sums && maxes && dz && dz_sc);
+  EPB_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0);
+  cudaStream_t st = as_stream(stream);
+  float* mx = const_cast<float*>(maxes);      // consumed here: overwritten by the coefficients
+  bn_bwd_coef_split_kernel<<<1, 1024, 0, st>>>(sums, mx, (double)M, C, gamma, invstd, dz_sc, dgamma,
+                                               dbeta);
+  EPB_LAUNCH_CHECK();
+  const int64_t total4 = M * (C / 4);
+  bn_bwd_apply_split_kernel<<<ew_blocks(total4), kThreads, 0, st>>>(
+      reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
+      reinterpret_cast<const uint2*>(mask_hi), reinterpret_cast<const float4*>(scale),
+      reinterpret_cast<const float4*>(shift), reinterpret_cast<const float4*>(mean),
+      reinterpret_cast<const float4*>(invstd), reinterpret_cast<const float4*>(gamma), relu,
+      reinterpret_cast<const float4*>(mx), reinterpret_cast<const float4*>(mx + C),
+      reinterpret_cast<uint2*>(dz), dz_sc, reinterpret_cast<float4*>(dy_masked), total4, C / 4);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_avgpool_split(const epb_half* x, const float* x_sc, float* y, int N, int HW, int C,
+                              epb_stream_t stream) {
+  EPB_CHECK_ARG(x && x_sc && y && N > 0 && HW > 0 && C > 0);
+  avgpool_split_kernel<<<dim3((C + 127) / 128, N), 128, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(x), x_sc, y, N, HW, C);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}

@@ -132,6 +132,24 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(m), "r"(bar_cluster), "r"(x), "r"(y)
       : "memory");
 }
+// CTA-pair 3-D / 5-D loads (weight planes / activation planes of the split-fp16 path)
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m,
+                                                 uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(m), "r"(bar_cluster), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* m,
+                                                 uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(m), "r"(bar_cluster), "r"(c0),
+      "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar,
                                             int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -194,6 +212,16 @@ __device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (fp16 / bf16 inputs, FP32 accumulate), CTA pair
+__device__ __forceinline__ void mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the mbarrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
   asm volatile(
@@ -240,6 +268,19 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t addr, uint32_t l
                                                        uint32_t sbo_bytes) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
          ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// MN-major 16-bit operand, SWIZZLE_128B: 128-byte rows hold 64 consecutive MN elements of
+// one k; 8 k-rows form a 1024 B atom (SBO = stride between k-atoms); LBO = byte stride
+// between successive 64-element MN chunks (cute: ((8,n),(8,k)):((1,LBO),(8,SBO)) in uint128).
+__device__ __forceinline__ uint64_t desc_mnmajor16_sw128(uint32_t addr, uint32_t lbo_bytes,
+                                                         uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 with fp16 A / B (format 0), FP32 accumulator
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) |

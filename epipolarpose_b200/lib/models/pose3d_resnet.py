@@ -19,11 +19,15 @@ import torch
 import torch.nn as nn
 
 from epipolarpose_b200 import net as _net
+from epipolarpose_b200 import net16 as _net16
 
 BN_MOMENTUM = 0.1
 logger = logging.getLogger(__name__)
 
-_PRECISIONS = {"fp32": 0, "tf32": 1, "tf32x3": 3}
+# f16x3: split-fp16 operands, three kind::f16 tensor passes (net16.Engine16); plans with
+# channel counts outside whole 64-element TMA boxes keep the 3xTF32 engine
+_PRECISIONS = {"fp32": 0, "tf32": 1, "tf32x3": 3, "f16x3": 4}
+DEFAULT_PRECISION = "tf32x3"
 
 
 def _no_forward(self, *a, **k):
@@ -172,7 +176,7 @@ class PoseResNet(nn.Module):
         self.volume = cfg.MODEL.VOLUME
         self.allreduce_grads = kwargs.get("allreduce_grads", True)
         prec = kwargs.get("precision", getattr(cfg.MODEL, "PRECISION", None)) or \
-            os.environ.get("EPB_PRECISION", "tf32x3")
+            os.environ.get("EPB_PRECISION", DEFAULT_PRECISION)
         self.precision = _PRECISIONS[os.environ.get("EPB_PRECISION", prec)]
         self.conv1 = _Conv(3, 64, 7, 2, 3, bias=False)
         self.bn1 = _BN(64, momentum=BN_MOMENTUM)
@@ -234,8 +238,13 @@ class PoseResNet(nn.Module):
 
     # ---- compute
     def _engine(self):
-        if self._eng is None or self._eng.precision != self.precision:
-            self._eng = _net.Engine(self._plan, precision=self.precision, ops=self._ops)
+        if self._eng is None or self._eng_precision != self.precision:
+            if self.precision == 4 and _net16.supported(self._plan):
+                self._eng = _net16.Engine16(self._plan, ops=self._ops)
+            else:
+                self._eng = _net.Engine(self._plan, precision=3 if self.precision == 4 else self.precision,
+                                        ops=self._ops)
+            self._eng_precision = self.precision
         return self._eng
 
     def forward(self, x):

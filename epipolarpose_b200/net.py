@@ -210,6 +210,8 @@ class Engine:
         if precision == 0:
             self.wgrad_precision = 0
         self.ops = ops or _default_ops
+        self.stem_kpad = plan.stem_kpad          # K of the stem's patch matrix (Engine16: 192)
+        self.stem_col = plan.stem_col
 
     # ------------------------------------------------------------------ helpers
     def _pack_weights(self, params):
@@ -225,7 +227,7 @@ class Engine:
             for conv in convs:
                 w = params[conv.name + ".weight"]
                 if conv is plan.stem:
-                    kpad = plan.stem_kpad
+                    kpad = self.stem_kpad
                     wcol = torch.zeros(64 * kpad, device=self.dev, dtype=torch.float32)
                     jobs.append((w, wcol, 64, 3, 49, 0, 3, 0, kpad))
                     packed[conv.name] = (wcol, None)
@@ -255,7 +257,7 @@ class Engine:
             sizes = []
             for conv in convs:
                 if conv is plan.stem:
-                    sizes.append(64 * plan.stem_kpad)
+                    sizes.append(64 * self.stem_kpad)
                 else:
                     sizes.append(conv.cout_p * conv.k * conv.k * conv.cin_p)
             flat = torch.zeros(sum(sizes), device=self.dev, dtype=torch.float32)
@@ -266,7 +268,7 @@ class Engine:
                 dwp[conv.name] = view
                 g = grads[conv.name + ".weight"]
                 if conv is plan.stem:
-                    jobs.append((view, g, 64, 3, 49, 0, 3, 1, plan.stem_kpad))
+                    jobs.append((view, g, 64, 3, 49, 0, 3, 1, self.stem_kpad))
                 else:
                     T = conv.k * conv.k
                     jobs.append((view, g, g.shape[0], g.shape[1], T, 0 if conv.kind == "conv" else 1,
@@ -417,7 +419,7 @@ class Engine:
             return S["packed"][conv.name][0]
 
         # ---- stem (pose3d_resnet.py:186-189)
-        stem, scol, kpad = plan.stem, plan.stem_col, plan.stem_kpad
+        stem, scol, kpad = plan.stem, self.stem_col, self.stem_kpad
         x = self._new(N, H, W, stem.cin_p)
         ops.nchw_to_nhwc(x_nchw, x, N, 3, H, W, stem.cin_p)
         H1, W1 = stem.out_hw(H, W)
@@ -615,4 +617,4 @@ class Engine:
         dz0 = self._bn_bwd(S["bn"]["bn1"], gpool, z0, None, 1, params, grads)
         # the stem's gradient w.r.t. the [64][kpad] patch-matrix operand lands in the flat
         # buffer; the batched unpack maps its first 147 columns back to [64,3,7,7]
-        self._conv_wgrad(plan.stem_col, col, dz0, N, H1, W1, None)
+        self._conv_wgrad(self.stem_col, col, dz0, N, H1, W1, None)

@@ -18,6 +18,7 @@ launches = 0
 # kernels launched per C-ABI call (for the gpu_launches accounting)
 _KERNELS_PER_CALL = {
     "epb_softargmax_fwd": 2, "epb_bn_bwd_apply": 2, "epb_colsum": 3,
+    "epb_split16_batch": 3, "epb_bn_bwd_apply_split": 2, "epb_conv16_wgrad": 2,
 }
 
 
@@ -177,6 +178,78 @@ def avgpool_bwd(dy, dx, N, HW, C, accumulate):
 
 def colsum(x, M, C, out):
     _call("epb_colsum", _p(x), M, C, _p(out), _stream())
+
+
+# ------------------------------------------------------------------ split-fp16 ("f16x3") family
+# A split tensor is a torch.float16 tensor [2, ...] (hi plane, lo plane) plus a device
+# float32[2] = (s, 1/s).
+
+_H = torch.float16
+
+
+def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc):
+    _call("epb_bn_act_split", _p(x), _p(scale), _p(shift), _p(r), _p(rscale), _p(rshift),
+          _p(r_split, _H), _p(r_sc), int(relu), M, C, _p(y, _H), _p(y_sc), _stream())
+
+
+def bn_relu_maxpool_split(x, scale, shift, y, y_sc, argidx, N, H, W, C):
+    _call("epb_bn_relu_maxpool_split", _p(x), _p(scale), _p(shift), _p(y, _H), _p(y_sc),
+          _p(argidx, torch.uint8), N, H, W, C, _stream())
+
+
+def im2col_split(img, col, col_sc, N, C, Hi, Wi, kh, kw, stride, pad, Ho, Wo, Kpad):
+    _call("epb_im2col_split", _p(img), _p(col, _H), _p(col_sc), N, C, Hi, Wi, kh, kw, stride, pad,
+          Ho, Wo, Kpad, _stream())
+
+
+class SplitBatch:
+    """A fixed list of fp32 -> split conversions (epb_split_job) with its device table.
+    jobs: (src fp32 [n], dst fp16 [2][n], sc fp32 [2]); the tensors must stay where they are."""
+
+    def __init__(self, jobs):
+        import struct
+        self.jobs = list(jobs)
+        blob, first = b"", 0
+        for (src, dst, sc) in self.jobs:
+            n = src.numel()
+            assert dst.numel() == 2 * n and dst.dtype == _H and sc.numel() == 2
+            blob += struct.pack("<QQQqq", src.data_ptr(), dst.data_ptr(), sc.data_ptr(), n, first)
+            first += (n + 2047) // 2048
+        self.total_blocks = first
+        dev = self.jobs[0][1].device
+        self.table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        self.amax = torch.zeros(len(self.jobs), dtype=torch.int32, device=dev)
+
+
+def split16_batch(batch):
+    _call("epb_split16_batch", _p(batch.table, torch.uint8), len(batch.jobs), batch.total_blocks,
+          _p(batch.amax, torch.int32), _stream())
+
+
+def conv16_fprop(g, x, x_sc, w, w_sc, out, bias=None, stats=None):
+    _call("epb_conv16_fprop", ctypes.byref(g), _p(x, _H), _p(x_sc), _p(w, _H), _p(w_sc), _p(bias),
+          _p(out), _p(stats, torch.float64), _stream())
+
+
+def conv16_wgrad(g, x, x_sc, dout, dout_sc, dw, ws):
+    _call("epb_conv16_wgrad", ctypes.byref(g), _p(x, _H), _p(x_sc), _p(dout, _H), _p(dout_sc),
+          _p(dw), _p(ws), ws.numel() if ws is not None else 0, _stream())
+
+
+def bn_bwd_reduce_mx(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, sums, maxes):
+    _call("epb_bn_bwd_reduce_mx", _p(dy), _p(x), _p(mask_hi, _H), _p(scale), _p(shift), _p(mean),
+          _p(invstd), int(relu), M, C, _p(sums, torch.float64), _p(maxes), _stream())
+
+
+def bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, sums, maxes, M, C,
+                       dz, dz_sc, dy_masked, dgamma, dbeta):
+    _call("epb_bn_bwd_apply_split", _p(dy), _p(x), _p(mask_hi, _H), _p(scale), _p(shift), _p(mean),
+          _p(invstd), _p(gamma), int(relu), _p(sums, torch.float64), _p(maxes), M, C, _p(dz, _H),
+          _p(dz_sc), _p(dy_masked), _p(dgamma), _p(dbeta), _stream())
+
+
+def avgpool_split(x, x_sc, y, N, HW, C):
+    _call("epb_avgpool_split", _p(x, _H), _p(x_sc), _p(y), N, HW, C, _stream())
 
 
 # ------------------------------------------------------------------ decode / loss

@@ -192,6 +192,89 @@ int epb_colsum(const float* x, int64_t M, int C, float* out,
                epb_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Split-fp16 operand family ("f16x3"): the same conv / BatchNorm call sites as above
+ * (pose3d_resnet.py:12-15,24,55-63,99,116-122,171-179), with every GEMM operand
+ * materialised ONCE as two fp16 planes and fed to tcgen05 kind::f16 by TMA.
+ *
+ * A split tensor holds x as   x * s = hi + lo   (hi = fp16(x*s), lo = fp16(x*s - hi),
+ * s a power of two), planes[0] = hi, planes[1] = lo, each [rows][C] fp16 (raw bits,
+ * epb_half), C % 8 == 0; `sc` is a DEVICE float[2] = {s, 1/s}.  Three tensor passes
+ * (lo*hi + hi*lo + hi*hi, fp32 accumulation) reproduce the fp32 product to ~2^-22.
+ * ---------------------------------------------------------------------- */
+typedef uint16_t epb_half;
+
+/* y_split = act(x*scale+shift [+ residual]).  The residual is either fp32 rows `r`
+ * (with optional affine rscale/rshift: the downsample BatchNorm) or a split tensor
+ * `r_split` / `r_sc` (the identity path: the previous block's output), or absent. */
+int epb_bn_act_split(const float* x, const float* scale, const float* shift,
+                     const float* r, const float* rscale, const float* rshift,
+                     const epb_half* r_split, const float* r_sc, int relu,
+                     int64_t M, int C, epb_half* y, const float* y_sc,
+                     epb_stream_t stream);
+/* stem: maxpool3x3s2p1(relu(x*scale+shift)) -> split tensor + argmax slot (0..8) */
+int epb_bn_relu_maxpool_split(const float* x, const float* scale, const float* shift,
+                              epb_half* y, const float* y_sc, uint8_t* argidx, int N,
+                              int H, int W, int C, epb_stream_t stream);
+/* patch matrix of the 7x7 stem straight from the NCHW image (pose3d_resnet.py:99,185):
+ * col[m][(r*kw+s)*C + c] = img[n][c][oh*stride-pad+r][ow*stride-pad+s], zero padded to
+ * Kpad (% 64 == 0) columns, as a split tensor [2][N*Ho*Wo][Kpad]. */
+int epb_im2col_split(const float* img_nchw, epb_half* col, const float* col_sc, int N,
+                     int C, int Hi, int Wi, int kh, int kw, int stride, int pad, int Ho,
+                     int Wo, int Kpad, epb_stream_t stream);
+/* fp32 tensors -> split tensors with a per-tensor power-of-two scale chosen from the
+ * tensor's max |x| (largest scaled magnitude in [2^13, 2^14)); job j: src[n] ->
+ * dst[2][n], sc[2] written.  Blocks of 2048 elements, jobs ordered by first_block.
+ * amax_ws: njobs uint32 of DEVICE scratch (zeroed by the call). */
+typedef struct epb_split_job {
+  const float* src;
+  epb_half* dst;
+  float* sc;
+  long long n;
+  long long first_block;
+} epb_split_job;
+int epb_split16_batch(const epb_split_job* jobs, int njobs, long long total_blocks,
+                      uint32_t* amax_ws, epb_stream_t stream);
+
+/* epb_conv_fprop on split operands: in [2][N,Hi,Wi,Cin], w [2][Cout][Tw*Cin] (the packed
+ * operand of epb_pack_weight, split).  Cin % 64 == 0, Cout % 4 == 0.  CTA pairs
+ * (tcgen05 cta_group::2, M = 256), A and B tiles by TMA (5-D / 3-D tensor maps; the
+ * zero padding of the convolution is the TMA out-of-bounds fill), fp32 accumulators
+ * in TMEM; out = acc / (s_in * s_w) (+ bias), optional accumulate / statistics as
+ * epb_conv_fprop.  g->precision, g->in_relu are ignored (operands are post-activation). */
+int epb_conv16_fprop(const epb_conv_geom* g, const epb_half* in, const float* in_sc,
+                     const epb_half* w, const float* w_sc, const float* bias,
+                     float* out, double* stats, epb_stream_t stream);
+/* epb_conv_wgrad on split operands (in as above, dout [2][N,Ho,Wo,Cout]); both operands
+ * MN-major by TMA, reduction over pixel tiles split across clusters and summed in a FIXED
+ * order from `ws` (deterministic): dw[co][wt[t]][ci] += sum.  ws: >= ws_floats floats of
+ * scratch (the call uses as many split partials as fit). */
+int epb_conv16_wgrad(const epb_conv_geom* g, const epb_half* in, const float* in_sc,
+                     const epb_half* dout, const float* dout_sc, float* dw, float* ws,
+                     long long ws_floats, epb_stream_t stream);
+
+/* BatchNorm(+ReLU) backward for the split path.  mask = (mask_hi > 0) when mask_hi != NULL
+ * (hi plane of the block output), else (x*scale+shift > 0) if relu, else 1.
+ * reduce: sums as epb_bn_bwd_reduce; maxes[0..C) = max |g|, maxes[C..2C) = max |xhat|
+ *         (float, caller zeroes; used to bound |dz| for the scale of the split output).
+ * apply : dz_split = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M) with the power-of-two
+ *         scale derived from the bound written to dz_sc[2]; if dy_masked != NULL the
+ *         masked gradient g is also written there (may alias dy: the identity path of
+ *         the residual block then accumulates into it). */
+int epb_bn_bwd_reduce_mx(const float* dy, const float* x, const epb_half* mask_hi,
+                         const float* scale, const float* shift, const float* mean,
+                         const float* invstd, int relu, int64_t M, int C, double* sums,
+                         float* maxes, epb_stream_t stream);
+int epb_bn_bwd_apply_split(const float* dy, const float* x, const epb_half* mask_hi,
+                           const float* scale, const float* shift, const float* mean,
+                           const float* invstd, const float* gamma, int relu,
+                           const double* sums, const float* maxes, int64_t M, int C,
+                           epb_half* dz, float* dz_sc, float* dy_masked, float* dgamma,
+                           float* dbeta, epb_stream_t stream);
+/* VOLUME=False head on a split tensor: y[n][c] = mean over HW of x (fp32 out) */
+int epb_avgpool_split(const epb_half* x, const float* x_sc, float* y, int N, int HW, int C,
+                      epb_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Soft-argmax (ATen softmax + 9 reductions: lib/core/integral_loss.py:49-86)
  * logits: volume per (n,j) of D*H*W float32.  layout 0 = NCHW contiguous
  * ([N][J*D][H][W]); layout 1 = NHWC ([N][H][W][J*D]).

@@ -472,3 +472,171 @@ def add3(a, b, c, out, n):
 def mask_scale(x, mask, scale, out, n):
     out.view(-1)[:n].copy_(torch.where(mask.reshape(-1)[:n] != 0, x.reshape(-1)[:n] * scale,
                                        torch.zeros(n, dtype=x.dtype)))
+
+
+# ------------------------------------------------------------------ split-fp16 ("f16x3") family
+# CPU emulation written from the contracts in include/epb.h: a split tensor is a float16
+# tensor [2, ...] (hi, lo) plus sc = (s, 1/s); products are formed from the exact fp16 planes
+# with the three-term rule (lo*hi + hi*lo + hi*hi) accumulated in float64.
+
+def _split(v, s):
+    v = (v.float() * s).clamp(-65504.0, 65504.0)
+    hi = v.half()
+    lo = (v - hi.float()).half()
+    return hi, lo
+
+
+def _join(t, sc):
+    return (t[0].float() + t[1].float()) * float(sc[1])
+
+
+def _store_split(dst, v, s):
+    hi, lo = _split(v, s)
+    dst[0].view(-1).copy_(hi.reshape(-1))
+    dst[1].view(-1).copy_(lo.reshape(-1))
+
+
+def _pow2_scale(amax):
+    import math
+    if not (amax > 0) or not math.isfinite(amax):
+        return 1.0
+    _, e = math.frexp(amax)
+    k = max(-100, min(100, 13 - (e - 1)))
+    return math.ldexp(1.0, k)
+
+
+def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc):
+    v = x.reshape(M, C)
+    if scale is not None:
+        v = v * scale + shift
+    if r is not None:
+        q = r.reshape(M, C)
+        if rscale is not None:
+            q = q * rscale + rshift
+        v = v + q
+    elif r_split is not None:
+        v = v + _join(r_split, r_sc).reshape(M, C)
+    if relu:
+        v = torch.relu(v)
+    _store_split(y, v, float(y_sc[0]))
+
+
+def bn_relu_maxpool_split(x, scale, shift, y, y_sc, argidx, N, H, W, C):
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    tmp = torch.empty(N, Ho, Wo, C)
+    bn_relu_maxpool(x, scale, shift, tmp, argidx, N, H, W, C)
+    _store_split(y, tmp, float(y_sc[0]))
+
+
+def im2col_split(img, col, col_sc, N, C, Hi, Wi, kh, kw, stride, pad, Ho, Wo, Kpad):
+    x = img.reshape(N, C, Hi, Wi).permute(0, 2, 3, 1).contiguous()
+    tmp = torch.empty(N, Ho, Wo, Kpad)
+    im2col(x, tmp, N, Hi, Wi, C, C, kh, kw, stride, pad, Ho, Wo, Kpad)
+    _store_split(col, tmp, float(col_sc[0]))
+
+
+class SplitBatch:
+    def __init__(self, jobs):
+        self.jobs = list(jobs)
+
+
+def split16_batch(batch):
+    for (src, dst, sc) in batch.jobs:
+        s = _pow2_scale(float(src.abs().max())) if src.numel() else 1.0
+        sc[0], sc[1] = s, 1.0 / s
+        n = src.numel()
+        hi, lo = _split(src.reshape(-1), s)
+        dst.view(-1)[:n].copy_(hi)
+        dst.view(-1)[n:2 * n].copy_(lo)
+
+
+def _three_term(g, x, w, Kw):
+    """phase-grid result [N,Hp,Wp,Cout] (float64, unscaled) of the three-term product."""
+    xh, xl = x[0].reshape(g.N, g.Hi, g.Wi, g.Cin).double(), x[1].reshape(g.N, g.Hi, g.Wi, g.Cin).double()
+    n = g.Cout * g.Tw * g.Cin
+    wh = w.view(-1)[:n].view(g.Cout, g.Tw, g.Cin).double()
+    wl = w.view(-1)[n:2 * n].view(g.Cout, g.Tw, g.Cin).double()
+    acc = torch.zeros(g.N, g.Hp, g.Wp, g.Cout, dtype=torch.float64)
+    for t in range(g.T):
+        ah = _gather(g, xh, t, None, None)
+        al = _gather(g, xl, t, None, None)
+        bh, bl = wh[:, g.wt[t], :].T, wl[:, g.wt[t], :].T
+        acc += al @ bh + ah @ bl + ah @ bh
+    return acc
+
+
+def conv16_fprop(g, x, x_sc, w, w_sc, out, bias=None, stats=None):
+    assert g.Cin % 64 == 0 and g.Cout % 4 == 0
+    acc = (_three_term(g, x, w, None) * (float(x_sc[1]) * float(w_sc[1]))).float()
+    if bias is not None:
+        acc = acc + bias
+    o = out.view(g.N, g.Ho, g.Wo, g.Cout)
+    sl = o[:, g.ph::g.os, g.pw::g.os][:, :g.Hp, :g.Wp]
+    if g.accumulate:
+        acc = acc + sl
+    o[:, g.ph::g.os, g.pw::g.os][:, :g.Hp, :g.Wp] = acc
+    if stats is not None:
+        flat = acc.reshape(-1, g.Cout).double()
+        stats[:g.Cout] += flat.sum(0)
+        stats[g.Cout:] += (flat * flat).sum(0)
+
+
+def conv16_wgrad(g, x, x_sc, dout, dout_sc, dw, ws):
+    assert g.Cin % 64 == 0 and g.Cout % 64 == 0
+    DW = dw.view(g.Cout, g.Tw, g.Cin)
+    xh, xl = x[0].reshape(g.N, g.Hi, g.Wi, g.Cin).double(), x[1].reshape(g.N, g.Hi, g.Wi, g.Cin).double()
+
+    def ph(p):
+        return p.reshape(g.N, g.Ho, g.Wo, g.Cout)[:, g.ph::g.os, g.pw::g.os][:, :g.Hp, :g.Wp] \
+            .reshape(-1, g.Cout).double()
+    dh_, dl_ = ph(dout[0]), ph(dout[1])
+    alpha = float(x_sc[1]) * float(dout_sc[1])
+    for t in range(g.T):
+        ah = _gather(g, xh, t, None, None).reshape(-1, g.Cin)
+        al = _gather(g, xl, t, None, None).reshape(-1, g.Cin)
+        DW[:, g.wt[t], :] += ((dh_.T @ al + dl_.T @ ah + dh_.T @ ah) * alpha).float()
+
+
+def _mask16(dy, x, mask_hi, scale, shift, relu, M, C):
+    g = dy.reshape(M, C)
+    if mask_hi is not None:
+        return g * (mask_hi.reshape(M, C).float() > 0).float()
+    if relu:
+        return g * ((x.reshape(M, C) * scale + shift) > 0).float()
+    return g
+
+
+def bn_bwd_reduce_mx(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, sums, maxes):
+    g = _mask16(dy, x, mask_hi, scale, shift, relu, M, C)
+    xh = (x.reshape(M, C) - mean) * invstd
+    sums[:C] += g.double().sum(0)
+    sums[C:] += (g.double() * xh.double()).sum(0)
+    maxes[:C] = torch.maximum(maxes[:C], g.abs().max(0).values)
+    maxes[C:] = torch.maximum(maxes[C:], xh.abs().max(0).values)
+
+
+def bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, sums, maxes, M, C,
+                       dz, dz_sc, dy_masked, dgamma, dbeta):
+    g = _mask16(dy, x, mask_hi, scale, shift, relu, M, C)
+    xh = (x.reshape(M, C) - mean) * invstd
+    k0 = gamma * invstd
+    k1 = (sums[:C] / M).float()
+    k2 = (sums[C:] / M).float()
+    bound = float((k0.abs() * (maxes[:C] + k1.abs() + maxes[C:] * k2.abs())).max())
+    s = _pow2_scale(bound)
+    dz_sc[0], dz_sc[1] = s, 1.0 / s
+    maxes[:C] = k1
+    maxes[C:] = k2
+    v = k0 * (g - k1 - xh * k2)
+    assert float(v.abs().max()) <= bound * (1 + 1e-5) + 1e-30, "dz exceeds its bound"
+    _store_split(dz, v, s)
+    if dy_masked is not None:
+        dy_masked.view(M, C).copy_(g)
+    if dgamma is not None:
+        dgamma.copy_(sums[C:].float())
+    if dbeta is not None:
+        dbeta.copy_(sums[:C].float())
+
+
+def avgpool_split(x, x_sc, y, N, HW, C):
+    y.view(N, C).copy_(_join(x, x_sc).reshape(N, HW, C).mean(1))

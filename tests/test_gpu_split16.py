@@ -1,0 +1,273 @@
+"""GPU (-m gpu): the split-fp16 ("f16x3") kernel family through the C ABI against the CPU
+emulation of the same contracts (tests/emul_ops.py: exact fp16 planes, three-term products
+accumulated in float64) on IDENTICAL split operands, so the bar is the fp32 accumulation
+noise of the tensor pipe (<= 2e-5 of the tensor's max), not a precision trade-off.
+Geometries: every conv kind of the network (reference lib/models/pose3d_resnet.py:12-15,
+55-60,99,116-122,171-178) incl. strided / transposed / phase-decomposed forms, ragged
+sizes, N tails, accumulate / bias / statistics epilogues."""
+import numpy as np
+import pytest
+import torch
+
+from tests import emul_ops as em
+from tests.conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+H16 = torch.float16
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from epipolarpose_b200 import ops
+    ops.device_check()
+    return torch.device("cuda:0")
+
+
+def _rand_split(shape, seed, scale=16.0, relu=True, mag=1.0):
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(shape, generator=g) * mag
+    if relu:
+        v = torch.relu(v)
+    if scale is None:
+        scale = em._pow2_scale(float(v.abs().max()))
+    t = torch.empty((2,) + tuple(shape), dtype=H16)
+    em._store_split(t, v, scale)
+    sc = torch.tensor([scale, 1.0 / scale])
+    return t, sc
+
+
+def _weights_split(cout, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(cout * K, generator=g) * (2.0 / K) ** 0.5
+    h = torch.empty(2 * cout * K, dtype=H16)
+    sc = torch.ones(2)
+    em.split16_batch(em.SplitBatch([(w, h, sc)]))
+    return h, sc
+
+
+def _conv_cases():
+    """(name, Conv ctor args, N, H, W, which) -- which in f(prop) / d(grad)."""
+    from epipolarpose_b200.net import Conv
+    C = []
+    C.append(("1x1_64_256", Conv("a", "conv", 64, 256, 1, 1, 0), 2, 16, 16))
+    C.append(("1x1_256_64", Conv("b", "conv", 256, 64, 1, 1, 0), 2, 16, 16))
+    C.append(("1x1_ragged_M", Conv("c", "conv", 128, 128, 1, 1, 0), 3, 14, 14))
+    C.append(("3x3_64_64", Conv("d", "conv", 64, 64, 3, 1, 1), 2, 16, 16))
+    C.append(("3x3_128_ragged", Conv("e", "conv", 128, 128, 3, 1, 1), 3, 14, 14))
+    C.append(("3x3_s2", Conv("f", "conv", 128, 128, 3, 2, 1), 2, 16, 16))
+    C.append(("3x3_s2_ragged", Conv("g", "conv", 64, 128, 3, 2, 1), 3, 12, 12))
+    C.append(("1x1_s2", Conv("h", "conv", 256, 512, 1, 2, 0), 2, 16, 16))
+    C.append(("3x3_512_8x8", Conv("i", "conv", 512, 512, 3, 1, 1), 4, 8, 8))
+    C.append(("3x3_256_4x4", Conv("j", "conv", 256, 256, 3, 1, 1), 5, 4, 4))
+    C.append(("deconv4", Conv("k", "deconv", 256, 256, 4, 2, 1), 2, 8, 8))
+    C.append(("deconv4_ragged", Conv("l", "deconv", 128, 64, 4, 2, 1), 3, 6, 6))
+    C.append(("deconv3", Conv("m", "deconv", 128, 128, 3, 2, 1, 1), 2, 8, 8))
+    C.append(("deconv2", Conv("n", "deconv", 64, 128, 2, 2, 0), 2, 8, 8))
+    C.append(("1x1_N_tail_320", Conv("o", "conv", 64, 320, 1, 1, 0), 2, 16, 16))
+    C.append(("final_1088", Conv("p", "conv", 256, 1088, 1, 1, 0), 1, 16, 16))
+    C.append(("final_24", Conv("q", "conv", 64, 24, 1, 1, 0), 2, 16, 16))
+    C.append(("3x3_final", Conv("r", "conv", 64, 24, 3, 1, 1), 2, 16, 16))
+    C.append(("big_M_pairs", Conv("s", "conv", 64, 64, 3, 1, 1), 8, 64, 64))
+    return C
+
+
+CASES = _conv_cases()
+
+
+def _run_fprop(dev, conv, N, H, W, geoms, x, x_sc, w, w_sc, Hin, Win, cin, Hout, Wout, cout, bias, stats, acc):
+    from epipolarpose_b200 import ops
+    out_ref = torch.zeros((N, Hout, Wout, cout))
+    if acc:
+        out_ref = torch.randn((N, Hout, Wout, cout), generator=torch.Generator().manual_seed(3))
+    out_gpu = out_ref.clone().to(dev)
+    st_ref = torch.zeros(2 * cout, dtype=torch.float64) if stats else None
+    st_gpu = torch.zeros(2 * cout, dtype=torch.float64, device=dev) if stats else None
+    xg, xs, wg, ws = x.to(dev), x_sc.to(dev), w.to(dev), w_sc.to(dev)
+    bg = bias.to(dev) if bias is not None else None
+    for g in geoms:
+        if g is None:
+            continue
+        g.in_relu, g.accumulate = 0, int(acc)
+        em.conv16_fprop(g, x, x_sc, w, w_sc, out_ref, bias, st_ref)
+        ops.conv16_fprop(g, xg, xs, wg, ws, out_gpu, bg, st_gpu)
+    torch.cuda.synchronize()
+    e = relerr(out_gpu.cpu().numpy(), out_ref.numpy())
+    assert e <= 2e-5, "output relerr %.3e" % e
+    if stats:
+        e = relerr(st_gpu.cpu().numpy(), st_ref.numpy())
+        assert e <= 1e-4, "stats relerr %.3e" % e
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv16_fprop_vs_emulation(dev, case):
+    name, conv, N, H, W = case
+    geoms = conv.fprop_geoms(em, N, H, W, 3)
+    Ho, Wo = conv.out_hw(H, W)
+    T = conv.k * conv.k
+    x, x_sc = _rand_split((N, H, W, conv.cin_p), 1)
+    w, w_sc = _weights_split(conv.cout_p, T * conv.cin_p, 2)
+    bias = torch.randn(conv.cout_p, generator=torch.Generator().manual_seed(5)) if "final" in name else None
+    stats = bias is None
+    _run_fprop(dev, conv, N, H, W, geoms, x, x_sc, w, w_sc, H, W, conv.cin_p, Ho, Wo, conv.cout_p,
+               bias, stats, False)
+
+
+DGRAD = [c for c in CASES if c[1].cout % 64 == 0]
+
+
+@pytest.mark.parametrize("case", DGRAD, ids=[c[0] for c in DGRAD])
+@pytest.mark.parametrize("acc", [0, 1])
+def test_conv16_dgrad_vs_emulation(dev, case, acc):
+    name, conv, N, H, W = case
+    geoms = conv.dgrad_geoms(em, N, H, W, 3)
+    Ho, Wo = conv.out_hw(H, W)
+    T = conv.k * conv.k
+    dz, dz_sc = _rand_split((N, Ho, Wo, conv.cout_p), 7, scale=None, relu=False, mag=3e-5)
+    w, w_sc = _weights_split(conv.cin_p, T * conv.cout_p, 8)
+    _run_fprop(dev, conv, N, H, W, geoms, dz, dz_sc, w, w_sc, Ho, Wo, conv.cout_p, H, W, conv.cin_p,
+               None, False, bool(acc))
+
+
+WGRAD = [c for c in CASES if c[1].cout % 64 == 0]
+
+
+@pytest.mark.parametrize("case", WGRAD, ids=[c[0] for c in WGRAD])
+def test_conv16_wgrad_vs_emulation(dev, case):
+    from epipolarpose_b200 import ops
+    name, conv, N, H, W = case
+    geoms = conv.fprop_geoms(em, N, H, W, 3)
+    Ho, Wo = conv.out_hw(H, W)
+    T = conv.k * conv.k
+    x, x_sc = _rand_split((N, H, W, conv.cin_p), 11)
+    dz, dz_sc = _rand_split((N, Ho, Wo, conv.cout_p), 12, scale=None, relu=False, mag=3e-5)
+    n = conv.cout_p * T * conv.cin_p
+    dw_ref = torch.zeros(n)
+    dw_gpu = torch.zeros(n, device=dev)
+    ws = torch.empty(8 << 20, device=dev)
+    xg, xs, dg, ds = x.to(dev), x_sc.to(dev), dz.to(dev), dz_sc.to(dev)
+    for rep in range(2):                      # second pass checks the += contract
+        for g in geoms:
+            if g is None:
+                continue
+            g.in_relu, g.accumulate = 0, 0
+            em.conv16_wgrad(g, x, x_sc, dz, dz_sc, dw_ref, None)
+            ops.conv16_wgrad(g, xg, xs, dg, ds, dw_gpu, ws)
+    torch.cuda.synchronize()
+    e = relerr(dw_gpu.cpu().numpy(), dw_ref.numpy())
+    assert e <= 2e-5, "dw relerr %.3e" % e
+    # deterministic: a second run from zero gives the same bits
+    a = torch.zeros(n, device=dev)
+    b = torch.zeros(n, device=dev)
+    for buf in (a, b):
+        for g in geoms:
+            if g is not None:
+                ops.conv16_wgrad(g, xg, xs, dg, ds, buf, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+
+def test_split_elementwise_vs_emulation(dev):
+    from epipolarpose_b200 import ops
+    gen = torch.Generator().manual_seed(21)
+    M, C = 1500, 192
+    x = torch.randn(M, C, generator=gen) * 3
+    sc, sh = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen)
+    r = torch.randn(M, C, generator=gen)
+    rsc, rsh = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen)
+    rs, rs_sc = _rand_split((M, C), 22)
+    asc = torch.tensor([16.0, 1 / 16.0])
+    for kind in ("plain", "res", "res_affine", "res_split", "noaffine"):
+        args = dict(plain=(sc, sh, None, None, None, None, None),
+                    res=(sc, sh, r, None, None, None, None),
+                    res_affine=(sc, sh, r, rsc, rsh, None, None),
+                    res_split=(sc, sh, None, None, None, rs, rs_sc),
+                    noaffine=(None, None, None, None, None, None, None))[kind]
+        y_ref = torch.empty(2, M, C, dtype=H16)
+        em.bn_act_split(x, *args, 1, M, C, y_ref, asc)
+        y = torch.empty(2, M, C, dtype=H16, device=dev)
+        ops.bn_act_split(x.to(dev), *[a.to(dev) if a is not None else None for a in args], 1, M, C,
+                         y, asc.to(dev))
+        a = em._join(y.cpu(), asc).numpy()
+        b = em._join(y_ref, asc).numpy()
+        assert np.max(np.abs(a - b)) <= 2e-6 * max(1.0, np.max(np.abs(b))), kind
+    # stem pool
+    N, H, W, Cc = 2, 14, 18, 64
+    z = torch.randn(N, H, W, Cc, generator=gen)
+    s2, h2 = torch.rand(Cc, generator=gen) + 0.5, torch.randn(Cc, generator=gen) * 0.1
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y_ref, a_ref = torch.empty(2, N, Ho, Wo, Cc, dtype=H16), torch.empty(N, Ho, Wo, Cc, dtype=torch.uint8)
+    em.bn_relu_maxpool_split(z, s2, h2, y_ref, asc, a_ref, N, H, W, Cc)
+    y, a = torch.empty_like(y_ref, device=dev), torch.empty_like(a_ref, device=dev)
+    ops.bn_relu_maxpool_split(z.to(dev), s2.to(dev), h2.to(dev), y, asc.to(dev), a, N, H, W, Cc)
+    assert np.max(np.abs(em._join(y.cpu(), asc).numpy() - em._join(y_ref, asc).numpy())) <= 1e-6
+    # argmax slots may differ only where two window entries tie (post-ReLU zeros)
+    diff = (a.cpu() != a_ref)
+    assert float(em._join(y_ref, asc)[diff].abs().max() if diff.any() else 0.0) == 0.0
+    # im2col
+    img = torch.randn(2, 3, 20, 24, generator=gen)
+    Ho, Wo = 10, 12
+    c_ref = torch.empty(2, 2, Ho, Wo, 192, dtype=H16)
+    em.im2col_split(img, c_ref, asc, 2, 3, 20, 24, 7, 7, 2, 3, Ho, Wo, 192)
+    c = torch.empty_like(c_ref, device=dev)
+    ops.im2col_split(img.to(dev), c, asc.to(dev), 2, 3, 20, 24, 7, 7, 2, 3, Ho, Wo, 192)
+    assert torch.equal(c.cpu().view(torch.int16), c_ref.view(torch.int16))
+    # batched fp32 -> split with amax scale
+    srcs = [torch.randn(n, generator=gen) * s for n, s in ((5000, 1e-3), (777, 40.0), (4096, 1.0))]
+    jobs_ref = [(s, torch.empty(2 * s.numel(), dtype=H16), torch.ones(2)) for s in srcs]
+    em.split16_batch(em.SplitBatch(jobs_ref))
+    jobs = [(s.to(dev), torch.empty(2 * s.numel(), dtype=H16, device=dev), torch.ones(2, device=dev)) for s in srcs]
+    ops.split16_batch(ops.SplitBatch(jobs))
+    for (s, h, c2), (_, hr, cr) in zip(jobs, jobs_ref):
+        assert torch.equal(c2.cpu(), cr)
+        assert torch.equal(h.cpu().view(torch.int16), hr.view(torch.int16))
+    # avgpool
+    t, tsc = _rand_split((3, 16, 2048), 31)
+    yr = torch.empty(3, 2048)
+    em.avgpool_split(t, tsc, yr, 3, 16, 2048)
+    yg = torch.empty(3, 2048, device=dev)
+    ops.avgpool_split(t.to(dev), tsc.to(dev), yg, 3, 16, 2048)
+    assert relerr(yg.cpu().numpy(), yr.numpy()) <= 1e-6
+
+
+@pytest.mark.parametrize("mode", ["relu", "mask", "mask_inplace", "plain"])
+def test_bn_bwd_split_vs_emulation(dev, mode):
+    from epipolarpose_b200 import ops
+    gen = torch.Generator().manual_seed(41)
+    M, C = 3000, 256
+    x = torch.randn(M, C, generator=gen) * 2 + 0.3
+    dy = torch.randn(M, C, generator=gen) * 1e-4
+    gamma, beta = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen) * 0.1
+    mean = x.mean(0)
+    invstd = 1.0 / torch.sqrt(x.var(0, unbiased=False) + 1e-5)
+    scale, shift = gamma * invstd, beta - mean * gamma * invstd
+    out, _ = _rand_split((M, C), 42)
+    mask = out[0].contiguous() if mode.startswith("mask") else None
+    relu = 1 if mode == "relu" else 0
+    sums_r, mx_r = torch.zeros(2 * C, dtype=torch.float64), torch.zeros(2 * C)
+    em.bn_bwd_reduce_mx(dy, x, mask, scale, shift, mean, invstd, relu, M, C, sums_r, mx_r)
+    D = lambda t: t.to(dev) if t is not None else None
+    sums, mx = torch.zeros(2 * C, dtype=torch.float64, device=dev), torch.zeros(2 * C, device=dev)
+    dyg = dy.to(dev)
+    ops.bn_bwd_reduce_mx(dyg, D(x), D(mask), D(scale), D(shift), D(mean), D(invstd), relu, M, C, sums, mx)
+    assert relerr(sums.cpu().numpy(), sums_r.numpy()) <= 1e-5
+    assert np.max(np.abs(mx.cpu().numpy() - mx_r.numpy())) <= 1e-6 * float(mx_r.max())
+    dz_r, sc_r = torch.empty(2, M, C, dtype=H16), torch.empty(2)
+    dm_r = dy.clone() if mode == "mask_inplace" else None
+    dg_r, db_r = torch.empty(C), torch.empty(C)
+    em.bn_bwd_apply_split(dy, x, mask, scale, shift, mean, invstd, gamma, relu, sums_r, mx_r, M, C,
+                          dz_r, sc_r, dm_r, dg_r, db_r)
+    dz, sc = torch.empty(2, M, C, dtype=H16, device=dev), torch.empty(2, device=dev)
+    dg, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    ops.bn_bwd_apply_split(dyg, D(x), D(mask), D(scale), D(shift), D(mean), D(invstd), D(gamma), relu,
+                           sums, mx, M, C, dz, sc, dyg if mode == "mask_inplace" else None, dg, db)
+    torch.cuda.synchronize()
+    s_g, s_r = float(sc.cpu()[0]), float(sc_r[0])
+    assert s_g in (s_r, 2 * s_r, s_r / 2)      # the bound is summed in a different order
+    a = em._join(dz.cpu(), sc.cpu()).numpy()
+    b = em._join(dz_r, sc_r).numpy()
+    assert relerr(a, b) <= 1e-5
+    assert float(np.max(np.abs(b))) * s_r < 32768
+    assert relerr(dg.cpu().numpy(), dg_r.numpy()) <= 1e-5 and relerr(db.cpu().numpy(), db_r.numpy()) <= 1e-5
+    if mode == "mask_inplace":
+        assert torch.equal(dyg.cpu(), dm_r)

@@ -138,7 +138,7 @@ class ClockSampler(threading.Thread):
 def run_gpu(args):
     import torch.distributed as dist
     from epipolarpose_b200 import ops
-    from oracle import refshim        # make_cfg only (no reference import)
+    from tools.bench_cfg import make_cfg
     import lib.models as models
     import lib.core.integral_loss as il
     import lib.utils.img_utils as iu
@@ -157,7 +157,7 @@ def run_gpu(args):
     ops.device_check()
 
     layers = args.layers
-    cfg = refshim.make_cfg(num_layers=layers, num_joints=J, volume=True, depth_res=D,
+    cfg = make_cfg(num_layers=layers, num_joints=J, volume=True, depth_res=D,
                            image_size=(HW, HW))
     torch.manual_seed(0)                               # identical weights on every rank
     model = models.pose3d_resnet.get_pose_net(cfg, False, precision=args.precision)
@@ -235,12 +235,24 @@ def run_gpu(args):
     # ---- dominant kernel family (conv GEMMs): CUDA events around every launch of the same
     # step, issued eagerly right after the timed region (events cannot be read back from
     # inside a replayed graph); the kernels and their arguments are identical
-    orig_f, orig_w = ops.conv_fprop, ops.conv_wgrad
+    orig_call = ops._call
+    engine_kind = type(model._engine()).__name__
+    ns = {"fp32": 0, "tf32": 1, "tf32x3": 3, "f16x3": 3}[args.precision]
 
-    ns = {"fp32": 0, "tf32": 1, "tf32x3": 3}[args.precision]
-
-    def kernel_class(kind, g):
+    def kernel_class(name, g):
         """Name of the kernel template the C dispatcher picks for this call (csrc/conv*.cu)."""
+        if name == "epb_conv16_fprop":
+            if g.Cout <= 64:
+                bn = 64
+            elif g.Cout <= 128:
+                bn = 128
+            else:
+                p256, p128 = (g.Cout + 255) // 256 * 256, (g.Cout + 127) // 128 * 128
+                bn = 128 if p256 * 4 > p128 * 5 else 256
+            return "conv16_kernel<%d>" % bn
+        if name == "epb_conv16_wgrad":
+            return "wgrad16_kernel<%d>" % (128 if g.Cout <= 128 else 256)
+        kind = "fprop" if name == "epb_conv_fprop" else "wgrad"
         if ns == 0 or g.Cin % 32 or (kind == "fprop" and g.Cout % 32):
             return "conv_%s_simt" % kind
         if kind == "fprop":
@@ -251,19 +263,24 @@ def run_gpu(args):
         bn = 128 if g.Cin >= 128 else (64 if g.Cin >= 64 else 32)
         return "conv_wgrad_tc_kernel<%d,%d>" % (bn, g.precision if g.precision else ns)
 
-    def timed(fnc, kind):
-        def wrapper(g, *a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()                       # torch's CURRENT stream = the one the kernel uses
-            fnc(g, *a, **k)
-            e1.record()
+    CONV_CALLS = ("epb_conv_fprop", "epb_conv_wgrad", "epb_conv16_fprop", "epb_conv16_wgrad")
+    other_t = {}
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()                       # torch's CURRENT stream = the one the kernel uses
+        orig_call(name, *a)
+        e1.record()
+        if name in CONV_CALLS:
+            g = a[0]._obj
             flops = 2.0 * g.N * g.Hp * g.Wp * g.Cin * g.Cout * g.T
-            conv_t["events"].append((e0, e1, kernel_class(kind, g), flops))
-        return wrapper
+            conv_t["events"].append((e0, e1, kernel_class(name, g), flops))
+        else:
+            other_t.setdefault(name, []).append((e0, e1))
 
     geom_dev = iu.pack_meta(meta_dev, n_img, dev)
     os.environ["EPB_OVERLAP_WGRAD"] = "0"      # serialise wgrad with the rest: clean per-kernel times
-    ops.conv_fprop, ops.conv_wgrad = timed(orig_f, "fprop"), timed(orig_w, "wgrad")
+    ops._call = timed_call
     l0 = ops.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -283,7 +300,8 @@ def run_gpu(args):
         c[1] += a.elapsed_time(b)
         c[2] += fl
     dom = max(per_class, key=lambda k: per_class[k][1])
-    ops.conv_fprop, ops.conv_wgrad = orig_f, orig_w
+    ops._call = orig_call
+    other_ms = {k: round(sum(a.elapsed_time(b) for a, b in v) / n_inst, 3) for k, v in other_t.items()}
     os.environ.pop("EPB_OVERLAP_WGRAD", None)
 
     # ---- e2e through the public loop API with HOST batches (H2D + loss read-back)
@@ -328,7 +346,9 @@ def run_gpu(args):
         return
     peaks, which = measured_peaks()
     total_flops, _ = conv_flops(model._plan, n_img, HW)
-    tensor_peak = peaks["bf16_tflops_sustained"] / 2.0      # TF32 rate = half the bf16 rate
+    f16 = args.precision == "f16x3" and engine_kind == "Engine16"
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0        # TF32 rate = half the bf16 rate
+    tensor_peak = peaks["bf16_tflops_sustained"] if f16 else tf32_peak   # peak of the tcgen05 kind used
     fam_achieved = total_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     d_n, d_ms, d_fl = per_class[dom]
     achieved = d_fl / (d_ms / 1e3) / 1e12        # padded-channel FLOPs of the dominant kernel's calls
@@ -343,7 +363,10 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32 (CUDA-core FFMA)", "tf32": "tf32 (tcgen05, f32 accumulate)",
                   "tf32x3": "tf32x3 (3-pass error-compensated tcgen05, f32 accumulate; f32 SIMT "
-                            "where the tensor path does not take the shape)"}[args.precision],
+                            "where the tensor path does not take the shape)",
+                  "f16x3": "f16x3 (fp32 operands split into two fp16 planes, 3-pass error-compensated "
+                           "tcgen05 kind::f16, f32 accumulate: fp32-grade results; the final layer's "
+                           "backward on tf32x3)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": workload_name(layers), "tuples_per_gpu": args.tuples,
                    "images_per_gpu": n_img, "parallelism": "dp%d" % world,
@@ -359,9 +382,18 @@ def run_gpu(args):
         "roofline": {"bound": "tensor", "kernel": dom,
                      "achieved": round(achieved, 3), "peak": round(tensor_peak, 1),
                      "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 5),
-                     "traffic": traffic, "peak_source": which + " bf16_tflops_sustained / 2 (tf32)",
-                     "note": "achieved counts algorithmic FLOPs (2MNK once); in 3xTF32 the tensor pipe "
-                             "executes 3x that",
+                     "traffic": traffic,
+                     "peak_source": which + (" bf16_tflops_sustained (kind::f16)" if f16 else
+                                             " bf16_tflops_sustained / 2 (tf32)"),
+                     "note": "achieved counts algorithmic FLOPs (2MNK once); the 3-pass split executes "
+                             "3x that on the tensor pipe (executed_frac); frac_vs_tf32_peak is the "
+                             "round-1 denominator (tf32 rate) for comparison",
+                     "executed_frac": round(3 * achieved / tensor_peak, 5) if ns == 3 else round(achieved / tensor_peak, 5),
+                     "frac_vs_tf32_peak": round(achieved / tf32_peak, 5),
+                     "whole_step": {"algorithmic_tflops": round(total_flops / (ms_step / 1e3) / 1e12, 2),
+                                    "mfu_vs_kind_peak": round(total_flops / (ms_step / 1e3) / 1e12 / tensor_peak, 5),
+                                    "mfu_vs_tf32_peak": round(total_flops / (ms_step / 1e3) / 1e12 / tf32_peak, 5)},
+                     "non_conv_ms_per_step": other_ms,
                      "launches_per_step": d_n // n_inst,
                      "avg_launch_ms": round(d_ms / d_n, 4),
                      "share_of_step": round(d_ms / n_inst / ms_step, 4) if ms_step > 0 else None,
@@ -480,8 +512,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("EPB_PRECISION", "tf32x3"),
-                    choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--precision", default=os.environ.get("EPB_PRECISION", "f16x3"),
+                    choices=["fp32", "tf32", "tf32x3", "f16x3"])
     ap.add_argument("--layers", type=int, default=50)
     ap.add_argument("--tuples", type=int, default=TUPLES, help="view-tuples per GPU per step")
     ap.add_argument("--cpu-tuples", type=int, default=2, help="bounded CPU sample size")

@@ -386,19 +386,6 @@ __global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ ou
   if (i < n) out[i] = (float)in[i];
 }
 
-// small persistent scratch (coefficients / double column sums)
-float* g_coef = nullptr;
-size_t g_coef_cap = 0;
-int ensure_coef(size_t nfloats) {
-  if (nfloats <= g_coef_cap) return EPB_OK;
-  if (g_coef) cudaFree(g_coef);
-  g_coef = nullptr;
-  g_coef_cap = 0;
-  EPB_CUDA(cudaMalloc(&g_coef, nfloats * sizeof(float)));
-  g_coef_cap = nfloats;
-  return EPB_OK;
-}
-
 inline int ew_blocks(int64_t total4) {
   int64_t b = (total4 + kThreads - 1) / kThreads;
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -508,13 +495,14 @@ extern "C" __attribute__((visibility("default"))) int epb_bn_bwd_apply(const flo
                                 float* dbeta, epb_stream_t stream) {
   EPB_CHECK_ARG(dy && x && scale && shift && mean && invstd && sums && dx);
   EPB_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0);
-  int rc = ensure_coef(3 * (size_t)8192);
-  if (rc) return rc;
   EPB_CHECK_ARG(C <= 8192);
-  float* k0 = g_coef;
-  float* k1 = g_coef + 8192;
-  float* k2 = g_coef + 2 * 8192;
   cudaStream_t st = as_stream(stream);
+  float* coef = nullptr;
+  int rc = epb_workspace(EPB_WS_BNCOEF, 3 * (size_t)8192 * sizeof(float), st, (void**)&coef);
+  if (rc) return rc;
+  float* k0 = coef;
+  float* k1 = coef + 8192;
+  float* k2 = coef + 2 * 8192;
   bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, (double)M, C, gamma, invstd, k0, k1, k2,
                                                       dgamma, dbeta);
   EPB_LAUNCH_CHECK();
@@ -558,10 +546,11 @@ extern "C" __attribute__((visibility("default"))) int epb_avgpool_bwd(const floa
 
 extern "C" __attribute__((visibility("default"))) int epb_colsum(const float* x, int64_t M, int C, float* out, epb_stream_t stream) {
   EPB_CHECK_ARG(x && out && M > 0 && C > 0 && C % 4 == 0 && C <= 8192);
-  int rc = ensure_coef(3 * (size_t)8192);
-  if (rc) return rc;
   cudaStream_t st = as_stream(stream);
-  double* ws = reinterpret_cast<double*>(g_coef);  // 8192 doubles fit in 3*8192 floats
+  float* coef = nullptr;
+  int rc = epb_workspace(EPB_WS_BNCOEF, 3 * (size_t)8192 * sizeof(float), st, (void**)&coef);
+  if (rc) return rc;
+  double* ws = reinterpret_cast<double*>(coef);  // 8192 doubles fit in 3*8192 floats
   EPB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * C, st));
   const RowMap rm = make_rowmap(C);
   const int64_t rows_per_cta = (int64_t)rm.rpi * kRowsPerThread;

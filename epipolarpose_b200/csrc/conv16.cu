@@ -19,8 +19,12 @@
 //   warp 0    TMA producer (one lane): A hi/lo + B hi/lo boxes per k-block, S-deep ring;
 //   warp 1    MMA issuer (leader CTA, one lane): 4 k-steps x 3 tcgen05.mma per k-block,
 //             FP32 accumulators double buffered in TMEM;
-//   warps 2-5 epilogue: tcgen05.ld -> scale / bias -> smem-staged 128-byte-line stores or
-//             accumulate, per-channel sum / sum of squares for the following BatchNorm.
+//   warps 2-5 epilogue: tcgen05.ld -> scale / bias -> 128B-swizzled smem box -> ONE TMA store
+//             (or TMA reduce-add for the accumulate form) per 32x32 block: no per-row address
+//             arithmetic, rows / columns outside the tensor are clipped by the TMA unit;
+//             per-channel sum / sum of squares for the following BatchNorm from the staged
+//             box, accumulated in shared memory ACROSS the CTA's tiles (one atomic per column
+//             and CTA instead of one per tile).
 // Every mbarrier wait is bounded (trap instead of hang).
 #include "split16_common.cuh"
 
@@ -38,6 +42,7 @@ struct Plan16 {
   int tw, th, tn, tiles_w, tiles_h;
   int m_tiles, n_tiles;
   int accumulate;
+  int m_fastest;                 // tile order: consecutive tiles walk M (statistics runs) or N
   int koff[EPB_MAX_TAPS];        // wt[t] * Cin: k offset of the tap inside a packed weight row
   short dwq[EPB_MAX_TAPS], dhq[EPB_MAX_TAPS];   // tap offset on its parity view
   unsigned char map[EPB_MAX_TAPS];              // parity view of the tap
@@ -46,6 +51,7 @@ struct Plan16 {
 struct Maps16 {
   CUtensorMap a[4];
   CUtensorMap w;
+  CUtensorMap o;                 // fp32 output, box = 32 channels x 32 tile rows
 };
 
 template <int BN>
@@ -59,12 +65,9 @@ struct Cfg16 {
   static constexpr int S_ = kStageBudget / STAGE;
   static constexpr int S = S_ > 6 ? 6 : S_;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int EPI_PITCH = 36;
-  static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_PITCH * 4;
-  static constexpr int STAT_BYTES = kEpiWarps * 2 * BN * 4;
-  static constexpr int PTAB_BYTES = kEpiWarps * 32 * 8;
-  static constexpr int SMEM = S * STAGE + 1024 /*align*/ + 1024 /*barriers*/ + STAT_BYTES +
-                              EPI_BYTES + PTAB_BYTES;
+  static constexpr int EPI_BYTES = kEpiWarps * 4096;           // one swizzled 32x32 fp32 box per warp
+  static constexpr int STAT_BYTES = kEpiWarps * 2 * BN * 4;    // per-warp [sum | sum of squares][BN]
+  static constexpr int SMEM = S * STAGE + EPI_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + STAT_BYTES;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static_assert(S >= 2, "ring too shallow");
 };
@@ -83,13 +86,11 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
   const uint32_t raw = tc::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  uint8_t* ctrl = sm + C::S * C::STAGE;
+  uint8_t* epi_stage = sm + C::S * C::STAGE;                   // [4 warps][4096], 1024-byte aligned
+  uint8_t* ctrl = epi_stage + C::EPI_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);          // full[8], empty[8], tfull[2], tempty[2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ctrl + 8 * 20);
   float* sstat = reinterpret_cast<float*>(ctrl + 1024);                      // [4 warps][2][BN]
-  float* epi_stage = sstat + kEpiWarps * 2 * BN;                             // [4][32][EPI_PITCH]
-  unsigned long long* eprow =
-      reinterpret_cast<unsigned long long*>(epi_stage + kEpiWarps * 32 * C::EPI_PITCH);
   const uint32_t bar0 = tc::smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
@@ -98,7 +99,10 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = P.T * P.CB;
-  const int total_tiles = ((P.m_tiles + 1) / 2) * P.n_tiles;
+  const int m_pairs = (P.m_tiles + 1) / 2;
+  const int total_tiles = m_pairs * P.n_tiles;
+  auto nt_of = [&](int tile) { return P.m_fastest ? tile / m_pairs : tile % P.n_tiles; };
+  auto mp_of = [&](int tile) { return P.m_fastest ? tile % m_pairs : tile / P.n_tiles; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::S; ++s) {
@@ -123,11 +127,12 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
     if (lane == 0) {
       for (int v = 0; v < 4; ++v) tc::tma_prefetch_desc(&maps.a[v]);
       tc::tma_prefetch_desc(&maps.w);
+      tc::tma_prefetch_desc(&maps.o);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < total_tiles; tile += tstep) {
-        const int nt = tile % P.n_tiles;
-        int it = 2 * (tile / P.n_tiles) + crank;        // this CTA's M tile (may lie past the end: all zero)
+        const int nt = nt_of(tile);
+        int it = 2 * mp_of(tile) + crank;               // this CTA's M tile (may lie past the end: all zero)
         const int w0 = (it % P.tiles_w) * P.tw; it /= P.tiles_w;
         const int h0 = (it % P.tiles_h) * P.th;
         const int n0 = (it / P.tiles_h) * P.tn;
@@ -187,30 +192,53 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int wq = warp - 2;
     const int et = wq * 32 + lane;             // 0..127
-    float* stg = epi_stage + wq * 32 * C::EPI_PITCH;
-    float* sst = sstat + wq * 2 * BN;
-    unsigned long long* ptab = eprow + wq * 32;
-    const int c4 = lane & 7, rsub = lane >> 3;
+    uint8_t* stg = epi_stage + wq * 4096;      // this warp's 32 rows x 128 B, SWIZZLE_128B
+    const uint32_t stg_u32 = tc::smem_u32(stg);
+    float* sst = sstat + wq * 2 * BN;          // this warp's statistics slice, summed over tiles
     const float alpha = in_sc[1] * w_sc[1];
     const int twh = P.tw * P.th;
-    int as = 0;
+    // the warp's 32 tile rows are the sub-box (ew, eh, en) of the tile at this offset
+    const int r0 = q * 32;
+    const int w_off = r0 % P.tw, h_off = (r0 / P.tw) % P.th, n_off = r0 / twh;
+    // staged element (row rr, column cc) of the swizzled box
+    auto stg_at = [&](int rr, int cc) -> float* {
+      return reinterpret_cast<float*>(stg + rr * 128 + ((((cc >> 2) ^ (rr & 7)) << 4) | ((cc & 3) << 2)));
+    };
+    if (stats) {
+      for (int c = lane; c < 2 * BN; c += 32) sst[c] = 0.f;
+      __syncwarp();
+    }
+    auto flush_stats = [&](int nt) {
+      // every column below Cout of N tile `nt` carries the sums of all tiles since the last flush
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int c = et; c < 2 * BN; c += 128) {
+        const int which = c / BN, col = nt * BN + (c % BN);
+        if (col < P.Cout) {
+          const float v = (sstat[c] + sstat[2 * BN + c]) + (sstat[4 * BN + c] + sstat[6 * BN + c]);
+          atomicAdd(stats + (int64_t)which * P.Cout + col, (double)v);
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int c = lane; c < 2 * BN; c += 32) sst[c] = 0.f;
+      __syncwarp();
+    };
+    int as = 0, nt_prev = -1;
     uint32_t aphase = 0;
     for (int tile = tile0; tile < total_tiles; tile += tstep) {
-      const int nt = tile % P.n_tiles;
-      const int mt = 2 * (tile / P.n_tiles) + crank;
+      const int nt = nt_of(tile);
+      const int mt = 2 * mp_of(tile) + crank;
+      if (stats && nt_prev >= 0 && nt != nt_prev) flush_stats(nt_prev);
+      nt_prev = nt;
       int it = mt;
       const int w0 = (it % P.tiles_w) * P.tw; it /= P.tiles_w;
       const int h0 = (it % P.tiles_h) * P.th;
       const int n0 = (it / P.tiles_h) * P.tn;
-      const int r = q * 32 + lane;             // tile row == TMEM lane
-      const int w = w0 + r % P.tw, h = h0 + (r / P.tw) % P.th, n = n0 + r / twh;
-      const bool valid = mt < P.m_tiles && w < P.Wp && h < P.Hp && n < P.N;
-      float* orow = nullptr;
-      if (valid)
-        orow = out + (((int64_t)n * P.Ho + (h * P.os + P.ph)) * P.Wo + (w * P.os + P.pw)) * P.Cout;
-      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-      ptab[lane] = reinterpret_cast<unsigned long long>(orow);
-      __syncwarp();
+      unsigned vmask = 0;
+      if (stats) {
+        const int r = r0 + lane;               // tile row == TMEM lane
+        const int w = w0 + r % P.tw, h = h0 + (r / P.tw) % P.th, n = n0 + r / twh;
+        vmask = __ballot_sync(0xffffffffu, mt < P.m_tiles && w < P.Wp && h < P.Hp && n < P.N);
+      }
       tc::mbar_wait(tfull_bar(as), aphase);
       tc::tc_fence_after();
 #pragma unroll 1
@@ -219,6 +247,9 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
         if (col0 >= P.Cout) break;             // N tail
         uint32_t rg[32];
         tc::tmem_ld32(tmem_base + as * BN + chunk * 32 + ((uint32_t)(q * 32) << 16), rg);
+        // the previous box must have been read by the TMA unit before it is overwritten
+        if (lane == 0) tc::tma_store_wait_read<0>();
+        __syncwarp();
         tc::tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
@@ -228,54 +259,39 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
             const float4 b = *reinterpret_cast<const float4*>(bias + col0 + c);
             x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
           }
-          *reinterpret_cast<float4*>(stg + lane * C::EPI_PITCH + c) = x;
+          *reinterpret_cast<float4*>(stg + lane * 128 + (((c >> 2) ^ (lane & 7)) << 4)) = x;
         }
+        tc::fence_proxy_async();               // generic-proxy writes -> visible to the TMA unit
         __syncwarp();
+        if (lane == 0 && mt < P.m_tiles) {
+          if (P.accumulate)
+            tc::tma_reduce_add_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
+          else
+            tc::tma_store_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
+          tc::tma_store_commit();
+        }
         if (stats) {
+          // lane = column: sum over the staged valid rows (conflict free: the swizzle spreads
+          // the 32 columns of a row over the 32 banks); four partial sums keep the chains short
           float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
-            const float x = ((vmask >> rr) & 1u) ? stg[rr * C::EPI_PITCH + lane] : 0.f;
+            const float x = ((vmask >> rr) & 1u) ? *stg_at(rr, lane) : 0.f;
             s1[rr & 3] += x;
             s2[rr & 3] = fmaf(x, x, s2[rr & 3]);
           }
-          sst[chunk * 32 + lane] = (s1[0] + s1[1]) + (s1[2] + s1[3]);
-          sst[BN + chunk * 32 + lane] = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+          sst[chunk * 32 + lane] += (s1[0] + s1[1]) + (s1[2] + s1[3]);
+          sst[BN + chunk * 32 + lane] += (s2[0] + s2[1]) + (s2[2] + s2[3]);
         }
-        if (col0 + c4 * 4 < P.Cout) {          // Cout % 4 == 0: whole float4 columns
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + rsub;
-            float* op = reinterpret_cast<float*>(ptab[rr]);
-            if (op) {
-              float4 x = *reinterpret_cast<const float4*>(stg + rr * C::EPI_PITCH + c4 * 4);
-              float4* o = reinterpret_cast<float4*>(op + col0) + c4;
-              if (P.accumulate) {
-                const float4 pv = *o;
-                x.x += pv.x; x.y += pv.y; x.z += pv.z; x.w += pv.w;
-              }
-              *o = x;
-            }
-          }
-        }
-        __syncwarp();
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(tempty_bar(as), 0));   // release at cluster scope
+      if (lane == 0) tc::mbar_arrive_cluster_relaxed(tc::mapa(tempty_bar(as), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
-      if (stats) {
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        for (int c = et; c < 2 * BN; c += 128) {
-          const int which = c / BN, cc = c % BN, col = nt * BN + cc;
-          if (col < P.Cout) {
-            const float v = (sstat[c] + sstat[2 * BN + c]) + (sstat[4 * BN + c] + sstat[6 * BN + c]);
-            atomicAdd(stats + (int64_t)which * P.Cout + col, (double)v);
-          }
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-      }
     }
+    if (stats && nt_prev >= 0) flush_stats(nt_prev);
+    if (lane == 0) tc::tma_store_wait<0>();    // the boxes are written before the CTA exits
+    __syncwarp();
   }
 
   tc::tc_fence_before();
@@ -360,6 +376,37 @@ extern "C" __attribute__((visibility("default"))) int epb_conv16_fprop(
       for (int u = 0; u < 4; ++u)
         if (need[u]) { maps.a[v] = maps.a[u]; break; }
     }
+  // tile order: statistics want runs of tiles with the same N tile (one flush per run); without
+  // statistics, N-fastest lets the concurrently running tiles of one M tile share its A rows in L2
+  P.m_fastest = stats != nullptr;
+  {
+    // output box of one epilogue warp: its 32 tile rows as the sub-box (ew, eh, en)
+    const int ew = P.tw < 32 ? P.tw : 32;
+    const int eh = P.th < 32 / ew ? P.th : 32 / ew;
+    const int en = 32 / (ew * eh);
+    epb_encode_tiled_fn enc = epb_get_encode_tiled();
+    if (!enc) {
+      epb_set_error("cuTensorMapEncodeTiled entry point unavailable");
+      return EPB_ECUDA;
+    }
+    const int os = g->os;
+    const int Wv = dense ? P.Wp : (g->Wo - g->pw + os - 1) / os, Hv = dense ? 1 : (g->Ho - g->ph + os - 1) / os;
+    const int64_t Wo = dense ? P.Wp : g->Wo, Ho = dense ? 1 : g->Ho;
+    const cuuint64_t dims[4] = {(cuuint64_t)g->Cout, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)os * g->Cout * 4, (cuuint64_t)os * Wo * g->Cout * 4,
+                                   (cuuint64_t)Ho * Wo * g->Cout * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)ew, (cuuint32_t)eh, (cuuint32_t)en};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    float* ob = out + ((int64_t)(dense ? 0 : g->ph) * Wo + (dense ? 0 : g->pw)) * g->Cout;
+    CUresult cr = enc(&maps.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ob, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      epb_set_error("cuTensorMapEncodeTiled(output %dx%dx%dx%d os %d) failed (%d)", g->N, g->Ho, g->Wo,
+                    g->Cout, os, (int)cr);
+      return EPB_ECUDA;
+    }
+  }
   // N tile: 256 unless that wastes more than a quarter of the columns
   int bn;
   if (g->Cout <= 64) bn = 64;

@@ -598,18 +598,6 @@ __global__ void prep_weight_tc(const float* __restrict__ w, float* __restrict__ 
   }
 }
 
-float* g_wws = nullptr;
-size_t g_wws_cap = 0;
-int ensure_wws(size_t nfloats) {
-  if (nfloats <= g_wws_cap) return EPB_OK;
-  if (g_wws) cudaFree(g_wws);
-  g_wws = nullptr;
-  g_wws_cap = 0;
-  EPB_CUDA(cudaMalloc(&g_wws, nfloats * sizeof(float)));
-  g_wws_cap = nfloats;
-  return EPB_OK;
-}
-
 // EPB_TUNE: memory-system switches of the A stream (bit 0 prefetch policy, bit 1 force next-tile
 // prefetch, bit 2 evict-first single-use loads, bit 3 CTA-scope arrive across the CTA pair)
 int tune_flags() {
@@ -693,12 +681,15 @@ int epb_conv_fprop_tc(const epb_conv_geom* g, const float* in, const float* w,
   const int bn = g->Cout >= 256 ? 256 : (g->Cout >= 128 ? 128 : 64);
   const int npad = (g->Cout + bn - 1) / bn * bn;
   const int64_t K = (int64_t)g->Tw * g->Cin;
-  int rc = ensure_wws((size_t)planes * npad * K);
+  // hi / lo operand planes of this call: scratch of this (device, stream); one slot per
+  // stream, so concurrent calls on different streams do not share it
+  float* wws = nullptr;
+  int rc = epb_workspace(EPB_WS_WPLANES, (size_t)planes * npad * K * sizeof(float), st, (void**)&wws);
   if (rc) return rc;
   {
     int64_t blocks = ((int64_t)npad * K + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    prep_weight_tc<<<(int)blocks, 256, 0, st>>>(w, g_wws, g->Cout, K, npad, planes);
+    prep_weight_tc<<<(int)blocks, 256, 0, st>>>(w, wws, g->Cout, K, npad, planes);
     EPB_LAUNCH_CHECK();
   }
   epb_encode_tiled_fn enc = epb_get_encode_tiled();
@@ -715,7 +706,7 @@ int epb_conv_fprop_tc(const epb_conv_geom* g, const float* in, const float* w,
                     (int64_t)g->N * g->Hp * g->Wp > BM;
   const cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(pair ? bn / 2 : bn)};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g_wws, dims, strides, box, estr,
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, wws, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {

@@ -412,23 +412,6 @@ heatmap_joint_loss_kernel(const float* __restrict__ hm, const float* __restrict_
   }
 }
 
-double* g_hm_parts = nullptr;                 // [kHmMaxBlocks] partials + ticket counter behind them
-
-// workspace for per-CTA partials (grows on demand; one per process, reused
-// stream-ordered -- the library is used from one stream per device at a time)
-Part* g_parts = nullptr;
-size_t g_parts_cap = 0;
-
-int ensure_parts(size_t n) {
-  if (n <= g_parts_cap) return EPB_OK;
-  if (g_parts) cudaFree(g_parts);
-  g_parts = nullptr;
-  g_parts_cap = 0;
-  EPB_CUDA(cudaMalloc(&g_parts, n * sizeof(Part)));
-  g_parts_cap = n;
-  return EPB_OK;
-}
-
 int pick_splits(int rows, int64_t work_per_row, int max_splits) {
   // aim for >= 4 CTAs per SM without making chunks smaller than ~16 KB
   int s = 1;
@@ -445,13 +428,14 @@ extern "C" __attribute__((visibility("default"))) int epb_softargmax_fwd(const f
   cudaStream_t st = as_stream(stream);
   const int NJ = N * J;
   int S;
+  Part* parts = nullptr;        // per-CTA partials: scratch of this (device, stream)
   if (layout == 0) {
     EPB_CHECK_ARG(W % 4 == 0);
     const int64_t vol = (int64_t)D * H * W;
     S = pick_splits(NJ, vol, 64);
-    int rc = ensure_parts((size_t)NJ * S);
+    int rc = epb_workspace(EPB_WS_SOFTARGMAX, (size_t)NJ * S * sizeof(Part), st, (void**)&parts);
     if (rc) return rc;
-    softargmax_fwd_nchw<<<dim3(S, NJ), kFwdThreads, 0, st>>>(logits, D, H, W, S, g_parts);
+    softargmax_fwd_nchw<<<dim3(S, NJ), kFwdThreads, 0, st>>>(logits, D, H, W, S, parts);
   } else if (layout == 1) {
     EPB_CHECK_ARG(D % 4 == 0);
     const int C4 = J * D / 4;
@@ -459,17 +443,17 @@ extern "C" __attribute__((visibility("default"))) int epb_softargmax_fwd(const f
     const int ppi = (512 / C4) > 0 ? (512 / C4) : 1;
     S = 1;
     while (N * S < 8 * kNumSMs && (H * W) / (S * 2) >= 16 * ppi) S *= 2;
-    int rc = ensure_parts((size_t)NJ * S);
+    int rc = epb_workspace(EPB_WS_SOFTARGMAX, (size_t)NJ * S * sizeof(Part), st, (void**)&parts);
     if (rc) return rc;
     const int threads = C4 * ppi;
     softargmax_fwd_nhwc<<<dim3(S, N), threads, threads * sizeof(Part), st>>>(
-        logits, J, D, H, W, S, ppi, g_parts);
+        logits, J, D, H, W, S, ppi, parts);
   } else {
     EPB_CHECK_ARG(layout == 0 || layout == 1);
     return EPB_EINVAL;
   }
   EPB_LAUNCH_CHECK();
-  softargmax_finalize<<<(NJ + 127) / 128, 128, 0, st>>>(g_parts, NJ, S, 1.f / W, 1.f / H, 1.f / D,
+  softargmax_finalize<<<(NJ + 127) / 128, 128, 0, st>>>(parts, NJ, S, 1.f / W, 1.f / H, 1.f / D,
                                                       coords, lse_ws);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
@@ -524,16 +508,16 @@ extern "C" __attribute__((visibility("default"))) int epb_heatmap_joint_loss(
   EPB_CHECK_ARG(n >= 0 && (n == 0 || (x && t && w)));
   EPB_CHECK_ARG(kind >= 0 && kind <= 2);
   EPB_CHECK_ARG(n == 0 || div != 0.f);
-  if (!g_hm_parts) {
-    EPB_CUDA(cudaMalloc(&g_hm_parts, (kHmMaxBlocks + 1) * sizeof(double)));
-    EPB_CUDA(cudaMemset(g_hm_parts, 0, (kHmMaxBlocks + 1) * sizeof(double)));
-  }
+  double* hm_parts = nullptr;   // [kHmMaxBlocks] partials + ticket counter (zero-filled when created)
+  int rc = epb_workspace(EPB_WS_HMLOSS, (kHmMaxBlocks + 1) * sizeof(double), as_stream(stream),
+                         (void**)&hm_parts);
+  if (rc) return rc;
   const int64_t work = ((int64_t)R * HW + 3) / 4;
   int64_t blocks = (work + kHmThreads - 1) / kHmThreads;
   if (blocks > kHmMaxBlocks) blocks = kHmMaxBlocks;
   heatmap_joint_loss_kernel<<<(int)blocks, kHmThreads, 0, as_stream(stream)>>>(
       hm, target, hm_weight, R, HW, hm_scale, x, t, w, n, kind, div, jt_scale, loss, dhm, dx,
-      g_hm_parts, reinterpret_cast<unsigned*>(g_hm_parts + kHmMaxBlocks));
+      hm_parts, reinterpret_cast<unsigned*>(hm_parts + kHmMaxBlocks));
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

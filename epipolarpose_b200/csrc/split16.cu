@@ -263,7 +263,7 @@ split_apply_kernel(const epb_split_job* __restrict__ jobs, int njobs,
 }
 
 // ------------------------------------------------------------------ BatchNorm backward
-constexpr int kRowsPerThread = 64;
+constexpr int kRowsPerThread = 32;
 
 struct RowMap {
   int C4, tpr, rpi, chunks;
@@ -410,28 +410,98 @@ bn_bwd_apply_split_kernel(const float4* dy /* may alias dy_masked */, const floa
                           uint2* __restrict__ dz, const float* __restrict__ dz_sc,
                           float4* dy_masked, int64_t total4, int C4) {
   const float s = dz_sc[0];
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total4;
-       i += (int64_t)gridDim.x * kThreads) {
-    const int c4 = (int)(i % C4);
-    const float4 xv = ldg_stream(x + i);
-    const float4 g = mask4(__ldcs(dy + i), xv, mask_hi, i, scale[c4], shift[c4], relu);
-    const float4 mu = mean[c4], is = invstd[c4], b = k1v[c4], c = k2v[c4];
-    float4 a = is;
-    if (gamma) {
-      const float4 ga = gamma[c4];
-      a.x *= ga.x; a.y *= ga.y; a.z *= ga.z; a.w *= ga.w;
+  // two independent elements per trip: six streaming loads in flight per thread
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x; i0 < total4; i0 += 2 * stride) {
+    const int64_t idx[2] = {i0, i0 + stride};
+    float4 xv[2], dv[2];
+    uint2 mk[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (idx[u] < total4) {
+        xv[u] = ldg_stream(x + idx[u]);
+        dv[u] = __ldcs(dy + idx[u]);
+        if (mask_hi) mk[u] = mask_hi[idx[u]];
+      }
     }
-    float4 o;
-    o.x = a.x * (g.x - b.x - (xv.x - mu.x) * is.x * c.x);
-    o.y = a.y * (g.y - b.y - (xv.y - mu.y) * is.y * c.y);
-    o.z = a.z * (g.z - b.z - (xv.z - mu.z) * is.z * c.z);
-    o.w = a.w * (g.w - b.w - (xv.w - mu.w) * is.w * c.w);
-    uint2 hi, lo;
-    split2(o.x, o.y, s, hi.x, lo.x);
-    split2(o.z, o.w, s, hi.y, lo.y);
-    dz[i] = hi;
-    dz[total4 + i] = lo;
-    if (dy_masked) dy_masked[i] = g;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = idx[u];
+      if (i >= total4) break;
+      const int c4 = (int)(i % C4);
+      float4 g = dv[u];
+      if (mask_hi) {
+        g = make_float4((mk[u].x & 0x7fffu) ? g.x : 0.f, (mk[u].x & 0x7fff0000u) ? g.y : 0.f,
+                        (mk[u].y & 0x7fffu) ? g.z : 0.f, (mk[u].y & 0x7fff0000u) ? g.w : 0.f);
+      } else {
+        g = mask4(g, xv[u], nullptr, i, scale[c4], shift[c4], relu);
+      }
+      const float4 mu = mean[c4], is = invstd[c4], b = k1v[c4], c = k2v[c4];
+      float4 a = is;
+      if (gamma) {
+        const float4 ga = gamma[c4];
+        a.x *= ga.x; a.y *= ga.y; a.z *= ga.z; a.w *= ga.w;
+      }
+      float4 o;
+      o.x = a.x * (g.x - b.x - (xv[u].x - mu.x) * is.x * c.x);
+      o.y = a.y * (g.y - b.y - (xv[u].y - mu.y) * is.y * c.y);
+      o.z = a.z * (g.z - b.z - (xv[u].z - mu.z) * is.z * c.z);
+      o.w = a.w * (g.w - b.w - (xv[u].w - mu.w) * is.w * c.w);
+      uint2 hi, lo;
+      split2(o.x, o.y, s, hi.x, lo.x);
+      split2(o.z, o.w, s, hi.y, lo.y);
+      dz[i] = hi;
+      dz[total4 + i] = lo;
+      if (dy_masked) dy_masked[i] = g;
+    }
+  }
+}
+
+// one CTA: hard bound of a post-activation tensor from the statistics of its conv output(s)
+__device__ __forceinline__ float group_bound(const double* stats, const float* scale,
+                                             const float* shift, double M, int C) {
+  float b = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = stats[c] / M;
+    double var = stats[C + c] / M - mean * mean;
+    if (var < 0) var = 0;
+    const double sc = scale[c], sh = shift[c];
+    // no element of a sample lies further than sqrt(M - 1) standard deviations from its mean
+    b = fmaxf(b, (float)(fabs(sc * mean + sh) + fabs(sc) * sqrt(M * var)));
+  }
+  return b;
+}
+
+__global__ void __launch_bounds__(1024)
+act_scale_kernel(const double* __restrict__ stats, const float* __restrict__ scale,
+                 const float* __restrict__ shift, double M, int C,
+                 const double* __restrict__ stats2, const float* __restrict__ scale2,
+                 const float* __restrict__ shift2, const float* __restrict__ res_sc,
+                 float* __restrict__ sc) {
+  float b1 = group_bound(stats, scale, shift, M, C);
+  float b2 = stats2 ? group_bound(stats2, scale2, shift2, M, C) : 0.f;
+  b1 = warp_max(b1);
+  b2 = warp_max(b2);
+  __shared__ float sm[2][32];
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = b1; sm[1][threadIdx.x >> 5] = b2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { b1 = fmaxf(b1, sm[0][w]); b2 = fmaxf(b2, sm[1][w]); }
+    float bound = (b1 + b2) * 1.001f + (res_sc ? res_sc[2] : 0.f);
+    if (!isfinite(bound)) bound = 3.0e38f;
+    // largest power of two with s * bound <= 2^15 (fp16 max is 65504)
+    float s = 1.f;
+    if (bound > 0.f) {
+      int e;
+      frexpf(bound, &e);                         // bound = f * 2^e, f in [0.5, 1)
+      int k = 15 - e;
+      k = k < -100 ? -100 : (k > 100 ? 100 : k);
+      s = ldexpf(1.f, k);
+    }
+    sc[0] = s;
+    sc[1] = 1.f / s;
+    sc[2] = bound;
+    sc[3] = 0.f;
   }
 }
 
@@ -553,6 +623,17 @@ EPB_API int epb_avgpool_split(const epb_half* x, const float* x_sc, float* y, in
   EPB_CHECK_ARG(x && x_sc && y && N > 0 && HW > 0 && C > 0);
   avgpool_split_kernel<<<dim3((C + 127) / 128, N), 128, 0, as_stream(stream)>>>(
       reinterpret_cast<const __half*>(x), x_sc, y, N, HW, C);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_act_scale(const double* stats, const float* scale, const float* shift, int64_t M,
+                          int C, const double* stats2, const float* scale2, const float* shift2,
+                          const float* res_sc, float* sc, epb_stream_t stream) {
+  EPB_CHECK_ARG(stats && scale && shift && sc && M > 0 && C > 0);
+  EPB_CHECK_ARG((stats2 == nullptr) == (scale2 == nullptr) && (scale2 == nullptr) == (shift2 == nullptr));
+  act_scale_kernel<<<1, 1024, 0, as_stream(stream)>>>(stats, scale, shift, (double)M, C, stats2,
+                                                      scale2, shift2, res_sc, sc);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

@@ -27,7 +27,7 @@ logger = logging.getLogger(__name__)
 # f16x3: split-fp16 operands, three kind::f16 tensor passes (net16.Engine16); plans with
 # channel counts outside whole 64-element TMA boxes keep the 3xTF32 engine
 _PRECISIONS = {"fp32": 0, "tf32": 1, "tf32x3": 3, "f16x3": 4}
-DEFAULT_PRECISION = "tf32x3"
+DEFAULT_PRECISION = "f16x3"
 
 
 def _no_forward(self, *a, **k):

@@ -22,7 +22,7 @@ import torch
 from . import net as _net
 from .net import BN_EPS, BN_MOMENTUM, Conv, _BNState
 
-ACT_SCALE = 16.0          # static scale of post-activation tensors (|x| <= 4094 representable)
+IMG_SCALE = 16.0          # static scale of the (normalised) input image planes
 STEM_KPAD16 = 192         # 7*7*3 = 147 padded to whole 64-element k-blocks
 WGRAD_WS_FLOATS = 48 << 20
 
@@ -59,8 +59,9 @@ class Engine16(_net.Engine):
         st = getattr(self, "_cst", None)
         if st is None or st["dev"] != self.dev:
             st = {"dev": self.dev,
-                  "act_sc": torch.tensor([ACT_SCALE, 1.0 / ACT_SCALE], device=self.dev,
-                                         dtype=torch.float32),
+                  # the image patch matrix keeps a static scale: |pixel| <= 4094 representable
+                  "img_sc": torch.tensor([IMG_SCALE, 1.0 / IMG_SCALE, 65504.0 / IMG_SCALE, 0.0],
+                                         device=self.dev, dtype=torch.float32),
                   "ws": torch.empty(WGRAD_WS_FLOATS, device=self.dev, dtype=torch.float32)}
             self._cst = st
         return st
@@ -178,17 +179,24 @@ class Engine16(_net.Engine):
         self.dev = x_nchw.device
         N, _, H, W = x_nchw.shape
         cst = self._consts()
-        asc = cst["act_sc"]
         S = {"N": N, "H": H, "W": W, "bn": {}, "blocks": []}
         bns = plan.all_bns()
         offs, tot = {}, 0
         for name, C in bns:
             offs[name] = tot
             tot += 2 * C
-        stats_all = torch.zeros(tot, device=self.dev, dtype=torch.float64) if training else None
+        # batch statistics of every conv output: BatchNorm in train(), and in both modes the
+        # bound that fixes the scale of the post-activation split tensor (epb_act_scale)
+        stats_all = torch.zeros(tot, device=self.dev, dtype=torch.float64)
+        scs = torch.empty((len(bns) + 1, 4), device=self.dev, dtype=torch.float32)
+        sc_slot = [0]
+
+        def new_sc():
+            sc_slot[0] += 1
+            return scs[sc_slot[0] - 1]
 
         def stats_of(name, C):
-            return stats_all[offs[name]:offs[name] + 2 * C] if training else None
+            return stats_all[offs[name]:offs[name] + 2 * C]
 
         def bn(name, C, M):
             st = self._bn_train(name, C, stats_of(name, C), M, params, None) if training \
@@ -202,75 +210,91 @@ class Engine16(_net.Engine):
         def w16(conv):
             return S["w16"][conv.name][0]
 
-        def act(z, st, shape):
+        def act(z, name, st, shape):
+            """post-BatchNorm/ReLU split tensor of conv output z and its scale"""
+            C = shape[-1]
+            M = z.numel() // C
+            sc = new_sc()
+            ops.act_scale(stats_of(name, C), st.scale, st.shift, M, C, None, None, None, None, sc)
             a = self._half(*shape)
-            ops.bn_act_split(z, st.scale, st.shift, None, None, None, None, None, 1,
-                             z.numel() // shape[-1], shape[-1], a, asc)
-            return a
+            ops.bn_act_split(z, st.scale, st.shift, None, None, None, None, None, 1, M, C, a, sc)
+            return a, sc
 
         # ---- stem (pose3d_resnet.py:186-189): patch matrix -> 1x1 GEMM -> BN+ReLU+maxpool
         stem, scol, kpad = plan.stem, self.stem_col, self.stem_kpad
         H1, W1 = stem.out_hw(H, W)
         col = self._half(N, H1, W1, kpad)
-        ops.im2col_split(x_nchw, col, asc, N, 3, H, W, 7, 7, 2, 3, H1, W1, kpad)
-        z0, _, _ = self._conv_fwd16(scol, col, asc, N, H1, W1, w16(stem), stats=stats_of("bn1", 64))
+        isc = cst["img_sc"]
+        ops.im2col_split(x_nchw, col, isc, N, 3, H, W, 7, 7, 2, 3, H1, W1, kpad)
+        z0, _, _ = self._conv_fwd16(scol, col, isc, N, H1, W1, w16(stem), stats=stats_of("bn1", 64))
         b0 = bn("bn1", 64, N * H1 * W1)
         H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
         cur = self._half(N, H2, W2, 64)
+        cur_sc = new_sc()
+        ops.act_scale(stats_of("bn1", 64), b0.scale, b0.shift, N * H1 * W1, 64, None, None, None, None,
+                      cur_sc)
         argidx = torch.empty((N, H2, W2, 64), device=self.dev, dtype=torch.uint8)
-        ops.bn_relu_maxpool_split(z0, b0.scale, b0.shift, cur, asc, argidx, N, H1, W1, 64)
+        ops.bn_relu_maxpool_split(z0, b0.scale, b0.shift, cur, cur_sc, argidx, N, H1, W1, 64)
         S["stem"] = (col, z0, argidx, H1, W1, H2, W2)
         h, w = H2, W2
 
         # ---- residual stages (:191-194)
         for blk in plan.blocks:
-            rec = {"in": cur, "h": h, "w": w, "z": [], "hw": [], "a": []}
-            src = cur
+            rec = {"in": (cur, cur_sc), "h": h, "w": w, "z": [], "hw": [], "a": []}
+            src, src_sc = cur, cur_sc
             hh, ww = h, w
             nconv = len(blk["convs"])
             for ci, conv in enumerate(blk["convs"]):
                 bname, C = blk["bns"][ci]
-                z, ho, wo = self._conv_fwd16(conv, src, asc, N, hh, ww, w16(conv),
+                z, ho, wo = self._conv_fwd16(conv, src, src_sc, N, hh, ww, w16(conv),
                                              stats=stats_of(bname, C))
                 st = bn(bname, C, N * ho * wo)
                 rec["z"].append(z)
                 rec["hw"].append((hh, ww))
                 hh, ww = ho, wo
                 if ci < nconv - 1:
-                    src = act(z, st, (N, hh, ww, conv.cout_p))
-                    rec["a"].append(src)
-            last = S["bn"][blk["bns"][-1][0]]
+                    src, src_sc = act(z, bname, st, (N, hh, ww, conv.cout_p))
+                    rec["a"].append((src, src_sc))
+            lname = blk["bns"][-1][0]
+            last = S["bn"][lname]
             zl = rec["z"][-1]
             Cl = blk["convs"][-1].cout_p
             M = N * hh * ww
             out = self._half(N, hh, ww, Cl)
+            out_sc = new_sc()
             if blk["down"]:
                 dconv, (dname, dC) = blk["down"]
-                zd, _, _ = self._conv_fwd16(dconv, cur, asc, N, h, w, w16(dconv),
+                zd, _, _ = self._conv_fwd16(dconv, cur, cur_sc, N, h, w, w16(dconv),
                                             stats=stats_of(dname, dC))
                 dst = bn(dname, dC, M)
                 rec["zd"] = zd
+                ops.act_scale(stats_of(lname, Cl), last.scale, last.shift, M, Cl,
+                              stats_of(dname, dC), dst.scale, dst.shift, None, out_sc)
                 ops.bn_act_split(zl, last.scale, last.shift, zd, dst.scale, dst.shift, None, None,
-                                 1, M, Cl, out, asc)
+                                 1, M, Cl, out, out_sc)
             else:
-                ops.bn_act_split(zl, last.scale, last.shift, None, None, None, cur, asc, 1, M, Cl,
-                                 out, asc)
-            rec["out"] = out
+                ops.act_scale(stats_of(lname, Cl), last.scale, last.shift, M, Cl, None, None, None,
+                              cur_sc, out_sc)
+                ops.bn_act_split(zl, last.scale, last.shift, None, None, None, cur, cur_sc, 1, M, Cl,
+                                 out, out_sc)
+            rec["out"] = (out, out_sc)
             S["blocks"].append(rec)
-            cur, h, w = out, hh, ww
+            cur, cur_sc, h, w = out, out_sc, hh, ww
 
-        S["trunk"] = (cur, h, w)
+        S["trunk"] = (cur, cur_sc, h, w)
         # ---- deconv head (:198)
-        src = cur
+        src, src_sc = cur, cur_sc
         S["deconv"] = []
         zlast, stlast = None, None
         for conv, (bname, C) in plan.deconvs:
-            z, ho, wo = self._conv_fwd16(conv, src, asc, N, h, w, w16(conv), stats=stats_of(bname, C))
+            z, ho, wo = self._conv_fwd16(conv, src, src_sc, N, h, w, w16(conv), stats=stats_of(bname, C))
             st = bn(bname, C, N * ho * wo)
-            a = act(z, st, (N, ho, wo, conv.cout_p))
-            S["deconv"].append((src, z, h, w))
-            src, h, w = a, ho, wo
+            S["deconv"].append((src, src_sc, z, h, w))
+            src, src_sc = act(z, bname, st, (N, ho, wo, conv.cout_p))
+            h, w = ho, wo
             zlast, stlast = z, st
+        if zlast is None:
+            raise RuntimeError("the split path expects at least one deconv layer")
         # ---- final 1x1 / 3x3 conv with bias (:199)
         fin = plan.final
         fbias = params[fin.name + ".bias"]
@@ -278,17 +302,15 @@ class Engine16(_net.Engine):
             fb = torch.zeros(fin.cout_p, device=self.dev)
             fb[:fin.cout] = fbias
             fbias = fb
-        logits, ho, wo = self._conv_fwd16(fin, src, asc, N, h, w, w16(fin), bias=fbias)
+        logits, ho, wo = self._conv_fwd16(fin, src, src_sc, N, h, w, w16(fin), bias=fbias)
         # the final layer's backward runs on the 3xTF32 kernels from (z, BatchNorm affine)
-        S["final"] = (zlast, (stlast.scale, stlast.shift) if stlast is not None else None, h, w)
-        if zlast is None:
-            raise RuntimeError("the split path expects at least one deconv layer")
+        S["final"] = (zlast, (stlast.scale, stlast.shift), h, w)
         depth = None
         if plan.fc is not None:                 # :202-210
-            tr, th, tw = S["trunk"]
+            tr, tr_sc, th, tw = S["trunk"]
             assert th == plan.pool_k and tw == plan.pool_k, "AvgPool(k) -> 1x1 expected"
             pooled = torch.empty((N, 1, 1, 2048), device=self.dev, dtype=torch.float32)
-            ops.avgpool_split(tr, asc, pooled, N, th * tw, 2048)
+            ops.avgpool_split(tr, tr_sc, pooled, N, th * tw, 2048)
             depth, _, _ = self._conv_fwd(plan.fc, pooled, N, 1, 1, S["packed"][plan.fc.name][0],
                                          bias=params["depth_fc.bias"])
             S["fc"] = pooled
@@ -305,7 +327,6 @@ class Engine16(_net.Engine):
     def _backward(self, S, dlogits, ddepth, params, grads):
         ops, plan = self.ops, self.plan
         N = S["N"]
-        asc = self._consts()["act_sc"]
 
         def wd16(conv):
             return S["w16"][conv.name][1]
@@ -324,15 +345,15 @@ class Engine16(_net.Engine):
         self._conv_wgrad(fin, src, dlogits, N, h, w, grads[fin.name + ".weight"], affine=aff)
         dcur = self._conv_dgrad(fin, dlogits, N, h, w, S["packed"][fin.name][1])
         # ---- deconv head, reversed
-        for (conv, (bname, C)), (dsrc, z, dh, dw) in zip(reversed(plan.deconvs),
-                                                         reversed(S["deconv"])):
+        for (conv, (bname, C)), (dsrc, dsrc_sc, z, dh, dw) in zip(reversed(plan.deconvs),
+                                                                  reversed(S["deconv"])):
             st = S["bn"][bname]
             dz, dsc = self._bn_bwd16(st, dcur, z, None, 1, params, grads)
-            self._conv_wgrad16(conv, dsrc, asc, dz, dsc, N, dh, dw)
+            self._conv_wgrad16(conv, dsrc, dsrc_sc, dz, dsc, N, dh, dw)
             dcur = self._conv_dgrad16(conv, dz, dsc, N, dh, dw, wd16(conv))
         # ---- VOLUME=False depth head (fp32 operands)
         if plan.fc is not None and ddepth is not None:
-            tr, th, tw = S["trunk"]
+            tr, tr_sc, th, tw = S["trunk"]
             dd = ddepth.reshape(N, 1, 1, -1).contiguous()
             ops.colsum(dd, N, plan.fc.cout_p, grads["depth_fc.bias"])
             self._conv_wgrad(plan.fc, S["fc"], dd, N, 1, 1, grads["depth_fc.weight"])
@@ -340,7 +361,7 @@ class Engine16(_net.Engine):
             ops.avgpool_bwd(dpool, dcur, N, th * tw, 2048, 1)
         # ---- residual stages, reversed
         for blk, rec in zip(reversed(plan.blocks), reversed(S["blocks"])):
-            out, xin, h, w = rec["out"], rec["in"], rec["h"], rec["w"]
+            (out, _), (xin, xin_sc), h, w = rec["out"], rec["in"], rec["h"], rec["w"]
             nconv = len(blk["convs"])
             mask = out[0]                       # hi plane of the block output: (out > 0)
             down = blk["down"]
@@ -360,14 +381,14 @@ class Engine16(_net.Engine):
                 else:
                     dz, dsc = self._bn_bwd16(st, g, z, None, 1, params, grads)
                 hh, ww = rec["hw"][ci]
-                xop = xin if ci == 0 else rec["a"][ci - 1]
-                self._conv_wgrad16(conv, xop, asc, dz, dsc, N, hh, ww)
+                xop, xop_sc = (xin, xin_sc) if ci == 0 else rec["a"][ci - 1]
+                self._conv_wgrad16(conv, xop, xop_sc, dz, dsc, N, hh, ww)
                 if ci == 0 and not down:
                     g = self._conv_dgrad16(conv, dz, dsc, N, hh, ww, wd16(conv), accumulate_into=dcur)
                 else:
                     g = self._conv_dgrad16(conv, dz, dsc, N, hh, ww, wd16(conv))
             if down:
-                self._conv_wgrad16(dconv, xin, asc, dzd, dzd_sc, N, h, w)
+                self._conv_wgrad16(dconv, xin, xin_sc, dzd, dzd_sc, N, h, w)
                 self._conv_dgrad16(dconv, dzd, dzd_sc, N, h, w, wd16(dconv), accumulate_into=g)
             dcur = g
         # ---- stem
@@ -375,4 +396,4 @@ class Engine16(_net.Engine):
         gpool = torch.empty((N, H1, W1, 64), device=self.dev, dtype=torch.float32)
         ops.maxpool_bwd(dcur, argidx, gpool, N, H1, W1, 64)
         dz0, dsc0 = self._bn_bwd16(S["bn"]["bn1"], gpool, z0, None, 1, params, grads)
-        self._conv_wgrad16(self.stem_col, col, asc, dz0, dsc0, N, H1, W1)
+        self._conv_wgrad16(self.stem_col, col, self._consts()["img_sc"], dz0, dsc0, N, H1, W1)

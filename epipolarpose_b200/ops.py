@@ -187,6 +187,11 @@ def colsum(x, M, C, out):
 _H = torch.float16
 
 
+def act_scale(stats, scale, shift, M, C, stats2, scale2, shift2, res_sc, sc):
+    _call("epb_act_scale", _p(stats, torch.float64), _p(scale), _p(shift), M, C,
+          _p(stats2, torch.float64), _p(scale2), _p(shift2), _p(res_sc), _p(sc), _stream())
+
+
 def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc):
     _call("epb_bn_act_split", _p(x), _p(scale), _p(shift), _p(r), _p(rscale), _p(rshift),
           _p(r_split, _H), _p(r_sc), int(relu), M, C, _p(y, _H), _p(y_sc), _stream())

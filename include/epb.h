@@ -203,6 +203,16 @@ int epb_colsum(const float* x, int64_t M, int C, float* out,
  * ---------------------------------------------------------------------- */
 typedef uint16_t epb_half;
 
+/* Power-of-two scale of a post-activation split tensor from STATISTICS only (no pass over the
+ * data): with stats[2C] the float64 (sum, sum of squares) of a conv output over M rows,
+ *   |x*scale_c + shift_c| <= |scale_c*mean_c + shift_c| + |scale_c| * sqrt(M * var_c)
+ * (no element lies further than sqrt(M) standard deviations from its mean), maximised over
+ * the channels; a second group (the downsample BatchNorm of a residual block) and the bound
+ * of a split residual (res_sc[2]) add.  sc[4] = {s, 1/s, bound, 0}, s the largest power of
+ * two with s*bound <= 2^15, so the fp16 planes can neither overflow nor saturate. */
+int epb_act_scale(const double* stats, const float* scale, const float* shift, int64_t M, int C,
+                  const double* stats2, const float* scale2, const float* shift2,
+                  const float* res_sc, float* sc, epb_stream_t stream);
 /* y_split = act(x*scale+shift [+ residual]).  The residual is either fp32 rows `r`
  * (with optional affine rscale/rshift: the downsample BatchNorm) or a split tensor
  * `r_split` / `r_sc` (the identity path: the previous block's output), or absent. */

@@ -505,6 +505,24 @@ def _pow2_scale(amax):
     return math.ldexp(1.0, k)
 
 
+def act_scale(stats, scale, shift, M, C, stats2, scale2, shift2, res_sc, sc):
+    import math
+
+    def grp(st, a, b):
+        mean = st[:C] / M
+        var = (st[C:] / M - mean * mean).clamp_min(0)
+        return float(((a.double() * mean + b.double()).abs() + a.double().abs() * torch.sqrt(M * var)).max())
+    bound = grp(stats, scale, shift)
+    if stats2 is not None:
+        bound += grp(stats2, scale2, shift2)
+    bound = bound * 1.001 + (float(res_sc[2]) if res_sc is not None else 0.0)
+    s = 1.0
+    if bound > 0:
+        _, e = math.frexp(bound)
+        s = math.ldexp(1.0, max(-100, min(100, 15 - e)))
+    sc[0], sc[1], sc[2], sc[3] = s, 1.0 / s, bound, 0.0
+
+
 def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc):
     v = x.reshape(M, C)
     if scale is not None:

@@ -184,3 +184,37 @@ def frame_case(tag):
                        rng.uniform(-800, 800, J)], axis=1)
     joints_vis = (rng.random((J, 3)) > 0.1).astype(np.float64)
     return img, box, joints, joints_vis, pw, ph, seed
+
+
+# ---- BASELINE.json configuration sizes (tests/golden/make_golden_sizes.py)
+SIZE_CASES = {
+    "c1": dict(layers=50, J=16, D=64, HW=256, N=1, train=False, seed=71),
+    "c2": dict(layers=50, J=17, D=64, HW=256, N=8, train=True, seed=72),
+}
+
+
+def grad_like_big(shape, seed):
+    """Output gradient for the large cases: N(0,1) float32, generated per image so that the
+    generator state never holds more than one image's worth."""
+    rng = np.random.default_rng(seed)
+    out = np.empty(tuple(shape), dtype=np.float32)
+    for n in range(shape[0]):
+        out[n] = rng.standard_normal(tuple(shape[1:]), dtype=np.float32)
+    return out
+
+
+def sample_output(out):
+    """Strided sample + per-(image, channel) sums of an [N,C,H,W] heat-map tensor."""
+    o = np.asarray(out)
+    return {"out_sample": o[:, :, 1::8, 2::8].copy(),
+            "out_chan_sum": o.sum((2, 3), dtype=np.float64),
+            "out_chan_abs": np.abs(o).sum((2, 3), dtype=np.float64),
+            "out_max": np.float64(np.abs(o).max())}
+
+
+def sample_grad(g):
+    """<= 4096 strided elements of a gradient tensor and [sum, sum |g|, max |g|] (float64)."""
+    f = np.asarray(g).reshape(-1)
+    stride = max(1, f.size // 4096)
+    return f[::stride].copy(), np.array([f.sum(dtype=np.float64), np.abs(f).sum(dtype=np.float64),
+                                         np.abs(f).max()], dtype=np.float64)

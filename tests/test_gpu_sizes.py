@@ -1,0 +1,198 @@
+"""GPU (-m gpu): parity at the BASELINE.json configuration sizes.
+
+  C1  configs[0]: R50, 256x256, batch 1, .eval(), J=16 -- against the UNMODIFIED reference
+      (tests/golden/net_c1.npz, made by tests/golden/make_golden_sizes.py)
+  C2  configs[1] slice: R50, 256x256, J=17, D=64, .train(), N=8, forward + backward -- every
+      one of the 161 gradient tensors against the unmodified reference (net_c2.npz)
+  C3  configs[2]: 16 tuples x 4 views through model -> soft-argmax -> patch->image ->
+      iterative-LS triangulation -> labels -> L1 loss -> backward, each stage against the
+      pinned numpy oracle on the SAME inputs at the stage boundary
+  C5  configs[4]: R101, 384x384, DEPTH_RES=96 (lib/core/integral_loss.py:191-192), a real
+      batch of 4 tuples x 4 views, against the oracle restatement evaluated in float64
+
+Tolerances (north_star): heat-maps / gradients <= 1e-3 rel (max|d| / max|ref| per tensor),
+soft-argmax coords <= 1e-5 abs, triangulated joints <= 1e-4 mm, losses <= 1e-5 rel."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, restate_net
+from tests import golden_inputs as gi
+from tests.conftest import relerr
+
+pytestmark = pytest.mark.gpu
+PRECISIONS = ["tf32x3", "f16x3"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from epipolarpose_b200 import ops
+    ops.device_check()
+    return torch.device("cuda:0")
+
+
+def _model(dev, c, precision, train):
+    import lib.models as models
+    from tools.bench_cfg import make_cfg
+    cfg = make_cfg(num_layers=c["layers"], num_joints=c["J"], volume=True, depth_res=c["D"],
+                   image_size=(c["HW"], c["HW"]))
+    model = models.pose3d_resnet.get_pose_net(cfg, False, precision=precision)
+    shapes = restate_net.param_shapes(num_layers=c["layers"], num_joints=c["J"], volume=True,
+                                      depth_res=c["D"])
+    model.load_state_dict(restate_net.init_state(shapes, c["seed"]))
+    model = model.to(dev)
+    return model.train() if train else model.eval()
+
+
+def _check_output(out, g):
+    o = out.detach().cpu().numpy()
+    s = gi.sample_output(o)
+    mx = float(g["out_max"])
+    assert np.max(np.abs(s["out_sample"] - g["out_sample"])) <= 1e-3 * mx
+    # per-(image, channel) sums over 4096 pixels: error relative to the summed magnitudes
+    assert np.max(np.abs(s["out_chan_sum"] - g["out_chan_sum"]) / (g["out_chan_abs"] + 1e-30)) <= 1e-3
+    assert abs(float(s["out_max"]) - mx) <= 1e-3 * mx
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_c1_eval_batch1_vs_reference(golden, dev, precision):
+    c = gi.SIZE_CASES["c1"]
+    g = golden("net_c1")
+    model = _model(dev, c, precision, train=False)
+    x = torch.from_numpy(gi.images(c["N"], c["HW"], c["seed"])).to(dev)
+    with torch.no_grad():
+        out = model(x)
+    assert tuple(out.shape) == (1, c["J"] * c["D"], c["HW"] // 4, c["HW"] // 4)
+    _check_output(out, g)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_c2_train_slice_vs_reference(golden, dev, precision):
+    c = gi.SIZE_CASES["c2"]
+    g = golden("net_c2")
+    model = _model(dev, c, precision, train=True)
+    x = torch.from_numpy(gi.images(c["N"], c["HW"], c["seed"])).to(dev)
+    out = model(x)
+    _check_output(out, g)
+    go = torch.from_numpy(gi.grad_like_big(out.shape, c["seed"] + 1)).to(dev)
+    (out * go).sum().backward()
+    worst, n = ("", 0.0), 0
+    for k, p in model.named_parameters():
+        smp, tot = gi.sample_grad(p.grad.cpu().numpy())
+        ref, rtot = g["grad/" + k], g["gsum/" + k]
+        e = float(np.max(np.abs(smp - ref)) / max(rtot[2], 1e-30))       # vs the tensor's max |g|
+        es = abs(tot[0] - rtot[0]) / max(rtot[1], 1e-30)                 # sum vs sum of |g|
+        if e > worst[1]:
+            worst = (k, e)
+        assert e <= 1e-3, "%s: sample %.3e" % (k, e)
+        assert es <= 1e-3, "%s: sum %.3e" % (k, es)
+        n += 1
+    assert n == 161
+    sd = model.state_dict()
+    assert relerr(sd["bn1.running_mean"].cpu().numpy(), g["bn1.running_mean"]) <= 1e-4
+    assert relerr(sd["bn1.running_var"].cpu().numpy(), g["bn1.running_var"]) <= 1e-4
+    print("C2 %s: worst gradient tensor %s %.2e" % (precision, worst[0], worst[1]))
+
+
+def _ring_meta(tuples, seed):
+    """Cameras / boxes of the bench workload: batch laid out
+    [view0 | view3 | view1 | view2] of every tuple so the half-split pairs (0,1) and (3,2)."""
+    from lib.dataset.synthetic import ring_camera
+    rng = np.random.default_rng(seed)
+    n_img = tuples * 4
+    order = [(t, 0) for t in range(tuples)] + [(t, 3) for t in range(tuples)] + \
+            [(t, 1) for t in range(tuples)] + [(t, 2) for t in range(tuples)]
+    cams = {(t, v): ring_camera(rng, v) for t in range(tuples) for v in range(4)}
+    return {"center_x": 500 + rng.uniform(-50, 50, n_img), "center_y": 500 + rng.uniform(-50, 50, n_img),
+            "width": 800 + rng.uniform(-100, 100, n_img), "height": 800 + rng.uniform(-100, 100, n_img),
+            "scale": np.ones(n_img), "rot": np.zeros(n_img),
+            "R": np.stack([cams[o][0] for o in order]), "T": np.stack([cams[o][1] for o in order]),
+            "f": np.stack([cams[o][2] for o in order]), "c": np.stack([cams[o][3] for o in order]),
+            "projection_matrix": np.stack([cams[o][4] for o in order])}
+
+
+@pytest.mark.parametrize("precision", ["f16x3"])
+def test_c3_selfsup_chain_64_images(dev, precision):
+    import lib.core.integral_loss as il
+    import lib.utils.img_utils as iu
+    c = dict(layers=50, J=16, D=64, HW=256, seed=73)
+    tuples = 16
+    B = tuples * 4
+    model = _model(dev, c, precision, train=True)
+    meta_np = _ring_meta(tuples, 1073)
+    meta = {k: torch.from_numpy(v) for k, v in meta_np.items()}
+    x = torch.from_numpy(gi.images(B, c["HW"], c["seed"])).to(dev)
+    preds = model(x)
+    preds.retain_grad()
+    J, D = c["J"], c["D"]
+    logits = preds.detach().cpu().numpy()                       # [B, J*D, 64, 64] (1 GiB)
+    # ---- soft-argmax on the GPU logits vs the oracle on the same logits
+    coords = il.softmax_integral_tensor(preds, J, True, D, D, D)
+    c_ref = restate.softmax_integral(logits, J, D, D, D)
+    assert np.max(np.abs(coords.detach().cpu().numpy() - c_ref)) <= 1e-5
+    # ---- geometry: every stage against the oracle on the GPU stage's own input
+    cg = coords.detach()
+    kps = iu.patch_to_image_device(cg, meta)
+    X = iu.triangulate_device(kps, meta, "iterative")
+    label, weight = iu.labels_from_global_coords_device(X, meta)
+    _, _, _, kps_ref = restate.self_supervision(cg.cpu().numpy(), meta_np, "iterative")
+    assert np.max(np.abs(kps.cpu().numpy() - kps_ref)) <= 5e-3       # px; float32 patch units in the reference
+    X_ref = restate.triangulate_batch(kps.cpu().numpy(), meta_np["projection_matrix"], "iterative")
+    assert np.max(np.abs(X.cpu().numpy() - X_ref)) <= 1e-4            # mm
+    lab_ref, w_ref = restate.labels_from_global_coords(X.cpu().numpy(), meta_np)
+    assert np.max(np.abs(label.cpu().numpy() - lab_ref)) <= 2e-5
+    assert np.array_equal(weight.cpu().numpy(), w_ref)
+    # ---- L1 loss and its gradient w.r.t. the logits
+    crit = il.L1JointLocationLoss(J)
+    loss = crit(preds, label, weight)
+    l_ref, dcoords_ref = restate.weighted_loss("l1", cg.cpu().numpy(), lab_ref, w_ref)
+    assert abs(loss.item() - l_ref) <= 1e-5 * abs(l_ref)
+    loss.backward()
+    dl = preds.grad.cpu().numpy()
+    sel = slice(0, 8)                                            # 8 images: 128 MiB of float64 work
+    dl_ref = restate.softmax_integral_grad(logits[sel], dcoords_ref[sel], J, D, D, D)
+    assert relerr(dl[sel], dl_ref) <= 1e-3
+    g = dict(model.named_parameters())["final_layer.bias"].grad.cpu().numpy()
+    assert relerr(g, dl.sum((0, 2, 3))) <= 1e-4                  # bias gradient = column sums
+    for k, p in model.named_parameters():
+        assert torch.isfinite(p.grad).all(), k
+
+
+@pytest.mark.parametrize("precision", ["f16x3"])
+def test_c5_r101_384_vs_float64_oracle(dev, precision):
+    """R101 / 384x384 / D=96 on a real batch (4 tuples x 4 views).  The checker is the oracle
+    restatement (oracle/restate_net.py, pinned to the unmodified reference on the small cases)
+    evaluated in FLOAT64 by torch on the same device -- cuDNN / cuBLAS fp64 kernels, none of
+    this repo's code.  Gradient tensors: <= 1e-3 of the tensor's max."""
+    c = dict(layers=101, J=17, D=96, HW=384, seed=75)
+    N = 16
+    model = _model(dev, c, precision, train=True)
+    x = torch.from_numpy(gi.images(N, c["HW"], c["seed"])).to(dev)
+    out = model(x)
+    assert tuple(out.shape) == (N, c["J"] * c["D"], 96, 96)
+    go = torch.from_numpy(gi.grad_like_big(out.shape, c["seed"] + 1)).to(dev)
+    (out * go).sum().backward()
+    got = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    out_g = out.detach().clone()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    del model, out
+    torch.cuda.empty_cache()
+    shapes = restate_net.param_shapes(num_layers=101, num_joints=c["J"], volume=True, depth_res=c["D"])
+    sd0 = restate_net.init_state(shapes, c["seed"])
+    p = {k: (v.double().to(dev).requires_grad_(True) if v.is_floating_point() and "running" not in k
+             else (v.double().to(dev) if v.is_floating_point() else v.to(dev))) for k, v in sd0.items()}
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        ref = restate_net.forward(p, x.double(), num_layers=101, volume=True, image_size=(384, 384))
+        e_out = float((out_g.double() - ref).abs().max() / ref.abs().max())
+        (ref * go.double()).sum().backward()
+    assert e_out <= 1e-3, "heat-maps %.3e" % e_out
+    worst = ("", 0.0)
+    for k, gq in got.items():
+        r = p[k].grad
+        e = float((gq.double() - r).abs().max() / r.abs().max().clamp_min(1e-300))
+        if e > worst[1]:
+            worst = (k, e)
+    print("C5 %s: heat-maps %.2e, worst gradient tensor %s %.2e" % (precision, e_out, worst[0], worst[1]))
+    assert worst[1] <= 1e-3, "%s: %.3e" % worst

@@ -1,7 +1,7 @@
 """GPU (-m gpu): the split-fp16 ("f16x3") kernel family through the C ABI against the CPU
 emulation of the same contracts (tests/emul_ops.py: exact fp16 planes, three-term products
 accumulated in float64) on IDENTICAL split operands, so the bar is the fp32 accumulation
-noise of the tensor pipe (<= 2e-5 of the tensor's max), not a precision trade-off.
+noise of the tensor pipe (<= 5e-5 of the tensor's max), not a precision trade-off.
 Geometries: every conv kind of the network (reference lib/models/pose3d_resnet.py:12-15,
 55-60,99,116-122,171-178) incl. strided / transposed / phase-decomposed forms, ragged
 sizes, N tails, accumulate / bias / statistics epilogues."""
@@ -93,7 +93,7 @@ def _run_fprop(dev, conv, N, H, W, geoms, x, x_sc, w, w_sc, Hin, Win, cin, Hout,
         ops.conv16_fprop(g, xg, xs, wg, ws, out_gpu, bg, st_gpu)
     torch.cuda.synchronize()
     e = relerr(out_gpu.cpu().numpy(), out_ref.numpy())
-    assert e <= 2e-5, "output relerr %.3e" % e
+    assert e <= 5e-5, "output relerr %.3e" % e      # fp32 accumulation over K up to 4608
     if stats:
         e = relerr(st_gpu.cpu().numpy(), st_ref.numpy())
         assert e <= 1e-4, "stats relerr %.3e" % e
@@ -155,7 +155,7 @@ def test_conv16_wgrad_vs_emulation(dev, case):
             ops.conv16_wgrad(g, xg, xs, dg, ds, dw_gpu, ws)
     torch.cuda.synchronize()
     e = relerr(dw_gpu.cpu().numpy(), dw_ref.numpy())
-    assert e <= 2e-5, "dw relerr %.3e" % e
+    assert e <= 5e-5, "dw relerr %.3e" % e
     # deterministic: a second run from zero gives the same bits
     a = torch.zeros(n, device=dev)
     b = torch.zeros(n, device=dev)

@@ -164,12 +164,29 @@ bn_relu_maxpool_split_kernel(const float* __restrict__ x, const float* __restric
   }
 }
 
-// one thread = 8 consecutive k of one patch row
+// one thread = 8 consecutive k of one patch row; the (channel, tap) decomposition of k is a
+// per-CTA lookup table (no integer divisions per element)
 __global__ void __launch_bounds__(kThreads)
 im2col_split_kernel(const float* __restrict__ img, uint4* __restrict__ col,
                     const float* __restrict__ col_sc, int N, int C, int Hi, int Wi, int kh, int kw,
                     int stride, int pad, int Ho, int Wo, int Kpad) {
-  const int K8 = Kpad >> 3, K = kh * kw * C;
+  extern __shared__ int lut[];                 // [Kpad]: (c*Hi + r)*Wi + s | r << 24 ... packed below
+  int* off = lut;                              // element offset of (c, r, s) relative to (ih0, iw0)
+  int* rs = lut + Kpad;                        // r << 16 | s ; -1 for padding columns
+  const int K = kh * kw * C;
+  for (int kk = threadIdx.x; kk < Kpad; kk += kThreads) {
+    if (kk < K) {
+      const int t = kk / C, c = kk - t * C;
+      const int r = t / kw, sx = t - r * kw;
+      off[kk] = (c * Hi + r) * Wi + sx;
+      rs[kk] = (r << 16) | sx;
+    } else {
+      off[kk] = 0;
+      rs[kk] = -1;
+    }
+  }
+  __syncthreads();
+  const int K8 = Kpad >> 3;
   const int64_t total = (int64_t)N * Ho * Wo * K8;
   const float s = col_sc[0];
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
@@ -179,18 +196,15 @@ im2col_split_kernel(const float* __restrict__ img, uint4* __restrict__ col,
     const int ow = (int)(m % Wo); m /= Wo;
     const int oh = (int)(m % Ho);
     const int n = (int)(m / Ho);
+    const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
+    const float* base = img + (int64_t)n * C * Hi * Wi + (int64_t)ih0 * Wi + iw0;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int kk = k8 * 8 + e;
-      v[e] = 0.f;
-      if (kk < K) {
-        const int t = kk / C, c = kk - t * C;
-        const int r = t / kw, sx = t - r * kw;
-        const int ih = oh * stride - pad + r, iw = ow * stride - pad + sx;
-        if (ih >= 0 && ih < Hi && iw >= 0 && iw < Wi)
-          v[e] = __ldg(img + ((int64_t)(n * C + c) * Hi + ih) * Wi + iw);
-      }
+      const int q = rs[kk];
+      const int ih = ih0 + (q >> 16), iw = iw0 + (q & 0xffff);
+      v[e] = (q >= 0 && ih >= 0 && ih < Hi && iw >= 0 && iw < Wi) ? __ldg(base + off[kk]) : 0.f;
     }
     uint4 hi, lo;
     split8(v, s, hi, lo);
@@ -301,8 +315,9 @@ bn_bwd_reduce_mx_kernel(const float4* __restrict__ dy, const float4* __restrict_
   const int slot = threadIdx.x / rm.tpr, tin = threadIdx.x % rm.tpr;
   const int c4 = blockIdx.y * rm.tpr + tin;
   const bool active = (c4 < rm.C4) && (slot < rm.rpi);
-  const int64_t rows_per_cta = (int64_t)rm.rpi * kRowsPerThread;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  // persistent over row blocks: CTA b takes rows (b + k*gridDim.x)*rpi + slot, so a thread
+  // folds M / (gridDim.x * rpi) rows into registers and the CTA issues ONE set of atomics
+  const int64_t nblk = (M + rm.rpi - 1) / rm.rpi;
   float4 acc[4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};   // sum g, sum g*xhat, max|g|, max|xhat|
   if (active) {
     const float4 s = scale[c4], b = shift[c4], mu = mean[c4], is = invstd[c4];
@@ -317,23 +332,28 @@ bn_bwd_reduce_mx_kernel(const float4* __restrict__ dy, const float4* __restrict_
       acc[3].x = fmaxf(acc[3].x, fabsf(xh.x)); acc[3].y = fmaxf(acc[3].y, fabsf(xh.y));
       acc[3].z = fmaxf(acc[3].z, fabsf(xh.z)); acc[3].w = fmaxf(acc[3].w, fabsf(xh.w));
     };
-    int k = 0;
-    for (; k + 4 <= kRowsPerThread; k += 4) {
-      const int64_t rl = r0 + (int64_t)(k + 3) * rm.rpi + slot;
-      if (rl >= M) break;
+    int64_t blk = blockIdx.x;
+    const int64_t step = gridDim.x;
+    for (; blk + 3 * step < nblk; blk += 4 * step) {       // four rows per trip: 8 loads in flight
       float4 xv[4], dv[4];
       int64_t idx[4];
+      bool ok[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        idx[u] = (r0 + (int64_t)(k + u) * rm.rpi + slot) * rm.C4 + c4;
-        xv[u] = ldg_stream(x + idx[u]);
-        dv[u] = ldg_stream(dy + idx[u]);
+        const int64_t r = (blk + u * step) * rm.rpi + slot;
+        ok[u] = r < M;
+        idx[u] = r * rm.C4 + c4;
+        if (ok[u]) {
+          xv[u] = ldg_stream(x + idx[u]);
+          dv[u] = ldg_stream(dy + idx[u]);
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) fold(dv[u], xv[u], idx[u]);
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) fold(dv[u], xv[u], idx[u]);
     }
-    for (; k < kRowsPerThread; ++k) {
-      const int64_t r = r0 + (int64_t)k * rm.rpi + slot;
+    for (; blk < nblk; blk += step) {
+      const int64_t r = blk * rm.rpi + slot;
       if (r >= M) break;
       const int64_t i = r * rm.C4 + c4;
       const float4 xv = ldg_stream(x + i);
@@ -557,7 +577,8 @@ EPB_API int epb_im2col_split(const float* img_nchw, epb_half* col, const float* 
                              int Kpad, epb_stream_t stream) {
   EPB_CHECK_ARG(img_nchw && col && col_sc && N > 0 && C > 0 && Kpad % 8 == 0 && Kpad >= kh * kw * C);
   const int64_t total = (int64_t)N * Ho * Wo * (Kpad / 8);
-  im2col_split_kernel<<<ew_blocks(total), kThreads, 0, as_stream(stream)>>>(
+  EPB_CHECK_ARG(Kpad <= 4096);
+  im2col_split_kernel<<<ew_blocks(total), kThreads, 2 * Kpad * sizeof(int), as_stream(stream)>>>(
       img_nchw, reinterpret_cast<uint4*>(col), col_sc, N, C, Hi, Wi, kh, kw, stride, pad, Ho, Wo, Kpad);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
@@ -582,8 +603,13 @@ EPB_API int epb_bn_bwd_reduce_mx(const float* dy, const float* x, const epb_half
   EPB_CHECK_ARG(dy && x && scale && shift && mean && invstd && sums && maxes);
   EPB_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0);
   const RowMap rm = make_rowmap(C);
-  const int64_t rows_per_cta = (int64_t)rm.rpi * kRowsPerThread;
-  dim3 grid((unsigned)((M + rows_per_cta - 1) / rows_per_cta), rm.chunks);
+  // ~6 CTAs per SM in all, each thread folding at least kRowsPerThread rows when M allows
+  const int64_t nblk = (M + rm.rpi - 1) / rm.rpi;
+  int64_t workers = (nblk + kRowsPerThread - 1) / kRowsPerThread;
+  const int64_t cap = (int64_t)kNumSMs * 6 / rm.chunks > 1 ? (int64_t)kNumSMs * 6 / rm.chunks : 1;
+  if (workers > cap) workers = cap;
+  if (workers < 1) workers = 1;
+  dim3 grid((unsigned)workers, rm.chunks);
   bn_bwd_reduce_mx_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
       reinterpret_cast<const uint2*>(mask_hi), reinterpret_cast<const float4*>(scale),

@@ -28,6 +28,9 @@ struct PlanW16 {
   int T, CB, CH;                 // taps, 64-channel blocks per tap, chunks = T * CB
   int tw, th, tn, tiles_w, tiles_h, ptiles;
   int groups, n_tiles, splits, tiles_per_split;
+  int swap;                      // 1: M side = 64-channel blocks of dout, N side = input channels
+  int Nn;                        // channels on the N side (Cout, or Cin when swapped)
+  int bdw, bdh;                  // box offset of the N-side operand (the tap, when swapped)
   int wt[EPB_MAX_TAPS];
   short dwq[EPB_MAX_TAPS], dhq[EPB_MAX_TAPS];
   unsigned char map[EPB_MAX_TAPS];
@@ -128,7 +131,7 @@ wgrad16_kernel(const __grid_constant__ PlanW16 P, const __grid_constant__ MapsW1
 #pragma unroll
           for (int jb = 0; jb < C::BCH; ++jb)
             tc::tma_load_5d_pair(b_dst + pl * C::B_PLANE + jb * kChunk, &maps.d, lead_bar,
-                                 nt * BN + (crank * C::BCH + jb) * 64, w0, h0, n0, pl);
+                                 nt * BN + (crank * C::BCH + jb) * 64, w0 + P.bdw, h0 + P.bdh, n0, pl);
         }
         if (++stage == C::S) { stage = 0; phase ^= 1; }
       }
@@ -166,28 +169,32 @@ wgrad16_kernel(const __grid_constant__ PlanW16 P, const __grid_constant__ MapsW1
     tc::mbar_wait(done_bar, 0);
     tc::tc_fence_after();
     if (c < P.CH) {
-      const int t = c / P.CB;
-      const int ci = (c % P.CB) * 64 + (q & 1) * 32 + lane;
       const int64_t K = (int64_t)P.Tw * P.Cin;
-      const int64_t off = (int64_t)P.wt[t] * P.Cin + ci;
       const float alpha = in_sc[1] * dout_sc[1];
       float* dst = P.splits > 1 ? ws + (int64_t)split * P.Cout * K : dw;
+      const int rowc = (q & 1) * 32 + lane;                   // this lane's row inside the chunk
+      // normal : row = input channel ci of tap t,  column = output channel co
+      // swapped: row = output channel co,          column = input channel ci (T == 1)
+      const int t = P.swap ? 0 : c / P.CB;
+      const int64_t row_off = P.swap ? (int64_t)(c * 64 + rowc) * K + (int64_t)P.wt[0] * P.Cin
+                                     : (int64_t)P.wt[t] * P.Cin + (c % P.CB) * 64 + rowc;
+      const int64_t col_stride = P.swap ? 1 : K;
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         const int col0 = nt * BN + chunk * 32;
-        if (col0 >= P.Cout) break;
+        if (col0 >= P.Nn) break;
         uint32_t rg[32];
         tc::tmem_ld32(tmem_base + chunk * 32 + ((uint32_t)(q * 32) << 16), rg);
         tc::tmem_ld_wait();
         if (P.splits > 1) {
 #pragma unroll
           for (int cc = 0; cc < 32; ++cc)
-            if (col0 + cc < P.Cout) dst[(int64_t)(col0 + cc) * K + off] = __uint_as_float(rg[cc]);
+            if (col0 + cc < P.Nn) dst[row_off + (int64_t)(col0 + cc) * col_stride] = __uint_as_float(rg[cc]);
         } else {
 #pragma unroll
           for (int cc = 0; cc < 32; ++cc)
-            if (col0 + cc < P.Cout) {
-              float* o = dst + (int64_t)(col0 + cc) * K + off;
+            if (col0 + cc < P.Nn) {
+              float* o = dst + row_off + (int64_t)(col0 + cc) * col_stride;
               *o += alpha * __uint_as_float(rg[cc]);
             }
         }
@@ -272,6 +279,10 @@ extern "C" __attribute__((visibility("default"))) int epb_conv16_wgrad(
   memset(&maps, 0, sizeof(maps));
   P.Cin = g->Cin; P.Cout = g->Cout; P.Tw = g->Tw; P.T = g->T; P.CB = g->Cin / 64;
   P.CH = P.T * P.CB;
+  // A 1x1 layer with few input channels leaves most of the 4 M-side chunks of a CTA pair
+  // empty: put the output channels on the M side instead (D^T; same products, same sums)
+  P.swap = (g->T == 1 && P.CH < 4 && g->Cout / 64 > P.CH) ? 1 : 0;
+  P.bdw = P.bdh = 0;
   const bool dense = g->T == 1 && g->is == 1 && g->os == 1 && g->dh[0] == 0 && g->dw[0] == 0 &&
                      g->Hp == g->Hi && g->Wp == g->Wi && g->Hp == g->Ho && g->Wp == g->Wo;
   int N = g->N, Hi = g->Hi, Wi = g->Wi, Ho = g->Ho, Wo = g->Wo;
@@ -299,20 +310,38 @@ extern "C" __attribute__((visibility("default"))) int epb_conv16_wgrad(
     P.wt[t] = g->wt[t];
     need[qh * 2 + qw] = true;
   }
+  CUtensorMap in_maps[4];
+  memset(in_maps, 0, sizeof(in_maps));
   for (int v = 0; v < 4; ++v) {
     if (!need[v]) continue;
-    rc = epb_make_act_map(&maps.a[v], in, N, Hi, Wi, g->Cin, g->is, v >> 1, v & 1, P.tw, P.th, P.tn);
+    rc = epb_make_act_map(&in_maps[v], in, N, Hi, Wi, g->Cin, g->is, v >> 1, v & 1, P.tw, P.th, P.tn);
     if (rc) return rc;
   }
   for (int v = 0; v < 4; ++v)
     if (!need[v]) {
       for (int u = 0; u < 4; ++u)
-        if (need[u]) { maps.a[v] = maps.a[u]; break; }
+        if (need[u]) { in_maps[v] = in_maps[u]; break; }
     }
-  rc = epb_make_act_map(&maps.d, dout, N, Ho, Wo, g->Cout, g->os, g->ph, g->pw, P.tw, P.th, P.tn);
+  CUtensorMap d_map;
+  rc = epb_make_act_map(&d_map, dout, N, Ho, Wo, g->Cout, g->os, g->ph, g->pw, P.tw, P.th, P.tn);
   if (rc) return rc;
-  const int bn = g->Cout <= 128 ? 128 : 256;
-  P.n_tiles = (g->Cout + bn - 1) / bn;
+  int bn;
+  if (!P.swap) {
+    for (int v = 0; v < 4; ++v) maps.a[v] = in_maps[v];
+    maps.d = d_map;
+    P.Nn = g->Cout;
+  } else {
+    // M side: the CH' = Cout / 64 blocks of dout (no tap shift); N side: the input, shifted by the tap
+    for (int v = 0; v < 4; ++v) maps.a[v] = d_map;
+    maps.d = in_maps[P.map[0]];
+    P.bdw = P.dwq[0]; P.bdh = P.dhq[0];
+    P.map[0] = 0; P.dwq[0] = 0; P.dhq[0] = 0;
+    P.CB = g->Cout / 64;
+    P.CH = P.CB;
+    P.Nn = g->Cin;
+  }
+  bn = P.Nn <= 128 ? 128 : 256;
+  P.n_tiles = (P.Nn + bn - 1) / bn;
   P.groups = (P.CH + 3) / 4;
   // pixel-range splits: fill one wave of cluster pairs, keep >= 8 stages per cluster, and
   // stay inside the scratch the caller gave

@@ -69,7 +69,10 @@ class GraphedTrainStep:
         self.online, self.method = online, method
         self.graph = None
         self.key = None
+        self.warm_key = None          # shape of the last eager (warm-up) step
+        self.failed = False
         self.calls = 0
+        self.copy_stream, self.pending, self.stage_next = None, None, 0
         # eager warm-up and capture share ONE side stream so that the parameters'
         # AccumulateGrad nodes are never bound to the legacy default stream (which
         # may not join a capture)
@@ -97,6 +100,43 @@ class GraphedTrainStep:
         self.optimizer.step()
         return loss.detach()
 
+    # ---- input staging: the H2D copy of batch i+1 overlaps the replay of step i
+    def prefetch(self, batch_data):
+        """Start copying a (pinned) host batch into the idle device staging buffer on a copy
+        stream; the next __call__ with the SAME tensor object hands it over to the graph's
+        static input with a device-side copy (100 MB at HBM speed instead of PCIe speed in
+        front of the replay)."""
+        if self.graph is None or not torch.cuda.is_available() or batch_data.is_cuda:
+            return
+        if tuple(batch_data.shape) != tuple(self.sx.shape):
+            return
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream()
+            self.stage = [torch.empty_like(self.sx) for _ in range(2)]
+            self.stage_evt = [torch.cuda.Event() for _ in range(2)]
+            self.stage_free = [None, None]
+        k = self.stage_next
+        with torch.cuda.stream(self.copy_stream):
+            if self.stage_free[k] is not None:
+                self.copy_stream.wait_event(self.stage_free[k])    # its previous hand-over is done
+            self.stage[k].copy_(batch_data, non_blocking=True)
+            self.stage_evt[k].record(self.copy_stream)
+        self.pending = (batch_data, k)
+        self.stage_next = 1 - k
+
+    def _load_input(self, batch_data):
+        if self.pending is not None and self.pending[0] is batch_data:
+            k = self.pending[1]
+            self.pending = None
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self.stage_evt[k])
+            self.sx.copy_(self.stage[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.stage_free[k] = ev
+        else:
+            self.sx.copy_(batch_data, non_blocking=True)
+
     def __call__(self, batch_data, label=None, weight=None, meta=None):
         dev = next(self.model.parameters()).device
         B = batch_data.shape[0]
@@ -107,7 +147,7 @@ class GraphedTrainStep:
         key = (tuple(batch_data.shape), self.online)
         self.calls += 1
         if self.graph is not None and key == self.key:
-            self.sx.copy_(batch_data, non_blocking=True)
+            self._load_input(batch_data)
             if self.online:
                 for k in self.sgeom:
                     self.sgeom[k].copy_(geom[k], non_blocking=True)
@@ -121,23 +161,48 @@ class GraphedTrainStep:
         x = batch_data.to(dev, non_blocking=True)
         if not self.online:
             label, weight = label.to(dev, non_blocking=True), weight.to(dev, non_blocking=True)
-        if self.calls == 1 or self.graph is not None or not torch.cuda.is_available():
-            return self.eager_step(x, label, weight, geom)   # warm-up / odd-shaped batch
-        # second call with this shape: capture, then replay (capture itself does not execute)
-        self.key = key
-        self.sx = x.clone()
-        self.sgeom = {k: v.clone() for k, v in geom.items()} if self.online else None
-        self.slabel = label.clone() if not self.online else None
-        self.sweight = weight.clone() if not self.online else None
+        # eager when: first call (sizes every scratch buffer), a shape other than the warmed-up
+        # one (ragged last batch), no CUDA, or a capture that failed before
+        if self.graph is not None or self.failed or not torch.cuda.is_available() \
+                or self.warm_key != key:
+            self.warm_key = key
+            return self.eager_step(x, label, weight, geom)
+        # second call with the warmed-up shape: capture, then replay (capture does not execute)
+        sx = x.clone()
+        sgeom = {k: v.clone() for k, v in geom.items()} if self.online else None
+        slabel = label.clone() if not self.online else None
+        sweight = weight.clone() if not self.online else None
         if hasattr(self.optimizer, "sync_hyper"):
             self.optimizer.sync_hyper()
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph, stream=self.stream):
-            self.sloss = self._eager(self.sx, self.slabel, self.sweight, self.sgeom)
+        try:
+            with torch.cuda.graph(graph, stream=self.stream):
+                sloss = self._eager(sx, slabel, sweight, sgeom)
+        except Exception as e:                     # non-capturable optimiser / wrapper / op
+            logger.warning("CUDA-graph capture of the training step failed (%s); running eagerly", e)
+            self.failed = True
+            torch.cuda.synchronize()
+            self.optimizer.zero_grad(set_to_none=True)
+            return self.eager_step(x, label, weight, geom)
+        # published only after a successful capture
+        self.sx, self.sgeom, self.slabel, self.sweight, self.sloss = sx, sgeom, slabel, sweight, sloss
+        self.graph, self.key = graph, key
         self.graph.replay()
         return self.sloss
+
+
+def _graph_capable(model, criterion, optimizer):
+    """The captured step needs the fused optimisers (hyper-parameters in device memory) and a
+    single-device model: torch.optim.Adam / SGD steps and nn.DataParallel scatter (more than
+    one device id: the reference's multi-GPU path, scripts/train.py:94) are not capturable."""
+    from ..utils.utils import _FlatOptimizer
+    if not hasattr(criterion, '_kind') or not isinstance(optimizer, _FlatOptimizer):
+        return False
+    if isinstance(model, torch.nn.DataParallel) and len(model.device_ids) != 1:
+        return False
+    return True
 
 
 def train_integral(config, train_loader, model, criterion, optimizer, epoch):
@@ -148,21 +213,31 @@ def train_integral(config, train_loader, model, criterion, optimizer, epoch):
     online = _online_tri(config)
     method = getattr(config.TRAIN, 'TRIANGULATION_METHOD', 'iterative') if online else None
     pending = []           # (device loss, batch size) not yet folded into `losses`
-    use_graph = bool(getattr(config.TRAIN, 'CUDA_GRAPH', True)) and hasattr(criterion, '_kind')
+    use_graph = bool(getattr(config.TRAIN, 'CUDA_GRAPH', True)) and \
+        _graph_capable(model, criterion, optimizer)
     stepper = getattr(model, '_epb_graphed_step', None)
     if use_graph and (stepper is None or stepper.optimizer is not optimizer
                       or stepper.criterion is not criterion or stepper.online != online):
         stepper = GraphedTrainStep(model, criterion, optimizer, online, method)
         model._epb_graphed_step = stepper
     end = time.time()
-    for i, data in enumerate(train_loader):
+    it = iter(train_loader)
+    nxt = next(it, None)
+    i = -1
+    while nxt is not None:
+        data, i = nxt, i + 1
+        nxt = next(it, None)
         data_time.update(time.time() - end)
         batch_data, batch_label, batch_label_weight, meta = data
         batch_size = batch_data.size(0)
         if use_graph:
+            if stepper.pending is None and stepper.graph is not None:
+                stepper.prefetch(batch_data)              # first replayed batch of this call
             loss = stepper(batch_data, batch_label, batch_label_weight, meta)
             if stepper.graph is not None:
                 loss = loss.clone()      # the static loss buffer is overwritten by the next replay
+                if nxt is not None:
+                    stepper.prefetch(nxt[0])     # H2D of the next batch overlaps this step
             pending.append((loss, batch_size))
             del loss
         else:

@@ -82,6 +82,86 @@ class _FlatOptimizer(torch.optim.Optimizer):
     def flat_params(self):
         return [f['buf'] for f in self._flat]
 
+    # ---- aliasing guard -------------------------------------------------------------------
+    _STATE_TENSORS = ()       # names of the per-element state buffers (subclass)
+
+    def _ensure_aliased(self):
+        """Every p.data must still be its slot of the flat buffer: model.cuda() / .to() / a
+        dtype or memory-format change after the optimiser was built re-materialises the
+        parameters, and the fused update would then silently train a dead copy.  When that
+        happened, the flat buffer (and the optimiser state) is rebuilt around the CURRENT
+        parameter values on their current device."""
+        for gi, (group, info) in enumerate(zip(self.param_groups, self._flat)):
+            ps = group['params']
+            base = info['buf'].data_ptr()
+            if all(p.data_ptr() == base + 4 * o and p.device == info['buf'].device
+                   for p, o in zip(ps, info['offs'])):
+                continue
+            if info_dev_is_capturing():
+                raise RuntimeError("parameters were re-materialised after the optimiser was built; "
+                                   "cannot re-flatten during CUDA graph capture")
+            dev = ps[0].device
+            if any(p.dtype != torch.float32 for p in ps):
+                raise TypeError("fused optimisers hold float32 parameters")
+            flat = torch.zeros(info['n'], device=dev, dtype=torch.float32)
+            for p, o, s in zip(ps, info['offs'], info['sizes']):
+                flat[o:o + s].copy_(p.data.reshape(-1))
+                p.data = flat[o:o + s].view(p.shape)
+            info['buf'] = flat
+            st = self.state.get('flat%d' % gi)
+            if st:
+                for k, v in list(st.items()):
+                    if torch.is_tensor(v) and v.device != dev:
+                        st[k] = v.to(dev)
+                st.pop('hyper_host', None)          # force a re-upload of the hyper-parameters
+
+    # ---- checkpoint interchange with torch.optim (reference scripts save optimizer.state_dict())
+    def _per_param_state(self, gi, o, s, shape):
+        raise NotImplementedError
+
+    def state_dict(self):
+        """torch.optim layout: state[index] = per-parameter tensors; param_groups[...]['params']
+        = indices -- interchangeable with torch.optim.Adam / SGD checkpoints."""
+        state, groups, idx = {}, [], 0
+        for gi, (group, info) in enumerate(zip(self.param_groups, self._flat)):
+            g = {k: v for k, v in group.items() if k != 'params'}
+            g['params'] = list(range(idx, idx + len(group['params'])))
+            st = self.state.get('flat%d' % gi)
+            for p, o, s in zip(group['params'], info['offs'], info['sizes']):
+                if st and 'step' in st and st['step'] > 0:
+                    state[idx] = self._per_param_state(st, o, s, p.shape)
+                idx += 1
+            groups.append(g)
+        return {'state': state, 'param_groups': groups}
+
+    def _load_param_state(self, st, o, s, entry):
+        raise NotImplementedError
+
+    def load_state_dict(self, state_dict):
+        sd_groups = state_dict['param_groups']
+        if len(sd_groups) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        idx = 0
+        for gi, (group, info, sg) in enumerate(zip(self.param_groups, self._flat, sd_groups)):
+            if len(sg['params']) != len(group['params']):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match "
+                                 "the size of optimizer's group")
+            for k, v in sg.items():
+                if k != 'params':
+                    group[k] = v
+            st = self.state.setdefault('flat%d' % gi, {})
+            self._init_state(st, info)
+            steps = []
+            for key, o, s in zip(sg['params'], info['offs'], info['sizes']):
+                entry = state_dict['state'].get(key, state_dict['state'].get(str(key)))
+                if entry is not None:
+                    steps.append(self._load_param_state(st, o, s, entry))
+                idx += 1
+            step = int(max(steps)) if steps else 0
+            st['step'] = step
+            st['step_dev'].fill_(step)
+            st.pop('hyper_host', None)
+
 
 class FusedAdam(_FlatOptimizer):
     """torch.optim.Adam semantics; hyper-parameters and the step count live in device
@@ -94,6 +174,23 @@ class FusedAdam(_FlatOptimizer):
     def _hyper(self, group):
         b1, b2 = group['betas']
         return [group['lr'], b1, b2, group['eps'], group['weight_decay'], 1.0]
+
+    def _init_state(self, st, info):
+        if 'exp_avg' not in st:
+            st['step'] = 0
+            st['step_dev'] = torch.zeros(1, device=info['buf'].device, dtype=torch.int32)
+            st['exp_avg'] = torch.zeros_like(info['buf'])
+            st['exp_avg_sq'] = torch.zeros_like(info['buf'])
+
+    def _per_param_state(self, st, o, s, shape):
+        return {'step': torch.tensor(float(st['step'])),
+                'exp_avg': st['exp_avg'][o:o + s].view(shape).clone(),
+                'exp_avg_sq': st['exp_avg_sq'][o:o + s].view(shape).clone()}
+
+    def _load_param_state(self, st, o, s, entry):
+        st['exp_avg'][o:o + s].copy_(entry['exp_avg'].reshape(-1))
+        st['exp_avg_sq'][o:o + s].copy_(entry['exp_avg_sq'].reshape(-1))
+        return float(entry['step'])
 
     def sync_hyper(self):
         """Push host-side hyper-parameters (e.g. after lr_scheduler.step()) to the device."""
@@ -112,15 +209,12 @@ class FusedAdam(_FlatOptimizer):
         loss = closure() if closure is not None else None
         ops = _backend[0]
         capturing = info_dev_is_capturing()
+        self._ensure_aliased()
         if not capturing:
             self.sync_hyper()
         for gi, (group, info) in enumerate(zip(self.param_groups, self._flat)):
             st = self.state.setdefault('flat%d' % gi, {})
-            if 'exp_avg' not in st:
-                st['step'] = 0
-                st['step_dev'] = torch.zeros(1, device=info['buf'].device, dtype=torch.int32)
-                st['exp_avg'] = torch.zeros_like(info['buf'])
-                st['exp_avg_sq'] = torch.zeros_like(info['buf'])
+            self._init_state(st, info)
             st['step'] += 1
             st['step_dev'] += 1
             b1, b2 = group['betas']
@@ -140,7 +234,8 @@ class FusedAdam(_FlatOptimizer):
 
 class FusedSGD(_FlatOptimizer):
     def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0, nesterov=False):
-        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay,
+        # dampening is carried (always 0) so the group dict loads into torch.optim.SGD unchanged
+        super().__init__(params, dict(lr=lr, momentum=momentum, dampening=0, weight_decay=weight_decay,
                                       nesterov=nesterov))
 
     def _hyper(self, group):
@@ -149,18 +244,32 @@ class FusedSGD(_FlatOptimizer):
 
     sync_hyper = FusedAdam.sync_hyper
 
+    def _init_state(self, st, info):
+        if 'buf' not in st:
+            st['step'] = 0
+            st['step_dev'] = torch.zeros(1, device=info['buf'].device, dtype=torch.int32)
+            st['buf'] = torch.zeros_like(info['buf'])
+
+    def _per_param_state(self, st, o, s, shape):
+        return {'momentum_buffer': st['buf'][o:o + s].view(shape).clone()}
+
+    def _load_param_state(self, st, o, s, entry):
+        mb = entry.get('momentum_buffer')
+        if mb is None:
+            return 0.0
+        st['buf'][o:o + s].copy_(mb.reshape(-1))
+        return 2.0          # a momentum buffer exists: this is not the first step any more
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         ops = _backend[0]
+        self._ensure_aliased()
         if not info_dev_is_capturing():
             self.sync_hyper()
         for gi, (group, info) in enumerate(zip(self.param_groups, self._flat)):
             st = self.state.setdefault('flat%d' % gi, {})
-            if 'buf' not in st:
-                st['step'] = 0
-                st['step_dev'] = torch.zeros(1, device=info['buf'].device, dtype=torch.int32)
-                st['buf'] = torch.zeros_like(info['buf'])
+            self._init_state(st, info)
             st['step'] += 1
             st['step_dev'] += 1
             gflat = self._grads_are_flat(group, info)

@@ -210,8 +210,9 @@ class Engine:
         if precision == 0:
             self.wgrad_precision = 0
         self.ops = ops or _default_ops
-        self.stem_kpad = plan.stem_kpad          # K of the stem's patch matrix (Engine16: 192)
-        self.stem_col = plan.stem_col
+        # K of the stem's patch matrix (Engine16: 192); plan is None for bare conv helpers
+        self.stem_kpad = plan.stem_kpad if plan is not None else None
+        self.stem_col = plan.stem_col if plan is not None else None
 
     # ------------------------------------------------------------------ helpers
     def _pack_weights(self, params):

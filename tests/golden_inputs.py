@@ -190,6 +190,7 @@ def frame_case(tag):
 SIZE_CASES = {
     "c1": dict(layers=50, J=16, D=64, HW=256, N=1, train=False, seed=71),
     "c2": dict(layers=50, J=17, D=64, HW=256, N=8, train=True, seed=72),
+    "c5": dict(layers=101, J=17, D=96, HW=384, N=16, train=True, seed=75),
 }
 
 
@@ -204,9 +205,12 @@ def grad_like_big(shape, seed):
 
 
 def sample_output(out):
-    """Strided sample + per-(image, channel) sums of an [N,C,H,W] heat-map tensor."""
+    """Strided sample (<= ~600k values) + per-(image, channel) sums of an [N,C,H,W] heat-map tensor."""
     o = np.asarray(out)
-    return {"out_sample": o[:, :, 1::8, 2::8].copy(),
+    st = 8
+    while o[:, :, 1::st, 2::st].size > 600000:
+        st *= 2
+    return {"out_sample": o[:, :, 1::st, 2::st].astype(np.float32),
             "out_chan_sum": o.sum((2, 3), dtype=np.float64),
             "out_chan_abs": np.abs(o).sum((2, 3), dtype=np.float64),
             "out_max": np.float64(np.abs(o).max())}
@@ -216,5 +220,5 @@ def sample_grad(g):
     """<= 4096 strided elements of a gradient tensor and [sum, sum |g|, max |g|] (float64)."""
     f = np.asarray(g).reshape(-1)
     stride = max(1, f.size // 4096)
-    return f[::stride].copy(), np.array([f.sum(dtype=np.float64), np.abs(f).sum(dtype=np.float64),
+    return f[::stride].astype(np.float32), np.array([f.sum(dtype=np.float64), np.abs(f).sum(dtype=np.float64),
                                          np.abs(f).max()], dtype=np.float64)

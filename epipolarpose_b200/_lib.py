@@ -54,6 +54,7 @@ _PROTOS = {
     "epb_heatmap_joint_loss": (c_int, [c_p, c_p, c_p, c_int, c_int, c_f, c_p, c_p, c_p, c_int, c_int, c_f, c_f,
                                        c_p, c_p, c_p, c_p]),
     "epb_argmax2d": (c_int, [c_p, c_int, c_int, c_int, c_p, c_p, c_p, c_p]),
+    "epb_final_preds": (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_p]),
     "epb_patch_to_image": (c_int, [c_p, c_p, c_int, c_int, c_d, c_d, c_d, c_p, c_p]),
     "epb_triangulate": (c_int, [c_p, c_p, c_int, c_p, c_p, c_int, c_int, c_int, c_d, c_p, c_p, c_p]),
     "epb_triangulate_nview": (c_int, [c_p, c_int, c_p, c_int, c_int, c_int, c_p, c_p, c_p]),

@@ -29,7 +29,8 @@ void epb_set_error(const char* fmt, ...);
 #define EPB_LAUNCH_CHECK() EPB_CUDA(cudaGetLastError())
 
 // per-(purpose, device, stream) internal scratch; see core.cu
-enum { EPB_WS_SOFTARGMAX = 1, EPB_WS_HMLOSS = 2, EPB_WS_BNCOEF = 3, EPB_WS_WPLANES = 4 };
+enum { EPB_WS_SOFTARGMAX = 1, EPB_WS_HMLOSS = 2, EPB_WS_BNCOEF = 3, EPB_WS_WPLANES = 4,
+       EPB_WS_FPAIR = 5 };
 int epb_workspace(int kind, size_t bytes, cudaStream_t st, void** out);
 
 static inline cudaStream_t as_stream(epb_stream_t s) { return (cudaStream_t)s; }

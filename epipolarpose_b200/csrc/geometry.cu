@@ -211,6 +211,11 @@ __host__ __device__ inline void fundamental_from_P(const double* P1, const doubl
     for (int c = 0; c < 3; ++c)
       R[r][c] = P2[r * 4 + 0] * Mi[0][c] + P2[r * 4 + 1] * Mi[1][c] + P2[r * 4 + 2] * Mi[2][c];
     t[r] = P2[r * 4 + 3] - (R[r][0] * P1[3] + R[r][1] * P1[7] + R[r][2] * P1[11]);
+    // a translation that is pure cancellation noise (identical camera centres) is exactly zero:
+    // the reference's F is then the zero matrix and its correction all-NaN (:213-217)
+    const double mag = fabs(P2[r * 4 + 3]) + fabs(R[r][0] * P1[3]) + fabs(R[r][1] * P1[7]) +
+                       fabs(R[r][2] * P1[11]);
+    if (fabs(t[r]) <= 64.0 * DBL_EPSILON * mag) t[r] = 0.0;
   }
   for (int c = 0; c < 3; ++c) {                            // F[:,c] = t x R[:,c]
     F[0 * 3 + c] = t[1] * R[2][c] - t[2] * R[1][c];
@@ -308,11 +313,144 @@ __host__ __device__ inline void correct_match(const double* F, double* u1, doubl
   u2[1] = (g2[1] + y2 * g2[2]) / g2[2];
 }
 
+// cv2.findFundamentalMat(u1, u2, FM_8POINT) for one pair (OpenCV calib3d fundam.cpp run8Point):
+// points rounded to float32 (findFundamentalMat converts its inputs to CV_32F), isotropic
+// normalisation (centroid, mean distance sqrt 2), the 9x9 normal matrix A^T A, its eigenvector of
+// the smallest eigenvalue, rank-2 projection through the SVD of the 3x3, de-normalisation,
+// F[2][2] = 1.  Returns false where OpenCV returns no matrix (degenerate point sets).
+__host__ __device__ inline bool fundamental_8point(const double* u1, const double* u2, int stride_u,
+                                                   int J, double* F) {
+  double c1[2] = {0, 0}, c2[2] = {0, 0};
+  for (int i = 0; i < J; ++i) {
+    c1[0] += (double)(float)u1[(int64_t)i * stride_u];
+    c1[1] += (double)(float)u1[(int64_t)i * stride_u + 1];
+    c2[0] += (double)(float)u2[(int64_t)i * stride_u];
+    c2[1] += (double)(float)u2[(int64_t)i * stride_u + 1];
+  }
+  const double t = 1.0 / J;
+  c1[0] *= t; c1[1] *= t; c2[0] *= t; c2[1] *= t;
+  double s1 = 0, s2 = 0;
+  for (int i = 0; i < J; ++i) {
+    const double x1 = (double)(float)u1[(int64_t)i * stride_u] - c1[0];
+    const double y1 = (double)(float)u1[(int64_t)i * stride_u + 1] - c1[1];
+    const double x2 = (double)(float)u2[(int64_t)i * stride_u] - c2[0];
+    const double y2 = (double)(float)u2[(int64_t)i * stride_u + 1] - c2[1];
+    s1 += sqrt(x1 * x1 + y1 * y1);
+    s2 += sqrt(x2 * x2 + y2 * y2);
+  }
+  s1 *= t; s2 *= t;
+  if (s1 < 1.1920929e-07 || s2 < 1.1920929e-07) return false;     // FLT_EPSILON
+  s1 = sqrt(2.0) / s1;
+  s2 = sqrt(2.0) / s2;
+  double G[9][9], V[9][9];
+  for (int a = 0; a < 9; ++a)
+    for (int b = 0; b < 9; ++b) G[a][b] = 0.0;
+  for (int i = 0; i < J; ++i) {
+    const double x1 = ((double)(float)u1[(int64_t)i * stride_u] - c1[0]) * s1;
+    const double y1 = ((double)(float)u1[(int64_t)i * stride_u + 1] - c1[1]) * s1;
+    const double x2 = ((double)(float)u2[(int64_t)i * stride_u] - c2[0]) * s2;
+    const double y2 = ((double)(float)u2[(int64_t)i * stride_u + 1] - c2[1]) * s2;
+    const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1.0};
+    for (int a = 0; a < 9; ++a)
+      for (int b = 0; b < 9; ++b) G[a][b] += r[a] * r[b];
+  }
+  // eigenvectors of the symmetric PSD normal matrix = its right singular vectors
+  jacobi_onesided<9, 9>(G, V);
+  int best = 0, nz = 0;
+  double bn = DBL_MAX;
+  for (int j = 0; j < 9; ++j) {
+    double n2 = 0;
+    for (int i = 0; i < 9; ++i) n2 += G[i][j] * G[i][j];
+    if (sqrt(n2) >= DBL_EPSILON) ++nz;
+    if (n2 < bn) { bn = n2; best = j; }
+  }
+  if (nz < 8) return false;                         // OpenCV: fewer than 8 non-zero eigenvalues
+  double F0[3][3], W[3][3];
+  for (int i = 0; i < 9; ++i) {
+    double v = V[i][0];
+    for (int j = 1; j < 9; ++j)
+      if (best == j) v = V[i][j];
+    F0[i / 3][i % 3] = v;
+  }
+  // rank 2: drop the smallest singular value
+  double A[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[i][j] = F0[i][j];
+  jacobi_onesided<3, 3>(A, W);                      // A = U diag(sigma) (columns), F0 = A W^T
+  int sm = 0;
+  double sn = DBL_MAX;
+  for (int j = 0; j < 3; ++j) {
+    const double n2 = A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j];
+    if (n2 < sn) { sn = n2; sm = j; }
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double v = 0;
+      for (int k = 0; k < 3; ++k)
+        if (k != sm) v += A[i][k] * W[j][k];
+      F0[i][j] = v;
+    }
+  // F = T2^T F0 T1, T = [s 0 -s*cx; 0 s -s*cy; 0 0 1]
+  const double T1[3][3] = {{s1, 0, -s1 * c1[0]}, {0, s1, -s1 * c1[1]}, {0, 0, 1}};
+  const double T2[3][3] = {{s2, 0, -s2 * c2[0]}, {0, s2, -s2 * c2[1]}, {0, 0, 1}};
+  double M[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double v = 0;
+      for (int k = 0; k < 3; ++k) v += F0[i][k] * T1[k][j];
+      M[i][j] = v;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double v = 0;
+      for (int k = 0; k < 3; ++k) v += T2[k][i] * M[k][j];
+      F[i * 3 + j] = v;
+    }
+  if (fabs(F[8]) > 1.1920929e-07) {
+    const double inv = 1.0 / F[8];
+    for (int k = 0; k < 9; ++k) F[k] *= inv;
+  }
+  return true;
+}
+
+// Fundamental matrix per pair for the polynomial method (triangulation.py:198-217): from the
+// projection matrices; when the optimal correction with it is NaN for EVERY joint of the pair
+// (identical / degenerate cameras) -- or always, for mode 4 -- the 8-point estimate from the
+// matches themselves, as the reference falls back to.  One thread per pair.
+__global__ void pair_fundamental_kernel(const double* __restrict__ u1, const double* __restrict__ u2,
+                                        int stride_u, const double* __restrict__ P1,
+                                        const double* __restrict__ P2, int NP, int J, int method,
+                                        double* __restrict__ Fout) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= NP) return;
+  double F[9];
+  fundamental_from_P(P1 + pair * 12, P2 + pair * 12, F);
+  bool fallback = method == 4;
+  if (!fallback) {
+    bool all1 = true, all2 = true;
+    for (int j = 0; j < J && (all1 || all2); ++j) {
+      const int64_t o = ((int64_t)pair * J + j) * stride_u;
+      double a1[2] = {u1[o], u1[o + 1]}, a2[2] = {u2[o], u2[o + 1]};
+      correct_match(F, a1, a2);
+      if (!(isnan(a1[0]) && isnan(a1[1]))) all1 = false;
+      if (!(isnan(a2[0]) && isnan(a2[1]))) all2 = false;
+    }
+    fallback = all1 || all2;
+  }
+  if (fallback) {
+    double F8[9];
+    if (fundamental_8point(u1 + (int64_t)pair * J * stride_u, u2 + (int64_t)pair * J * stride_u,
+                           stride_u, J, F8))
+      for (int k = 0; k < 9; ++k) F[k] = F8[k];
+  }
+  for (int k = 0; k < 9; ++k) Fout[pair * 9 + k] = F[k];
+}
+
 __global__ void triangulate_kernel(const double* __restrict__ u1, const double* __restrict__ u2,
                                    int stride_u, const double* __restrict__ P1,
                                    const double* __restrict__ P2, int NP, int J, int method,
-                                   double tol, double* __restrict__ X,
-                                   int32_t* __restrict__ status) {
+                                   double tol, const double* __restrict__ Fpair,
+                                   double* __restrict__ X, int32_t* __restrict__ status) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= NP * J) return;
   const int pair = idx / J;
@@ -323,12 +461,13 @@ __global__ void triangulate_kernel(const double* __restrict__ u1, const double* 
   double a2[2] = {u2[(int64_t)idx * stride_u], u2[(int64_t)idx * stride_u + 1]};
   double x[3];
   int st;
-  if (method == 3) {   // triangulation.py:184-220: optimal correction, then the homogeneous DLT
+  if (method >= 3) {   // triangulation.py:184-220: optimal correction, then the homogeneous DLT
     double F[9];
-    fundamental_from_P(p1, p2, F);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[k] = Fpair[pair * 9 + k];
     correct_match(F, a1, a2);
   }
-  if (method == 0 || method == 3) {
+  if (method == 0 || method >= 3) {
     // triangulation.py:22 cv2.triangulatePoints: A rows x*P[2]-P[0], y*P[2]-P[1]
     double A[4][4], V[4][4];
 #pragma unroll
@@ -726,11 +865,21 @@ extern "C" __attribute__((visibility("default"))) int epb_triangulate(const doub
                                int32_t* status, epb_stream_t stream) {
   EPB_CHECK_ARG(u1 && u2 && P1 && P2 && X);
   EPB_CHECK_ARG(NP >= 0 && J >= 0 && stride_u >= 2);
-  EPB_CHECK_ARG(method >= 0 && method <= 3);
+  EPB_CHECK_ARG(method >= 0 && method <= 4);
   if (NP * J == 0) return EPB_OK;
   const int n = NP * J;
-  triangulate_kernel<<<(n + 63) / 64, 64, 0, as_stream(stream)>>>(u1, u2, stride_u, P1, P2, NP, J,
-                                                                  method, tol, X, status);
+  cudaStream_t st = as_stream(stream);
+  double* Fpair = nullptr;
+  if (method >= 3) {
+    // one fundamental matrix per pair (from the projection matrices, or the 8-point fallback)
+    int rc = epb_workspace(EPB_WS_FPAIR, (size_t)NP * 9 * sizeof(double), st, (void**)&Fpair);
+    if (rc) return rc;
+    pair_fundamental_kernel<<<(NP + 63) / 64, 64, 0, st>>>(u1, u2, stride_u, P1, P2, NP, J, method,
+                                                           Fpair);
+    EPB_LAUNCH_CHECK();
+  }
+  triangulate_kernel<<<(n + 63) / 64, 64, 0, st>>>(u1, u2, stride_u, P1, P2, NP, J, method, tol,
+                                                   Fpair, X, status);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

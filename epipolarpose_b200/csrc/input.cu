@@ -203,6 +203,83 @@ __global__ void patch_joints_kernel(const double* __restrict__ joints, const dou
   patch_joint(joints + (int64_t)i * 3, trans + b * 6, patch_w, patch_h, den, label + (int64_t)i * 3);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// lib/core/inference.py:43-68 get_final_preds on the device: hard argmax per (n, j) map
+// (first index on ties, masked to (0,0) where max <= 0, :12-40), +-0.25 px toward the higher
+// neighbour (:49-61), and transform_preds (lib/utils/transforms.py:39-44): the heat-map ->
+// image affine of get_affine_transform(center, scale, 0, (W, H), inv=1) (:47-79: float32
+// point triplets, cv2.getAffineTransform = the 6x6 LU above), applied in float64 and stored
+// as float32 like the reference's `preds[i] = ...` assignment.  One warp per map.
+__device__ __forceinline__ bool fp_better(float v, int i, float bv, int bi) {
+  return v > bv || (v == bv && i < bi);
+}
+
+__global__ void __launch_bounds__(256)
+final_preds_kernel(const float* __restrict__ hm, int NJ, int J, int H, int W,
+                   const double* __restrict__ center, const double* __restrict__ scale,
+                   int post_process, float* __restrict__ preds, float* __restrict__ maxvals) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= NJ) return;
+  const int HW = H * W;
+  const float* p = hm + (int64_t)warp * HW;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < HW; i += 32) {
+    const float v = p[i];
+    if (fp_better(v, i, bv, bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (fp_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (lane != 0) return;
+  if (bi == 0x7fffffff) bi = 0;
+  const float mask = (bv > 0.f) ? 1.f : 0.f;
+  float cx = (float)(bi % W) * mask, cy = floorf((float)bi / (float)W) * mask;
+  if (post_process) {
+    const int px = (int)floor((double)cx + 0.5), py = (int)floor((double)cy + 0.5);
+    if (1 < px && px < W - 1 && 1 < py && py < H - 1) {
+      const float dx = p[py * W + px + 1] - p[py * W + px - 1];
+      const float dy = p[(py + 1) * W + px] - p[(py - 1) * W + px];
+      cx += (dx > 0.f ? 0.25f : (dx < 0.f ? -0.25f : 0.f));
+      cy += (dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f));
+    }
+  }
+  // get_affine_transform(center, scale, rot = 0, [W, H], inv = 1)
+  const int n = warp / J;
+  const double c0 = center[2 * n], c1 = center[2 * n + 1];
+  const double src_w = scale[2 * n] * 200.0;
+  const double dir0 = 0.0 * 1.0 - (src_w * -0.5) * 0.0, dir1 = 0.0 * 0.0 + (src_w * -0.5) * 1.0;   // get_dir, rot 0
+  float src[3][2], dst[3][2];
+  src[0][0] = (float)(c0 + src_w * 0.0);   src[0][1] = (float)(c1 + scale[2 * n + 1] * 200.0 * 0.0);
+  src[1][0] = (float)(c0 + dir0 + src_w * 0.0);
+  src[1][1] = (float)(c1 + dir1 + scale[2 * n + 1] * 200.0 * 0.0);
+  const float dst_dir1 = (float)((double)W * -0.5);
+  dst[0][0] = (float)((double)W * 0.5);    dst[0][1] = (float)((double)H * 0.5);
+  dst[1][0] = (float)((double)W * 0.5 + 0.0);
+  dst[1][1] = (float)((double)H * 0.5 + (double)dst_dir1);
+  // get_3rd_point(a, b) = b + (-(a - b)[1], (a - b)[0]) in float32
+  {
+    const float d0 = src[0][0] - src[1][0], d1 = src[0][1] - src[1][1];
+    src[2][0] = src[1][0] + (-d1);  src[2][1] = src[1][1] + d0;
+    const float e0 = dst[0][0] - dst[1][0], e1 = dst[0][1] - dst[1][1];
+    dst[2][0] = dst[1][0] + (-e1);  dst[2][1] = dst[1][1] + e0;
+  }
+  double M[6];
+  if (!affine_lu6(dst, src, M)) {
+    for (int k = 0; k < 6; ++k) M[k] = 0.0;
+  }
+  // affine_transform: np.dot(t, [x, y, 1.]) in float64, stored to the float32 result
+  const double x = (double)cx, y = (double)cy;
+  preds[warp * 2 + 0] = (float)(M[0] * x + M[1] * y + M[2] * 1.0);
+  preds[warp * 2 + 1] = (float)(M[3] * x + M[4] * y + M[5] * 1.0);
+  if (maxvals) maxvals[warp] = bv;
+}
+
 }  // namespace
 
 extern "C" __attribute__((visibility("default"))) int epb_patch_sample(
@@ -237,6 +314,21 @@ extern "C" __attribute__((visibility("default"))) int epb_patch_joints(
   patch_joints_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(joints, box, trans, B, J, patch_w,
                                                                      patch_h, rect_3d_w, depth_in_image,
                                                                      label);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_final_preds(
+    const float* hm, int N, int J, int H, int W, const double* center, const double* scale,
+    int post_process, float* preds, float* maxvals, epb_stream_t stream) {
+  EPB_CHECK_ARG(hm && center && scale && preds);
+  EPB_CHECK_ARG(N >= 0 && J > 0 && H > 0 && W > 0 && (int64_t)H * W < (1LL << 31));
+  if (N == 0) return EPB_OK;
+  const int NJ = N * J;
+  const int threads = 256;
+  const int blocks = (NJ * 32 + threads - 1) / threads;
+  final_preds_kernel<<<blocks, threads, 0, as_stream(stream)>>>(hm, NJ, J, H, W, center, scale,
+                                                                post_process, preds, maxvals);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

@@ -3,13 +3,10 @@ lib/core/inference.py:12-68 (`get_max_preds`, `get_final_preds`), with the
 per-(n,j) argmax running in the warp-shuffle kernel epb_argmax2d (first-index
 tie-break == numpy.argmax; indices are bit-exact).  numpy in / numpy out like
 the reference; `get_max_preds_device` is the tensor-in / tensor-out variant."""
-import math
-
 import numpy as np
 import torch
 
 from epipolarpose_b200 import ops as _ops
-from ..utils.transforms import transform_preds
 
 _backend = [_ops]
 
@@ -39,21 +36,30 @@ def get_max_preds(batch_heatmaps):
     return preds.cpu().numpy(), maxvals.cpu().numpy().astype(batch_heatmaps.dtype)
 
 
-def get_final_preds(config, batch_heatmaps, center, scale):
-    """reference :43-68."""
-    coords, maxvals = get_max_preds(batch_heatmaps)
-    h, w = batch_heatmaps.shape[2], batch_heatmaps.shape[3]
-    if config.TEST.POST_PROCESS:        # +-0.25 px toward the higher neighbour (:49-61)
-        for n in range(coords.shape[0]):
-            for p in range(coords.shape[1]):
-                hm = batch_heatmaps[n][p]
-                px = int(math.floor(coords[n][p][0] + 0.5))
-                py = int(math.floor(coords[n][p][1] + 0.5))
-                if 1 < px < w - 1 and 1 < py < h - 1:
-                    diff = np.array([hm[py][px + 1] - hm[py][px - 1],
-                                     hm[py + 1][px] - hm[py - 1][px]])
-                    coords[n][p] += np.sign(diff) * .25
-    preds = coords.copy()
-    for i in range(coords.shape[0]):
-        preds[i] = transform_preds(coords[i], center[i], scale[i], [w, h])
+def get_final_preds_device(heatmaps, center, scale, post_process=True):
+    """heatmaps [N,J,H,W] float32 (device), center / scale [N,2] -> (preds [N,J,2] f32 image
+    coordinates, maxvals [N,J,1] f32) on the device: argmax, +-0.25 px refinement and the
+    heat-map -> image affine in ONE launch (epb_final_preds)."""
+    ops = _backend[0]
+    hm = heatmaps.contiguous()
+    N, J, H, W = hm.shape
+    dev = hm.device
+    c = torch.as_tensor(np.asarray(center, dtype=np.float64).reshape(N, 2)).to(dev)
+    sc = torch.as_tensor(np.asarray(scale, dtype=np.float64).reshape(N, 2)).to(dev)
+    preds = torch.empty((N, J, 2), device=dev, dtype=torch.float32)
+    maxvals = torch.empty((N, J, 1), device=dev, dtype=torch.float32)
+    if N * J:
+        ops.final_preds(hm, N, J, H, W, c, sc, post_process, preds, maxvals)
     return preds, maxvals
+
+
+def get_final_preds(config, batch_heatmaps, center, scale):
+    """reference :43-68 (numpy in / numpy out)."""
+    assert isinstance(batch_heatmaps, np.ndarray), 'batch_heatmaps should be numpy.ndarray'
+    dev = torch.device("cuda") if _backend[0] is _ops else torch.device("cpu")
+    hm = torch.from_numpy(np.ascontiguousarray(batch_heatmaps, dtype=np.float32)).to(dev)
+    scale = np.stack([np.asarray(s_, dtype=np.float64).reshape(-1)[:2] if np.ndim(s_) else
+                      np.array([s_, s_], dtype=np.float64) for s_ in scale])
+    preds, maxvals = get_final_preds_device(hm, np.asarray(center), scale,
+                                            config.TEST.POST_PROCESS)
+    return preds.cpu().numpy(), maxvals.cpu().numpy().astype(batch_heatmaps.dtype)

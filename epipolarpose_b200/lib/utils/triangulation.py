@@ -8,9 +8,10 @@ SVD per joint) runs in the sm_100a kernel epb_triangulate; numpy in / numpy out
 like the reference.  `triangulate_pairs` is the batched tensor API the training
 loop uses (no host round trip).  polynomial_triangulation (:184-220: fundamental matrix
 from the projection matrices, cv2.correctMatches = Hartley-Sturm optimal correction, then
-the homogeneous DLT) runs as method "polynomial" of the same kernel; the reference's 8-point
-fallback for an all-NaN correction (:215-217, a purely sideways camera pair) is not built:
-the NaNs are returned with status False."""
+the homogeneous DLT) runs as method "polynomial" of the same kernel, including the reference's
+8-point fallback (:215-217): when the correction is NaN for every joint of a pair, F is
+re-estimated from the matches (cv2.findFundamentalMat FM_8POINT) on the device and the
+correction repeated; "polynomial_8point" runs that branch unconditionally."""
 import numpy as np
 import torch
 
@@ -18,6 +19,7 @@ from epipolarpose_b200 import ops as _ops
 
 _backend = [_ops]
 METHODS = {"linear_eigen": 0, "linear_LS": 1, "iterative_LS": 2, "polynomial": 3,
+           "polynomial_8point": 4,
            "eigen": 0, "ls": 1, "iterative": 2}
 
 output_dtype = float

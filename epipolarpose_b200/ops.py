@@ -284,6 +284,11 @@ def argmax2d(hm, NJ, H, W, idx, maxval, preds):
     _call("epb_argmax2d", _p(hm), NJ, H, W, _p(idx, torch.int32), _p(maxval), _p(preds), _stream())
 
 
+def final_preds(hm, N, J, H, W, center, scale, post_process, preds, maxvals):
+    _call("epb_final_preds", _p(hm), N, J, H, W, _p(center, torch.float64), _p(scale, torch.float64),
+          int(bool(post_process)), _p(preds), _p(maxvals), _stream())
+
+
 # ------------------------------------------------------------------ geometry (fp64)
 
 def patch_to_image(coords, box, B, J, patch_w, patch_h, rect3d_w, kps):

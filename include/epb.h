@@ -331,6 +331,16 @@ int epb_heatmap_joint_loss(const float* hm, const float* target, const float* hm
 int epb_argmax2d(const float* hm, int NJ, int H, int W, int32_t* idx,
                  float* maxval, float* preds, epb_stream_t stream);
 
+/* lib/core/inference.py:43-68 get_final_preds in one launch: the argmax above, the +-0.25 px
+ * refinement toward the higher neighbour (:49-61, when post_process != 0) and transform_preds
+ * (lib/utils/transforms.py:39-44) with the inverse affine of get_affine_transform(center,
+ * scale, 0, (W, H), inv=1) (:47-79; cv2.getAffineTransform's 6x6 LU on the float32 point
+ * triplets).  hm [N][J][H][W] float32; center, scale [N][2] float64 (scale in units of
+ * 200 px, :57).  preds [N][J][2] float32 image coordinates, maxvals [N][J] (or NULL). */
+int epb_final_preds(const float* hm, int N, int J, int H, int W, const double* center,
+                    const double* scale, int post_process, float* preds, float* maxvals,
+                    epb_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Epipolar geometry in float64 (OpenCV/numpy call sites).
  * ---------------------------------------------------------------------- */
@@ -348,7 +358,11 @@ int epb_patch_to_image(const float* coords, const double* box, int B, int J,
  * re-weighting rounds, tol 3e-5 (:104-181); method 3: polynomial / optimal
  * (:184-220): F = [t]x R of the canonical pair, cv2.correctMatches
  * (Hartley-Sturm: degree-6 polynomial per match, roots by Laguerre iteration),
- * then method 0 on the corrected matches. */
+ * then method 0 on the corrected matches; when the correction is NaN for every
+ * joint of a pair (F = 0: identical / degenerate cameras) F is re-estimated from
+ * the matches with the normalised 8-point algorithm (cv2.findFundamentalMat(...,
+ * FM_8POINT), :215-217) and the correction repeated.  method 4: always the
+ * 8-point F (the fallback branch on its own). */
 int epb_triangulate(const double* u1, const double* u2, int stride_u,
                     const double* P1, const double* P2, int NP, int J,
                     int method, double tol, double* X, int32_t* status,

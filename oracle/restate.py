@@ -164,6 +164,75 @@ def final_preds_refine(batch_heatmaps, coords):
     return c
 
 
+def _lu6_affine(src, dst):
+    """cv2.getAffineTransform(src, dst): the 6x6 system A.x = b solved as cv::solve(DECOMP_LU)
+    does (partial pivoting by largest magnitude, in float64) -- the same elimination order as
+    OpenCV so that the float64 coefficients agree to the last bit (lib/utils/transforms.py:75-77)."""
+    A = np.zeros((6, 6))
+    b = np.zeros(6)
+    for i in range(3):
+        A[2 * i, 0:3] = [float(src[i][0]), float(src[i][1]), 1.0]
+        A[2 * i + 1, 3:6] = [float(src[i][0]), float(src[i][1]), 1.0]
+        b[2 * i], b[2 * i + 1] = float(dst[i][0]), float(dst[i][1])
+    for i in range(6):
+        k = i
+        for j in range(i + 1, 6):
+            if abs(A[j, i]) > abs(A[k, i]):
+                k = j
+        if k != i:
+            A[[i, k], i:] = A[[k, i], i:]
+            b[[i, k]] = b[[k, i]]
+        d = -1.0 / A[i, i]
+        for j in range(i + 1, 6):
+            alpha = A[j, i] * d
+            for kk in range(i + 1, 6):
+                A[j, kk] += alpha * A[i, kk]
+            b[j] += alpha * b[i]
+    for i in range(5, -1, -1):
+        s_ = b[i]
+        for kk in range(i + 1, 6):
+            s_ -= A[i, kk] * b[kk]
+        b[i] = s_ / A[i, i]
+    return b.reshape(2, 3)
+
+
+def final_preds(batch_heatmaps, center, scale, post_process=True):
+    """inference.py:43-68: get_max_preds, +-0.25 px refinement, transform_preds
+    (transforms.py:39-44 with get_affine_transform(center, scale, 0, [W, H], inv=1), :47-79).
+    Returns (preds [N,J,2] float32, maxvals [N,J,1])."""
+    hm = np.asarray(batch_heatmaps)
+    n, j, h, w = hm.shape
+    coords, maxvals, _ = get_max_preds(hm)
+    if post_process:
+        coords = final_preds_refine(hm, coords)
+    preds = coords.copy()
+    for i in range(n):
+        sc = np.asarray(scale[i], dtype=np.float64).reshape(-1)
+        if sc.size == 1:
+            sc = np.array([sc[0], sc[0]])
+        scale_tmp = sc * 200.0
+        src_w = scale_tmp[0]
+        src_dir = [0 * 1.0 - (src_w * -0.5) * 0.0, 0 * 0.0 + (src_w * -0.5) * 1.0]    # get_dir, rot = 0
+        dst_dir = np.array([0, w * -0.5], np.float32)
+        src = np.zeros((3, 2), dtype=np.float32)
+        dst = np.zeros((3, 2), dtype=np.float32)
+        c = np.asarray(center[i], dtype=np.float64)
+        src[0, :] = c
+        src[1, :] = c + src_dir
+        dst[0, :] = [w * 0.5, h * 0.5]
+        dst[1, :] = np.array([w * 0.5, h * 0.5]) + dst_dir
+        d = src[0] - src[1]
+        src[2, :] = src[1] + np.array([-d[1], d[0]], dtype=np.float32)
+        d = dst[0] - dst[1]
+        dst[2, :] = dst[1] + np.array([-d[1], d[0]], dtype=np.float32)
+        t = _lu6_affine(dst, src)                       # inv = 1: heat-map -> image
+        for p_ in range(j):
+            x, y = float(coords[i, p_, 0]), float(coords[i, p_, 1])
+            preds[i, p_, 0] = t[0, 0] * x + t[0, 1] * y + t[0, 2] * 1.0
+            preds[i, p_, 1] = t[1, 0] * x + t[1, 1] * y + t[1, 2] * 1.0
+    return preds, maxvals
+
+
 # --------------------------------------------------------------------------
 # a10: decode  (lib/core/integral_loss.py:187-207)
 # --------------------------------------------------------------------------
@@ -390,6 +459,10 @@ def correct_matches(F, u1, u2):
         g = np.polysub(np.polymul([1.0, 0.0], np.polymul(q, q)),
                        (a * d - b * c) * np.polymul(np.polymul([f1 * f1, 0, 1.0], [f1 * f1, 0, 1.0]),
                                                     np.polymul([a, b], [c, d])))
+        if not np.isfinite(g).all():               # F = 0 (identical cameras): no epipoles
+            o1[p] = np.nan
+            o2[p] = np.nan
+            continue
         cand = [r.real for r in np.roots(g)]
 
         def cost(t):
@@ -422,15 +495,67 @@ def fundamental_from_projections(P1, P2):
     P1f, P2f = np.eye(4), np.eye(4)
     P1f[0:3, :] = np.asarray(P1, dtype=np.float64)[0:3, :]
     P2f[0:3, :] = np.asarray(P2, dtype=np.float64)[0:3, :]
-    Pc = P2f.dot(np.linalg.inv(P1f))
-    return np.cross(Pc[0:3, 3], Pc[0:3, 0:3], axisb=0).T
+    Pi = np.linalg.inv(P1f)
+    Pc = P2f.dot(Pi)
+    t = Pc[0:3, 3].copy()
+    # a translation that is pure cancellation noise (identical camera centres) is exactly zero:
+    # the reference's F is then the zero matrix and its correction all-NaN (:213-217)
+    mag = np.abs(P2f[0:3, :]).dot(np.abs(Pi[:, 3]))
+    t[np.abs(t) <= 64 * np.finfo(np.float64).eps * mag] = 0.0
+    return np.cross(t, Pc[0:3, 0:3], axisb=0).T
+
+
+def fundamental_8point(u1, u2):
+    """cv2.findFundamentalMat(u1, u2, cv2.FM_8POINT)[0] restated (OpenCV calib3d fundam.cpp
+    run8Point; called by the reference at lib/utils/triangulation.py:216): inputs rounded to
+    float32, isotropic normalisation, eigenvector of the smallest eigenvalue of the 9x9 normal
+    matrix, rank-2 projection, de-normalisation, F[2,2] = 1.  None for degenerate point sets."""
+    a = np.asarray(u1, dtype=np.float64).astype(np.float32).astype(np.float64)
+    b = np.asarray(u2, dtype=np.float64).astype(np.float32).astype(np.float64)
+    c1, c2 = a.mean(0), b.mean(0)
+    s1 = np.sqrt(((a - c1) ** 2).sum(1)).mean()
+    s2 = np.sqrt(((b - c2) ** 2).sum(1)).mean()
+    if s1 < np.finfo(np.float32).eps or s2 < np.finfo(np.float32).eps:
+        return None
+    s1, s2 = np.sqrt(2.0) / s1, np.sqrt(2.0) / s2
+    p, q = (a - c1) * s1, (b - c2) * s2
+    r = np.stack([q[:, 0] * p[:, 0], q[:, 0] * p[:, 1], q[:, 0], q[:, 1] * p[:, 0], q[:, 1] * p[:, 1],
+                  q[:, 1], p[:, 0], p[:, 1], np.ones(len(p))], axis=1)
+    w, v = np.linalg.eigh(r.T @ r)
+    if (np.abs(w) >= np.finfo(np.float64).eps).sum() < 8:
+        return None
+    F0 = v[:, 0].reshape(3, 3)
+    U, sv, Vt = np.linalg.svd(F0)
+    sv[2] = 0.0
+    F0 = U @ np.diag(sv) @ Vt
+    T1 = np.array([[s1, 0, -s1 * c1[0]], [0, s1, -s1 * c1[1]], [0, 0, 1]])
+    T2 = np.array([[s2, 0, -s2 * c2[0]], [0, s2, -s2 * c2[1]], [0, 0, 1]])
+    F = T2.T @ F0 @ T1
+    if abs(F[2, 2]) > np.finfo(np.float32).eps:
+        F = F / F[2, 2]
+    return F
+
+
+def polynomial_triangulation_8point(u1, P1, u2, P2):
+    """The fallback branch of triangulation.py:215-217 on its own: F from the matches."""
+    F = fundamental_8point(u1, u2)
+    n1, n2 = correct_matches(F, u1, u2)
+    return linear_eigen_triangulation(n1, P1, n2, P2)
 
 
 def polynomial_triangulation(u1, P1, u2, P2):
-    """lib/utils/triangulation.py:184-220 (the 8-point fallback for an all-NaN correction,
-    :215-217, is not restated: it needs >= 8 matches and a degenerate camera pair)."""
+    """lib/utils/triangulation.py:184-220, including the fallback of :213-217: when the optimal
+    correction is NaN for every match (F = 0: identical / degenerate cameras), F is re-estimated
+    from the matches with the 8-point algorithm and the correction repeated."""
+    u1 = np.asarray(u1, dtype=np.float64)[:, :2]
+    u2 = np.asarray(u2, dtype=np.float64)[:, :2]
     F = fundamental_from_projections(P1, P2)
-    n1, n2 = correct_matches(F, np.asarray(u1, dtype=np.float64)[:, :2], np.asarray(u2, dtype=np.float64)[:, :2])
+    with np.errstate(all="ignore"):
+        n1, n2 = correct_matches(F, u1, u2)
+    if np.isnan(n1).all() or np.isnan(n2).all():
+        F8 = fundamental_8point(u1, u2)
+        if F8 is not None:
+            n1, n2 = correct_matches(F8, u1, u2)
     return linear_eigen_triangulation(n1, P1, n2, P2)
 
 

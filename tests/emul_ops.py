@@ -658,3 +658,12 @@ def bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, 
 
 def avgpool_split(x, x_sc, y, N, HW, C):
     y.view(N, C).copy_(_join(x, x_sc).reshape(N, HW, C).mean(1))
+
+
+def final_preds(hm, N, J, H, W, center, scale, post_process, preds, maxvals):
+    from oracle import restate
+    p, m = restate.final_preds(hm.reshape(N, J, H, W).numpy(), center.numpy(), scale.numpy(),
+                               bool(post_process))
+    preds.view(N, J, 2).copy_(torch.from_numpy(p))
+    if maxvals is not None:
+        maxvals.view(N, J).copy_(torch.from_numpy(m.reshape(N, J)))

@@ -222,3 +222,25 @@ def sample_grad(g):
     stride = max(1, f.size // 4096)
     return f[::stride].astype(np.float32), np.array([f.sum(dtype=np.float64), np.abs(f).sum(dtype=np.float64),
                                          np.abs(f).max()], dtype=np.float64)
+
+
+
+def final_preds_case(seed=23):
+    """Heat-maps for get_final_preds (lib/core/inference.py:43-68): the argmax cases plus smooth
+    blobs with interior / border / corner peaks and exact-tie neighbours (sign(0) = 0);
+    per-image centres and (box / 200) scales as the MPII loaders pass them."""
+    rng = np.random.default_rng(seed)
+    hm = argmax_heatmaps()                                   # [3, 6, 16, 12]
+    n, j, h, w = hm.shape
+    yy, xx = np.mgrid[0:h, 0:w]
+    for (a, b, cy, cx) in ((1, 2, 7.3, 5.6), (1, 3, 1.2, 1.4), (1, 4, 14.0, 10.2), (2, 0, 8.0, 6.0),
+                           (2, 1, 0.0, 0.0), (2, 2, 15.0, 11.0)):
+        hm[a, b] = np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 6.0).astype(np.float32)
+    hm[2, 4] = 0.0
+    hm[2, 4, 6, 5] = 1.0
+    hm[2, 4, 6, 6] = 0.5
+    hm[2, 4, 6, 4] = 0.5                                       # x neighbours tie -> no x shift
+    hm[2, 4, 7, 5] = 0.25
+    center = np.stack([500 + rng.uniform(-60, 60, n), 480 + rng.uniform(-60, 60, n)], axis=1)
+    scale = np.stack([2.0 + rng.uniform(0, 2, n)] * 2, axis=1) * np.array([1.0, 1.25])
+    return hm, center, scale

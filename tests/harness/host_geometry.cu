@@ -3,6 +3,7 @@
 // the oracle in the CPU test suite too.  Binary protocol on stdin/stdout (little-endian doubles):
 //   "eval" S J root mask  then pred[S*J*3] gt[S*J*3] cam[S*5]  ->  metrics[S*9] per_joint[S*J] poses[S*J*9]
 //   "correct" N  then P1[12] P2[12] u1[N*2] u2[N*2]  ->  F[9] u1'[N*2] u2'[N*2]
+//   "f8" N  then u1[N*2] u2[N*2]  ->  ok[1] F[9]   (cv2.findFundamentalMat FM_8POINT)
 //   "nview" V J  then u[V*J*2] P[V*12]  ->  X[J*3]
 //   "patch" H W pw ph flip J  then box[6] color[3] mean_std[6] depth_den[1] joints[J*3] img[H*W*3 as doubles]
 //           ->  trans[6] patch[3*ph*pw] (float32 values widened) label[J*3]
@@ -11,6 +12,7 @@
 #include <cstring>
 #include <vector>
 void epb_set_error(const char*, ...) {}
+int epb_workspace(int, size_t, struct CUstream_st*, void**) { return -1; }   // entry points are not run here
 #include "../../epipolarpose_b200/csrc/geometry.cu"
 #include "../../epipolarpose_b200/csrc/input.cu"
 
@@ -73,6 +75,14 @@ int main(int argc, char** argv) {
     fwrite(M, 8, 6, stdout);
     fwrite(patch.data(), 8, patch.size(), stdout);
     fwrite(label.data(), 8, label.size(), stdout);
+    return 0;
+  }
+  if (!strcmp(argv[1], "f8")) {
+    const int N = atoi(argv[2]);
+    std::vector<double> u1(N * 2), u2(N * 2), out(10, 0.0);
+    rd(u1.data(), N * 16); rd(u2.data(), N * 16);
+    out[0] = fundamental_8point(u1.data(), u2.data(), 2, N, &out[1]) ? 1.0 : 0.0;
+    fwrite(out.data(), 8, 10, stdout);
     return 0;
   }
   if (!strcmp(argv[1], "correct")) {

@@ -217,6 +217,31 @@ def test_input_pipeline_bit_exact(golden, dev):
         assert np.array_equal(big[i].cpu().numpy(), t), i
 
 
+def test_final_preds_bit_exact(golden, dev):
+    """lib/core/inference.py:43-68 on the device (epb_final_preds) against the unmodified
+    reference: coordinates bit-exact (float32), through the reference-shaped numpy API and
+    the tensor API."""
+    import types
+    import lib.core.inference as inf
+    g = golden("final_preds")
+    hm, center, scale = gi.final_preds_case()
+    for pp in (1, 0):
+        cfg = types.SimpleNamespace(TEST=types.SimpleNamespace(POST_PROCESS=bool(pp)))
+        preds, maxvals = inf.get_final_preds(cfg, hm.copy(), center, scale)
+        assert preds.dtype == np.float32 and np.array_equal(preds, g["preds_pp%d" % pp])
+        assert np.array_equal(maxvals, g["maxvals_pp%d" % pp])
+        pd, md = inf.get_final_preds_device(torch.from_numpy(hm).to(dev), center, scale, bool(pp))
+        assert np.array_equal(pd.cpu().numpy(), g["preds_pp%d" % pp])
+    # a batch the size of a validation step: equals the oracle on every map
+    rng = np.random.default_rng(3)
+    big = rng.standard_normal((64, 16, 64, 64)).astype(np.float32)
+    c = np.stack([500 + rng.uniform(-50, 50, 64), 500 + rng.uniform(-50, 50, 64)], 1)
+    s = np.stack([4 + rng.uniform(-1, 1, 64)] * 2, 1)
+    pd, md = inf.get_final_preds_device(torch.from_numpy(big).to(dev), c, s, True)
+    pr, mr = restate.final_preds(big, c, s, True)
+    assert np.array_equal(pd.cpu().numpy(), pr) and np.array_equal(md.cpu().numpy(), mr)
+
+
 def test_argmax_bit_exact(golden, dev):
     import lib.core.inference as inf
     g = golden("argmax")
@@ -249,6 +274,24 @@ def test_triangulators_golden(golden, dev):
     for m in ("linear_eigen", "linear_LS", "iterative_LS"):
         Xg, _ = tri.triangulate_pairs(t(u1e), t(u2e), t(P1), t(P2), m)
         assert np.max(np.abs(Xg.cpu().numpy() - X)) <= 1e-6             # known answer
+
+
+def test_eight_point_fallback_golden(golden, dev):
+    """polynomial_triangulation's fallback (lib/utils/triangulation.py:213-217) on the device:
+    "polynomial_8point" (the branch on its own: 8-point F from the matches, correction, DLT)
+    against the same composition of OpenCV / reference calls, and the natural trigger --
+    identical cameras, F = 0, all-NaN correction -- against the reference's own output."""
+    import lib.utils.triangulation as tri
+    g = golden("triangulation_8point")
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    Xg, st = tri.triangulate_pairs(t(u1), t(u2), t(P1), t(P2), "polynomial_8point")
+    assert np.max(np.abs(Xg.cpu().numpy() - g["x_8pt"])) <= 1e-4          # mm
+    Xs, st = tri.triangulate_pairs(t(u1), t(u2), t(P1), t(P1), "polynomial")
+    assert np.max(np.abs(Xs.cpu().numpy() - g["x_same"])) <= 1e-4
+    assert np.array_equal(st.cpu().numpy().astype(np.int64), g["st_same"])
+    x, s1 = tri.polynomial_triangulation(u1[3], P1[3], u2[3], P1[3])     # reference-shaped API
+    assert np.max(np.abs(x - g["x_same"][3])) <= 1e-4 and s1.all()
 
 
 def test_polynomial_triangulation_golden(golden, dev):

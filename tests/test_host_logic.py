@@ -177,6 +177,14 @@ def test_losses_and_decode_surface_emulated():
         assert np.array_equal(p, rp) and np.array_equal(mv, rm)
         with pytest.raises(AssertionError):
             inf.get_max_preds(hm[0])
+        # get_final_preds through the reference-shaped numpy API (emulated epb_final_preds)
+        import types
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "final_preds.npz")))
+        fh, fc, fs = gi.final_preds_case()
+        for pp in (1, 0):
+            cfg = types.SimpleNamespace(TEST=types.SimpleNamespace(POST_PROCESS=bool(pp)))
+            fp, fm = inf.get_final_preds(cfg, fh.copy(), fc, fs)
+            assert np.array_equal(fp, g["preds_pp%d" % pp]) and np.array_equal(fm, g["maxvals_pp%d" % pp])
     finally:
         il._backend[0] = __import__("epipolarpose_b200.ops", fromlist=["ops"])
         inf._backend[0] = il._backend[0]
@@ -309,6 +317,24 @@ def test_polynomial_correction_kernel_body_on_host(host_geometry):
     u1e, u2e = gi.exact_projections(P1, P2, X)
     a = host_geometry(["correct", 17], P1[0], P2[0], u1e[0], u2e[0])
     assert np.max(np.abs(a[9:9 + 34].reshape(17, 2) - u1e[0])) <= 1e-8
+
+
+def test_eight_point_kernel_body_on_host(host_geometry):
+    """fundamental_8point of csrc/geometry.cu (Jacobi eigenvectors of the 9x9 normal matrix,
+    rank-2 projection), executed on the CPU, against cv2.findFundamentalMat(FM_8POINT)."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "triangulation_8point.npz")))
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    for i in range(len(u1)):
+        a = host_geometry(["f8", len(u1[i])], u1[i], u2[i])
+        assert a[0] == 1.0
+        F = a[1:].reshape(3, 3)
+        assert np.max(np.abs(F - g["f8"][i])) <= 1e-9 * np.abs(g["f8"][i]).max()
+    a = host_geometry(["f8", 17], np.ones((17, 2)), np.ones((17, 2)))     # degenerate: no matrix
+    assert a[0] == 0.0
+    # identical cameras: F is exactly zero and the correction NaN for every match (the trigger
+    # of the fallback, lib/utils/triangulation.py:213-215)
+    a = host_geometry(["correct", 17], P1[0], P1[0], u1[0], u2[0])
+    assert np.all(a[:9] == 0.0) and np.isnan(a[9:]).all()
 
 
 MEAN = np.array([123.675, 116.280, 103.530])

@@ -208,3 +208,30 @@ def test_refiner_oracle(golden):
     with torch.no_grad():
         e1, e2 = rr.forward(sd_after, x.detach(), training=False)
     assert relerr(e1.numpy(), g["eval_p1"]) <= 1e-5 and relerr(e2.numpy(), g["eval_p2"]) <= 1e-5
+
+
+def test_final_preds_bit_exact(golden):
+    """get_final_preds (lib/core/inference.py:43-68): argmax, +-0.25 px refinement and the
+    cv2.getAffineTransform-based transform_preds, restated -- bit-equal to the reference run."""
+    g = golden("final_preds")
+    hm, center, scale = gi.final_preds_case()
+    for pp in (1, 0):
+        p, m = restate.final_preds(hm, center, scale, bool(pp))
+        assert np.array_equal(p, g["preds_pp%d" % pp])
+        assert np.array_equal(m, g["maxvals_pp%d" % pp])
+
+
+def test_eight_point_fallback(golden):
+    """The fallback of polynomial_triangulation (lib/utils/triangulation.py:213-217):
+    restate.fundamental_8point against cv2.findFundamentalMat(FM_8POINT), the branch on its own
+    against the same composition of reference / OpenCV calls, and the natural trigger
+    (P2 == P1: the correction is all-NaN, the reference itself falls back)."""
+    g = golden("triangulation_8point")
+    u1, u2, P1, P2, X = gi.triangulation_case()
+    for i in range(len(u1)):
+        F = restate.fundamental_8point(u1[i], u2[i])
+        assert np.max(np.abs(F - g["f8"][i])) <= 1e-10 * np.abs(g["f8"][i]).max()
+        x, st = restate.polynomial_triangulation_8point(u1[i], P1[i], u2[i], P2[i])
+        assert np.max(np.abs(x - g["x_8pt"][i])) <= 1e-4
+        x, st = restate.polynomial_triangulation(u1[i], P1[i], u2[i], P1[i])
+        assert np.max(np.abs(x - g["x_same"][i])) <= 1e-4 and np.array_equal(st.astype(np.int64), g["st_same"][i])

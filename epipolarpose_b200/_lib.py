@@ -63,6 +63,7 @@ _PROTOS = {
     "epb_add3": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_p]),
     "epb_mask_scale": (c_int, [c_p, c_p, c_f, c_p, c_i64, c_p]),
     "epb_patch_sample": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p, c_p]),
+    "epb_patch_sample_occ": (c_int, [c_p] * 7 + [c_int, c_int, c_int] + [c_p] * 5 + [c_p]),
     "epb_patch_joints": (c_int, [c_p, c_p, c_p, c_int, c_int, c_d, c_d, c_d, c_int, c_p, c_p]),
     "epb_act_scale": (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
     "epb_bn_act_split": (c_int, [c_p] * 8 + [c_int, c_i64, c_int, c_p, c_p, c_p]),
@@ -74,6 +75,8 @@ _PROTOS = {
     "epb_bn_bwd_reduce_mx": (c_int, [c_p] * 7 + [c_int, c_i64, c_int, c_p, c_p, c_p]),
     "epb_bn_bwd_apply_split": (c_int, [c_p] * 8 + [c_int, c_p, c_p, c_i64, c_int] + [c_p] * 6),
     "epb_avgpool_split": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
+    "epb_sumsq": (c_int, [c_p, c_i64, c_p, c_p]),
+    "epb_clip_scale": (c_int, [c_p, c_i64, c_p, c_d, c_p]),
     "epb_adam_step": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_p]),
     "epb_sgd_step": (c_int, [c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_int, c_int, c_f, c_p]),
     "epb_adam_step_dev": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p]),

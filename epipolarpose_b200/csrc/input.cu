@@ -144,11 +144,32 @@ struct PatchArgs {
   int norm;
 };
 
+// lib/utils/augmentation.py:81-114 paste_over for ONE patch pixel (x, y) and one occluder: the
+// RGBA occluder (w x h) centred at (cx, cy) (already np.round'ed), alpha-blended in float32
+//   alpha * src + (1 - alpha) * dst   with alpha = a / 255 (float32),
+// and stored back into the uint8 image (C truncation), exactly as numpy evaluates :112-113.
+__host__ __device__ inline void paste_pixel(const uint8_t* occ, int w, int h, int cx, int cy, int x,
+                                            int y, int (&rgb)[3]) {
+  const int sx = x - (cx - w / 2), sy = y - (cy - h / 2);     // raw_start_dst = center - wh // 2
+  if (sx < 0 || sx >= w || sy < 0 || sy >= h) return;
+  const uint8_t* p = occ + ((int64_t)sy * w + sx) * 4;
+  const float alpha = (float)p[3] / 255.f;
+  const float om = 1.f - alpha;
+  for (int c = 0; c < 3; ++c) {
+    const float v = alpha * (float)p[c] + om * (float)rgb[c];
+    rgb[c] = (int)(uint8_t)v;
+  }
+}
+
+constexpr int kMaxOccluders = 7;       // count = np.random.randint(1, 8)  (:67)
+
 __global__ void __launch_bounds__(256)
 patch_sample_kernel(const uint8_t* __restrict__ img_base, const int64_t* __restrict__ img_off,
                     const int32_t* __restrict__ img_hwp, const double* __restrict__ box,
                     const int32_t* __restrict__ flip, const float* __restrict__ color, PatchArgs pa,
-                    int patch_w, int patch_h, float* __restrict__ out, double* __restrict__ trans) {
+                    int patch_w, int patch_h, const uint8_t* __restrict__ occ_base,
+                    const int64_t* __restrict__ occ_desc, const int32_t* __restrict__ occ_count,
+                    float* __restrict__ out, double* __restrict__ trans) {
   const int b = blockIdx.z;
   __shared__ double siM[6];
   const int H = img_hwp[b * 3 + 0], W = img_hwp[b * 3 + 1];
@@ -171,12 +192,20 @@ patch_sample_kernel(const uint8_t* __restrict__ img_base, const int64_t* __restr
   if (x >= patch_w || y >= patch_h) return;
   int bgr[3];
   warp_pixel_u8(img_base + img_off[b], H, W, pitch, fl, siM, x, y, bgr);
+  int rgb[3] = {bgr[2], bgr[1], bgr[0]};              // image[:, :, ::-1] (:268)
+  if (occ_count) {                                     // occlude_with_objects (:269-270), in order
+    const int cnt = occ_count[b];
+    for (int k = 0; k < cnt && k < kMaxOccluders; ++k) {
+      const int64_t* d = occ_desc + ((int64_t)b * kMaxOccluders + k) * 5;
+      paste_pixel(occ_base + d[0], (int)d[1], (int)d[2], (int)d[3], (int)d[4], x, y, rgb);
+    }
+  }
   const int64_t plane = (int64_t)patch_w * patch_h;
   float* o = out + (int64_t)b * 3 * plane + (int64_t)y * patch_w + x;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float cs = color ? color[b * 3 + c] : 1.f;
-    o[c * plane] = finish_pixel(bgr[2 - c], cs, pa.norm != 0, pa.mean[c], pa.stdv[c]);   // BGR -> RGB
+    o[c * plane] = finish_pixel(rgb[c], cs, pa.norm != 0, pa.mean[c], pa.stdv[c]);
   }
 }
 
@@ -282,12 +311,14 @@ final_preds_kernel(const float* __restrict__ hm, int NJ, int J, int H, int W,
 
 }  // namespace
 
-extern "C" __attribute__((visibility("default"))) int epb_patch_sample(
+extern "C" __attribute__((visibility("default"))) int epb_patch_sample_occ(
     const uint8_t* img_base, const int64_t* img_off, const int32_t* img_hwp, const double* box,
     const int32_t* flip, const float* color, const double* mean_std_host, int B, int patch_w,
-    int patch_h, float* out, double* trans, epb_stream_t stream) {
+    int patch_h, const uint8_t* occ_base, const int64_t* occ_desc, const int32_t* occ_count,
+    float* out, double* trans, epb_stream_t stream) {
   EPB_CHECK_ARG(img_base && img_off && img_hwp && box && out);
   EPB_CHECK_ARG(B >= 0 && patch_w > 0 && patch_h > 0 && B <= 65535);
+  EPB_CHECK_ARG((occ_base == nullptr) == (occ_desc == nullptr) && (occ_desc == nullptr) == (occ_count == nullptr));
   if (B == 0) return EPB_OK;
   PatchArgs pa;
   pa.norm = mean_std_host ? 1 : 0;
@@ -299,9 +330,18 @@ extern "C" __attribute__((visibility("default"))) int epb_patch_sample(
   const dim3 block(64, 4);
   const dim3 grid((patch_w + 63) / 64, (patch_h + 3) / 4, B);
   patch_sample_kernel<<<grid, block, 0, as_stream(stream)>>>(img_base, img_off, img_hwp, box, flip, color,
-                                                            pa, patch_w, patch_h, out, trans);
+                                                            pa, patch_w, patch_h, occ_base, occ_desc,
+                                                            occ_count, out, trans);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_patch_sample(
+    const uint8_t* img_base, const int64_t* img_off, const int32_t* img_hwp, const double* box,
+    const int32_t* flip, const float* color, const double* mean_std_host, int B, int patch_w,
+    int patch_h, float* out, double* trans, epb_stream_t stream) {
+  return epb_patch_sample_occ(img_base, img_off, img_hwp, box, flip, color, mean_std_host, B, patch_w,
+                              patch_h, nullptr, nullptr, nullptr, out, trans, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int epb_patch_joints(

@@ -421,3 +421,56 @@ extern "C" __attribute__((visibility("default"))) int epb_mask_scale(const float
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }
+
+
+// torch.nn.utils.clip_grad_norm_(parameters, max_norm) (reference refiner/main.py:57) over a list
+// of gradient tensors: epb_sumsq accumulates sum(x^2) of one tensor into a float64 scalar;
+// epb_clip_scale multiplies one tensor by min(1, max_norm / (sqrt(total) + 1e-6)).
+namespace {
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ total) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const double v = (double)x[i];
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) acc += sm[w];
+    atomicAdd(total, acc);
+  }
+}
+__global__ void __launch_bounds__(256)
+clip_scale_kernel(float* __restrict__ x, int64_t n, const double* __restrict__ total, double max_norm) {
+  const double coef = max_norm / (sqrt(*total) + 1e-6);
+  if (coef >= 1.0) return;                      // clamp(coef, max=1): nothing to do
+  const float c = (float)coef;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    x[i] *= c;
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int epb_sumsq(const float* x, int64_t n, double* total,
+                                                            epb_stream_t stream) {
+  EPB_CHECK_ARG(x && total && n >= 0);
+  if (n == 0) return EPB_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, n, total);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int epb_clip_scale(float* x, int64_t n, const double* total,
+                                                                 double max_norm, epb_stream_t stream) {
+  EPB_CHECK_ARG(x && total && n >= 0 && max_norm > 0);
+  if (n == 0) return EPB_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  clip_scale_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, n, total, max_norm);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}

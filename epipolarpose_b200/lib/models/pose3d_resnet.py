@@ -151,18 +151,37 @@ class _PoseNetFn(torch.autograd.Function):
             stage = module._grad_stage = (sflat, sgrads)
         sflat, sgrads = stage
         sflat.zero_()
-        eng.backward(S, dlogits, ddepth, params, sgrads)
+        # pure data parallel over view-tuples: the flat gradient is all-reduced in FIVE stage
+        # slices (net.STAGES), each issued as soon as the backward pass has completed it, so
+        # all but the last (stem + layer1, < 1 MB) overlap the remaining backward kernels
+        import torch.distributed as dist
+        works = []
+        on_stage = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
+                and module.allreduce_grads:
+            bounds = getattr(module, "_stage_bounds", None)
+            if bounds is None:
+                bounds, off = {}, 0
+                for n, ps in zip(names, padded):
+                    k = _net.stage_of(n)
+                    a, b = bounds.get(k, (off, off))
+                    bounds[k] = (min(a, off), max(b, off + ps))
+                    off += ps
+                module._stage_bounds = bounds
+
+            def on_stage(k):
+                if k in bounds:
+                    a, b = bounds[k]
+                    works.append(dist.all_reduce(sflat[a:b], op=dist.ReduceOp.AVG, async_op=True))
+        eng.backward(S, dlogits, ddepth, params, sgrads, on_stage=on_stage)
+        for w_ in works:
+            w_.wait()                                   # the current stream waits for the collectives
         flat = sflat.clone()
         grads, off = {}, 0
         for n, s, ps in zip(names, sizes, padded):
             grads[n] = flat[off:off + s].view(params[n].shape)
             off += ps
         ctx.saved_state = None
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
-                and module.allreduce_grads:
-            # pure data parallel over view-tuples: ONE collective per step
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
         return (None, None, None) + tuple(grads[n] if params[n].requires_grad else None for n in names)
 
 

@@ -186,9 +186,12 @@ def fliplr_joints(_joints, _joints_vis, width, matched_parts):
 
 
 def generate_patch_batch_device(images, center_x, center_y, width, height, patch_width, patch_height,
-                                scale=None, rot=None, do_flip=None, color_scale=None, mean=None, std=None):
+                                scale=None, rot=None, do_flip=None, color_scale=None, mean=None, std=None,
+                                occluders=None):
     """B decoded BGR frames (uint8 [H,W,3] numpy arrays or tensors, sizes may differ) ->
-    (patches float32 [B,3,ph,pw] on the device, trans float64 [B,2,3], box float64 [B,6])."""
+    (patches float32 [B,3,ph,pw] on the device, trans float64 [B,2,3], box float64 [B,6]).
+    occluders: per sample a list of (rgba uint8 [h,w,4], (cx, cy)) pasted onto the uint8 patch
+    in order (augmentation.draw_occluders), or None."""
     ops = _backend[0]
     dev = _dev()
     B = len(images)
@@ -219,9 +222,16 @@ def generate_patch_batch_device(images, center_x, center_y, width, height, patch
         ms = [float(v) for v in np.asarray(mean).reshape(3)] + [float(v) for v in np.asarray(std).reshape(3)]
     out = torch.empty((B, 3, int(patch_height), int(patch_width)), device=dev, dtype=torch.float32)
     trans = torch.empty((B, 6), device=dev, dtype=torch.float64)
-    ops.patch_sample(base.to(dev), torch.tensor(offs, dtype=torch.int64, device=dev),
-                     torch.tensor(hwp, dtype=torch.int32, device=dev), t_box, t_flip, t_col, ms, B,
-                     int(patch_width), int(patch_height), out, trans)
+    if occluders is not None:
+        from .augmentation import pack_occluders
+        ob, od, oc = pack_occluders(occluders, dev)
+        ops.patch_sample_occ(base.to(dev), torch.tensor(offs, dtype=torch.int64, device=dev),
+                             torch.tensor(hwp, dtype=torch.int32, device=dev), t_box, t_flip, t_col, ms,
+                             B, int(patch_width), int(patch_height), ob, od, oc, out, trans)
+    else:
+        ops.patch_sample(base.to(dev), torch.tensor(offs, dtype=torch.int64, device=dev),
+                         torch.tensor(hwp, dtype=torch.int32, device=dev), t_box, t_flip, t_col, ms, B,
+                         int(patch_width), int(patch_height), out, trans)
     return out, trans.reshape(B, 2, 3), t_box
 
 
@@ -245,8 +255,6 @@ def get_single_patch_sample(img_path, center_x, center_y, width, height,
     """reference :246-298, same arguments and return tuple (img_patch f32 [3,ph,pw] numpy, label,
     label_weight, scale, rot).  `img_path` may also be an already decoded BGR uint8 array.
     `label_func` is honoured when it is not the default generate_joint_location_label."""
-    if occluder:
-        raise NotImplementedError("occluder paste (lib/utils/augmentation.py) is not built")
     if isinstance(img_path, np.ndarray):
         cvimg = img_path
     else:
@@ -259,9 +267,13 @@ def get_single_patch_sample(img_path, center_x, center_y, width, height,
         scale, rot, do_flip, color_scale = do_augmentation()
     else:
         scale, rot, do_flip, color_scale = 1.0, 0, False, [1.0, 1.0, 1.0]
+    occ = None
+    if occluder:                      # :269-270: drawn after do_augmentation(), pasted on the patch
+        from .augmentation import draw_occluders
+        occ = [draw_occluders(int(patch_width), int(patch_height), occluder)]
     patches, trans, box = generate_patch_batch_device(
         [cvimg], [center_x], [center_y], [width], [height], patch_width, patch_height, [scale], [rot],
-        [do_flip], [color_scale], mean, std)
+        [do_flip], [color_scale], mean, std, occluders=occ)
     joints = np.array(joints, dtype=np.float64, copy=True)
     joints_vis = np.array(joints_vis, copy=True)
     if do_flip:

@@ -188,6 +188,20 @@ class PoseNetPlan:
         return out
 
 
+# Gradient stages, in the order the backward pass completes them (parameters of a stage are
+# contiguous in the flat gradient buffer): the data-parallel all-reduce of a stage is issued as
+# soon as its weight gradients are unpacked and overlaps the rest of the backward pass.
+STAGES = (("deconv_layers", "final_layer", "depth_fc"), ("layer4",), ("layer3",), ("layer2",),
+          ("layer1", "conv1", "bn1"))
+
+
+def stage_of(name):
+    for k, prefixes in enumerate(STAGES):
+        if any(name == p or name.startswith(p + ".") for p in prefixes):
+            return k
+    raise KeyError(name)
+
+
 class _BNState:
     __slots__ = ("name", "C", "scale", "shift", "mean", "invstd", "M")
 
@@ -262,18 +276,19 @@ class Engine:
                 else:
                     sizes.append(conv.cout_p * conv.k * conv.k * conv.cin_p)
             flat = torch.zeros(sum(sizes), device=self.dev, dtype=torch.float32)
-            dwp, jobs, off = {}, [], 0
+            dwp, jobs, off = {}, [[] for _ in STAGES], 0
             for conv, n in zip(convs, sizes):
                 view = flat[off:off + n]
                 off += n
                 dwp[conv.name] = view
                 g = grads[conv.name + ".weight"]
+                js = jobs[stage_of(conv.name)]
                 if conv is plan.stem:
-                    jobs.append((view, g, 64, 3, 49, 0, 3, 1, self.stem_kpad))
+                    js.append((view, g, 64, 3, 49, 0, 3, 1, self.stem_kpad))
                 else:
                     T = conv.k * conv.k
-                    jobs.append((view, g, g.shape[0], g.shape[1], T, 0 if conv.kind == "conv" else 1,
-                                 conv.cin_p, 1, T * conv.cin_p))
+                    js.append((view, g, g.shape[0], g.shape[1], T, 0 if conv.kind == "conv" else 1,
+                               conv.cin_p, 1, T * conv.cin_p))
             bns = plan.all_bns()
             sums = torch.zeros(sum(2 * C for _, C in bns), device=self.dev, dtype=torch.float64)
             bsum, off = {}, 0
@@ -281,7 +296,7 @@ class Engine:
                 bsum[name] = sums[off:off + 2 * C]
                 off += 2 * C
             st = {"key": key, "flat": flat, "dwp": dwp, "sums": sums, "bsum": bsum,
-                  "batch": ops.PackBatch(jobs)}
+                  "batches": [ops.PackBatch(j) if j else None for j in jobs]}
             self._gstate = st
         return st
 
@@ -515,9 +530,32 @@ class Engine:
                          grads[st.name + ".weight"], grads[st.name + ".bias"])
         return dz
 
-    def backward(self, S, dlogits, ddepth, params, grads):
+    def _stage_done(self, k):
+        """Every gradient of stage k has been issued: unpack its packed weight gradients into the
+        state_dict-shaped buffers (on the weight-gradient stream, behind them) and hand the stage
+        to the caller (the data-parallel all-reduce of its slice of the flat buffer)."""
+        if k in self._stages_done:
+            return
+        self._stages_done.add(k)
+        batch = self._gs["batches"][k]
+        side = self._side
+        if side is None:
+            if batch is not None:
+                self.ops.pack_weight_batch(batch)
+            if self._on_stage is not None:
+                self._on_stage(k)
+            return
+        side.wait_stream(torch.cuda.current_stream())       # BatchNorm gradients of the stage (main stream)
+        with torch.cuda.stream(side):
+            if batch is not None:
+                self.ops.pack_weight_batch(batch)
+            if self._on_stage is not None:
+                self._on_stage(k)
+
+    def backward(self, S, dlogits, ddepth, params, grads, on_stage=None):
         """dlogits [N,Ho,Wo,cout_p] NHWC contiguous.  grads: dict name -> tensor
-        (state_dict shape) to be filled for every trainable parameter."""
+        (state_dict shape) to be filled for every trainable parameter.  on_stage(k) is called
+        (with the weight-gradient stream current) as soon as stage k of net.STAGES is complete."""
         ops, plan = self.ops, self.plan
         N = S["N"]
         self.dev = dlogits.device
@@ -530,15 +568,15 @@ class Engine:
         self._gs = self._grad_state(grads)
         self._gs["flat"].zero_()
         self._gs["sums"].zero_()
+        self._on_stage, self._stages_done = on_stage, set()
         try:
             self._backward(S, dlogits, ddepth, params, grads)
-            if self._side is not None:
-                torch.cuda.current_stream().wait_stream(self._side)   # join before grads are used
-            ops.pack_weight_batch(self._gs["batch"])                  # packed dW -> state_dict layout
+            for k in range(len(STAGES)):
+                self._stage_done(k)                                   # whatever is still open
         finally:
             if self._side is not None:
-                torch.cuda.current_stream().wait_stream(self._side)
-            self._side, self._keep, self._gs = None, [], None
+                torch.cuda.current_stream().wait_stream(self._side)   # join before grads are used
+            self._side, self._keep, self._gs, self._on_stage = None, [], None, None
 
     def _backward(self, S, dlogits, ddepth, params, grads):
         ops, plan = self.ops, self.plan
@@ -578,8 +616,14 @@ class Engine:
             self._conv_wgrad(plan.fc, S["fc"], dd, N, 1, 1, grads["depth_fc.weight"])
             dpool = self._conv_dgrad(plan.fc, dd, N, 1, 1, wd_of(plan.fc))
             ops.avgpool_bwd(dpool, dcur, N, th * tw, 2048, 1)
+        self._stage_done(0)                     # head (deconvs, final layer, depth_fc) complete
         # ---- residual stages, reversed
+        prev_stage = None
         for blk, rec in zip(reversed(plan.blocks), reversed(S["blocks"])):
+            sk = stage_of(blk["name"])
+            if prev_stage is not None and sk != prev_stage:
+                self._stage_done(prev_stage)
+            prev_stage = sk
             out, xin, h, w = rec["out"], rec["in"], rec["h"], rec["w"]
             nconv = len(blk["convs"])
             dres = None

@@ -317,12 +317,12 @@ class Engine16(_net.Engine):
         return logits, depth, (S if save else None)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, S, dlogits, ddepth, params, grads):
+    def backward(self, S, dlogits, ddepth, params, grads, on_stage=None):
         self.dev = dlogits.device
         self._gs = None
         gs = self._grad_state(grads)
         gs["maxes"].zero_()
-        super().backward(S, dlogits, ddepth, params, grads)
+        super().backward(S, dlogits, ddepth, params, grads, on_stage=on_stage)
 
     def _backward(self, S, dlogits, ddepth, params, grads):
         ops, plan = self.ops, self.plan
@@ -359,8 +359,14 @@ class Engine16(_net.Engine):
             self._conv_wgrad(plan.fc, S["fc"], dd, N, 1, 1, grads["depth_fc.weight"])
             dpool = self._conv_dgrad(plan.fc, dd, N, 1, 1, S["packed"][plan.fc.name][1])
             ops.avgpool_bwd(dpool, dcur, N, th * tw, 2048, 1)
+        self._stage_done(0)                     # head (deconvs, final layer, depth_fc) complete
         # ---- residual stages, reversed
+        prev_stage = None
         for blk, rec in zip(reversed(plan.blocks), reversed(S["blocks"])):
+            sk = _net.stage_of(blk["name"])
+            if prev_stage is not None and sk != prev_stage:
+                self._stage_done(prev_stage)
+            prev_stage = sk
             (out, _), (xin, xin_sc), h, w = rec["out"], rec["in"], rec["h"], rec["w"]
             nconv = len(blk["convs"])
             mask = out[0]                       # hi plane of the block output: (out > 0)

@@ -320,6 +320,17 @@ def patch_sample(img_base, img_off, img_hwp, box, flip, color, mean_std, B, patc
           _p(trans, torch.float64), _stream())
 
 
+def patch_sample_occ(img_base, img_off, img_hwp, box, flip, color, mean_std, B, patch_w, patch_h,
+                     occ_base, occ_desc, occ_count, out, trans):
+    ms = None
+    if mean_std is not None:
+        ms = (ctypes.c_double * 6)(*[float(v) for v in mean_std])
+    _call("epb_patch_sample_occ", _p(img_base, torch.uint8), _p(img_off, torch.int64),
+          _p(img_hwp, torch.int32), _p(box, torch.float64), _p(flip, torch.int32), _p(color), ms, B,
+          patch_w, patch_h, _p(occ_base, torch.uint8), _p(occ_desc, torch.int64),
+          _p(occ_count, torch.int32), _p(out), _p(trans, torch.float64), _stream())
+
+
 def patch_joints(joints, box, trans, B, J, patch_w, patch_h, rect_3d_w, depth_in_image, label):
     _call("epb_patch_joints", _p(joints, torch.float64), _p(box, torch.float64), _p(trans, torch.float64),
           B, J, float(patch_w), float(patch_h), float(rect_3d_w), int(depth_in_image),
@@ -344,6 +355,13 @@ def project_labels(X, cam, box, B, J, patch_w, patch_h, rect3d_w, label, weight)
 
 
 # ------------------------------------------------------------------ optimiser
+def sumsq(x, n, total):
+    _call("epb_sumsq", _p(x), n, _p(total, torch.float64), _stream())
+
+
+def clip_scale(x, n, total, max_norm):
+    _call("epb_clip_scale", _p(x), n, _p(total, torch.float64), float(max_norm), _stream())
+
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step,
               grad_scale=1.0):

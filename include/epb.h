@@ -403,9 +403,16 @@ int epb_add3(const float* a, const float* b, const float* c, float* out, int64_t
 int epb_mask_scale(const float* x, const uint8_t* mask, float scale, float* out, int64_t n,
                    epb_stream_t stream);
 
+/* torch.nn.utils.clip_grad_norm_(parameters, max_norm) of the refiner loop (refiner/main.py:57)
+ * over a list of gradient tensors, without a host round trip: epb_sumsq adds sum(x^2) of one
+ * tensor to the DEVICE float64 scalar *total (caller zeroes); epb_clip_scale multiplies one
+ * tensor by clamp(max_norm / (sqrt(*total) + 1e-6), max = 1). */
+int epb_sumsq(const float* x, int64_t n, double* total, epb_stream_t stream);
+int epb_clip_scale(float* x, int64_t n, const double* total, double max_norm, epb_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Input pipeline (lib/utils/img_utils.py:246-298 get_single_patch_sample after the frame is
- * decoded; the occluder paste of lib/utils/augmentation.py is not built).
+ * decoded, including the occluder paste of lib/utils/augmentation.py:61-114).
  * ---------------------------------------------------------------------- */
 /* Crop + colour + normalisation of B frames in one launch, bit-exact against OpenCV:
  * generate_patch_image_cv (:114-127: gen_trans_from_patch_cv :72-105 with float32 point
@@ -423,6 +430,19 @@ int epb_patch_sample(const uint8_t* img_base, const int64_t* img_off, const int3
                      const double* box, const int32_t* flip, const float* color,
                      const double* mean_std_host, int B, int patch_w, int patch_h, float* out,
                      double* trans, epb_stream_t stream);
+/* The same with the synthetic-occlusion augmentation (img_utils.py:269-270, augmentation.py:
+ * 61-114 occlude_with_objects / paste_over): after the crop and BGR->RGB, up to 7 RGBA occluders
+ * per sample are alpha-blended IN ORDER into the uint8 patch -- float32 alpha*src + (1-alpha)*dst,
+ * truncated to uint8, bit-exact against numpy -- before the colour scale / normalisation.  The
+ * random draws and the cv2.resize of each occluder are host-side augmentation parameters:
+ *   occ_base            uint8 RGBA occluder images (already resized), one device buffer
+ *   occ_desc [B][7][5]  int64: byte offset, width, height, centre x, centre y (np.round'ed)
+ *   occ_count [B]       int32: occluders of sample b (0..7); all three NULL = no occluders. */
+int epb_patch_sample_occ(const uint8_t* img_base, const int64_t* img_off, const int32_t* img_hwp,
+                         const double* box, const int32_t* flip, const float* color,
+                         const double* mean_std_host, int B, int patch_w, int patch_h,
+                         const uint8_t* occ_base, const int64_t* occ_desc, const int32_t* occ_count,
+                         float* out, double* trans, epb_stream_t stream);
 /* Joint half (:283-296 + lib/core/integral_loss.py:170-177): joints [B][J][3] f64 (x, y image px;
  * z mm) through trans [B][6] (from epb_patch_sample), z / (rect_3d_w*scale) * patch_w (or the
  * box width when depth_in_image), then x/pw - 0.5, y/ph - 0.5, z/pw -> label [B][J*3] f64. */

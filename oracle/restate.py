@@ -819,11 +819,31 @@ def warp_affine_linear_u8(img, M, dst_w, dst_h):
     return out
 
 
+def paste_over(im_src, im_dst, center):
+    """lib/utils/augmentation.py:81-114: alpha-blend the RGBA im_src onto the uint8 im_dst in
+    place, centred at np.round(center); float32 arithmetic, truncated back to uint8."""
+    wh_src = np.asarray([im_src.shape[1], im_src.shape[0]])
+    wh_dst = np.asarray([im_dst.shape[1], im_dst.shape[0]])
+    center = np.round(center).astype(np.int32)
+    raw_start = center - wh_src // 2
+    raw_end = raw_start + wh_src
+    start = np.clip(raw_start, 0, wh_dst)
+    end = np.clip(raw_end, 0, wh_dst)
+    region_dst = im_dst[start[1]:end[1], start[0]:end[0]]
+    s0 = start - raw_start
+    s1 = wh_src + (end - raw_end)
+    region_src = im_src[s0[1]:s1[1], s0[0]:s1[0]]
+    alpha = region_src[..., 3:].astype(np.float32) / np.float32(255)
+    blend = alpha * region_src[..., 0:3].astype(np.float32) + (np.float32(1) - alpha) * region_dst.astype(np.float32)
+    im_dst[start[1]:end[1], start[0]:end[0]] = blend.astype(np.uint8)
+
+
 def patch_sample(cvimg, center_x, center_y, width, height, joints, joints_vis, patch_width,
                  patch_height, rect_3d_width, mean, std, scale=1.0, rot=0.0, do_flip=False,
-                 color_scale=(1.0, 1.0, 1.0), flip_pairs=(), depth_in_image=False):
+                 color_scale=(1.0, 1.0, 1.0), flip_pairs=(), depth_in_image=False, occluders=None):
     """lib/utils/img_utils.py:246-298 (get_single_patch_sample) after the image is decoded and
-    the augmentation parameters are drawn, without the occluder paste: crop by warpAffine
+    the augmentation parameters are drawn (occluders: the already resized RGBA images and their
+    centres, pasted by paste_over in order): crop by warpAffine
     (:114-127), BGR->RGB (:268), per-channel colour scale + clip + (x-mean)/std (:277-281,
     float32 * python float stays float32; minus / divided by np.float64 scalars is float64,
     stored back as float32 -- numpy >= 2 promotion, the version the golden run used), joints
@@ -838,6 +858,10 @@ def patch_sample(cvimg, center_x, center_y, width, height, joints, joints_vis, p
     trans = gen_trans_from_patch(c_x, center_y, width, height, patch_width, patch_height, scale, rot, inv=False)
     patch = warp_affine_linear_u8(img, trans, int(patch_width), int(patch_height))
     image = patch[:, :, ::-1]
+    if occluders:                      # :269-270, augmentation.py:61-78 after the draws / resizes
+        image = image.copy()
+        for rgba, center in occluders:
+            paste_over(rgba, image, np.asarray(center, dtype=np.float64))
     t = np.transpose(image, (2, 0, 1)).astype(np.float32)
     for c in range(t.shape[0]):
         t[c] = np.clip(t[c] * np.float32(color_scale[c]), 0, 255)

@@ -452,6 +452,34 @@ def patch_sample(img_base, img_off, img_hwp, box, flip, color, mean_std, B, patc
             trans[b].copy_(torch.from_numpy(tr.reshape(-1)))
 
 
+def patch_sample_occ(img_base, img_off, img_hwp, box, flip, color, mean_std, B, patch_w, patch_h,
+                     occ_base, occ_desc, occ_count, out, trans):
+    """CPU emulation of epb_patch_sample_occ through the numpy oracle (test infrastructure)."""
+    from oracle import restate
+    base = img_base.numpy().reshape(-1)
+    ob = occ_base.numpy().reshape(-1) if occ_base is not None else None
+    for b in range(B):
+        H, W, pitch = [int(v) for v in img_hwp[b]]
+        off = int(img_off[b])
+        img = np.lib.stride_tricks.as_strided(base[off:], shape=(H, W, 3), strides=(pitch, 3, 1))
+        bx = box[b].numpy()
+        fl = bool(flip[b]) if flip is not None else False
+        cs = color[b].numpy() if color is not None else np.ones(3, np.float32)
+        mean = None if mean_std is None else np.asarray(mean_std[:3], dtype=np.float64)
+        std = None if mean_std is None else np.asarray(mean_std[3:], dtype=np.float64)
+        occ = []
+        if ob is not None:
+            for k in range(int(occ_count[b])):
+                o, w, h, cx, cy = [int(v) for v in occ_desc[b, k]]
+                occ.append((ob[o:o + w * h * 4].reshape(h, w, 4), (cx, cy)))
+        t, _, _, tr = restate.patch_sample(img, bx[0], bx[1], bx[2], bx[3], np.zeros((1, 3)), np.zeros((1, 3)),
+                                           patch_w, patch_h, 2000.0, mean, std, bx[4], bx[5], fl, cs,
+                                           occluders=occ)
+        out[b].copy_(torch.from_numpy(t))
+        if trans is not None:
+            trans[b].copy_(torch.from_numpy(tr.reshape(-1)))
+
+
 def patch_joints(joints, box, trans, B, J, patch_w, patch_h, rect_3d_w, depth_in_image, label):
     jt = joints.reshape(B, J, 3).double()
     M = trans.reshape(B, 2, 3).double()
@@ -667,3 +695,13 @@ def final_preds(hm, N, J, H, W, center, scale, post_process, preds, maxvals):
     preds.view(N, J, 2).copy_(torch.from_numpy(p))
     if maxvals is not None:
         maxvals.view(N, J).copy_(torch.from_numpy(m.reshape(N, J)))
+
+
+def sumsq(x, n, total):
+    total += (x.reshape(-1)[:n].double() ** 2).sum()
+
+
+def clip_scale(x, n, total, max_norm):
+    coef = max_norm / (float(total.reshape(-1)[0]) ** 0.5 + 1e-6)
+    if coef < 1.0:
+        x.view(-1)[:n].mul_(float(np.float32(coef)))

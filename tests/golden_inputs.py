@@ -244,3 +244,19 @@ def final_preds_case(seed=23):
     center = np.stack([500 + rng.uniform(-60, 60, n), 480 + rng.uniform(-60, 60, n)], axis=1)
     scale = np.stack([2.0 + rng.uniform(0, 2, n)] * 2, axis=1) * np.array([1.0, 1.25])
     return hm, center, scale
+
+
+def occluder_set(seed=97, n=5):
+    """Synthetic stand-ins for the Pascal-VOC occluders of lib/utils/augmentation.py:8-58 (no
+    dataset offline): RGBA uint8 blobs of various sizes whose alpha plane has the three levels
+    the loader produces (0 outside, 192 on the eroded border, 255 inside)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        h, w = int(rng.integers(40, 140)), int(rng.integers(40, 140))
+        yy, xx = np.mgrid[0:h, 0:w]
+        r = np.sqrt(((xx - w / 2) / (w / 2)) ** 2 + ((yy - h / 2) / (h / 2)) ** 2)
+        alpha = np.where(r < 0.8, 255, np.where(r < 0.95, 192, 0)).astype(np.uint8)
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        out.append(np.concatenate([rgb, alpha[..., None]], axis=-1))
+    return out

@@ -217,6 +217,60 @@ def test_input_pipeline_bit_exact(golden, dev):
         assert np.array_equal(big[i].cpu().numpy(), t), i
 
 
+def test_occluder_paste_bit_exact(golden, dev):
+    """Synthetic-occlusion augmentation (lib/utils/augmentation.py:61-123) fused into the patch
+    kernel (epb_patch_sample_occ): get_single_patch_sample(..., occluder=...) BIT-EXACT against
+    the unmodified reference (same draws, cv2.resize of the occluders on the host, blend on the
+    device); occlude_with_objects / paste_over in their numpy form; a batch of 64 samples with
+    1..7 occluders each against the oracle."""
+    import random
+    pytest.importorskip("cv2")
+    import lib.utils.img_utils as iu
+    import lib.utils.augmentation as aug_m
+    g = golden("patch_occluders")
+    occ = gi.occluder_set()
+    for tag in gi.PATCH_CASES:
+        img, box, joints, vis, pw, ph, seed = gi.frame_case(tag)
+        for aug in (False, True):
+            k = tag + ("_aug" if aug else "")
+            np.random.seed(seed + 7); random.seed(seed + 7)
+            patch, label, weight, scale, rot = iu.get_single_patch_sample(
+                img, box[0], box[1], box[2], box[3], joints.copy(), vis.copy(), [], None, pw, ph, 2000.0, 2000.0,
+                MEAN, STD, aug, None, occluder=occ)
+            assert np.array_equal(patch, g[k + "_patch"]), k
+            assert np.max(np.abs(label - g[k + "_label"])) <= 1e-12
+    # numpy-form API: occlude_with_objects / paste_over == the oracle's paste_over
+    rng = np.random.default_rng(11)
+    im = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    np.random.seed(5); random.seed(5)
+    lst = aug_m.draw_occluders(128, 96, occ)
+    np.random.seed(5); random.seed(5)
+    got = aug_m.occlude_with_objects(im, occ)
+    want = im.copy()
+    for rgba, c in lst:
+        restate.paste_over(rgba, want, np.asarray(c, dtype=np.float64))
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    dst = im.copy()
+    aug_m.paste_over(occ[0], dst, np.array([10.4, 90.6]))                 # partly outside the image
+    want = im.copy()
+    restate.paste_over(occ[0], want, np.array([10.4, 90.6]))
+    assert np.array_equal(dst, want)
+    # a loader-sized batch
+    a = gi.frame_case("noise64")
+    B = 64
+    cx, cy = 500 + rng.uniform(-50, 50, B), 500 + rng.uniform(-50, 50, B)
+    w, h = 800 + rng.uniform(-100, 100, B), 800 + rng.uniform(-100, 100, B)
+    sc, rot = 1 + rng.uniform(-0.25, 0.25, B), rng.uniform(-60, 60, B)
+    np.random.seed(9); random.seed(9)
+    per = [aug_m.draw_occluders(256, 256, occ) for _ in range(B)]
+    big, _, _ = iu.generate_patch_batch_device([a[0]] * B, cx, cy, w, h, 256, 256, scale=sc, rot=rot, mean=MEAN,
+                                               std=STD, occluders=per)
+    for i in (0, 17, 63):
+        t, _, _, _ = restate.patch_sample(a[0], cx[i], cy[i], w[i], h[i], a[2], a[3], 256, 256, 2000.0, MEAN, STD,
+                                          sc[i], rot[i], occluders=per[i])
+        assert np.array_equal(big[i].cpu().numpy(), t), i
+
+
 def test_final_preds_bit_exact(golden, dev):
     """lib/core/inference.py:43-68 on the device (epb_final_preds) against the unmodified
     reference: coordinates bit-exact (float32), through the reference-shaped numpy API and
@@ -766,3 +820,59 @@ def test_refiner_vs_reference_golden(golden, dev, precision):
     masks = [(torch.rand(24, 128, device=dev) >= 0.5).cpu() for _ in range(10)]
     o1, o2 = rr.forward(sd, x.detach().cpu(), training=True, masks=masks, p_dropout=0.5)
     assert relerr(q1.detach().cpu().numpy(), o1.numpy()) <= 1e-3 and relerr(q2.detach().cpu().numpy(), o2.numpy()) <= 1e-3
+
+
+def test_refiner_train_loop_and_checkpoint_gpu(dev, tmp_path):
+    """refiner/main.py train() / test() / save_ckpt on the device (reference refiner/main.py:31-84):
+    one epoch against an independent loop (oracle network + torch.optim.Adam + torch's
+    clip_grad_norm_ on the CPU), checkpoint resumes in torch.optim.Adam; prints samples/s."""
+    import logging
+    import time
+    import types
+    from oracle import restate_refiner as rr
+    from epipolarpose_b200.refiner import main as rmain, model as rmodel, utils as rutils, data as rdata
+    import lib.utils.utils as U
+    sd = rr.init_state(rr.param_shapes(1024, 45, 45), 17)
+    m = rmodel.LinearModelPG(linear_size=1024, p_dropout=0.0, input_size=45, output_size=45).to(dev)
+    m.load_state_dict(sd)
+    ds = rdata.SyntheticPoses(is_train=True, n=256, seed=3)
+    dl = torch.utils.data.DataLoader(ds, batch_size=64, shuffle=False)
+    args = types.SimpleNamespace(lr=1e-3, lr_decay=2, lr_gamma=0.9)
+    opt = U.FusedAdam(list(m.parameters()), lr=args.lr)
+    crit = torch.nn.MSELoss(reduction='mean')
+    step, lr_now = rmain.train(m, dl, opt, 0, args.lr, crit, args, logging.getLogger("t"))
+    assert step == 4
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    plist = [v for k, v in p.items() if torch.is_tensor(v) and v.requires_grad]
+    ro = torch.optim.Adam(plist, lr=args.lr)
+    g = 0
+    for inp, tar in dl:
+        g += 1
+        if g % args.lr_decay == 0 or g == 1:
+            for pg in ro.param_groups:
+                pg['lr'] = args.lr * args.lr_gamma ** (g / args.lr_decay)
+        o1, o2 = rr.forward(p, inp, training=True)
+        ro.zero_grad()
+        (torch.nn.functional.mse_loss(o1, tar) + torch.nn.functional.mse_loss(o2, tar)).backward()
+        torch.nn.utils.clip_grad_norm_(plist, max_norm=1.)
+        ro.step()
+    for k, q in m.named_parameters():
+        a, b = q.detach().cpu().numpy(), p[k].detach().numpy()
+        assert np.max(np.abs(a - b)) <= 1e-3 * np.max(np.abs(b)) + 5e-3 * (1 if k.endswith(".bias") else 0), k
+    err = rmain.test(m, torch.utils.data.DataLoader(rdata.SyntheticPoses(False, n=128, seed=3), batch_size=64))
+    assert np.isfinite(err)
+    rutils.save_ckpt({'epoch': 1, 'lr': lr_now, 'step': step, 'err': err, 'state_dict': m.state_dict(),
+                      'optimizer': opt.state_dict()}, ckpt_path=str(tmp_path), is_best=False)
+    ck = torch.load(str(tmp_path / 'last.pth.tar'), weights_only=False)
+    t_opt = torch.optim.Adam([torch.nn.Parameter(v.detach().cpu().clone()) for v in m.parameters()], lr=1e-3)
+    t_opt.load_state_dict(ck['optimizer'])
+    # throughput of the loop body at the reference's batch size (64): steps/s -> samples/s
+    big = torch.utils.data.DataLoader(rdata.SyntheticPoses(True, n=64 * 50, seed=5), batch_size=64)
+    rmain.train(m, big, opt, step, lr_now, crit, args, logging.getLogger("t"))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rmain.train(m, big, opt, step, lr_now, crit, args, logging.getLogger("t"))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print("refiner train loop: %.0f samples/s (batch 64, %.2f ms/step, eager)" % (64 * 50 / dt, dt / 50 * 1e3))

@@ -385,9 +385,19 @@ def test_input_pipeline_surface_emulated(tmp_path):
                                                        [a[1][2], b[1][2]], [a[1][3], b[1][3]], 48, 48,
                                                        mean=MEAN, std=STD)
         assert np.array_equal(out[1].numpy(), g["edge48_patch"]) and out.shape == (2, 3, 48, 48)
-        with pytest.raises(NotImplementedError):
-            iu.get_single_patch_sample(a[0], 1, 1, 1, 1, a[2], a[3], [], None, 8, 8, 1, 1, None, None, False, None,
-                                       occluder=[1])
+        # occluder augmentation (augmentation.py:61-123) through the emulated epb_patch_sample_occ:
+        # same draws / resizes as the unmodified reference, bit-exact patches
+        go = dict(np.load(os.path.join(ROOT, "tests", "golden", "patch_occluders.npz")))
+        occ = gi.occluder_set()
+        for tag in ("noise64", "edge48"):
+            img, box, joints, vis, pw, ph, seed = gi.frame_case(tag)
+            for aug in (False, True):
+                k = tag + ("_aug" if aug else "")
+                np.random.seed(seed + 7); random.seed(seed + 7)
+                patch, label, weight, scale, rot = iu.get_single_patch_sample(
+                    img, box[0], box[1], box[2], box[3], joints.copy(), vis.copy(), [], None, pw, ph, 2000.0,
+                    2000.0, MEAN, STD, aug, None, occluder=occ)
+                assert np.array_equal(patch, go[k + "_patch"]), k
         with pytest.raises(ValueError):
             iu.generate_patch_batch_device([a[0].astype(np.float32)], [1], [1], [1], [1], 8, 8)
         with pytest.raises(IOError):
@@ -540,18 +550,39 @@ def _ddp_worker(rank, world, port, q):
     import torch.distributed as d2
     orig = d2.all_reduce
 
-    def avg(t, op=None):          # gloo has no AVG: emulate with SUM / world
+    class _Done:
+        def wait(self):
+            return True
+
+    def avg(t, op=None, async_op=False):          # gloo has no AVG: emulate with SUM / world
         orig(t)
         t /= world
+        return _Done()
     d2.all_reduce = avg
     (m(x) * g).sum().backward()
-    q.put((rank, {k: p.grad.numpy().copy() for k, p in m.named_parameters()}))
+    got = {k: p.grad.numpy().copy() for k, p in m.named_parameters()}
+    # the semantics of nn.DataParallel over replicas (scripts/train.py:94,143): the all-reduced
+    # gradient is the MEAN of the per-replica gradients, each with its own BatchNorm statistics
+    # -- recomputed here on one process, replica by replica, without any collective
+    ref = None
+    for r in range(world):
+        m1 = models.pose3d_resnet.get_pose_net(cfg, False, ops=emul_ops, allreduce_grads=False)
+        m1.load_state_dict(restate_net.init_state(restate_net.param_shapes(18, 2, True, 4), 1))
+        m1.train()
+        xr = torch.from_numpy(gi.images(4, 32, 100))[2 * r:2 * r + 2]
+        gr = torch.from_numpy(gi.grad_like((4, 8, 8, 8), 101))[2 * r:2 * r + 2]
+        (m1(xr) * gr).sum().backward()
+        cur = {k: p.grad.numpy().astype(np.float64) / world for k, p in m1.named_parameters()}
+        ref = cur if ref is None else {k: ref[k] + cur[k] for k in ref}
+    worst = max(float(np.max(np.abs(got[k] - ref[k])) / max(np.max(np.abs(ref[k])), 1e-30)) for k in got)
+    q.put((rank, (got, worst)))
     dist.destroy_process_group()
 
 
 def test_data_parallel_allreduce_world2_gloo():
-    """Two ranks, each with its own half batch: after the single all-reduce in
-    the model's backward both ranks hold identical (averaged) gradients."""
+    """Two ranks, each with its own half batch: after the stage-wise all-reduce in the model's
+    backward both ranks hold identical gradients, equal to the mean of the per-replica gradients
+    (per-replica BatchNorm statistics: the reference's nn.DataParallel semantics)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -562,9 +593,10 @@ def test_data_parallel_allreduce_world2_gloo():
     res = dict(q.get(timeout=240) for _ in ps)
     for p in ps:
         p.join(60)
-    for k in res[0]:
-        assert np.array_equal(res[0][k], res[1][k]), k
-    assert any(np.abs(v).max() > 0 for v in res[0].values())
+    for k in res[0][0]:
+        assert np.array_equal(res[0][0][k], res[1][0][k]), k
+    assert any(np.abs(v).max() > 0 for v in res[0][0].values())
+    assert res[0][1] <= 1e-5 and res[1][1] <= 1e-5      # == mean of the per-replica gradients
 
 
 def test_bench_reference_arm_cli():
@@ -671,3 +703,81 @@ def test_fused_optimizers_interchange_with_torch_optim_and_survive_rematerialisa
             q.data = q.data.clone()                               # what model.to(device) does
         step(((pa, oa), (pb, ob)), [torch.randn_like(w) for w in ws])
         assert max((a - b).abs().max().item() for a, b in zip(pa, pb)) <= 1e-6
+
+
+def test_refiner_train_loop_and_checkpoint_interop_emulated(tmp_path):
+    """epipolarpose_b200/refiner/main.py train() / test() / save_ckpt (reference refiner/main.py:
+    31-84, refiner/utils.py:18-36) through the emulated ABI: parameters after an epoch equal an
+    independent loop built from the oracle network + torch.optim.Adam + torch's clip_grad_norm_
+    + the reference's lr_decay; the checkpoint resumes in torch.optim.Adam (and back)."""
+    import logging
+    import types
+    from oracle import restate_refiner as rr
+    from epipolarpose_b200.refiner import main as rmain, model as rmodel, utils as rutils, data as rdata
+    import lib.utils.utils as U
+    rmodel.LinearModelPG._backend[0] = emul_ops
+    rutils._backend[0] = emul_ops
+    U._backend[0] = emul_ops
+    try:
+        sd = rr.init_state(rr.param_shapes(128, 45, 45), 17)
+        m = rmodel.LinearModelPG(linear_size=128, p_dropout=0.0, input_size=45, output_size=45, precision="fp32")
+        m.load_state_dict(sd)
+        ds = rdata.SyntheticPoses(is_train=True, n=96, seed=3)
+        dl = torch.utils.data.DataLoader(ds, batch_size=32, shuffle=False)
+        args = types.SimpleNamespace(lr=1e-3, lr_decay=2, lr_gamma=0.9)
+        opt = U.FusedAdam(list(m.parameters()), lr=args.lr)
+        crit = torch.nn.MSELoss(reduction='mean')
+        step, lr_now = rmain.train(m, dl, opt, 0, args.lr, crit, args, logging.getLogger("t"))
+        assert step == 3 and abs(lr_now - 1e-3 * 0.9 ** 1.0) < 1e-12      # decayed at steps 1 and 2
+        # independent loop
+        p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+             for k, v in sd.items()}
+        plist = [v for k, v in p.items() if torch.is_tensor(v) and v.requires_grad]
+        ro = torch.optim.Adam(plist, lr=args.lr)
+        g = 0
+        for inp, tar in dl:
+            g += 1
+            if g % args.lr_decay == 0 or g == 1:
+                for pg in ro.param_groups:
+                    pg['lr'] = args.lr * args.lr_gamma ** (g / args.lr_decay)
+            o1, o2 = rr.forward(p, inp, training=True)
+            ro.zero_grad()
+            (torch.nn.functional.mse_loss(o1, tar) + torch.nn.functional.mse_loss(o2, tar)).backward()
+            torch.nn.utils.clip_grad_norm_(plist, max_norm=1.)
+            ro.step()
+        for k, q in m.named_parameters():
+            # Adam normalises by sqrt(v): a bias in front of a BatchNorm has a noise-only gradient
+            # (exactly zero in exact arithmetic) that becomes +-lr steps of arbitrary sign
+            a, b = q.detach().numpy(), p[k].detach().numpy()
+            assert np.max(np.abs(a - b)) <= 2e-4 * np.max(np.abs(b)) + 3 * 1e-3 * (1 if k.endswith(".bias") else 0), k
+        err = rmain.test(m, torch.utils.data.DataLoader(rdata.SyntheticPoses(False, n=64, seed=3), batch_size=32))
+        assert np.isfinite(err) and err > 0
+        # checkpoint: the reference's dictionary, optimizer state in the torch.optim layout
+        rutils.save_ckpt({'epoch': 1, 'lr': lr_now, 'step': step, 'err': err, 'state_dict': m.state_dict(),
+                          'optimizer': opt.state_dict()}, ckpt_path=str(tmp_path), is_best=True)
+        ck = torch.load(str(tmp_path / 'best.pth.tar'), weights_only=False)
+        m2 = rmodel.get_model(str(tmp_path / 'best.pth.tar'), linear_size=128, p_dropout=0.0, precision="fp32")
+        for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+            assert torch.equal(a, b), k
+        t_opt = torch.optim.Adam([torch.nn.Parameter(v.detach().clone()) for v in m.parameters()], lr=1e-3)
+        t_opt.load_state_dict(ck['optimizer'])                  # loads into the reference's optimiser
+        assert int(t_opt.state[t_opt.param_groups[0]['params'][0]]['step']) == 3
+        opt2 = U.FusedAdam(list(m2.parameters()), lr=1e-3)
+        opt2.load_state_dict(ro.state_dict())                   # and a torch.optim checkpoint into ours
+        assert opt2.state['flat0']['step'] == 3
+        # clip_grad_norm_ alone against torch
+        ws = [torch.nn.Parameter(torch.randn(7, 5)), torch.nn.Parameter(torch.randn(11))]
+        for w in ws:
+            w.grad = torch.randn_like(w) * 3
+        ref = [w.grad.clone() for w in ws]
+        tn = torch.nn.utils.clip_grad_norm_([torch.nn.Parameter(r) for r in ref], 1.0)   # dummy: norm only
+        want = [r * min(1.0, 1.0 / (float(torch.sqrt(sum((r ** 2).sum() for r in ref))) + 1e-6)) for r in ref]
+        got_norm = rutils.clip_grad_norm_(ws, 1.0)
+        assert abs(float(got_norm) - float(torch.sqrt(sum((r ** 2).sum() for r in ref)))) <= 1e-5
+        for w, r in zip(ws, want):
+            assert relerr(w.grad.numpy(), r.numpy()) <= 1e-6
+    finally:
+        real = __import__("epipolarpose_b200.ops", fromlist=["ops"])
+        rmodel.LinearModelPG._backend[0] = None
+        rutils._backend[0] = real
+        U._backend[0] = real

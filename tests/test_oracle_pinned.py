@@ -2,13 +2,16 @@
 against golden vectors produced by the UNMODIFIED reference
 (tests/golden/make_golden.py).  The reference ships no tests of its own
 (SURVEY.md section 4), so these vectors are the pin."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import restate, restate_net
 from tests import golden_inputs as gi
-from tests.conftest import relerr
+from tests.conftest import ROOT, relerr
 
 
 @pytest.mark.parametrize("tag", list(gi.SOFTARGMAX_CASES))
@@ -235,3 +238,29 @@ def test_eight_point_fallback(golden):
         assert np.max(np.abs(x - g["x_8pt"][i])) <= 1e-4
         x, st = restate.polynomial_triangulation(u1[i], P1[i], u2[i], P1[i])
         assert np.max(np.abs(x - g["x_same"][i])) <= 1e-4 and np.array_equal(st.astype(np.int64), g["st_same"][i])
+
+
+def test_occluder_paste_bit_exact(golden):
+    """Synthetic-occlusion augmentation (lib/utils/augmentation.py:61-123 inside
+    get_single_patch_sample, img_utils.py:269-270): the mirror's draws (draw_occluders: same
+    np.random / random calls, cv2.resize) + restate.paste_over reproduce the unmodified
+    reference's patches BIT-EXACTLY."""
+    import random
+    cv2 = pytest.importorskip("cv2")
+    sys.path.insert(0, os.path.join(ROOT, "epipolarpose_b200"))
+    import lib.utils.img_utils as iu
+    from lib.utils.augmentation import draw_occluders
+    g = golden("patch_occluders")
+    occ = gi.occluder_set()
+    mean, std = np.array([123.675, 116.280, 103.530]), np.array([58.395, 57.120, 57.375])
+    for tag in gi.PATCH_CASES:
+        img, box, joints, vis, pw, ph, seed = gi.frame_case(tag)
+        for aug in (False, True):
+            np.random.seed(seed + 7); random.seed(seed + 7)
+            scale, rot, fl, cs = iu.do_augmentation() if aug else (1.0, 0, False, [1.0, 1.0, 1.0])
+            lst = draw_occluders(pw, ph, occ)
+            t, lab, wt, tr = restate.patch_sample(img, box[0], box[1], box[2], box[3], joints, vis, pw, ph,
+                                                  2000.0, mean, std, scale, rot, fl, cs, occluders=lst)
+            k = tag + ("_aug" if aug else "")
+            assert np.array_equal(t, g[k + "_patch"]), k
+            assert np.max(np.abs(lab - g[k + "_label"])) <= 1e-9

@@ -479,7 +479,20 @@ def cpu_reference(steps, warmup, tuples, layers=50):
     for _ in range(steps):
         one()
     dt = (time.perf_counter() - t0) / max(steps, 1)
+    model_name, phys = "unknown", None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    model_name = line.split(":", 1)[1].strip()
+                    break
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+    except Exception:
+        pass
     return {"value": round(tuples / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_model": model_name, "physical_cores": phys, "logical_cores": os.cpu_count(),
+            "threads_used": cores,
             "sample": "%d step(s) of %d view-tuples (%d images) of the same workload, R%d, "
                       "%.1f s/step; cv2.solve restated with numpy.linalg, cv2.getAffineTransform as its 6x6 LU"
                       % (steps, tuples, n_img, layers, dt),
@@ -516,7 +529,7 @@ def main():
                     choices=["fp32", "tf32", "tf32x3", "f16x3"])
     ap.add_argument("--layers", type=int, default=50)
     ap.add_argument("--tuples", type=int, default=TUPLES, help="view-tuples per GPU per step")
-    ap.add_argument("--cpu-tuples", type=int, default=2, help="bounded CPU sample size")
+    ap.add_argument("--cpu-tuples", type=int, default=8, help="bounded CPU sample size (view-tuples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly")
     args = ap.parse_args()

@@ -3,7 +3,7 @@
   C1  configs[0]: R50, 256x256, batch 1, .eval(), J=16 -- against the UNMODIFIED reference
       (tests/golden/net_c1.npz, made by tests/golden/make_golden_sizes.py)
   C2  configs[1] slice: R50, 256x256, J=17, D=64, .train(), N=8, forward + backward -- every
-      one of the 161 gradient tensors against the unmodified reference (net_c2.npz)
+      one of the 170 gradient tensors against the unmodified reference (net_c2.npz)
   C3  configs[2]: 16 tuples x 4 views through model -> soft-argmax -> patch->image ->
       iterative-LS triangulation -> labels -> L1 loss -> backward, each stage against the
       pinned numpy oracle on the SAME inputs at the stage boundary
@@ -123,7 +123,7 @@ def test_c2_train_slice_vs_reference(golden, dev, precision):
     go = torch.from_numpy(gi.grad_like_big(out.shape, c["seed"] + 1)).to(dev)
     (out * go).sum().backward()
     rows = _check_gradients(model, g, ("final_layer.weight", "final_layer.bias"))
-    assert len(rows) == 161
+    assert len(rows) == len(list(model.named_parameters())) == 170
     sd = model.state_dict()
     assert relerr(sd["bn1.running_mean"].cpu().numpy(), g["ref/bn1.running_mean"]) <= 1e-4
     assert relerr(sd["bn1.running_var"].cpu().numpy(), g["ref/bn1.running_var"]) <= 1e-4

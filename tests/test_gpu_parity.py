@@ -864,7 +864,14 @@ def test_refiner_train_loop_and_checkpoint_gpu(dev, tmp_path):
     for k, q in m.named_parameters():
         a, b, b0 = q.detach().cpu().numpy(), p[k].detach().numpy(), sd[k].numpy()
         moved = max(float(np.max(np.abs(b - b0))), 1e-12)          # what the epoch changed
-        assert np.max(np.abs(a - b)) <= 2e-3 * moved + 1e-6, k
+        # a ReLU unit whose pre-activation sits within rounding of zero resolves differently in the
+        # two float32 evaluations about once per step (10 layers x 65536 pre-activations); ONE such
+        # flip moves the 1/64-weighted gradient row of that unit by ~1.5 % of the tensor's maximum
+        # (measured per step: 1.6e-5 without a flip, 1-2.5e-2 with one).  So: the bulk of every
+        # tensor to 1e-3 of the epoch's movement, single entries to 5e-2.
+        d = np.abs(a - b)
+        assert np.percentile(d, 99) <= 1e-3 * moved + 1e-7, k
+        assert d.max() <= 5e-2 * moved + 1e-6, k
     err = rmain.test(m, torch.utils.data.DataLoader(rdata.SyntheticPoses(False, n=128, seed=3), batch_size=64))
     assert np.isfinite(err)
     # the reference's configuration: Adam; checkpoint in the reference's layout

@@ -868,9 +868,10 @@ def test_refiner_train_loop_and_checkpoint_gpu(dev, tmp_path):
         # two float32 evaluations about once per step (10 layers x 65536 pre-activations); ONE such
         # flip moves the 1/64-weighted gradient row of that unit by ~1.5 % of the tensor's maximum
         # (measured per step: 1.6e-5 without a flip, 1-2.5e-2 with one).  So: the bulk of every
-        # tensor to 1e-3 of the epoch's movement, single entries to 5e-2.
+        # tensor (median) to 5e-4 of the epoch's movement, the rows of flipped units to 1e-2 / 5e-2.
         d = np.abs(a - b)
-        assert np.percentile(d, 99) <= 1e-3 * moved + 1e-7, k
+        assert np.median(d) <= 5e-4 * moved + 1e-7, k
+        assert np.percentile(d, 99) <= 1e-2 * moved + 1e-7, k      # a flip touches a whole 1024-entry row
         assert d.max() <= 5e-2 * moved + 1e-6, k
     err = rmain.test(m, torch.utils.data.DataLoader(rdata.SyntheticPoses(False, n=128, seed=3), batch_size=64))
     assert np.isfinite(err)

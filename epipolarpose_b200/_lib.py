@@ -69,6 +69,7 @@ _PROTOS = {
     "epb_bn_act_split": (c_int, [c_p] * 8 + [c_int, c_i64, c_int, c_p, c_p, c_p]),
     "epb_bn_relu_maxpool_split": (c_int, [c_p] * 6 + [c_int] * 4 + [c_p]),
     "epb_im2col_split": (c_int, [c_p] * 3 + [c_int] * 11 + [c_p]),
+    "epb_split16": (c_int, [c_p, ctypes.c_longlong, c_p, c_p, c_p, c_p]),
     "epb_split16_batch": (c_int, [c_p, c_int, ctypes.c_longlong, c_p, c_p]),
     "epb_conv16_fprop": (c_int, [ctypes.POINTER(ConvGeom)] + [c_p] * 8),
     "epb_conv16_wgrad": (c_int, [ctypes.POINTER(ConvGeom)] + [c_p] * 6 + [ctypes.c_longlong, c_p]),

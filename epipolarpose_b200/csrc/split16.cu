@@ -276,6 +276,43 @@ split_apply_kernel(const epb_split_job* __restrict__ jobs, int njobs,
   }
 }
 
+// single tensor, pointers as kernel arguments (no device job table: usable on tensors whose
+// address is only known at call time, e.g. the logit gradient handed over by autograd)
+__global__ void __launch_bounds__(kThreads)
+split_amax_one_kernel(const float4* __restrict__ src, int64_t n4, uint32_t* __restrict__ amax) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
+    const float4 v = ldg_stream(src + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  m = warp_max(m);
+  __shared__ float sm[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, sm[w]);
+    if (m > 0.f) atomicMax(amax, __float_as_uint(m));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+split_apply_one_kernel(const float4* __restrict__ src, int64_t n4, const uint32_t* __restrict__ amax,
+                       uint2* __restrict__ dst, float* __restrict__ sc) {
+  const float s = pow2_scale(__uint_as_float(*amax));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc[0] = s;
+    sc[1] = 1.f / s;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
+    const float4 v = ldg_stream(src + i);
+    uint2 hi, lo;
+    split2(v.x, v.y, s, hi.x, lo.x);
+    split2(v.z, v.w, s, hi.y, lo.y);
+    dst[i] = hi;
+    dst[n4 + i] = lo;
+  }
+}
+
 // ------------------------------------------------------------------ BatchNorm backward
 constexpr int kRowsPerThread = 32;
 
@@ -660,6 +697,21 @@ EPB_API int epb_act_scale(const double* stats, const float* scale, const float* 
   EPB_CHECK_ARG((stats2 == nullptr) == (scale2 == nullptr) && (scale2 == nullptr) == (shift2 == nullptr));
   act_scale_kernel<<<1, 1024, 0, as_stream(stream)>>>(stats, scale, shift, (double)M, C, stats2,
                                                       scale2, shift2, res_sc, sc);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_split16(const float* src, long long n, epb_half* dst, float* sc, uint32_t* amax_ws,
+                        epb_stream_t stream) {
+  EPB_CHECK_ARG(src && dst && sc && amax_ws && n > 0 && n % 4 == 0);
+  cudaStream_t st = as_stream(stream);
+  EPB_CUDA(cudaMemsetAsync(amax_ws, 0, sizeof(uint32_t), st));
+  const int64_t n4 = n / 4;
+  split_amax_one_kernel<<<ew_blocks(n4), kThreads, 0, st>>>(reinterpret_cast<const float4*>(src), n4,
+                                                            amax_ws);
+  EPB_LAUNCH_CHECK();
+  split_apply_one_kernel<<<ew_blocks(n4), kThreads, 0, st>>>(reinterpret_cast<const float4*>(src), n4,
+                                                             amax_ws, reinterpret_cast<uint2*>(dst), sc);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

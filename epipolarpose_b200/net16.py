@@ -12,8 +12,9 @@ Kept per conv: the raw output z (fp32, for the BatchNorm backward) and the post-
 split tensor (the next layer's operand).  Gradients w.r.t. activations stay fp32 (dgrad
 epilogue output, accumulate target of the residual joins); gradients w.r.t. conv outputs
 (dz) are split tensors with a per-tensor power-of-two scale derived on the device from the
-BatchNorm-backward reductions.  The backward of the final layer consumes the fp32 logit
-gradient directly through the 3xTF32 kernels of net.Engine (its operands are not split).
+BatchNorm-backward reductions; the fp32 logit gradient that enters the network's backward is
+split once (amax + split).  Heads whose channel count is not a whole number of 64-channel blocks
+(test-sized) keep their backward on the 3xTF32 kernels of net.Engine.
 """
 import os
 
@@ -62,7 +63,8 @@ class Engine16(_net.Engine):
                   # the image patch matrix keeps a static scale: |pixel| <= 4094 representable
                   "img_sc": torch.tensor([IMG_SCALE, 1.0 / IMG_SCALE, 65504.0 / IMG_SCALE, 0.0],
                                          device=self.dev, dtype=torch.float32),
-                  "ws": torch.empty(WGRAD_WS_FLOATS, device=self.dev, dtype=torch.float32)}
+                  "ws": torch.empty(WGRAD_WS_FLOATS, device=self.dev, dtype=torch.float32),
+                  "amax1": torch.zeros(1, device=self.dev, dtype=torch.int32)}
             self._cst = st
         return st
 
@@ -303,8 +305,10 @@ class Engine16(_net.Engine):
             fb[:fin.cout] = fbias
             fbias = fb
         logits, ho, wo = self._conv_fwd16(fin, src, src_sc, N, h, w, w16(fin), bias=fbias)
-        # the final layer's backward runs on the 3xTF32 kernels from (z, BatchNorm affine)
+        # the final layer's backward: split operands when the head has whole 64-channel blocks,
+        # else the 3xTF32 kernels from (z, BatchNorm affine)
         S["final"] = (zlast, (stlast.scale, stlast.shift), h, w)
+        S["final16"] = (src, src_sc)
         depth = None
         if plan.fc is not None:                 # :202-210
             tr, tr_sc, th, tw = S["trunk"]
@@ -331,7 +335,7 @@ class Engine16(_net.Engine):
         def wd16(conv):
             return S["w16"][conv.name][1]
 
-        # ---- final layer (fp32 logit gradient: 3xTF32 kernels)
+        # ---- final layer
         fin = plan.final
         src, aff, h, w = S["final"]
         Ho, Wo = fin.out_hw(h, w)
@@ -342,8 +346,19 @@ class Engine16(_net.Engine):
             gb.copy_(tmp[:fin.cout])
         else:
             ops.colsum(dlogits, N * Ho * Wo, fin.cout_p, gb)
-        self._conv_wgrad(fin, src, dlogits, N, h, w, grads[fin.name + ".weight"], affine=aff)
-        dcur = self._conv_dgrad(fin, dlogits, N, h, w, S["packed"][fin.name][1])
+        if fin.cout_p % 64 == 0:
+            # the fp32 logit gradient becomes a split operand (amax + split, one batched call):
+            # data and weight gradient on the split kernels like every other layer (deterministic)
+            dl16 = self._half(N, Ho, Wo, fin.cout_p)
+            dl_sc = torch.empty(2, device=self.dev, dtype=torch.float32)
+            ops.split16(dlogits.reshape(-1), dl16.reshape(-1), dl_sc, self._consts()["amax1"])
+            fsrc, fsrc_sc = S["final16"]
+            self._conv_wgrad16(fin, fsrc, fsrc_sc, dl16, dl_sc, N, h, w)
+            dcur = self._conv_dgrad16(fin, dl16, dl_sc, N, h, w, wd16(fin))
+        else:
+            # few output channels (test-sized heads): the 3xTF32 kernels take the fp32 gradient
+            self._conv_wgrad(fin, src, dlogits, N, h, w, grads[fin.name + ".weight"], affine=aff)
+            dcur = self._conv_dgrad(fin, dlogits, N, h, w, S["packed"][fin.name][1])
         # ---- deconv head, reversed
         for (conv, (bname, C)), (dsrc, dsrc_sc, z, dh, dw) in zip(reversed(plan.deconvs),
                                                                   reversed(S["deconv"])):

@@ -18,7 +18,7 @@ launches = 0
 # kernels launched per C-ABI call (for the gpu_launches accounting)
 _KERNELS_PER_CALL = {
     "epb_softargmax_fwd": 2, "epb_bn_bwd_apply": 2, "epb_colsum": 3,
-    "epb_split16_batch": 3, "epb_bn_bwd_apply_split": 2, "epb_conv16_wgrad": 2,
+    "epb_split16_batch": 3, "epb_split16": 3, "epb_bn_bwd_apply_split": 2, "epb_conv16_wgrad": 2,
 }
 
 
@@ -224,6 +224,10 @@ class SplitBatch:
         dev = self.jobs[0][1].device
         self.table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
         self.amax = torch.zeros(len(self.jobs), dtype=torch.int32, device=dev)
+
+
+def split16(src, dst, sc, amax_ws):
+    _call("epb_split16", _p(src), src.numel(), _p(dst, _H), _p(sc), _p(amax_ws, torch.int32), _stream())
 
 
 def split16_batch(batch):

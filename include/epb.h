@@ -245,6 +245,12 @@ typedef struct epb_split_job {
 int epb_split16_batch(const epb_split_job* jobs, int njobs, long long total_blocks,
                       uint32_t* amax_ws, epb_stream_t stream);
 
+/* one tensor (n % 4 == 0), pointers as arguments: for tensors whose address is only known at
+ * call time (the logit gradient autograd hands to the network's backward).  amax_ws: one
+ * uint32 of DEVICE scratch. */
+int epb_split16(const float* src, long long n, epb_half* dst, float* sc, uint32_t* amax_ws,
+                epb_stream_t stream);
+
 /* epb_conv_fprop on split operands: in [2][N,Hi,Wi,Cin], w [2][Cout][Tw*Cin] (the packed
  * operand of epb_pack_weight, split).  Cin % 64 == 0, Cout % 4 == 0.  CTA pairs
  * (tcgen05 cta_group::2, M = 256), A and B tiles by TMA (5-D / 3-D tensor maps; the

@@ -596,6 +596,10 @@ def split16_batch(batch):
         dst.view(-1)[n:2 * n].copy_(lo)
 
 
+def split16(src, dst, sc, amax_ws):
+    split16_batch(SplitBatch([(src, dst, sc)]))
+
+
 def _three_term(g, x, w, Kw):
     """phase-grid result [N,Hp,Wp,Cout] (float64, unscaled) of the three-term product."""
     xh, xl = x[0].reshape(g.N, g.Hi, g.Wi, g.Cin).double(), x[1].reshape(g.N, g.Hi, g.Wi, g.Cin).double()

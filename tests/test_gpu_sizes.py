@@ -211,3 +211,24 @@ def test_c5_r101_384_slice_vs_reference(golden, dev, precision):
     (out * go).sum().backward()
     rows = _check_gradients(model, g, ())
     assert len(rows) == len(list(model.named_parameters()))
+
+
+def test_backward_is_run_to_run_deterministic(dev):
+    """the split-path weight gradients are reduced in a FIXED order (per-split
+    partial tiles summed by wgrad16_reduce_kernel; no floating-point atomics on the data path),
+    and the float64 atomics of the BatchNorm statistics add float32 partial sums whose float64
+    sum is exact, i.e. order-independent.  Two complete forward + backward runs of the C2 slice
+    give bit-identical gradients for every parameter."""
+    c = gi.SIZE_CASES["c2"]
+    grads = []
+    for rep in range(2):
+        model = _model(dev, c, "f16x3", train=True)
+        x = torch.from_numpy(gi.images(c["N"], c["HW"], c["seed"])).to(dev)
+        out = model(x)
+        go = torch.from_numpy(gi.grad_like_big(out.shape, c["seed"] + 1)).to(dev)
+        (out * go).sum().backward()
+        torch.cuda.synchronize()
+        grads.append({k: p.grad.detach().clone() for k, p in model.named_parameters()})
+        del model, out
+    diff = [k for k in grads[0] if not torch.equal(grads[0][k], grads[1][k])]
+    assert not diff, "%d tensors differ between two runs: %s" % (len(diff), diff[:5])

@@ -656,6 +656,23 @@ def test_engine16_matches_oracle_through_emulated_abi():
     (ref * go.double()).sum().backward()
     for k, q in m.named_parameters():
         assert relerr(q.grad.numpy(), p[k].grad.numpy()) <= 1e-4, k
+    # a head with a whole 64-channel block (J*D = 64): the final layer's backward also runs on
+    # the split kernels (the fp32 logit gradient is split by epb_split16)
+    J2, D2 = 4, 16
+    cfg2 = refshim.make_cfg(num_layers=18, num_joints=J2, volume=True, depth_res=D2, image_size=(64, 64))
+    sd2 = restate_net.init_state(restate_net.param_shapes(18, J2, True, D2), 9)
+    m2 = models.pose3d_resnet.get_pose_net(cfg2, False, ops=emul_ops, precision="f16x3")
+    m2.load_state_dict(sd2)
+    m2.train()
+    p2 = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+              else (v.double() if v.is_floating_point() else v)) for k, v in sd2.items()}
+    ref2 = restate_net.forward(p2, x.double(), num_layers=18, volume=True, image_size=(64, 64))
+    out2 = m2(x)
+    go2 = torch.from_numpy(gi.grad_like(out2.shape, 11))
+    (out2 * go2).sum().backward()
+    (ref2 * go2.double()).sum().backward()
+    for k, q in m2.named_parameters():
+        assert relerr(q.grad.numpy(), p2[k].grad.numpy()) <= 1e-4, k
 
 
 def test_engine16_falls_back_when_channels_do_not_fit():

@@ -709,3 +709,15 @@ def clip_scale(x, n, total, max_norm):
     coef = max_norm / (float(total.reshape(-1)[0]) ** 0.5 + 1e-6)
     if coef < 1.0:
         x.view(-1)[:n].mul_(float(np.float32(coef)))
+
+
+def patch_to_image(coords, box, B, J, patch_w, patch_h, rect3d_w, kps):
+    """CPU emulation of epb_patch_to_image through the numpy oracle: soft-argmax coordinates ->
+    image-frame keypoints (integral_loss.py:196-205 + img_utils.py:141-155)."""
+    from oracle import restate
+    res = restate.joint_location_result(patch_w, patch_h, coords.reshape(B, J * 3).numpy())
+    bx = box.reshape(B, 6).numpy()
+    out = np.stack([restate.trans_coords_from_patch_to_org_3d(
+        res[i], bx[i, 0], bx[i, 1], bx[i, 2], bx[i, 3], patch_w, patch_h, rect3d_w, rect3d_w,
+        scale=bx[i, 4], rot=bx[i, 5]) for i in range(B)])
+    kps.view(B, J, 4).copy_(torch.from_numpy(out))

@@ -36,14 +36,14 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 TUPLES, VIEWS, HW, J, D = 32, 4, 256, 16, 64
+WORKLOAD_TAG = "C4"
 METRIC = "multi-view samples/sec (4-view 256x256, bs32)"
 UNIT = "view-tuples/s"
 
 
 def workload_name(layers=50):
-    return ("C4: R%d pose3d_resnet VOLUME J%d D%d, %d tuples x %d views of %dx%d per GPU, "
-            "self-supervised step (fwd, soft-argmax, iterative-LS triangulation, SmoothL1, bwd, Adam)"
-            % (layers, J, D, TUPLES, VIEWS, HW, HW))
+    return ("%s: R%d pose3d_resnet VOLUME J%d D%d, %d tuples x %d views of %dx%d per GPU, " % (WORKLOAD_TAG, layers, J, D, TUPLES, VIEWS, HW, HW) +
+            "self-supervised step (fwd, soft-argmax, iterative-LS triangulation, SmoothL1, bwd, Adam)")
 
 
 def measured_peaks():
@@ -360,7 +360,7 @@ def run_gpu(args):
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32 (CUDA-core FFMA)", "tf32": "tf32 (tcgen05, f32 accumulate)",
                   "tf32x3": "tf32x3 (3-pass error-compensated tcgen05, f32 accumulate; f32 SIMT "
                             "where the tensor path does not take the shape)",
@@ -520,6 +520,7 @@ def run_reference(args):
 
 
 def main():
+    global TUPLES, HW, J, D, WORKLOAD_TAG
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -532,7 +533,22 @@ def main():
     ap.add_argument("--cpu-tuples", type=int, default=8, help="bounded CPU sample size (view-tuples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4 (default, the BASELINE metric config): R50 256x256 J16 D64, 32 tuples/GPU; "
+                         "c5 (extra line, not the headline): R101 384x384 J17 D96, 16 tuples/GPU")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the tuples of ONE GPU's batch are divided among the ranks")
     args = ap.parse_args()
+    if args.workload == "c5":
+        HW, J, D, WORKLOAD_TAG = 384, 17, 96, "C5"
+        args.layers = 101
+        if args.tuples == 32:
+            args.tuples = 16
+    if args.strong:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        assert args.tuples % world == 0, "tuples must divide among the ranks"
+        args.tuples //= world
+    TUPLES = args.tuples
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

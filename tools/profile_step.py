@@ -6,15 +6,15 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "epipolarpose_b200"))
-from oracle import refshim
+from tools.bench_cfg import make_cfg
 import lib.models as models, lib.core.integral_loss as il, lib.utils.img_utils as iu, lib.utils.utils as U
 from lib.dataset.synthetic import ring_camera
 
 tuples = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-prec = sys.argv[2] if len(sys.argv) > 2 else "tf32x3"
+prec = sys.argv[2] if len(sys.argv) > 2 else "f16x3"
 J, D, HW, V = 16, 64, 256, 4
 dev = torch.device("cuda:0")
-cfg = refshim.make_cfg(num_layers=50, num_joints=J, volume=True, depth_res=D, image_size=(HW, HW))
+cfg = make_cfg(num_layers=50, num_joints=J, volume=True, depth_res=D, image_size=(HW, HW))
 torch.manual_seed(0)
 model = models.pose3d_resnet.get_pose_net(cfg, False, precision=prec).to(dev).train()
 crit = il.SmoothL1JointLocationLoss(J)

@@ -126,6 +126,50 @@ softargmax_fwd_nchw(const float* __restrict__ logits, int D, int H, int W, int S
   }
 }
 
+// Scalar variant for W % 4 != 0 (any volume shape; the reference accepts every J/D/H/W,
+// integral_loss.py:71-86).  Same partition, one logit per thread and iteration.
+__global__ void __launch_bounds__(kFwdThreads)
+softargmax_fwd_nchw_scalar(const float* __restrict__ logits, int D, int H, int W, int S,
+                           Part* __restrict__ parts) {
+  const int nj = blockIdx.y, sp = blockIdx.x;
+  const int64_t vol = (int64_t)D * H * W;
+  const int64_t per = (vol + S - 1) / S;
+  const int64_t beg = (int64_t)sp * per;
+  const int64_t end = min(vol, beg + per);
+  const float* base = logits + (int64_t)nj * vol;
+  Part p;
+  part_init(p);
+  for (int64_t f = beg + threadIdx.x; f < end; f += kFwdThreads) {
+    const int64_t row = f / W;
+    const int x = (int)(f - row * W);
+    const int z = (int)(row / H);
+    const int y = (int)(row - (int64_t)z * H);
+    const float v = __ldg(base + f);
+    if (v > p.m) {
+      const float g = __expf(p.m - v);
+      p.s *= g; p.sx *= g; p.sy *= g; p.sz *= g;
+      p.m = v;
+    }
+    const float e = __expf(v - p.m);
+    p.s += e;
+    p.sx += e * (float)x;
+    p.sy += e * (float)y;
+    p.sz += e * (float)z;
+  }
+  p = warp_merge(p);
+  __shared__ Part sh[kFwdThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = p;
+  __syncthreads();
+  if (wid == 0) {
+    Part q;
+    part_init(q);
+    if (lane < kFwdThreads / 32) q = sh[lane];
+    q = warp_merge(q);
+    if (lane == 0) parts[(int64_t)nj * S + sp] = q;
+  }
+}
+
 // ---------------------------------------------------------------- NHWC fwd
 // grid (S, N); CTA handles a pixel range of one image for ALL joints, reading
 // fully contiguous memory.  C = J*D channels, C4 = C/4 threads per pixel,
@@ -222,6 +266,30 @@ softargmax_bwd_nchw(const float* __restrict__ logits, int D, int H, int W, int S
     y += step_rows;
     if (x4 >= W4) { x4 -= W4; ++y; }
     while (y >= H) { y -= H; ++z; }
+  }
+}
+
+__global__ void __launch_bounds__(kFwdThreads)
+softargmax_bwd_nchw_scalar(const float* __restrict__ logits, int D, int H, int W, int S,
+                           const float* __restrict__ coords, const float* __restrict__ lse,
+                           const float* __restrict__ dcoords, float* __restrict__ dlogits) {
+  const int nj = blockIdx.y, sp = blockIdx.x;
+  const int64_t vol = (int64_t)D * H * W;
+  const int64_t per = (vol + S - 1) / S;
+  const int64_t beg = (int64_t)sp * per;
+  const int64_t end = min(vol, beg + per);
+  const float* base = logits + (int64_t)nj * vol;
+  float* obase = dlogits + (int64_t)nj * vol;
+  const float m = lse[nj * 2], inv = lse[nj * 2 + 1];
+  const float gx = dcoords[nj * 3] / W, gy = dcoords[nj * 3 + 1] / H, gz = dcoords[nj * 3 + 2] / D;
+  const float sbar = gx * (coords[nj * 3] + 0.5f) * W + gy * (coords[nj * 3 + 1] + 0.5f) * H +
+                     gz * (coords[nj * 3 + 2] + 0.5f) * D;
+  for (int64_t f = beg + threadIdx.x; f < end; f += kFwdThreads) {
+    const int64_t row = f / W;
+    const int x = (int)(f - row * W);
+    const int z = (int)(row / H);
+    const int y = (int)(row - (int64_t)z * H);
+    obase[f] = __expf(__ldg(base + f) - m) * inv * (gy * y + gz * z + gx * (float)x - sbar);
   }
 }
 
@@ -430,12 +498,14 @@ extern "C" __attribute__((visibility("default"))) int epb_softargmax_fwd(const f
   int S;
   Part* parts = nullptr;        // per-CTA partials: scratch of this (device, stream)
   if (layout == 0) {
-    EPB_CHECK_ARG(W % 4 == 0);
     const int64_t vol = (int64_t)D * H * W;
     S = pick_splits(NJ, vol, 64);
     int rc = epb_workspace(EPB_WS_SOFTARGMAX, (size_t)NJ * S * sizeof(Part), st, (void**)&parts);
     if (rc) return rc;
-    softargmax_fwd_nchw<<<dim3(S, NJ), kFwdThreads, 0, st>>>(logits, D, H, W, S, parts);
+    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0)
+      softargmax_fwd_nchw<<<dim3(S, NJ), kFwdThreads, 0, st>>>(logits, D, H, W, S, parts);
+    else
+      softargmax_fwd_nchw_scalar<<<dim3(S, NJ), kFwdThreads, 0, st>>>(logits, D, H, W, S, parts);
   } else if (layout == 1) {
     EPB_CHECK_ARG(D % 4 == 0);
     const int C4 = J * D / 4;
@@ -467,10 +537,13 @@ extern "C" __attribute__((visibility("default"))) int epb_softargmax_bwd(const f
   cudaStream_t st = as_stream(stream);
   const int NJ = N * J;
   if (layout == 0) {
-    EPB_CHECK_ARG(W % 4 == 0);
     const int S = pick_splits(NJ, (int64_t)D * H * W, 64);
-    softargmax_bwd_nchw<<<dim3(S, NJ), kFwdThreads, 0, st>>>(logits, D, H, W, S, coords, lse_ws,
-                                                              dcoords, dlogits);
+    if (W % 4 == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0)
+      softargmax_bwd_nchw<<<dim3(S, NJ), kFwdThreads, 0, st>>>(logits, D, H, W, S, coords, lse_ws,
+                                                                dcoords, dlogits);
+    else
+      softargmax_bwd_nchw_scalar<<<dim3(S, NJ), kFwdThreads, 0, st>>>(logits, D, H, W, S, coords,
+                                                                       lse_ws, dcoords, dlogits);
   } else if (layout == 1) {
     EPB_CHECK_ARG(D % 4 == 0);
     const int C4 = J * D / 4;

@@ -32,11 +32,14 @@ _KIND = {"mse": 0, "l1": 1, "smoothl1": 2}
 _backend = [_ops]     # test hook: tests may swap in the CPU emulation of the C ABI
 
 
-def _layout_of(preds):
-    """0: NCHW contiguous, 1: channels_last (NHWC memory).  Otherwise copy."""
+def _layout_of(preds, J=None, D=None):
+    """0: NCHW contiguous, 1: channels_last (NHWC memory).  Otherwise copy.  The channels_last
+    kernels read 4 depth bins per thread with one CTA row per pixel: D % 4 == 0 and
+    J*D/4 <= 1024; other volumes take the NCHW kernels (any J/D/H/W, like the reference)."""
     if preds.is_contiguous():
         return preds, 0
-    if preds.dim() == 4 and preds.permute(0, 2, 3, 1).is_contiguous():
+    if preds.dim() == 4 and preds.permute(0, 2, 3, 1).is_contiguous() \
+            and (D is None or (D % 4 == 0 and J * D // 4 <= 1024)):
         return preds, 1
     return preds.contiguous(), 0
 
@@ -49,7 +52,7 @@ class _SoftArgmaxFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, preds, J, D, H, W):
         ops = _backend[0]
-        preds, layout = _layout_of(preds)
+        preds, layout = _layout_of(preds, J, D)
         N = preds.shape[0]
         coords = torch.empty((N, J * 3), device=preds.device, dtype=torch.float32)
         lse = torch.empty((N * J * 2,), device=preds.device, dtype=torch.float32)
@@ -80,6 +83,19 @@ def softmax_integral_tensor(preds, num_joints, output_3d, hm_width, hm_height, h
     return _SoftArgmaxFn.apply(preds, num_joints, hm_depth, hm_height, hm_width)
 
 
+def _like(x, t, name):
+    """target / weights as float32 tensors of x's shape: broadcast the way the reference's
+    elementwise arithmetic does (integral_loss.py:12-14), raise where it would raise."""
+    t = t.float()
+    if t.shape != x.shape:
+        try:
+            t = torch.broadcast_to(t, x.shape)
+        except RuntimeError as e:
+            raise RuntimeError("%s of shape %s does not broadcast to the input's %s"
+                               % (name, tuple(t.shape), tuple(x.shape))) from e
+    return t.contiguous()
+
+
 class _WeightedLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inp, target, weights, kind, size_average, norm):
@@ -88,7 +104,8 @@ class _WeightedLossFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         loss = torch.empty((), device=x.device, dtype=torch.float32)
         div = float(len(inp)) if size_average else 1.0
-        ops.jointloss(x, target.contiguous().float(), weights.contiguous().float(), x.numel(),
+        target, weights = _like(x, target, "target"), _like(x, weights, "weights")
+        ops.jointloss(x, target, weights, x.numel(),
                       _KIND[kind], norm, div, loss, dx)
         ctx.save_for_backward(dx)
         return loss
@@ -165,6 +182,8 @@ class _HeatmapJointLossFn(torch.autograd.Function):
         N, J = hm.shape[0], hm.shape[1]
         R, HW = N * J, int(np.prod(hm.shape[2:]))
         h = hm.contiguous()
+        if target.numel() != h.numel():
+            raise ValueError("heat-map target has %d elements, the heat-maps %d" % (target.numel(), h.numel()))
         tg = target.contiguous().float()
         wh = None
         if hm_weight is not None:
@@ -177,7 +196,7 @@ class _HeatmapJointLossFn(torch.autograd.Function):
         xc = tc = wc = dx = None
         if x is not None:
             xc = x.contiguous()
-            tc, wc = t.contiguous().float(), w.contiguous().float()
+            tc, wc = _like(xc, t, "gt_jts"), _like(xc, w, "jts_weight")
             n = xc.numel()
             div = float(len(x)) if size_average else 1.0
             dx = torch.empty_like(xc)

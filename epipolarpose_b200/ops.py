@@ -33,6 +33,11 @@ def _p(t, dtype=torch.float32):
         raise _lib.EpbError("tensor must live on a CUDA device (no CPU fallback)")
     if t.dtype != dtype:
         raise _lib.EpbError("expected dtype %s, got %s" % (dtype, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # the stream handed to the C ABI is the CURRENT device's; a tensor of another device
+        # would be dereferenced by a kernel running on the wrong GPU
+        raise _lib.EpbError("tensor lives on cuda:%d but the current device is cuda:%d (wrap the call in "
+                            "torch.cuda.device(tensor.device))" % (t.device.index, torch.cuda.current_device()))
     if not t.is_contiguous():
         raise _lib.EpbError("tensor must be contiguous")
     return ctypes.c_void_p(t.data_ptr())

@@ -27,8 +27,6 @@ def dev():
 def test_softargmax_loss_golden(golden, dev, tag, layout):
     import lib.core.integral_loss as il
     N, J, D, H, W, seed, scale = gi.SOFTARGMAX_CASES[tag]
-    if layout == "nchw" and W % 4:
-        pytest.skip("NCHW kernel needs W % 4 == 0")
     g = golden("softargmax_" + tag)
     x = torch.from_numpy(gi.logits(N, J, D, H, W, seed, scale)).to(dev)
     if layout == "nhwc":
@@ -93,6 +91,32 @@ def test_softargmax_vs_oracle_medium(dev):
         il.softmax_integral_tensor(x, J, True, D, D, D).backward(torch.from_numpy(g).to(dev))
         gref = restate.softmax_integral_grad(logits, g, J, D, D, D)
         assert relerr(x.grad.cpu().numpy(), gref) <= 1e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 6, 5, 7), (1, 17, 10, 9, 13), (2, 2, 5, 8, 8)])
+@pytest.mark.parametrize("memory", ["nchw", "channels_last", "sliced"])
+def test_softargmax_any_volume_shape(dev, shape, memory):
+    """The reference accepts every J/D/H/W and any memory format (integral_loss.py:71-86): widths that are
+    not a multiple of 4, depths that are not (channels_last falls back to the NCHW kernels), and a
+    mis-aligned slice take the scalar-load kernels; same 1e-5 / 1e-3 bars as the vector paths."""
+    import lib.core.integral_loss as il
+    N, J, D, H, W = shape
+    logits = gi.logits(N, J, D, H, W, 91, 3.0)
+    ref = restate.softmax_integral(logits, J, D, H, W)
+    x = torch.from_numpy(logits).to(dev)
+    if memory == "channels_last":
+        x = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    elif memory == "sliced":
+        big = torch.zeros(N * J * D * H * W + 1, device=dev)
+        big[1:] = x.reshape(-1)
+        x = big[1:].view(N, J * D, H, W)                    # 4-byte aligned only
+    x.requires_grad_(True)
+    c = il.softmax_integral_tensor(x, J, True, W, H, D)
+    assert np.max(np.abs(c.detach().cpu().numpy() - ref)) <= 1e-5
+    g = np.random.default_rng(4).standard_normal((N, J * 3)).astype(np.float32)
+    c.backward(torch.from_numpy(g).to(dev))
+    gref = restate.softmax_integral_grad(logits, g, J, D, H, W)
+    assert relerr(x.grad.cpu().numpy(), gref) <= 1e-3
 
 
 # ------------------------------------------------------------------ argmax

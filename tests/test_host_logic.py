@@ -798,3 +798,36 @@ def test_refiner_train_loop_and_checkpoint_interop_emulated(tmp_path):
         rmodel.LinearModelPG._backend[0] = None
         rutils._backend[0] = real
         U._backend[0] = real
+
+
+def test_joint_loss_broadcasts_or_raises_like_the_reference():
+    """target / weights smaller than the input must broadcast the way the reference's
+    elementwise arithmetic does (integral_loss.py:12-14) or raise -- never be read out of bounds."""
+    import lib.core.integral_loss as il
+    il._backend[0] = emul_ops
+    try:
+        rng = np.random.default_rng(0)
+        x = torch.from_numpy(rng.standard_normal((4, 15)).astype(np.float32)).requires_grad_(True)
+        t = torch.from_numpy(rng.standard_normal((4, 15)).astype(np.float32))
+        w_col = torch.from_numpy((rng.random((4, 1)) > 0.3).astype(np.float32))
+        loss = il.weighted_l1_loss(x, t, w_col, True)
+        ref = (torch.abs(x.detach() - t) * w_col).sum() / 4
+        assert abs(loss.item() - ref.item()) <= 1e-6
+        loss.backward()
+        assert torch.allclose(x.grad, torch.sign(x.detach() - t) * w_col / 4, atol=1e-7)
+        row = il.weighted_smooth_l1_loss(x, t[:1], torch.ones(15), False)       # [1,15] and [15] broadcast
+        d = x.detach() - t[:1]
+        ref = torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5).sum()
+        assert abs(row.item() - ref.item()) <= 1e-5 * ref.item()
+        with pytest.raises(RuntimeError):
+            il.weighted_l1_loss(x, t[:, :7], torch.ones(4, 15), True)
+        with pytest.raises(RuntimeError):
+            il.weighted_l1_loss(x, t, torch.ones(3, 15), True)
+        hm, tg = torch.rand(4, 5, 8, 8), torch.rand(4, 5, 8, 8)
+        with pytest.raises(ValueError):
+            il.heatmap_joint_loss(hm, tg[:2])
+        total, parts = il.heatmap_joint_loss(hm, tg, None, x.detach(), t, w_col)
+        ref_jt = (torch.abs(x.detach() - t) * w_col).sum() / 4
+        assert abs(parts[1].item() - ref_jt.item()) <= 1e-6 and torch.isfinite(total)
+    finally:
+        il._backend[0] = __import__("epipolarpose_b200.ops", fromlist=["ops"])

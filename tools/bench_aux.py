@@ -79,3 +79,52 @@ Xo = torch.empty(NP, J, 3, device=dev, dtype=torch.float64); st = torch.empty(NP
 for m, name in ((0, "linear_eigen"), (1, "linear_LS"), (2, "iterative_LS"), (3, "polynomial")):
     tt = timeit(lambda: ops.triangulate(tu1, tu2, 2, tP1, tP2, NP, J, m, 3e-5, Xo, st), reps=5)
     line("triangulate " + name, NP, "17-joint pair", 1144, tt)
+
+# input pipeline after decode: 512 frames of 1000 x 1002 x 3 (H36M camera frames) -> 256 x 256 patches.
+# Algorithmic bytes per output pixel: 12 written (3 float planes) + 12 read (4 bilinear taps x 3 channels, the
+# source footprint of a 0.8-1.2x crop is about one source pixel per output pixel) = 24 B.
+B, HI, WI, PW = 512, 1002, 1000, 256
+img = torch.randint(0, 256, (HI * WI * 3,), dtype=torch.uint8, device=dev)
+per = (img.numel() + 15) // 16 * 16
+base = torch.zeros(per * 8, dtype=torch.uint8, device=dev)
+for i in range(8):
+    base[i * per:i * per + img.numel()] = torch.roll(img, i * 977)
+offs = torch.tensor([(i % 8) * per for i in range(B)], dtype=torch.int64, device=dev)
+hwp = torch.tensor([[HI, WI, WI * 3]] * B, dtype=torch.int32, device=dev)
+g = torch.Generator().manual_seed(3)
+box = torch.stack([500 + 40 * torch.randn(B, generator=g, dtype=torch.float64),
+                   500 + 40 * torch.randn(B, generator=g, dtype=torch.float64),
+                   torch.full((B,), 300.0, dtype=torch.float64), torch.full((B,), 300.0, dtype=torch.float64),
+                   1 + 0.25 * (torch.rand(B, generator=g, dtype=torch.float64) - 0.5),
+                   30 * (torch.rand(B, generator=g, dtype=torch.float64) - 0.5)], dim=1).contiguous().to(dev)
+flip = (torch.rand(B, generator=g) < 0.5).to(torch.int32).to(dev)
+col = (0.8 + 0.4 * torch.rand(B, 3, generator=g)).to(dev)
+ms = [0.485, 0.456, 0.406, 0.229, 0.224, 0.225]
+out = torch.empty(B, 3, PW, PW, device=dev); trans = torch.empty(B, 6, device=dev, dtype=torch.float64)
+tt = timeit(lambda: ops.patch_sample(base, offs, hwp, box, flip, col, ms, B, PW, PW, out, trans))
+line("patch_sample 256x256 (warpAffine+colour+normalise)", B * PW * PW, "output pixel", 24, tt)
+
+from epipolarpose_b200.lib.utils.augmentation import pack_occluders
+rs = np.random.RandomState(5)
+occ_lists = []
+for b in range(B):
+    lst = []
+    for k in range(rs.randint(1, 8)):                       # augmentation.py:65 count = randint(1, 8)
+        h, w = rs.randint(30, 120), rs.randint(30, 120)
+        rgba = rs.randint(0, 256, (h, w, 4)).astype(np.uint8)
+        lst.append((rgba, (int(rs.randint(0, PW)), int(rs.randint(0, PW)))))
+    occ_lists.append(lst)
+ob, od, oc = pack_occluders(occ_lists, dev)
+occ_px = float(sum(r.shape[0] * r.shape[1] for l in occ_lists for r, _ in l)) / (B * PW * PW)
+tt = timeit(lambda: ops.patch_sample_occ(base, offs, hwp, box, flip, col, ms, B, PW, PW, ob, od, oc, out, trans))
+line("patch_sample_occ (+%.2f RGBA occluder px per output px)" % occ_px, B * PW * PW, "output pixel",
+     round(24 + 4 * occ_px, 2), tt)
+
+# decode: hard argmax and get_final_preds over 1024 x 17 heat-maps of 64 x 64 (4 B per element read once)
+N, J, H, W = 1024, 17, 64, 64
+hm = torch.rand(N, J, H, W, device=dev)
+ctr = torch.full((N, 2), 500.0, dtype=torch.float64, device=dev)
+scl = torch.full((N, 2), 1.5, dtype=torch.float64, device=dev)
+preds = torch.empty(N, J, 2, device=dev); mv = torch.empty(N, J, 1, device=dev)
+tt = timeit(lambda: ops.final_preds(hm, N, J, H, W, ctr, scl, True, preds, mv))
+line("final_preds (argmax + refine + transform_preds)", N * J * H * W, "heat-map element", 4, tt)

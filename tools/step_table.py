@@ -40,6 +40,13 @@ rec = []
 orig_call = ops._call
 
 
+# elementwise passes: name -> (index of M, index of C, algorithmic bytes per element,
+#                               [(index of an optional pointer argument, extra bytes per element)])
+ELEM = {"epb_bn_bwd_reduce_mx": (8, 9, 8, [(2, 2)]),
+        "epb_bn_bwd_apply_split": (11, 12, 12, [(2, 2), (15, 4)]),
+        "epb_bn_act_split": (9, 10, 8, [(3, 4), (6, 4)])}
+
+
 def timed_call(name, *args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -49,6 +56,10 @@ def timed_call(name, *args):
     shape = None
     if g is not None and hasattr(g, "Hp"):
         shape = (g.N * g.Hp * g.Wp, g.Cin, g.Cout, g.T, g.os, g.is_)
+    elif name in ELEM:
+        im, ic, b, opt_ = ELEM[name]
+        extra = sum(bb for (ia, bb) in opt_ if args[ia] is not None)
+        shape = ("elem", int(args[im]), int(args[ic]), b + extra)
     rec.append((name, shape, e0, e1))
 
 
@@ -82,7 +93,7 @@ for name, (c, ms) in sorted(by.items(), key=lambda kv: -kv[1][1]):
 print("| **total** | %d | %.3f | |\n" % (len(rec), tot))
 agg = collections.OrderedDict()
 for name, shape, e0, e1 in rec:
-    if shape is None:
+    if shape is None or shape[0] == "elem":
         continue
     a = agg.setdefault((name,) + shape, [0, 0.0])
     a[0] += 1
@@ -99,3 +110,15 @@ for (name, M, ci, co, T, os_, is_), (cnt, ms) in sorted(agg.items(), key=lambda 
 print()
 for name, (fl, ms) in fam.items():
     print("* %s: %.2f TFLOP in %.2f ms = %.1f TFLOP/s algorithmic" % (name, fl / 1e12, ms, fl / ms / 1e9))
+
+print("\n| elementwise pass | M | C | B/elem | calls | ms | GB/s |\n|---|---:|---:|---:|---:|---:|---:|")
+el = collections.OrderedDict()
+for name, shape, e0, e1 in rec:
+    if shape is None or shape[0] != "elem":
+        continue
+    a = el.setdefault((name,) + shape[1:], [0, 0.0])
+    a[0] += 1
+    a[1] += e0.elapsed_time(e1)
+for (name, M, C, b), (cnt, ms) in sorted(el.items(), key=lambda kv: -kv[1][1]):
+    print("| %s | %d | %d | %d | %d | %.3f | %.0f |" % (name.replace("epb_", ""), M, C, b, cnt, ms,
+                                                      float(M) * C * b * cnt / ms / 1e6))

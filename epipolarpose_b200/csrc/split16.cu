@@ -314,7 +314,6 @@ split_apply_one_kernel(const float4* __restrict__ src, int64_t n4, const uint32_
 }
 
 // ------------------------------------------------------------------ BatchNorm backward
-constexpr int kRowsPerThread = 32;
 
 struct RowMap {
   int C4, tpr, rpi, chunks;
@@ -343,23 +342,35 @@ __device__ __forceinline__ float4 mask4(float4 dy, float4 xv, const uint2* mask_
   return dy;
 }
 
-__global__ void __launch_bounds__(kThreads)
-bn_bwd_reduce_mx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
-                        const uint2* __restrict__ mask_hi, const float4* __restrict__ scale,
-                        const float4* __restrict__ shift, const float4* __restrict__ mean,
-                        const float4* __restrict__ invstd, int relu, int64_t M, int C, RowMap rm,
-                        double* __restrict__ sums, float* __restrict__ maxes) {
+// Pass 1: per-CTA partial reductions.  CTA (w, chunk) folds rows (w + k*gridDim.x)*rpi + slot
+// into registers and stores FOUR per-channel partials (sum g, sum g*xhat, max|g|, max|xhat|)
+// to parts[(v*W + w)*C + c] -- no atomics: the second pass adds them in a fixed order, so the
+// parameter gradients and the scale of dz are run-to-run identical.
+template <bool MASK>
+__global__ void __launch_bounds__(kThreads, 3)
+bn_bwd_partial_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                      const uint2* __restrict__ mask_hi, const float4* __restrict__ scale,
+                      const float4* __restrict__ shift, const float4* __restrict__ mean,
+                      const float4* __restrict__ invstd, int relu, int64_t M, int C, RowMap rm,
+                      float* __restrict__ parts, uint32_t* __restrict__ bound_bits) {
+  if (bound_bits && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *bound_bits = 0u;
   const int slot = threadIdx.x / rm.tpr, tin = threadIdx.x % rm.tpr;
   const int c4 = blockIdx.y * rm.tpr + tin;
   const bool active = (c4 < rm.C4) && (slot < rm.rpi);
-  // persistent over row blocks: CTA b takes rows (b + k*gridDim.x)*rpi + slot, so a thread
-  // folds M / (gridDim.x * rpi) rows into registers and the CTA issues ONE set of atomics
   const int64_t nblk = (M + rm.rpi - 1) / rm.rpi;
-  float4 acc[4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};   // sum g, sum g*xhat, max|g|, max|xhat|
+  float4 acc[4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
   if (active) {
-    const float4 s = scale[c4], b = shift[c4], mu = mean[c4], is = invstd[c4];
-    auto fold = [&](float4 dv, float4 xv, int64_t i) {
-      const float4 g = mask4(dv, xv, mask_hi, i, s, b, relu);
+    const float4 mu = mean[c4], is = invstd[c4];
+    float4 s = make_float4(0, 0, 0, 0), b = s;
+    if (!MASK) { s = scale[c4]; b = shift[c4]; }
+    auto fold = [&](float4 dv, float4 xv, uint2 mk) {
+      float4 g;
+      if (MASK) {
+        g = make_float4((mk.x & 0x7fffu) ? dv.x : 0.f, (mk.x & 0x7fff0000u) ? dv.y : 0.f,
+                        (mk.y & 0x7fffu) ? dv.z : 0.f, (mk.y & 0x7fff0000u) ? dv.w : 0.f);
+      } else {
+        g = mask4(dv, xv, nullptr, 0, s, b, relu);
+      }
       const float4 xh = make_float4((xv.x - mu.x) * is.x, (xv.y - mu.y) * is.y,
                                     (xv.z - mu.z) * is.z, (xv.w - mu.w) * is.w);
       acc[0].x += g.x; acc[0].y += g.y; acc[0].z += g.z; acc[0].w += g.w;
@@ -371,30 +382,33 @@ bn_bwd_reduce_mx_kernel(const float4* __restrict__ dy, const float4* __restrict_
     };
     int64_t blk = blockIdx.x;
     const int64_t step = gridDim.x;
-    for (; blk + 3 * step < nblk; blk += 4 * step) {       // four rows per trip: 8 loads in flight
+    for (; blk + 3 * step < nblk; blk += 4 * step) {       // four rows per trip: 8-12 loads in flight
       float4 xv[4], dv[4];
-      int64_t idx[4];
+      uint2 mk[4];
       bool ok[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t r = (blk + u * step) * rm.rpi + slot;
         ok[u] = r < M;
-        idx[u] = r * rm.C4 + c4;
+        mk[u] = make_uint2(0u, 0u);
         if (ok[u]) {
-          xv[u] = ldg_stream(x + idx[u]);
-          dv[u] = ldg_stream(dy + idx[u]);
+          const int64_t i = r * rm.C4 + c4;
+          xv[u] = ldg_stream(x + i);
+          dv[u] = ldg_stream(dy + i);
+          if (MASK) mk[u] = __ldg(mask_hi + i);
         }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (ok[u]) fold(dv[u], xv[u], idx[u]);
+        if (ok[u]) fold(dv[u], xv[u], mk[u]);
     }
     for (; blk < nblk; blk += step) {
       const int64_t r = blk * rm.rpi + slot;
       if (r >= M) break;
       const int64_t i = r * rm.C4 + c4;
       const float4 xv = ldg_stream(x + i);
-      fold(ldg_stream(dy + i), xv, i);
+      const float4 dv = ldg_stream(dy + i);
+      fold(dv, xv, MASK ? __ldg(mask_hi + i) : make_uint2(0u, 0u));
     }
   }
   __shared__ float4 sh[4][kThreads];
@@ -402,27 +416,72 @@ bn_bwd_reduce_mx_kernel(const float4* __restrict__ dy, const float4* __restrict_
   for (int v = 0; v < 4; ++v) sh[v][threadIdx.x] = acc[v];
   __syncthreads();
   if (slot == 0 && active) {
+    const int64_t W = gridDim.x;
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      for (int q = 0; q < rm.rpi; ++q) {
-        const float4 t = sh[v][q * rm.tpr + tin];
-        a0 += t.x; a1 += t.y; a2 += t.z; a3 += t.w;
+    for (int v = 0; v < 4; ++v) {
+      float4 t = sh[v][tin];
+      for (int q = 1; q < rm.rpi; ++q) {
+        const float4 u = sh[v][q * rm.tpr + tin];
+        if (v < 2) { t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        else { t.x = fmaxf(t.x, u.x); t.y = fmaxf(t.y, u.y); t.z = fmaxf(t.z, u.z); t.w = fmaxf(t.w, u.w); }
       }
-      double* o = sums + (int64_t)v * C + c4 * 4;
-      atomicAdd(o + 0, a0); atomicAdd(o + 1, a1); atomicAdd(o + 2, a2); atomicAdd(o + 3, a3);
+      *reinterpret_cast<float4*>(parts + ((int64_t)v * W + blockIdx.x) * C + c4 * 4) = t;
     }
-#pragma unroll
-    for (int v = 2; v < 4; ++v) {
-      float4 m = make_float4(0, 0, 0, 0);
-      for (int q = 0; q < rm.rpi; ++q) {
-        const float4 t = sh[v][q * rm.tpr + tin];
-        m.x = fmaxf(m.x, t.x); m.y = fmaxf(m.y, t.y); m.z = fmaxf(m.z, t.z); m.w = fmaxf(m.w, t.w);
-      }
-      uint32_t* o = reinterpret_cast<uint32_t*>(maxes) + (int64_t)(v - 2) * C + c4 * 4;
-      atomicMax(o + 0, __float_as_uint(m.x)); atomicMax(o + 1, __float_as_uint(m.y));
-      atomicMax(o + 2, __float_as_uint(m.z)); atomicMax(o + 3, __float_as_uint(m.w));
+  }
+}
+
+// Pass 2: 32 channels per CTA, 8 groups of partials per channel added in a fixed order.
+//   coef == NULL : sums[0..2C) += (sum g, sum g*xhat), maxes = max(maxes, ...)   (epb_bn_bwd_reduce_mx)
+//   coef != NULL : coef[0..2C) = (k1 = sum_g/M, k2 = sum_gx/M), parameter gradients, and the bound
+//     |dz_c| <= |gamma_c*invstd_c| * (max|g|_c + |k1_c| + max|xhat|_c * |k2_c|)  max-ed into *bound_bits
+__global__ void __launch_bounds__(256)
+bn_bwd_combine_kernel(const float* __restrict__ parts, int W, double M, int C,
+                      double* __restrict__ sums, float* __restrict__ maxes, float* __restrict__ coef,
+                      const float* __restrict__ gamma, const float* __restrict__ invstd,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                      uint32_t* __restrict__ bound_bits) {
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double a0 = 0, a1 = 0;
+  float m0 = 0.f, m1 = 0.f;
+  if (c < C) {
+    for (int w = g; w < W; w += 8) {
+      a0 += (double)parts[((int64_t)0 * W + w) * C + c];
+      a1 += (double)parts[((int64_t)1 * W + w) * C + c];
+      m0 = fmaxf(m0, parts[((int64_t)2 * W + w) * C + c]);
+      m1 = fmaxf(m1, parts[((int64_t)3 * W + w) * C + c]);
     }
+  }
+  __shared__ double sa[2][8][32];
+  __shared__ float sm[2][8][32];
+  sa[0][g][lane] = a0; sa[1][g][lane] = a1;
+  sm[0][g][lane] = m0; sm[1][g][lane] = m1;
+  __syncthreads();
+  if (g != 0) return;
+  for (int q = 1; q < 8; ++q) {
+    a0 += sa[0][q][lane]; a1 += sa[1][q][lane];
+    m0 = fmaxf(m0, sm[0][q][lane]); m1 = fmaxf(m1, sm[1][q][lane]);
+  }
+  float bound = 0.f;
+  if (c < C) {
+    if (!coef) {
+      sums[c] += a0;
+      sums[C + c] += a1;
+      maxes[c] = fmaxf(maxes[c], m0);
+      maxes[C + c] = fmaxf(maxes[C + c], m1);
+    } else {
+      const float k0 = (gamma ? gamma[c] : 1.f) * invstd[c];
+      const float k1 = (float)(a0 / M), k2 = (float)(a1 / M);
+      coef[c] = k1;
+      coef[C + c] = k2;
+      if (dgamma) dgamma[c] = (float)a1;
+      if (dbeta) dbeta[c] = (float)a0;
+      bound = fabsf(k0) * (m0 + fabsf(k1) + m1 * fabsf(k2));
+    }
+  }
+  if (coef) {
+    bound = warp_max(bound);
+    if (lane == 0) atomicMax(bound_bits, __float_as_uint(bound));   // order-independent
   }
 }
 
@@ -464,9 +523,14 @@ bn_bwd_apply_split_kernel(const float4* dy /* may alias dy_masked */, const floa
                           const float4* __restrict__ shift, const float4* __restrict__ mean,
                           const float4* __restrict__ invstd, const float4* __restrict__ gamma,
                           int relu, const float4* __restrict__ k1v, const float4* __restrict__ k2v,
-                          uint2* __restrict__ dz, const float* __restrict__ dz_sc,
-                          float4* dy_masked, int64_t total4, int C4) {
-  const float s = dz_sc[0];
+                          uint2* __restrict__ dz, float* __restrict__ dz_sc,
+                          const float* __restrict__ bound, float4* dy_masked, int64_t total4, int C4) {
+  // scale of dz: from the bound the combine pass left (fused entry point), else as published in dz_sc
+  const float s = bound ? pow2_scale(*bound) : dz_sc[0];
+  if (bound && blockIdx.x == 0 && threadIdx.x == 0) {
+    dz_sc[0] = s;
+    dz_sc[1] = 1.f / s;
+  }
   // two independent elements per trip: six streaming loads in flight per thread
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x; i0 < total4; i0 += 2 * stride) {
@@ -529,6 +593,24 @@ __device__ __forceinline__ float group_bound(const double* stats, const float* s
   return b;
 }
 
+// sc = {s, 1/s, bound, 0}: s the largest power of two with s * bound <= 2^15 (fp16 max is 65504)
+__device__ __forceinline__ void publish_act_scale(float b1, float b2, const float* res_sc, float* sc) {
+  float bound = (b1 + b2) * 1.001f + (res_sc ? res_sc[2] : 0.f);
+  if (!isfinite(bound)) bound = 3.0e38f;
+  float s = 1.f;
+  if (bound > 0.f) {
+    int e;
+    frexpf(bound, &e);                         // bound = f * 2^e, f in [0.5, 1)
+    int k = 15 - e;
+    k = k < -100 ? -100 : (k > 100 ? 100 : k);
+    s = ldexpf(1.f, k);
+  }
+  sc[0] = s;
+  sc[1] = 1.f / s;
+  sc[2] = bound;
+  sc[3] = 0.f;
+}
+
 __global__ void __launch_bounds__(1024)
 act_scale_kernel(const double* __restrict__ stats, const float* __restrict__ scale,
                  const float* __restrict__ shift, double M, int C,
@@ -544,21 +626,49 @@ act_scale_kernel(const double* __restrict__ stats, const float* __restrict__ sca
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { b1 = fmaxf(b1, sm[0][w]); b2 = fmaxf(b2, sm[1][w]); }
-    float bound = (b1 + b2) * 1.001f + (res_sc ? res_sc[2] : 0.f);
-    if (!isfinite(bound)) bound = 3.0e38f;
-    // largest power of two with s * bound <= 2^15 (fp16 max is 65504)
-    float s = 1.f;
-    if (bound > 0.f) {
-      int e;
-      frexpf(bound, &e);                         // bound = f * 2^e, f in [0.5, 1)
-      int k = 15 - e;
-      k = k < -100 ? -100 : (k > 100 ? 100 : k);
-      s = ldexpf(1.f, k);
+    publish_act_scale(b1, b2, res_sc, sc);
+  }
+}
+
+// BatchNorm finalize (as bn.cu bn_finalize_kernel) + epb_act_scale of the same layer in ONE single-CTA
+// launch: group 1 is the layer being finalised, group 2 (optional) an already finalised one.
+__global__ void __launch_bounds__(1024)
+bn_finalize_scale_kernel(const double* __restrict__ stats, double M, int C,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                         float momentum, float* __restrict__ running_mean,
+                         float* __restrict__ running_var, float* __restrict__ scale,
+                         float* __restrict__ shift, float* __restrict__ mean_out,
+                         float* __restrict__ invstd_out, const double* __restrict__ stats2,
+                         const float* __restrict__ scale2, const float* __restrict__ shift2,
+                         const float* __restrict__ res_sc, float* __restrict__ sc) {
+  float b1 = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = stats[c] / M;
+    double var = stats[C + c] / M - mean * mean;   // biased (normalisation)
+    if (var < 0) var = 0;
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float scf = (float)(g * invstd), shf = (float)(b - mean * g * invstd);
+    scale[c] = scf;
+    shift[c] = shf;
+    if (mean_out) mean_out[c] = (float)mean;
+    if (invstd_out) invstd_out[c] = (float)invstd;
+    if (running_mean) {
+      const double unbiased = var * (M / (M > 1.0 ? (M - 1.0) : 1.0));
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
     }
-    sc[0] = s;
-    sc[1] = 1.f / s;
-    sc[2] = bound;
-    sc[3] = 0.f;
+    b1 = fmaxf(b1, (float)(fabs((double)scf * mean + (double)shf) + fabs((double)scf) * sqrt(M * var)));
+  }
+  float b2 = stats2 ? group_bound(stats2, scale2, shift2, M, C) : 0.f;
+  b1 = warp_max(b1);
+  b2 = warp_max(b2);
+  __shared__ float sm[2][32];
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = b1; sm[1][threadIdx.x >> 5] = b2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { b1 = fmaxf(b1, sm[0][w]); b2 = fmaxf(b2, sm[1][w]); }
+    publish_act_scale(b1, b2, res_sc, sc);
   }
 }
 
@@ -633,25 +743,90 @@ EPB_API int epb_split16_batch(const epb_split_job* jobs, int njobs, long long to
   return EPB_OK;
 }
 
+// launch geometry of the partial pass: the three resident CTAs per SM, >= 4 rows per thread
+static int bn_bwd_workers(const RowMap& rm, int64_t M) {
+  const int64_t nblk = (M + rm.rpi - 1) / rm.rpi;
+  int64_t workers = (nblk + 3) / 4;
+  const int64_t cap = (int64_t)kNumSMs * 3 / rm.chunks > 1 ? (int64_t)kNumSMs * 3 / rm.chunks : 1;
+  if (workers > cap) workers = cap;
+  return (int)(workers < 1 ? 1 : workers);
+}
+// scratch of this (device, stream): parts[4][W][C] | coef[2C] | bound
+static int bn_bwd_scratch(int W, int C, cudaStream_t st, float** parts, float** coef, uint32_t** bound) {
+  void* p = nullptr;
+  const size_t nparts = (size_t)4 * W * C;
+  size_t bytes = (nparts + 2 * (size_t)C + 4) * sizeof(float);
+  const size_t usual = ((size_t)4 * 3 * kNumSMs * 2048 + 2 * 2048 + 4) * sizeof(float);   // every ResNet layer
+  if (bytes < usual) bytes = usual;
+  int rc = epb_workspace(EPB_WS_BNPART, bytes, st, &p);
+  if (rc) return rc;
+  *parts = static_cast<float*>(p);
+  *coef = *parts + nparts;
+  *bound = reinterpret_cast<uint32_t*>(*coef + 2 * (size_t)C);
+  return EPB_OK;
+}
+
+static void launch_bn_bwd_partial(const float* dy, const float* x, const epb_half* mask_hi,
+                                  const float* scale, const float* shift, const float* mean,
+                                  const float* invstd, int relu, int64_t M, int C, const RowMap& rm,
+                                  int W, float* parts, uint32_t* bound, cudaStream_t st) {
+  auto k = mask_hi ? bn_bwd_partial_kernel<true> : bn_bwd_partial_kernel<false>;
+  k<<<dim3(W, rm.chunks), kThreads, 0, st>>>(
+      reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
+      reinterpret_cast<const uint2*>(mask_hi), reinterpret_cast<const float4*>(scale),
+      reinterpret_cast<const float4*>(shift), reinterpret_cast<const float4*>(mean),
+      reinterpret_cast<const float4*>(invstd), relu, M, C, rm, parts, bound);
+}
+
 EPB_API int epb_bn_bwd_reduce_mx(const float* dy, const float* x, const epb_half* mask_hi,
                                  const float* scale, const float* shift, const float* mean,
                                  const float* invstd, int relu, int64_t M, int C, double* sums,
                                  float* maxes, epb_stream_t stream) {
   EPB_CHECK_ARG(dy && x && scale && shift && mean && invstd && sums && maxes);
   EPB_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0);
+  cudaStream_t st = as_stream(stream);
   const RowMap rm = make_rowmap(C);
-  // ~6 CTAs per SM in all, each thread folding at least kRowsPerThread rows when M allows
-  const int64_t nblk = (M + rm.rpi - 1) / rm.rpi;
-  int64_t workers = (nblk + kRowsPerThread - 1) / kRowsPerThread;
-  const int64_t cap = (int64_t)kNumSMs * 6 / rm.chunks > 1 ? (int64_t)kNumSMs * 6 / rm.chunks : 1;
-  if (workers > cap) workers = cap;
-  if (workers < 1) workers = 1;
-  dim3 grid((unsigned)workers, rm.chunks);
-  bn_bwd_reduce_mx_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
+  const int W = bn_bwd_workers(rm, M);
+  float *parts, *coef;
+  uint32_t* bound;
+  int rc = bn_bwd_scratch(W, C, st, &parts, &coef, &bound);
+  if (rc) return rc;
+  launch_bn_bwd_partial(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, rm, W, parts, nullptr, st);
+  EPB_LAUNCH_CHECK();
+  bn_bwd_combine_kernel<<<(C + 31) / 32, 256, 0, st>>>(parts, W, (double)M, C, sums, maxes, nullptr,
+                                                        nullptr, nullptr, nullptr, nullptr, nullptr);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_bn_bwd_split(const float* dy, const float* x, const epb_half* mask_hi,
+                             const float* scale, const float* shift, const float* mean,
+                             const float* invstd, const float* gamma, int relu, int64_t M, int C,
+                             epb_half* dz, float* dz_sc, float* dy_masked, float* dgamma,
+                             float* dbeta, epb_stream_t stream) {
+  EPB_CHECK_ARG(dy && x && scale && shift && mean && invstd && dz && dz_sc);
+  EPB_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0);
+  cudaStream_t st = as_stream(stream);
+  const RowMap rm = make_rowmap(C);
+  const int W = bn_bwd_workers(rm, M);
+  float *parts, *coef;
+  uint32_t* bound;
+  int rc = bn_bwd_scratch(W, C, st, &parts, &coef, &bound);
+  if (rc) return rc;
+  launch_bn_bwd_partial(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, rm, W, parts, bound, st);
+  EPB_LAUNCH_CHECK();
+  bn_bwd_combine_kernel<<<(C + 31) / 32, 256, 0, st>>>(parts, W, (double)M, C, nullptr, nullptr, coef,
+                                                        gamma, invstd, dgamma, dbeta, bound);
+  EPB_LAUNCH_CHECK();
+  const int64_t total4 = M * (C / 4);
+  bn_bwd_apply_split_kernel<<<ew_blocks(total4), kThreads, 0, st>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
       reinterpret_cast<const uint2*>(mask_hi), reinterpret_cast<const float4*>(scale),
       reinterpret_cast<const float4*>(shift), reinterpret_cast<const float4*>(mean),
-      reinterpret_cast<const float4*>(invstd), relu, M, C, rm, sums, maxes);
+      reinterpret_cast<const float4*>(invstd), reinterpret_cast<const float4*>(gamma), relu,
+      reinterpret_cast<const float4*>(coef), reinterpret_cast<const float4*>(coef + C),
+      reinterpret_cast<uint2*>(dz), dz_sc, reinterpret_cast<const float*>(bound),
+      reinterpret_cast<float4*>(dy_masked), total4, C / 4);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }
@@ -676,7 +851,7 @@ EPB_API int epb_bn_bwd_apply_split(const float* dy, const float* x, const epb_ha
       reinterpret_cast<const float4*>(shift), reinterpret_cast<const float4*>(mean),
       reinterpret_cast<const float4*>(invstd), reinterpret_cast<const float4*>(gamma), relu,
       reinterpret_cast<const float4*>(mx), reinterpret_cast<const float4*>(mx + C),
-      reinterpret_cast<uint2*>(dz), dz_sc, reinterpret_cast<float4*>(dy_masked), total4, C / 4);
+      reinterpret_cast<uint2*>(dz), dz_sc, nullptr, reinterpret_cast<float4*>(dy_masked), total4, C / 4);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }
@@ -697,6 +872,22 @@ EPB_API int epb_act_scale(const double* stats, const float* scale, const float* 
   EPB_CHECK_ARG((stats2 == nullptr) == (scale2 == nullptr) && (scale2 == nullptr) == (shift2 == nullptr));
   act_scale_kernel<<<1, 1024, 0, as_stream(stream)>>>(stats, scale, shift, (double)M, C, stats2,
                                                       scale2, shift2, res_sc, sc);
+  EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_bn_finalize_scale(const double* stats, int64_t M, int C, const float* gamma,
+                                  const float* beta, float eps, float momentum, float* running_mean,
+                                  float* running_var, float* scale, float* shift, float* mean,
+                                  float* invstd, const double* stats2, const float* scale2,
+                                  const float* shift2, const float* res_sc, float* sc,
+                                  epb_stream_t stream) {
+  EPB_CHECK_ARG(stats && scale && shift && sc && M > 0 && C > 0);
+  EPB_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr));
+  EPB_CHECK_ARG((stats2 == nullptr) == (scale2 == nullptr) && (scale2 == nullptr) == (shift2 == nullptr));
+  bn_finalize_scale_kernel<<<1, 1024, 0, as_stream(stream)>>>(
+      stats, (double)M, C, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
+      invstd, stats2, scale2, shift2, res_sc, sc);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

@@ -379,7 +379,9 @@ class Engine:
         if not batched:
             conv.unpack_grad(ops, dwp, grad_out)
 
-    def _bn_train(self, name, C, stats, M, params, new_buffers):
+    def _bn_train(self, name, C, stats, M, params, new_buffers, act_scale=None):
+        """act_scale = (stats2, scale2, shift2, res_sc, sc): also publish the scale of the layer's
+        post-activation split tensor in the same launch (split path)."""
         ops = self.ops
         st = _BNState()
         st.name, st.C, st.M = name, C, M
@@ -387,11 +389,19 @@ class Engine:
                                                   self._new(C))
         rm = params[name + ".running_mean"]
         rv = params[name + ".running_var"]
-        ops.bn_finalize(stats, M, C, params[name + ".weight"], params[name + ".bias"], BN_EPS,
-                        BN_MOMENTUM, rm, rv, st.scale, st.shift, st.mean, st.invstd)
+        if act_scale is None:
+            ops.bn_finalize(stats, M, C, params[name + ".weight"], params[name + ".bias"], BN_EPS,
+                            BN_MOMENTUM, rm, rv, st.scale, st.shift, st.mean, st.invstd)
+        else:
+            ops.bn_finalize_scale(stats, M, C, params[name + ".weight"], params[name + ".bias"], BN_EPS,
+                                  BN_MOMENTUM, rm, rv, st.scale, st.shift, st.mean, st.invstd, *act_scale)
         nbt = params.get(name + ".num_batches_tracked")
         if nbt is not None:
-            nbt += 1
+            tick = getattr(self, "_nbt_tick", None)
+            if tick is None:
+                nbt += 1
+            else:
+                tick.append(nbt)            # one multi-tensor increment at the end of the forward
         return st
 
     def _bn_eval(self, name, C, params):

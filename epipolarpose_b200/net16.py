@@ -92,18 +92,6 @@ class Engine16(_net.Engine):
         ops.split16_batch(st["batch"])
         return st["w"]
 
-    def _grad_state(self, grads):
-        st = super()._grad_state(grads)
-        if "bmax" not in st:
-            bns = self.plan.all_bns()
-            mx = torch.zeros(sum(2 * C for _, C in bns), device=self.dev, dtype=torch.float32)
-            bmax, off = {}, 0
-            for name, C in bns:
-                bmax[name] = mx[off:off + 2 * C]
-                off += 2 * C
-            st["maxes"], st["bmax"] = mx, bmax
-        return st
-
     # ------------------------------------------------------------------ conv helpers
     def _conv_fwd16(self, conv, x, x_sc, N, H, W, w16, bias=None, stats=None):
         ops = self.ops
@@ -165,14 +153,11 @@ class Engine16(_net.Engine):
         ops = self.ops
         C = st.C
         M = z.numel() // C
-        sums, maxes = self._gs["bsum"][st.name], self._gs["bmax"][st.name]
-        ops.bn_bwd_reduce_mx(dy, z, mask_hi, st.scale, st.shift, st.mean, st.invstd, relu, M, C,
-                             sums, maxes)
         dz = self._half(*z.shape)
         dz_sc = torch.empty(2, device=self.dev, dtype=torch.float32)
-        ops.bn_bwd_apply_split(dy, z, mask_hi, st.scale, st.shift, st.mean, st.invstd,
-                               params[st.name + ".weight"], relu, sums, maxes, M, C, dz, dz_sc,
-                               dy_masked, grads[st.name + ".weight"], grads[st.name + ".bias"])
+        ops.bn_bwd_split(dy, z, mask_hi, st.scale, st.shift, st.mean, st.invstd,
+                         params[st.name + ".weight"], relu, M, C, dz, dz_sc, dy_masked,
+                         grads[st.name + ".weight"], grads[st.name + ".bias"])
         return dz, dz_sc
 
     # ------------------------------------------------------------------ forward
@@ -200,11 +185,20 @@ class Engine16(_net.Engine):
         def stats_of(name, C):
             return stats_all[offs[name]:offs[name] + 2 * C]
 
-        def bn(name, C, M):
-            st = self._bn_train(name, C, stats_of(name, C), M, params, None) if training \
-                else self._bn_eval(name, C, params)
+        def bn(name, C, M, sc=None, group2=(None, None, None), res_sc=None):
+            """BatchNorm state of conv output `name`; with sc also the scale of its post-activation
+            split tensor (train(): the same launch)."""
+            if training:
+                fused = None if sc is None else group2 + (res_sc, sc)
+                st = self._bn_train(name, C, stats_of(name, C), M, params, None, act_scale=fused)
+            else:
+                st = self._bn_eval(name, C, params)
+                if sc is not None:
+                    ops.act_scale(stats_of(name, C), st.scale, st.shift, M, C, *group2, res_sc, sc)
             S["bn"][name] = st
             return st
+
+        self._nbt_tick = []
 
         S["packed"] = self._pack_weights(params)
         S["w16"] = self._split_weights(S["packed"])
@@ -212,15 +206,15 @@ class Engine16(_net.Engine):
         def w16(conv):
             return S["w16"][conv.name][0]
 
-        def act(z, name, st, shape):
-            """post-BatchNorm/ReLU split tensor of conv output z and its scale"""
+        def bn_act(z, name, shape):
+            """BatchNorm state of conv output z, its post-BatchNorm/ReLU split tensor and scale"""
             C = shape[-1]
             M = z.numel() // C
             sc = new_sc()
-            ops.act_scale(stats_of(name, C), st.scale, st.shift, M, C, None, None, None, None, sc)
+            st = bn(name, C, M, sc)
             a = self._half(*shape)
             ops.bn_act_split(z, st.scale, st.shift, None, None, None, None, None, 1, M, C, a, sc)
-            return a, sc
+            return st, a, sc
 
         # ---- stem (pose3d_resnet.py:186-189): patch matrix -> 1x1 GEMM -> BN+ReLU+maxpool
         stem, scol, kpad = plan.stem, self.stem_col, self.stem_kpad
@@ -229,12 +223,10 @@ class Engine16(_net.Engine):
         isc = cst["img_sc"]
         ops.im2col_split(x_nchw, col, isc, N, 3, H, W, 7, 7, 2, 3, H1, W1, kpad)
         z0, _, _ = self._conv_fwd16(scol, col, isc, N, H1, W1, w16(stem), stats=stats_of("bn1", 64))
-        b0 = bn("bn1", 64, N * H1 * W1)
+        cur_sc = new_sc()
+        b0 = bn("bn1", 64, N * H1 * W1, cur_sc)
         H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
         cur = self._half(N, H2, W2, 64)
-        cur_sc = new_sc()
-        ops.act_scale(stats_of("bn1", 64), b0.scale, b0.shift, N * H1 * W1, 64, None, None, None, None,
-                      cur_sc)
         argidx = torch.empty((N, H2, W2, 64), device=self.dev, dtype=torch.uint8)
         ops.bn_relu_maxpool_split(z0, b0.scale, b0.shift, cur, cur_sc, argidx, N, H1, W1, 64)
         S["stem"] = (col, z0, argidx, H1, W1, H2, W2)
@@ -250,15 +242,13 @@ class Engine16(_net.Engine):
                 bname, C = blk["bns"][ci]
                 z, ho, wo = self._conv_fwd16(conv, src, src_sc, N, hh, ww, w16(conv),
                                              stats=stats_of(bname, C))
-                st = bn(bname, C, N * ho * wo)
                 rec["z"].append(z)
                 rec["hw"].append((hh, ww))
                 hh, ww = ho, wo
                 if ci < nconv - 1:
-                    src, src_sc = act(z, bname, st, (N, hh, ww, conv.cout_p))
+                    _, src, src_sc = bn_act(z, bname, (N, hh, ww, conv.cout_p))
                     rec["a"].append((src, src_sc))
             lname = blk["bns"][-1][0]
-            last = S["bn"][lname]
             zl = rec["z"][-1]
             Cl = blk["convs"][-1].cout_p
             M = N * hh * ww
@@ -270,13 +260,11 @@ class Engine16(_net.Engine):
                                             stats=stats_of(dname, dC))
                 dst = bn(dname, dC, M)
                 rec["zd"] = zd
-                ops.act_scale(stats_of(lname, Cl), last.scale, last.shift, M, Cl,
-                              stats_of(dname, dC), dst.scale, dst.shift, None, out_sc)
+                last = bn(lname, Cl, M, out_sc, (stats_of(dname, dC), dst.scale, dst.shift))
                 ops.bn_act_split(zl, last.scale, last.shift, zd, dst.scale, dst.shift, None, None,
                                  1, M, Cl, out, out_sc)
             else:
-                ops.act_scale(stats_of(lname, Cl), last.scale, last.shift, M, Cl, None, None, None,
-                              cur_sc, out_sc)
+                last = bn(lname, Cl, M, out_sc, res_sc=cur_sc)
                 ops.bn_act_split(zl, last.scale, last.shift, None, None, None, cur, cur_sc, 1, M, Cl,
                                  out, out_sc)
             rec["out"] = (out, out_sc)
@@ -290,9 +278,8 @@ class Engine16(_net.Engine):
         zlast, stlast = None, None
         for conv, (bname, C) in plan.deconvs:
             z, ho, wo = self._conv_fwd16(conv, src, src_sc, N, h, w, w16(conv), stats=stats_of(bname, C))
-            st = bn(bname, C, N * ho * wo)
             S["deconv"].append((src, src_sc, z, h, w))
-            src, src_sc = act(z, bname, st, (N, ho, wo, conv.cout_p))
+            st, src, src_sc = bn_act(z, bname, (N, ho, wo, conv.cout_p))
             h, w = ho, wo
             zlast, stlast = z, st
         if zlast is None:
@@ -318,14 +305,14 @@ class Engine16(_net.Engine):
             depth, _, _ = self._conv_fwd(plan.fc, pooled, N, 1, 1, S["packed"][plan.fc.name][0],
                                          bias=params["depth_fc.bias"])
             S["fc"] = pooled
+        tick, self._nbt_tick = self._nbt_tick, None
+        if tick:
+            torch._foreach_add_(tick, 1)        # num_batches_tracked of every BatchNorm: one launch
         return logits, depth, (S if save else None)
 
     # ------------------------------------------------------------------ backward
     def backward(self, S, dlogits, ddepth, params, grads, on_stage=None):
         self.dev = dlogits.device
-        self._gs = None
-        gs = self._grad_state(grads)
-        gs["maxes"].zero_()
         super().backward(S, dlogits, ddepth, params, grads, on_stage=on_stage)
 
     def _backward(self, S, dlogits, ddepth, params, grads):

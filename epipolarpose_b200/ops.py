@@ -19,6 +19,7 @@ launches = 0
 _KERNELS_PER_CALL = {
     "epb_softargmax_fwd": 2, "epb_bn_bwd_apply": 2, "epb_colsum": 3,
     "epb_split16_batch": 3, "epb_split16": 3, "epb_bn_bwd_apply_split": 2, "epb_conv16_wgrad": 2,
+    "epb_bn_bwd_reduce_mx": 2, "epb_bn_bwd_split": 3,
 }
 
 
@@ -197,6 +198,13 @@ def act_scale(stats, scale, shift, M, C, stats2, scale2, shift2, res_sc, sc):
           _p(stats2, torch.float64), _p(scale2), _p(shift2), _p(res_sc), _p(sc), _stream())
 
 
+def bn_finalize_scale(stats, M, C, gamma, beta, eps, momentum, running_mean, running_var, scale, shift,
+                      mean, invstd, stats2, scale2, shift2, res_sc, sc):
+    _call("epb_bn_finalize_scale", _p(stats, torch.float64), M, C, _p(gamma), _p(beta), eps, momentum,
+          _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd),
+          _p(stats2, torch.float64), _p(scale2), _p(shift2), _p(res_sc), _p(sc), _stream())
+
+
 def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc):
     _call("epb_bn_act_split", _p(x), _p(scale), _p(shift), _p(r), _p(rscale), _p(rshift),
           _p(r_split, _H), _p(r_sc), int(relu), M, C, _p(y, _H), _p(y_sc), _stream())
@@ -260,6 +268,13 @@ def bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, 
     _call("epb_bn_bwd_apply_split", _p(dy), _p(x), _p(mask_hi, _H), _p(scale), _p(shift), _p(mean),
           _p(invstd), _p(gamma), int(relu), _p(sums, torch.float64), _p(maxes), M, C, _p(dz, _H),
           _p(dz_sc), _p(dy_masked), _p(dgamma), _p(dbeta), _stream())
+
+
+def bn_bwd_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, M, C, dz, dz_sc, dy_masked,
+                 dgamma, dbeta):
+    _call("epb_bn_bwd_split", _p(dy), _p(x), _p(mask_hi, _H), _p(scale), _p(shift), _p(mean),
+          _p(invstd), _p(gamma), int(relu), M, C, _p(dz, _H), _p(dz_sc), _p(dy_masked), _p(dgamma),
+          _p(dbeta), _stream())
 
 
 def avgpool_split(x, x_sc, y, N, HW, C):

@@ -213,6 +213,14 @@ typedef uint16_t epb_half;
 int epb_act_scale(const double* stats, const float* scale, const float* shift, int64_t M, int C,
                   const double* stats2, const float* scale2, const float* shift2,
                   const float* res_sc, float* sc, epb_stream_t stream);
+/* epb_bn_finalize of one layer + epb_act_scale of its post-activation tensor in ONE launch
+ * (train() forward of the split path: one single-CTA kernel per BatchNorm instead of two).
+ * Group 1 = (stats, the scale / shift this call produces); group 2 / res_sc as epb_act_scale. */
+int epb_bn_finalize_scale(const double* stats, int64_t M, int C, const float* gamma,
+                          const float* beta, float eps, float momentum, float* running_mean,
+                          float* running_var, float* scale, float* shift, float* mean,
+                          float* invstd, const double* stats2, const float* scale2,
+                          const float* shift2, const float* res_sc, float* sc, epb_stream_t stream);
 /* y_split = act(x*scale+shift [+ residual]).  The residual is either fp32 rows `r`
  * (with optional affine rscale/rshift: the downsample BatchNorm) or a split tensor
  * `r_split` / `r_sc` (the identity path: the previous block's output), or absent. */
@@ -272,6 +280,7 @@ int epb_conv16_wgrad(const epb_conv_geom* g, const epb_half* in, const float* in
  * (hi plane of the block output), else (x*scale+shift > 0) if relu, else 1.
  * reduce: sums as epb_bn_bwd_reduce; maxes[0..C) = max |g|, maxes[C..2C) = max |xhat|
  *         (float, caller zeroes; used to bound |dz| for the scale of the split output).
+ *         Two launches: per-CTA partials, then a fixed-order combine (deterministic).
  * apply : dz_split = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M) with the power-of-two
  *         scale derived from the bound written to dz_sc[2]; if dy_masked != NULL the
  *         masked gradient g is also written there (may alias dy: the identity path of
@@ -286,6 +295,13 @@ int epb_bn_bwd_apply_split(const float* dy, const float* x, const epb_half* mask
                            const double* sums, const float* maxes, int64_t M, int C,
                            epb_half* dz, float* dz_sc, float* dy_masked, float* dgamma,
                            float* dbeta, epb_stream_t stream);
+/* Both passes in one call (what the engine uses): per-CTA partial reductions, a fixed-order
+ * combine (no atomics: dgamma / dbeta / the scale of dz are run-to-run identical), apply.
+ * Outputs as epb_bn_bwd_apply_split; the sums / maxes live in internal scratch of the stream. */
+int epb_bn_bwd_split(const float* dy, const float* x, const epb_half* mask_hi, const float* scale,
+                     const float* shift, const float* mean, const float* invstd,
+                     const float* gamma, int relu, int64_t M, int C, epb_half* dz, float* dz_sc,
+                     float* dy_masked, float* dgamma, float* dbeta, epb_stream_t stream);
 /* VOLUME=False head on a split tensor: y[n][c] = mean over HW of x (fp32 out) */
 int epb_avgpool_split(const epb_half* x, const float* x_sc, float* y, int N, int HW, int C,
                       epb_stream_t stream);

@@ -551,6 +551,13 @@ def act_scale(stats, scale, shift, M, C, stats2, scale2, shift2, res_sc, sc):
     sc[0], sc[1], sc[2], sc[3] = s, 1.0 / s, bound, 0.0
 
 
+def bn_finalize_scale(stats, M, C, gamma, beta, eps, momentum, running_mean, running_var, scale, shift,
+                      mean, invstd, stats2, scale2, shift2, res_sc, sc):
+    bn_finalize(stats, M, C, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
+                invstd)
+    act_scale(stats, scale, shift, M, C, stats2, scale2, shift2, res_sc, sc)
+
+
 def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc):
     v = x.reshape(M, C)
     if scale is not None:
@@ -686,6 +693,15 @@ def bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, 
         dgamma.copy_(sums[C:].float())
     if dbeta is not None:
         dbeta.copy_(sums[:C].float())
+
+
+def bn_bwd_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, M, C, dz, dz_sc, dy_masked,
+                 dgamma, dbeta):
+    sums = torch.zeros(2 * C, dtype=torch.float64)
+    maxes = torch.zeros(2 * C)
+    bn_bwd_reduce_mx(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, sums, maxes)
+    bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, sums, maxes, M, C,
+                       dz, dz_sc, dy_masked, dgamma, dbeta)
 
 
 def avgpool_split(x, x_sc, y, N, HW, C):

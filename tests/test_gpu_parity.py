@@ -102,7 +102,7 @@ def test_softargmax_any_volume_shape(dev, shape, memory):
     import lib.core.integral_loss as il
     N, J, D, H, W = shape
     logits = gi.logits(N, J, D, H, W, 91, 3.0)
-    ref = restate.softmax_integral(logits, J, D, H, W)
+    ref = restate.softmax_integral(logits, J, W, H, D)
     x = torch.from_numpy(logits).to(dev)
     if memory == "channels_last":
         x = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
@@ -115,7 +115,7 @@ def test_softargmax_any_volume_shape(dev, shape, memory):
     assert np.max(np.abs(c.detach().cpu().numpy() - ref)) <= 1e-5
     g = np.random.default_rng(4).standard_normal((N, J * 3)).astype(np.float32)
     c.backward(torch.from_numpy(g).to(dev))
-    gref = restate.softmax_integral_grad(logits, g, J, D, H, W)
+    gref = restate.softmax_integral_grad(logits, g, J, W, H, D)
     assert relerr(x.grad.cpu().numpy(), gref) <= 1e-3
 
 

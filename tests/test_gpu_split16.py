@@ -273,6 +273,81 @@ def test_bn_bwd_split_vs_emulation(dev, mode):
         assert torch.equal(dyg.cpu(), dm_r)
 
 
+@pytest.mark.parametrize("C,second,res", [(64, False, False), (256, True, False), (2048, False, True)])
+def test_bn_finalize_scale_vs_two_calls(dev, C, second, res):
+    """epb_bn_finalize_scale == epb_bn_finalize followed by epb_act_scale (same device kernels' arithmetic):
+    scale / shift / mean / invstd / running statistics bit-identical, published scale identical."""
+    from epipolarpose_b200 import ops
+    gen = torch.Generator().manual_seed(7 + C)
+    M = 5000
+
+    def stats():
+        x = torch.randn(M, C, generator=gen, dtype=torch.float64) * 3 + 0.7
+        return torch.cat([x.sum(0), (x * x).sum(0)]).to(dev)
+
+    st1, st2 = stats(), (stats() if second else None)
+    gamma, beta = (torch.rand(C, generator=gen) + 0.5).to(dev), (torch.randn(C, generator=gen) * 0.1).to(dev)
+    s2 = (torch.rand(C, generator=gen) + 0.5).to(dev) if second else None
+    h2 = (torch.randn(C, generator=gen) * 0.1).to(dev) if second else None
+    res_sc = torch.tensor([4.0, 0.25, 37.5, 0.0], device=dev) if res else None
+    outs = []
+    for fused in (False, True):
+        rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        sc_, sh_, mu, iv = (torch.empty(C, device=dev) for _ in range(4))
+        sc = torch.empty(4, device=dev)
+        if fused:
+            ops.bn_finalize_scale(st1, M, C, gamma, beta, 1e-5, 0.1, rm, rv, sc_, sh_, mu, iv, st2, s2, h2, res_sc, sc)
+        else:
+            ops.bn_finalize(st1, M, C, gamma, beta, 1e-5, 0.1, rm, rv, sc_, sh_, mu, iv)
+            ops.act_scale(st1, sc_, sh_, M, C, st2, s2, h2, res_sc, sc)
+        outs.append([t.cpu() for t in (sc_, sh_, mu, iv, rm, rv, sc)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("M,C,mode", [(3000, 256, "mask_inplace"), (70001, 64, "relu"), (517, 2048, "mask"),
+                                       (9, 64, "plain"), (40000, 1024, "relu"), (2, 512, "mask")])
+def test_bn_bwd_fused_entry_vs_emulation_and_deterministic(dev, M, C, mode):
+    """epb_bn_bwd_split (partials -> fixed-order combine -> apply, what the engine calls) against the
+    emulation of the two-call form; two runs are bit-identical (no atomics in the reduction)."""
+    from epipolarpose_b200 import ops
+    gen = torch.Generator().manual_seed(43 + C)
+    x = torch.randn(M, C, generator=gen) * 2 + 0.3
+    dy = torch.randn(M, C, generator=gen) * 1e-4
+    gamma, beta = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen) * 0.1
+    mean = x.mean(0)
+    invstd = 1.0 / torch.sqrt(x.var(0, unbiased=False) + 1e-5)
+    scale, shift = gamma * invstd, beta - mean * gamma * invstd
+    out, _ = _rand_split((M, C), 44)
+    mask = out[0].contiguous() if mode.startswith("mask") else None
+    relu = 1 if mode == "relu" else 0
+    dz_r, sc_r = torch.empty(2, M, C, dtype=H16), torch.empty(2)
+    dm_r = dy.clone() if mode == "mask_inplace" else None
+    dg_r, db_r = torch.empty(C), torch.empty(C)
+    em.bn_bwd_split(dy, x, mask, scale, shift, mean, invstd, gamma, relu, M, C, dz_r, sc_r, dm_r, dg_r, db_r)
+    D = lambda t: t.to(dev) if t is not None else None
+    runs = []
+    for _ in range(2):
+        dyg = dy.to(dev)
+        dz, sc = torch.empty(2, M, C, dtype=H16, device=dev), torch.empty(2, device=dev)
+        dg, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
+        ops.bn_bwd_split(dyg, D(x), D(mask), D(scale), D(shift), D(mean), D(invstd), D(gamma), relu, M, C,
+                         dz, sc, dyg if mode == "mask_inplace" else None, dg, db)
+        torch.cuda.synchronize()
+        runs.append((dz.cpu(), sc.cpu(), dg.cpu(), db.cpu(), dyg.cpu()))
+    dz, sc, dg, db, dyg = runs[0]
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a.view(torch.int16) if a.dtype == H16 else a, b.view(torch.int16) if b.dtype == H16 else b)
+    s_g, s_r = float(sc[0]), float(sc_r[0])
+    assert s_g in (s_r, 2 * s_r, s_r / 2) and float(sc[1]) == 1.0 / s_g
+    b = em._join(dz_r, sc_r).numpy()
+    assert relerr(em._join(dz, sc).numpy(), b) <= 1e-5
+    assert float(np.max(np.abs(b))) * s_g <= 65504
+    assert relerr(dg.numpy(), dg_r.numpy()) <= 2e-5 and relerr(db.numpy(), db_r.numpy()) <= 2e-5
+    if mode == "mask_inplace":
+        assert torch.equal(dyg, dm_r)
+
+
 # ------------------------------------------------------------------ the bench's own layer shapes
 # (profiles/r2_step_table_f16x3.md): N = 128 images, every distinct conv kind / channel pair of
 # ResNet-50 at 256x256.  Reference: torch float64 convolutions (cuDNN / cuBLAS fp64 on the same

@@ -430,7 +430,8 @@ bn_bwd_partial_kernel(const float4* __restrict__ dy, const float4* __restrict__ 
   }
 }
 
-// Pass 2: 32 channels per CTA, 8 groups of partials per channel added in a fixed order.
+// Pass 2: 8 channels per CTA (one 32-byte sector per row), 32 groups of partials per channel, every
+// group and then the groups added in a fixed order.
 //   coef == NULL : sums[0..2C) += (sum g, sum g*xhat), maxes = max(maxes, ...)   (epb_bn_bwd_reduce_mx)
 //   coef != NULL : coef[0..2C) = (k1 = sum_g/M, k2 = sum_gx/M), parameter gradients, and the bound
 //     |dz_c| <= |gamma_c*invstd_c| * (max|g|_c + |k1_c| + max|xhat|_c * |k2_c|)  max-ed into *bound_bits
@@ -440,28 +441,49 @@ bn_bwd_combine_kernel(const float* __restrict__ parts, int W, double M, int C,
                       const float* __restrict__ gamma, const float* __restrict__ invstd,
                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                       uint32_t* __restrict__ bound_bits) {
-  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+  const int ch = threadIdx.x & 7, g = threadIdx.x >> 3;        // 32 groups
+  const int c = blockIdx.x * 8 + ch;
   double a0 = 0, a1 = 0;
   float m0 = 0.f, m1 = 0.f;
   if (c < C) {
-    for (int w = g; w < W; w += 8) {
-      a0 += (double)parts[((int64_t)0 * W + w) * C + c];
-      a1 += (double)parts[((int64_t)1 * W + w) * C + c];
-      m0 = fmaxf(m0, parts[((int64_t)2 * W + w) * C + c]);
-      m1 = fmaxf(m1, parts[((int64_t)3 * W + w) * C + c]);
+    const float* p0 = parts + c;
+    const int64_t plane = (int64_t)W * C;
+    for (int w0 = g; w0 < W; w0 += 32 * 8) {       // batches of 8 rows: 32 independent loads in flight
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int w = w0 + 32 * u;
+        const int64_t o = (int64_t)(w < W ? w : 0) * C;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k][u] = (w < W) ? __ldg(p0 + k * plane + o) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a0 += (double)v[0][u];
+        a1 += (double)v[1][u];
+        m0 = fmaxf(m0, v[2][u]);
+        m1 = fmaxf(m1, v[3][u]);
+      }
     }
   }
-  __shared__ double sa[2][8][32];
-  __shared__ float sm[2][8][32];
-  sa[0][g][lane] = a0; sa[1][g][lane] = a1;
-  sm[0][g][lane] = m0; sm[1][g][lane] = m1;
+  __shared__ double sa[2][32][8];
+  __shared__ float sm[2][32][8];
+  sa[0][g][ch] = a0; sa[1][g][ch] = a1;
+  sm[0][g][ch] = m0; sm[1][g][ch] = m1;
   __syncthreads();
-  if (g != 0) return;
-  for (int q = 1; q < 8; ++q) {
-    a0 += sa[0][q][lane]; a1 += sa[1][q][lane];
-    m0 = fmaxf(m0, sm[0][q][lane]); m1 = fmaxf(m1, sm[1][q][lane]);
+#pragma unroll
+  for (int half = 16; half > 0; half >>= 1) {      // fixed pairing: run-to-run identical
+    if (g < half) {
+      sa[0][g][ch] += sa[0][g + half][ch];
+      sa[1][g][ch] += sa[1][g + half][ch];
+      sm[0][g][ch] = fmaxf(sm[0][g][ch], sm[0][g + half][ch]);
+      sm[1][g][ch] = fmaxf(sm[1][g][ch], sm[1][g + half][ch]);
+    }
+    __syncthreads();
   }
+  if (g != 0) return;
+  a0 = sa[0][0][ch]; a1 = sa[1][0][ch];
+  m0 = sm[0][0][ch]; m1 = sm[1][0][ch];
   float bound = 0.f;
   if (c < C) {
     if (!coef) {
@@ -479,9 +501,9 @@ bn_bwd_combine_kernel(const float* __restrict__ parts, int W, double M, int C,
       bound = fabsf(k0) * (m0 + fabsf(k1) + m1 * fabsf(k2));
     }
   }
-  if (coef) {
-    bound = warp_max(bound);
-    if (lane == 0) atomicMax(bound_bits, __float_as_uint(bound));   // order-independent
+  if (coef) {                                  // threads 0..7 of warp 0
+    for (int o = 4; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffu, bound, o));
+    if (ch == 0) atomicMax(bound_bits, __float_as_uint(bound));   // order-independent
   }
 }
 
@@ -672,6 +694,114 @@ bn_finalize_scale_kernel(const double* __restrict__ stats, double M, int C,
   }
 }
 
+// ------------------------------------------------------------------ soft-argmax backward -> split logit gradient
+// dlogit = p * (s - sbar) (softargmax.cu softargmax_bwd_nhwc) written straight as the split operand of the
+// final layer's backward, plus per-CTA column sums for the bias gradient (summed in a fixed order).
+// Scale from a hard bound: p <= 1/sum(e^{v-m}) = lse[1], |s - sbar| <= |gx| + |gy| + |gz|.
+__global__ void __launch_bounds__(1024)
+softargmax_bwd_bound_kernel(const float* __restrict__ lse, const float* __restrict__ dcoords, int NJ,
+                            float* __restrict__ sc) {
+  float b = 0.f;
+  for (int i = threadIdx.x; i < NJ; i += blockDim.x)
+    b = fmaxf(b, lse[i * 2 + 1] * (fabsf(dcoords[i * 3]) + fabsf(dcoords[i * 3 + 1]) + fabsf(dcoords[i * 3 + 2])));
+  b = warp_max(b);
+  __shared__ float sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) b = fmaxf(b, sm[w]);
+    const float s = pow2_scale(b);
+    sc[0] = s;
+    sc[1] = 1.f / s;
+  }
+}
+
+// grid (S, N), block C4 * ppi (C4 = J*D/4 channel quads, ppi pixels per trip); as softargmax_bwd_nhwc
+__global__ void softargmax_bwd_split_kernel(const float* __restrict__ logits, int J, int D, int H, int W,
+                                            int S, int ppi, const float* __restrict__ coords,
+                                            const float* __restrict__ lse,
+                                            const float* __restrict__ dcoords,
+                                            const float* __restrict__ sc, uint2* __restrict__ planes,
+                                            int64_t total4, float* __restrict__ parts) {
+  extern __shared__ float4 shq[];            // [blockDim]
+  const int n = blockIdx.y, sp = blockIdx.x;
+  const int C4 = (J * D) >> 2;
+  const int HW = H * W;
+  const int per = (HW + S - 1) / S;
+  const int pbeg = sp * per, pend = min(HW, pbeg + per);
+  const int c4 = threadIdx.x % C4, sub = threadIdx.x / C4;
+  const int D4 = D >> 2;
+  const int j = c4 / D4;
+  const float z0 = (float)((c4 % D4) << 2);
+  const int nj = n * J + j;
+  const float m = lse[nj * 2], inv = lse[nj * 2 + 1];
+  const float gx = dcoords[nj * 3] / W, gy = dcoords[nj * 3 + 1] / H, gz = dcoords[nj * 3 + 2] / D;
+  const float sbar = gx * (coords[nj * 3] + 0.5f) * W + gy * (coords[nj * 3 + 1] + 0.5f) * H +
+                     gz * (coords[nj * 3 + 2] + 0.5f) * D;
+  const float s = sc[0];
+  const int64_t img = (int64_t)n * HW * C4 + c4;
+  const float4* base = reinterpret_cast<const float4*>(logits) + img;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int pix = pbeg + sub;
+  int y = pix / W, x = pix - y * W;
+  for (; pix < pend; pix += ppi) {
+    const float4 v = ldg_stream(base + (int64_t)pix * C4);
+    const float s0 = gx * x + gy * y + gz * z0 - sbar;
+    float4 o;
+    o.x = __expf(v.x - m) * inv * (s0);
+    o.y = __expf(v.y - m) * inv * (s0 + gz);
+    o.z = __expf(v.z - m) * inv * (s0 + 2.f * gz);
+    o.w = __expf(v.w - m) * inv * (s0 + 3.f * gz);
+    uint2 hi, lo;
+    split2(o.x, o.y, s, hi.x, lo.x);
+    split2(o.z, o.w, s, hi.y, lo.y);
+    const int64_t i = img + (int64_t)pix * C4;
+    planes[i] = hi;
+    planes[total4 + i] = lo;
+    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    x += ppi;
+    while (x >= W) { x -= W; ++y; }
+  }
+  shq[threadIdx.x] = acc;
+  __syncthreads();
+  if (sub == 0) {
+    for (int q = 1; q < ppi; ++q) {
+      const float4 t = shq[q * C4 + c4];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    reinterpret_cast<float4*>(parts)[((int64_t)n * S + sp) * C4 + c4] = acc;
+  }
+}
+
+// out[c] = sum over rows of parts[r][c] in a fixed order (8 channels x 32 row groups per CTA)
+__global__ void __launch_bounds__(256)
+colsum_parts_kernel(const float* __restrict__ parts, int rows, int C, float* __restrict__ out) {
+  const int ch = threadIdx.x & 7, g = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + ch;
+  double a = 0;
+  if (c < C) {
+    for (int r0 = g; r0 < rows; r0 += 32 * 16) {     // 16 independent loads in flight
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int r = r0 + 32 * u;
+        v[u] = (r < rows) ? __ldg(parts + (int64_t)r * C + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) a += (double)v[u];
+    }
+  }
+  __shared__ double sa[32][8];
+  sa[g][ch] = a;
+  __syncthreads();
+#pragma unroll
+  for (int half = 16; half > 0; half >>= 1) {
+    if (g < half) sa[g][ch] += sa[g + half][ch];
+    __syncthreads();
+  }
+  if (g == 0 && c < C) out[c] = (float)sa[0][ch];
+}
+
 __global__ void avgpool_split_kernel(const __half* __restrict__ x, const float* __restrict__ x_sc,
                                      float* __restrict__ y, int N, int HW, int C) {
   const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -793,7 +923,7 @@ EPB_API int epb_bn_bwd_reduce_mx(const float* dy, const float* x, const epb_half
   if (rc) return rc;
   launch_bn_bwd_partial(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, rm, W, parts, nullptr, st);
   EPB_LAUNCH_CHECK();
-  bn_bwd_combine_kernel<<<(C + 31) / 32, 256, 0, st>>>(parts, W, (double)M, C, sums, maxes, nullptr,
+  bn_bwd_combine_kernel<<<(C + 7) / 8, 256, 0, st>>>(parts, W, (double)M, C, sums, maxes, nullptr,
                                                         nullptr, nullptr, nullptr, nullptr, nullptr);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
@@ -815,7 +945,7 @@ EPB_API int epb_bn_bwd_split(const float* dy, const float* x, const epb_half* ma
   if (rc) return rc;
   launch_bn_bwd_partial(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, rm, W, parts, bound, st);
   EPB_LAUNCH_CHECK();
-  bn_bwd_combine_kernel<<<(C + 31) / 32, 256, 0, st>>>(parts, W, (double)M, C, nullptr, nullptr, coef,
+  bn_bwd_combine_kernel<<<(C + 7) / 8, 256, 0, st>>>(parts, W, (double)M, C, nullptr, nullptr, coef,
                                                         gamma, invstd, dgamma, dbeta, bound);
   EPB_LAUNCH_CHECK();
   const int64_t total4 = M * (C / 4);
@@ -889,6 +1019,35 @@ EPB_API int epb_bn_finalize_scale(const double* stats, int64_t M, int C, const f
       stats, (double)M, C, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean,
       invstd, stats2, scale2, shift2, res_sc, sc);
   EPB_LAUNCH_CHECK();
+  return EPB_OK;
+}
+
+EPB_API int epb_softargmax_bwd_split(const float* logits, int N, int J, int D, int H, int W,
+                                     const float* coords, const float* lse_ws, const float* dcoords,
+                                     epb_half* dlogits16, float* sc, float* dbias, epb_stream_t stream) {
+  EPB_CHECK_ARG(logits && coords && lse_ws && dcoords && dlogits16 && sc);
+  EPB_CHECK_ARG(N > 0 && J > 0 && D > 0 && H > 0 && W > 0 && D % 4 == 0);
+  const int C4 = J * D / 4;
+  EPB_CHECK_ARG(C4 <= 1024);
+  cudaStream_t st = as_stream(stream);
+  const int ppi = (512 / C4) > 0 ? (512 / C4) : 1;
+  int S = 1;
+  while (N * S < 8 * kNumSMs && (H * W) / (S * 2) >= 16 * ppi) S *= 2;
+  void* parts = nullptr;
+  int rc = epb_workspace(EPB_WS_SABWD, (size_t)N * S * C4 * 4 * sizeof(float), st, &parts);
+  if (rc) return rc;
+  softargmax_bwd_bound_kernel<<<1, 1024, 0, st>>>(lse_ws, dcoords, N * J, sc);
+  EPB_LAUNCH_CHECK();
+  const int threads = C4 * ppi;
+  softargmax_bwd_split_kernel<<<dim3(S, N), threads, threads * sizeof(float4), st>>>(
+      logits, J, D, H, W, S, ppi, coords, lse_ws, dcoords, sc, reinterpret_cast<uint2*>(dlogits16),
+      (int64_t)N * H * W * C4, static_cast<float*>(parts));
+  EPB_LAUNCH_CHECK();
+  if (dbias) {
+    colsum_parts_kernel<<<(C4 * 4 + 7) / 8, 256, 0, st>>>(static_cast<const float*>(parts), N * S,
+                                                            C4 * 4, dbias);
+    EPB_LAUNCH_CHECK();
+  }
   return EPB_OK;
 }
 

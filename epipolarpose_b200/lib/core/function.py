@@ -28,6 +28,24 @@ from ..utils.utils import AverageMeter
 logger = logging.getLogger(__name__)
 
 
+class _fused_head:
+    """Inside the training step nobody but the criterion consumes the logits: let the criterion hand
+    their gradient to the network's backward as split planes (_sinks.py).  Off elsewhere, so that
+    user code that inspects the logit gradient (retain_grad, hooks, autograd.grad) sees fp32 values."""
+
+    def __init__(self, model):
+        net = getattr(model, "module", model)
+        self.net = net if hasattr(net, "fused_head_gradient") else None
+
+    def __enter__(self):
+        if self.net is not None:
+            self.prev, self.net.fused_head_gradient = self.net.fused_head_gradient, True
+
+    def __exit__(self, *exc):
+        if self.net is not None:
+            self.net.fused_head_gradient = self.prev
+
+
 def _online_tri(config):
     train = getattr(config, 'TRAIN', None)
     return bool(train is not None and getattr(train, 'ONLINE_TRIANGULATION', False))
@@ -91,7 +109,8 @@ class GraphedTrainStep:
 
     def _eager(self, x, label, weight, geom):
         self.optimizer.zero_grad()
-        preds = self.model(x)
+        with _fused_head(self.model):
+            preds = self.model(x)
         if self.online:
             loss = online_epipolar_loss(self.criterion, preds, {"_packed": geom}, self.method)
         else:
@@ -243,7 +262,8 @@ def train_integral(config, train_loader, model, criterion, optimizer, epoch):
         else:
             optimizer.zero_grad()
             batch_data = batch_data.cuda(non_blocking=True)
-            preds = model(batch_data)
+            with _fused_head(model):
+                preds = model(batch_data)
             if online:
                 # one soft-argmax pass serves both the epipolar labels and the loss
                 loss = online_epipolar_loss(criterion, preds, meta, method)

@@ -52,6 +52,7 @@ class _SoftArgmaxFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, preds, J, D, H, W):
         ops = _backend[0]
+        sink = getattr(preds, "_epb_logit_sink", None)     # attached by PoseResNet.forward (_sinks.py)
         preds, layout = _layout_of(preds, J, D)
         N = preds.shape[0]
         coords = torch.empty((N, J * 3), device=preds.device, dtype=torch.float32)
@@ -59,6 +60,7 @@ class _SoftArgmaxFn(torch.autograd.Function):
         ops.softargmax_fwd(_storage(preds, layout), layout, N, J, D, H, W, coords, lse)
         ctx.save_for_backward(preds, coords, lse)
         ctx.cfg = (layout, N, J, D, H, W)
+        ctx.sink = sink if (sink is not None and layout == 1 and sink.matches(preds)) else None
         return coords
 
     @staticmethod
@@ -67,6 +69,17 @@ class _SoftArgmaxFn(torch.autograd.Function):
         preds, coords, lse = ctx.saved_tensors
         layout, N, J, D, H, W = ctx.cfg
         st = _storage(preds, layout)
+        sink = ctx.sink
+        if sink is not None and not sink.filled:
+            # the gradient goes to the network's backward as split planes + bias gradient; autograd
+            # carries a zero token (see _sinks.py)
+            sink.planes = torch.empty((2,) + tuple(st.shape), device=st.device, dtype=torch.float16)
+            sink.sc = torch.empty(2, device=st.device, dtype=torch.float32)
+            sink.dbias = torch.empty(J * D, device=st.device, dtype=torch.float32)
+            ops.softargmax_bwd_split(st, N, J, D, H, W, coords, lse, dcoords.contiguous(), sink.planes,
+                                     sink.sc, sink.dbias)
+            sink.filled = True
+            return sink.token.expand(preds.shape), None, None, None, None
         dst = torch.empty_like(st)
         ops.softargmax_bwd(st, layout, N, J, D, H, W, coords, lse, dcoords.contiguous(), dst)
         dl = dst if layout == 0 else dst.permute(0, 3, 1, 2)

@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from epipolarpose_b200 import net as _net
 from epipolarpose_b200 import net16 as _net16
+from epipolarpose_b200 import _sinks
 
 BN_MOMENTUM = 0.1
 logger = logging.getLogger(__name__)
@@ -104,10 +105,15 @@ class _PoseNetFn(torch.autograd.Function):
         ctx.has_depth = depth is not None
         fin = module._plan.final
         N, Ho, Wo, Cp = logits.shape
+        ctx.sink = module._last_sink = None
         if module.volume:
             out = logits.permute(0, 3, 1, 2)          # NCHW view, channels_last memory
             if Cp != fin.cout:
                 out = out[:, :fin.cout]
+            elif need_grad and module.training and module.fused_head_gradient \
+                    and getattr(eng, "takes_logit_sink", lambda: False)():
+                # the criterion may hand the logit gradient over as split planes (_sinks.py)
+                ctx.sink = module._last_sink = _sinks.LogitGradSink(out)
             return out
         hm = torch.empty((N, fin.cout, Ho, Wo), device=x.device, dtype=torch.float32)
         eng.ops.nhwc_to_nchw(logits, hm, N, fin.cout, Ho, Wo, Cp)
@@ -125,8 +131,19 @@ class _PoseNetFn(torch.autograd.Function):
         fin = module._plan.final
         g0 = gouts[0]
         N, Ho, Wo = S["N"], g0.shape[2], g0.shape[3]
+        sink, head = getattr(ctx, "sink", None), None
+        if sink is not None and sink.filled:
+            if sink.is_token(g0):
+                head = sink                             # the whole gradient is in the sink
+            else:
+                # the logits had other consumers too: their (fp32) gradients accumulated onto the
+                # zero token; add the sink's share back and take the fp32 route
+                share = (sink.planes[0].float() + sink.planes[1].float()) * sink.sc[1]
+                g0 = g0 + share.permute(0, 3, 1, 2)
         nhwc = g0.permute(0, 2, 3, 1)
-        if fin.cout_p == fin.cout and nhwc.is_contiguous():
+        if head is not None:
+            dlogits = None
+        elif fin.cout_p == fin.cout and nhwc.is_contiguous():
             dlogits = nhwc                              # zero-copy (channels_last gradient)
         else:
             dlogits = torch.zeros((N, Ho, Wo, fin.cout_p), device=g0.device, dtype=torch.float32)
@@ -173,7 +190,10 @@ class _PoseNetFn(torch.autograd.Function):
                 if k in bounds:
                     a, b = bounds[k]
                     works.append(dist.all_reduce(sflat[a:b], op=dist.ReduceOp.AVG, async_op=True))
-        eng.backward(S, dlogits, ddepth, params, sgrads, on_stage=on_stage)
+        if head is not None:
+            eng.backward(S, None, ddepth, params, sgrads, on_stage=on_stage, head=head)
+        else:
+            eng.backward(S, dlogits, ddepth, params, sgrads, on_stage=on_stage)
         for w_ in works:
             w_.wait()                                   # the current stream waits for the collectives
         flat = sflat.clone()
@@ -194,6 +214,9 @@ class PoseResNet(nn.Module):
         self.deconv_with_bias = extra.DECONV_WITH_BIAS
         self.volume = cfg.MODEL.VOLUME
         self.allreduce_grads = kwargs.get("allreduce_grads", True)
+        # set by the training loops (lib/core/function.py) for the duration of their forward: the
+        # criterion may then pass the logit gradient to backward() as split planes (_sinks.py)
+        self.fused_head_gradient = False
         prec = kwargs.get("precision", getattr(cfg.MODEL, "PRECISION", None)) or \
             os.environ.get("EPB_PRECISION", DEFAULT_PRECISION)
         self.precision = _PRECISIONS[os.environ.get("EPB_PRECISION", prec)]
@@ -272,7 +295,11 @@ class PoseResNet(nn.Module):
         if x.dtype != torch.float32:
             raise TypeError("expected float32 NCHW images")
         params = [p for _, p in self.named_parameters()]
-        return _PoseNetFn.apply(self, x.contiguous(), torch.is_grad_enabled(), *params)
+        out = _PoseNetFn.apply(self, x.contiguous(), torch.is_grad_enabled(), *params)
+        sink = getattr(self, "_last_sink", None)
+        if sink is not None and isinstance(out, torch.Tensor) and sink.ptr == out.data_ptr():
+            out._epb_logit_sink = sink        # read by the soft-argmax criterion (integral_loss.py)
+        return out
 
     # ---- weights (reference :214-286)
     def init_weights(self, pretrained=''):

@@ -568,10 +568,11 @@ class Engine:
         (with the weight-gradient stream current) as soon as stage k of net.STAGES is complete."""
         ops, plan = self.ops, self.plan
         N = S["N"]
-        self.dev = dlogits.device
+        anchor = dlogits if dlogits is not None else self._head.planes    # split path: gradient sink
+        self.dev = anchor.device
         import os
         self._side, self._keep = None, []
-        if dlogits.is_cuda and os.environ.get("EPB_OVERLAP_WGRAD", "1") != "0":
+        if anchor.is_cuda and os.environ.get("EPB_OVERLAP_WGRAD", "1") != "0":
             if getattr(self, "_side_stream", None) is None:
                 self._side_stream = torch.cuda.Stream()
             self._side = self._side_stream

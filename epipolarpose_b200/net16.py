@@ -311,9 +311,18 @@ class Engine16(_net.Engine):
         return logits, depth, (S if save else None)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, S, dlogits, ddepth, params, grads, on_stage=None):
-        self.dev = dlogits.device
-        super().backward(S, dlogits, ddepth, params, grads, on_stage=on_stage)
+    def backward(self, S, dlogits, ddepth, params, grads, on_stage=None, head=None):
+        """head: a filled _sinks.LogitGradSink (the criterion wrote the logit gradient as split planes
+        + bias gradient) instead of the fp32 dlogits."""
+        self._head = head
+        try:
+            super().backward(S, dlogits, ddepth, params, grads, on_stage=on_stage)
+        finally:
+            self._head = None
+
+    def takes_logit_sink(self):
+        fin = self.plan.final
+        return self.plan.fc is None and fin.cout_p == fin.cout and fin.cout_p % 64 == 0
 
     def _backward(self, S, dlogits, ddepth, params, grads):
         ops, plan = self.ops, self.plan
@@ -327,18 +336,24 @@ class Engine16(_net.Engine):
         src, aff, h, w = S["final"]
         Ho, Wo = fin.out_hw(h, w)
         gb = grads[fin.name + ".bias"]
-        if fin.cout_p != fin.cout:
+        head = getattr(self, "_head", None)
+        if head is not None:
+            gb.copy_(head.dbias)                # column sums from the soft-argmax backward itself
+        elif fin.cout_p != fin.cout:
             tmp = torch.empty(fin.cout_p, device=self.dev)
             ops.colsum(dlogits, N * Ho * Wo, fin.cout_p, tmp)
             gb.copy_(tmp[:fin.cout])
         else:
             ops.colsum(dlogits, N * Ho * Wo, fin.cout_p, gb)
         if fin.cout_p % 64 == 0:
-            # the fp32 logit gradient becomes a split operand (amax + split, one batched call):
-            # data and weight gradient on the split kernels like every other layer (deterministic)
-            dl16 = self._half(N, Ho, Wo, fin.cout_p)
-            dl_sc = torch.empty(2, device=self.dev, dtype=torch.float32)
-            ops.split16(dlogits.reshape(-1), dl16.reshape(-1), dl_sc, self._consts()["amax1"])
+            if head is not None:
+                dl16, dl_sc = head.planes, head.sc
+            else:
+                # the fp32 logit gradient becomes a split operand (amax + split): data and weight
+                # gradient on the split kernels like every other layer (deterministic)
+                dl16 = self._half(N, Ho, Wo, fin.cout_p)
+                dl_sc = torch.empty(2, device=self.dev, dtype=torch.float32)
+                ops.split16(dlogits.reshape(-1), dl16.reshape(-1), dl_sc, self._consts()["amax1"])
             fsrc, fsrc_sc = S["final16"]
             self._conv_wgrad16(fin, fsrc, fsrc_sc, dl16, dl_sc, N, h, w)
             dcur = self._conv_dgrad16(fin, dl16, dl_sc, N, h, w, wd16(fin))

@@ -19,7 +19,7 @@ launches = 0
 _KERNELS_PER_CALL = {
     "epb_softargmax_fwd": 2, "epb_bn_bwd_apply": 2, "epb_colsum": 3,
     "epb_split16_batch": 3, "epb_split16": 3, "epb_bn_bwd_apply_split": 2, "epb_conv16_wgrad": 2,
-    "epb_bn_bwd_reduce_mx": 2, "epb_bn_bwd_split": 3,
+    "epb_bn_bwd_reduce_mx": 2, "epb_bn_bwd_split": 3, "epb_softargmax_bwd_split": 3,
 }
 
 
@@ -306,6 +306,11 @@ def heatmap_joint_loss(hm, target, hm_weight, R, HW, hm_scale, x, t, w, n, kind,
 
 def argmax2d(hm, NJ, H, W, idx, maxval, preds):
     _call("epb_argmax2d", _p(hm), NJ, H, W, _p(idx, torch.int32), _p(maxval), _p(preds), _stream())
+
+
+def softargmax_bwd_split(logits, N, J, D, H, W, coords, lse, dcoords, dlogits16, sc, dbias):
+    _call("epb_softargmax_bwd_split", _p(logits), N, J, D, H, W, _p(coords), _p(lse), _p(dcoords),
+          _p(dlogits16, _H), _p(sc), _p(dbias), _stream())
 
 
 def final_preds(hm, N, J, H, W, center, scale, post_process, preds, maxvals):

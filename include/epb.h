@@ -322,6 +322,15 @@ int epb_softargmax_bwd(const float* logits, int layout, int N, int J, int D,
                        int H, int W, const float* coords, const float* lse_ws,
                        const float* dcoords, float* dlogits,
                        epb_stream_t stream);
+/* The same gradient written straight as the split operand of the final layer's backward
+ * (channels_last logits only, D % 4 == 0, J*D/4 <= 1024): dlogits16 = planes [2][N][H][W][J*D],
+ * sc = {s, 1/s} with s from the hard bound max_nj p_max * (|gx|+|gy|+|gz|), and (optional)
+ * dbias[J*D] = column sums of the gradient = the final layer's bias gradient, added in a fixed
+ * order.  Replaces epb_softargmax_bwd + epb_split16 + epb_colsum of the fp32 form (the logit
+ * gradient never exists in fp32: 1 read + 1 write of the volume instead of 4 + 2). */
+int epb_softargmax_bwd_split(const float* logits, int N, int J, int D, int H, int W,
+                             const float* coords, const float* lse_ws, const float* dcoords,
+                             epb_half* dlogits16, float* sc, float* dbias, epb_stream_t stream);
 
 /* Fused joint-location loss (integral_loss.py:7-47): kind 0 = weighted MSE,
  * 1 = weighted L1, 2 = weighted SmoothL1(beta=1).  loss = sum(w*l(x-t))/div,

@@ -289,6 +289,19 @@ def softargmax_bwd(logits, layout, N, J, D, H, W, coords, lse, dcoords, dlogits)
         dlogits.view(N, H, W, J, D).copy_(d.permute(0, 3, 4, 1, 2))
 
 
+def softargmax_bwd_split(logits, N, J, D, H, W, coords, lse, dcoords, dlogits16, sc, dbias):
+    d = torch.empty(N, H, W, J * D)
+    softargmax_bwd(logits, 1, N, J, D, H, W, coords, lse, dcoords, d)
+    g = dcoords.view(N * J, 3).abs().sum(1)
+    bound = float((lse.view(N * J, 2)[:, 1] * g).max())
+    assert float(d.abs().max()) <= bound * (1 + 1e-5) + 1e-30, "logit gradient exceeds its bound"
+    s = _pow2_scale(bound)
+    sc[0], sc[1] = s, 1.0 / s
+    _store_split(dlogits16, d.reshape(-1, J * D), s)
+    if dbias is not None:
+        dbias.copy_(d.reshape(-1, J * D).double().sum(0).float())
+
+
 def heatmap_joint_loss(hm, target, hm_weight, R, HW, hm_scale, x, t, w, n, kind, div, jt_scale,
                        loss, dhm, dx):
     h = hm.reshape(R, HW).double()

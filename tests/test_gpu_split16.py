@@ -273,6 +273,35 @@ def test_bn_bwd_split_vs_emulation(dev, mode):
         assert torch.equal(dyg.cpu(), dm_r)
 
 
+@pytest.mark.parametrize("N,J,D,H,W", [(2, 4, 16, 8, 8), (3, 16, 64, 16, 16), (1, 17, 12, 5, 7), (5, 1, 4, 3, 9)])
+def test_softargmax_bwd_split_vs_emulation(dev, N, J, D, H, W):
+    """epb_softargmax_bwd_split: planes == split of the fp32 gradient (same scale, values <= 2e-6 of the
+    maximum apart: __expf), bias column sums, scale from the hard bound."""
+    from epipolarpose_b200 import ops
+    gen = torch.Generator().manual_seed(N * 100 + J)
+    C = J * D
+    logits = (torch.randn(N, H, W, C, generator=gen) * 3).contiguous()
+    dco = torch.randn(N, J * 3, generator=gen)
+    coords_r, lse_r = torch.empty(N, J * 3), torch.empty(N * J * 2)
+    em.softargmax_fwd(logits, 1, N, J, D, H, W, coords_r, lse_r)
+    pl_r, sc_r, db_r = torch.empty(2, N, H, W, C, dtype=H16), torch.empty(2), torch.empty(C)
+    em.softargmax_bwd_split(logits, N, J, D, H, W, coords_r, lse_r, dco, pl_r, sc_r, db_r)
+    lg = logits.to(dev)
+    coords, lse = torch.empty(N, J * 3, device=dev), torch.empty(N * J * 2, device=dev)
+    ops.softargmax_fwd(lg, 1, N, J, D, H, W, coords, lse)
+    pl, sc, db = torch.empty(2, N, H, W, C, dtype=H16, device=dev), torch.empty(2, device=dev), torch.empty(C, device=dev)
+    ops.softargmax_bwd_split(lg, N, J, D, H, W, coords, lse, dco.to(dev), pl, sc, db)
+    ref32 = torch.empty(N, H, W, C, device=dev)
+    ops.softargmax_bwd(lg, 1, N, J, D, H, W, coords, lse, dco.to(dev), ref32)
+    torch.cuda.synchronize()
+    assert float(sc.cpu()[0]) in (float(sc_r[0]), 2 * float(sc_r[0]), float(sc_r[0]) / 2)
+    got = em._join(pl.cpu(), sc.cpu()).numpy()
+    assert relerr(got, em._join(pl_r, sc_r).numpy()) <= 5e-6
+    assert relerr(got, ref32.cpu().numpy()) <= 2e-6                    # == the fp32 kernel's gradient
+    assert float(np.abs(got).max()) * float(sc.cpu()[0]) <= 32768
+    assert relerr(db.cpu().numpy(), db_r.numpy()) <= 1e-5
+
+
 @pytest.mark.parametrize("C,second,res", [(64, False, False), (256, True, False), (2048, False, True)])
 def test_bn_finalize_scale_vs_two_calls(dev, C, second, res):
     """epb_bn_finalize_scale == epb_bn_finalize followed by epb_act_scale (same device kernels' arithmetic):

@@ -831,3 +831,42 @@ def test_joint_loss_broadcasts_or_raises_like_the_reference():
         assert abs(parts[1].item() - ref_jt.item()) <= 1e-6 and torch.isfinite(total)
     finally:
         il._backend[0] = __import__("epipolarpose_b200.ops", fromlist=["ops"])
+
+
+@pytest.mark.parametrize("extra_consumer", [False, True])
+def test_logit_gradient_sink_equals_fp32_route_emulated(extra_consumer):
+    """The criterion hands the logit gradient to the network's backward as split planes + bias gradient
+    (_sinks.py, epb_softargmax_bwd_split).  Same parameter gradients as the fp32 route (sink detached);
+    with a second consumer of the logits the zero token keeps autograd's accumulation exact."""
+    import lib.models as models
+    import lib.core.integral_loss as il
+    from tools.bench_cfg import make_cfg
+    il._backend[0] = emul_ops
+    try:
+        J, D = 4, 16
+        cfg = make_cfg(num_layers=18, num_joints=J, volume=True, depth_res=D, image_size=(64, 64))
+        grads = []
+        for use_sink in (True, False):
+            torch.manual_seed(0)
+            m = models.pose3d_resnet.get_pose_net(cfg, False, precision="f16x3")
+            m._ops = emul_ops
+            m.train()
+            assert getattr(m(torch.randn(2, 3, 64, 64)), "_epb_logit_sink", None) is None   # opt-in only
+            m.fused_head_gradient = True        # what lib/core/function.py sets around its forward
+            out = m(torch.randn(2, 3, 64, 64))
+            sink = getattr(out, "_epb_logit_sink", None)
+            assert sink is not None and type(m._engine()).__name__ == "Engine16"
+            if not use_sink:
+                del out._epb_logit_sink
+            lab, wt = torch.rand(2, J * 3) - 0.5, torch.ones(2, J * 3)
+            loss = il.L1JointLocationLoss(J)(out, lab, wt)
+            if extra_consumer:
+                loss = loss + 1e-3 * (out * out).mean()
+            loss.backward()
+            assert sink.filled == use_sink
+            grads.append({n: p.grad.clone() for n, p in m.named_parameters()})
+        worst = max(float((grads[0][k] - grads[1][k]).abs().max() / (grads[1][k].abs().max() + 1e-30))
+                    for k in grads[0])
+        assert worst <= 5e-6, worst
+    finally:
+        il._backend[0] = __import__("epipolarpose_b200.ops", fromlist=["ops"])

@@ -37,7 +37,7 @@ def timeit(fn, name, nbytes):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = sorted(ts)[len(ts) // 2]
-    print("%-10s M=%d C=%d: %.3f ms, %.0f GB/s" % (name, M, C, t, nbytes / t / 1e6))
+    print("%-24s M=%d C=%d: %.3f ms, %.0f GB/s" % (name, M, C, t, nbytes / t / 1e6))
 
 
 def reduce():
@@ -53,6 +53,19 @@ def act():
     ops.bn_act_split(z, scale, shift, None, None, None, None, None, 1, M, C, a, asc)
 
 
+def fused():
+    ops.bn_bwd_split(dy, z, None, scale, shift, mean, invstd, gamma, 1, M, C, dz, sc, None, dg, db)
+
+
+mask = (torch.rand(M, C, device=dev) > 0.5).to(torch.float16)
+
+
+def fused_mask():
+    ops.bn_bwd_split(dy, z, mask, scale, shift, mean, invstd, gamma, 0, M, C, dz, sc, dy, dg, db)
+
+
+timeit(fused, "bwd_split", 20.0 * M * C)
+timeit(fused_mask, "bwd_split+mask+inplace", 28.0 * M * C)
 timeit(reduce, "reduce_mx", 8.0 * M * C)
 reduce()
 timeit(apply, "apply", 12.0 * M * C)

@@ -30,6 +30,7 @@ dev = torch.device("cuda:0")
 cfg = make_cfg(num_layers=layers, num_joints=J, volume=True, depth_res=D, image_size=(HW, HW))
 torch.manual_seed(0)
 model = models.pose3d_resnet.get_pose_net(cfg, False, precision=prec).to(dev).train()
+model.fused_head_gradient = True          # as inside train_integral / GraphedTrainStep
 crit = il.SmoothL1JointLocationLoss(J)
 opt = U.FusedAdam(list(model.parameters()), lr=1e-3)
 n = tuples * V
@@ -44,7 +45,8 @@ orig_call = ops._call
 #                               [(index of an optional pointer argument, extra bytes per element)])
 ELEM = {"epb_bn_bwd_reduce_mx": (8, 9, 8, [(2, 2)]),
         "epb_bn_bwd_apply_split": (11, 12, 12, [(2, 2), (15, 4)]),
-        "epb_bn_act_split": (9, 10, 8, [(3, 4), (6, 4)])}
+        "epb_bn_act_split": (9, 10, 8, [(3, 4), (6, 4)]),
+        "epb_bn_bwd_split": (9, 10, 20, [(2, 4), (13, 4)])}
 
 
 def timed_call(name, *args):

@@ -43,6 +43,7 @@ struct Plan16 {
   int m_tiles, n_tiles;
   int accumulate;
   int m_fastest;                 // tile order: consecutive tiles walk M (statistics runs) or N
+  int probe;                     // EPB_C16_PROBE (profiling only, wrong results): 4 no stores, 8 no statistics
   int koff[EPB_MAX_TAPS];        // wt[t] * Cin: k offset of the tap inside a packed weight row
   short dwq[EPB_MAX_TAPS], dhq[EPB_MAX_TAPS];   // tap offset on its parity view
   unsigned char map[EPB_MAX_TAPS];              // parity view of the tap
@@ -263,14 +264,14 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
         }
         tc::fence_proxy_async();               // generic-proxy writes -> visible to the TMA unit
         __syncwarp();
-        if (lane == 0 && mt < P.m_tiles) {
+        if (lane == 0 && mt < P.m_tiles && !(P.probe & 4)) {
           if (P.accumulate)
             tc::tma_reduce_add_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
           else
             tc::tma_store_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
           tc::tma_store_commit();
         }
-        if (stats) {
+        if (stats && !(P.probe & 8)) {
           // lane = column: sum over the staged valid rows (conflict free: the swizzle spreads
           // the 32 columns of a row over the 32 banks); four partial sums keep the chains short
           float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -379,6 +380,11 @@ extern "C" __attribute__((visibility("default"))) int epb_conv16_fprop(
   // tile order: statistics want runs of tiles with the same N tile (one flush per run); without
   // statistics, N-fastest lets the concurrently running tiles of one M tile share its A rows in L2
   P.m_fastest = stats != nullptr;
+  // profiling switches (tools/one_conv16.py): 1 flips the tile order, 2 forces the 128-column N tile,
+  // 4 / 8 drop the epilogue's stores / statistics (wrong results; never set in a product run)
+  static const int probe = getenv("EPB_C16_PROBE") ? atoi(getenv("EPB_C16_PROBE")) : 0;
+  P.probe = probe;
+  if (probe & 1) P.m_fastest = !P.m_fastest;
   {
     // output box of one epilogue warp: its 32 tile rows as the sub-box (ew, eh, en)
     const int ew = P.tw < 32 ? P.tw : 32;
@@ -414,6 +420,7 @@ extern "C" __attribute__((visibility("default"))) int epb_conv16_fprop(
   else {
     const int p256 = (g->Cout + 255) / 256 * 256, p128 = (g->Cout + 127) / 128 * 128;
     bn = (p256 * 4 > p128 * 5) ? 128 : 256;
+    if (probe & 2) bn = 128;
   }
   P.n_tiles = (g->Cout + bn - 1) / bn;
   {

@@ -163,31 +163,40 @@ __host__ __device__ inline void paste_pixel(const uint8_t* occ, int w, int h, in
 
 constexpr int kMaxOccluders = 7;       // count = np.random.randint(1, 8)  (:67)
 
+// per sample, once: the forward patch affine (returned as `trans`) and its inverse (what warpAffine
+// walks); the pixel kernel's blocks only read the six inverse coefficients
+__global__ void patch_affine_kernel(const int32_t* __restrict__ img_hwp, const double* __restrict__ box,
+                                    const int32_t* __restrict__ flip, int B, int patch_w, int patch_h,
+                                    double* __restrict__ trans, double* __restrict__ inv) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int W = img_hwp[b * 3 + 1];
+  double bx[6];
+  for (int k = 0; k < 6; ++k) bx[k] = box[b * 6 + k];
+  if (flip && flip[b]) bx[0] = (double)W - bx[0] - 1.0;          // c_x = img_width - c_x - 1 (:120)
+  double M[6] = {0, 0, 0, 0, 0, 0};
+  patch_affine_fwd(bx, (double)patch_w, (double)patch_h, M);
+  double iM[6];
+  invert_affine(M, iM);
+  for (int k = 0; k < 6; ++k) inv[b * 6 + k] = iM[k];
+  if (trans)
+    for (int k = 0; k < 6; ++k) trans[b * 6 + k] = M[k];
+}
+
 __global__ void __launch_bounds__(256)
 patch_sample_kernel(const uint8_t* __restrict__ img_base, const int64_t* __restrict__ img_off,
-                    const int32_t* __restrict__ img_hwp, const double* __restrict__ box,
+                    const int32_t* __restrict__ img_hwp, const double* __restrict__ inv,
                     const int32_t* __restrict__ flip, const float* __restrict__ color, PatchArgs pa,
                     int patch_w, int patch_h, const uint8_t* __restrict__ occ_base,
                     const int64_t* __restrict__ occ_desc, const int32_t* __restrict__ occ_count,
-                    float* __restrict__ out, double* __restrict__ trans) {
+                    float* __restrict__ out) {
   const int b = blockIdx.z;
-  __shared__ double siM[6];
   const int H = img_hwp[b * 3 + 0], W = img_hwp[b * 3 + 1];
   const int64_t pitch = img_hwp[b * 3 + 2];
   const int fl = flip ? flip[b] : 0;
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    double bx[6];
-    for (int k = 0; k < 6; ++k) bx[k] = box[b * 6 + k];
-    if (fl) bx[0] = (double)W - bx[0] - 1.0;          // c_x = img_width - c_x - 1 (:120)
-    double M[6] = {0, 0, 0, 0, 0, 0};
-    patch_affine_fwd(bx, (double)patch_w, (double)patch_h, M);
-    double iM[6];
-    invert_affine(M, iM);
-    for (int k = 0; k < 6; ++k) siM[k] = iM[k];
-    if (trans && blockIdx.x == 0 && blockIdx.y == 0)
-      for (int k = 0; k < 6; ++k) trans[b * 6 + k] = M[k];
-  }
-  __syncthreads();
+  double siM[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) siM[k] = inv[b * 6 + k];
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= patch_w || y >= patch_h) return;
   int bgr[3];
@@ -329,9 +338,16 @@ extern "C" __attribute__((visibility("default"))) int epb_patch_sample_occ(
   }
   const dim3 block(64, 4);
   const dim3 grid((patch_w + 63) / 64, (patch_h + 3) / 4, B);
-  patch_sample_kernel<<<grid, block, 0, as_stream(stream)>>>(img_base, img_off, img_hwp, box, flip, color,
-                                                            pa, patch_w, patch_h, occ_base, occ_desc,
-                                                            occ_count, out, trans);
+  cudaStream_t st = as_stream(stream);
+  void* inv = nullptr;
+  int rc = epb_workspace(EPB_WS_PATCHINV, (size_t)65536 * 6 * sizeof(double), st, &inv);
+  if (rc) return rc;
+  patch_affine_kernel<<<(B + 127) / 128, 128, 0, st>>>(img_hwp, box, flip, B, patch_w, patch_h, trans,
+                                                      static_cast<double*>(inv));
+  EPB_LAUNCH_CHECK();
+  patch_sample_kernel<<<grid, block, 0, st>>>(img_base, img_off, img_hwp, static_cast<const double*>(inv),
+                                              flip, color, pa, patch_w, patch_h, occ_base, occ_desc,
+                                              occ_count, out);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

@@ -20,6 +20,7 @@ _KERNELS_PER_CALL = {
     "epb_softargmax_fwd": 2, "epb_bn_bwd_apply": 2, "epb_colsum": 3,
     "epb_split16_batch": 3, "epb_split16": 3, "epb_bn_bwd_apply_split": 2, "epb_conv16_wgrad": 2,
     "epb_bn_bwd_reduce_mx": 2, "epb_bn_bwd_split": 3, "epb_softargmax_bwd_split": 3,
+    "epb_patch_sample": 2, "epb_patch_sample_occ": 2,
 }
 
 

@@ -68,7 +68,8 @@ bn_act_split_kernel(const float* __restrict__ x, const float* __restrict__ scale
                     const float* __restrict__ shift, const float* __restrict__ r,
                     const float* __restrict__ rscale, const float* __restrict__ rshift,
                     const uint4* __restrict__ rs, const float* __restrict__ rs_sc, int relu,
-                    int64_t total8, int C8, uint4* __restrict__ y, const float* __restrict__ y_sc) {
+                    int64_t total8, int C8, uint4* __restrict__ y, const float* __restrict__ y_sc,
+                    uint8_t* __restrict__ mask_bits) {
   const float s = y_sc[0];
   const float rinv = rs ? rs_sc[1] : 0.f;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total8;
@@ -100,6 +101,12 @@ bn_act_split_kernel(const float* __restrict__ x, const float* __restrict__ scale
       join8(rs[i], rs[total8 + i], rinv, q);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] += q[k];
+    }
+    if (mask_bits) {                          // bit k of byte i: element 8*i + k passes the ReLU
+      unsigned bits = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bits |= (v[k] > 0.f ? 1u : 0u) << k;
+      mask_bits[i] = (uint8_t)bits;
     }
     if (relu) {
 #pragma unroll
@@ -346,7 +353,16 @@ __device__ __forceinline__ float4 mask4(float4 dy, float4 xv, const uint2* mask_
 // into registers and stores FOUR per-channel partials (sum g, sum g*xhat, max|g|, max|xhat|)
 // to parts[(v*W + w)*C + c] -- no atomics: the second pass adds them in a fixed order, so the
 // parameter gradients and the scale of dz are run-to-run identical.
-template <bool MASK>
+// mask of element quad i: MASK 1 = four fp16 values of the block output's hi plane, MASK 2 = four bits
+// (low / high nibble of byte i/2 of the bit mask bn_act_split wrote)
+template <int MASK>
+__device__ __forceinline__ uint2 load_mask(const uint2* mask, int64_t i) {
+  if (MASK == 1) return __ldg(mask + i);
+  const unsigned byte = __ldg(reinterpret_cast<const uint8_t*>(mask) + (i >> 1));
+  return make_uint2((i & 1) ? (byte >> 4) : (byte & 15u), 0u);
+}
+
+template <int MASK>
 __global__ void __launch_bounds__(kThreads, 3)
 bn_bwd_partial_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
                       const uint2* __restrict__ mask_hi, const float4* __restrict__ scale,
@@ -365,9 +381,12 @@ bn_bwd_partial_kernel(const float4* __restrict__ dy, const float4* __restrict__ 
     if (!MASK) { s = scale[c4]; b = shift[c4]; }
     auto fold = [&](float4 dv, float4 xv, uint2 mk) {
       float4 g;
-      if (MASK) {
+      if (MASK == 1) {
         g = make_float4((mk.x & 0x7fffu) ? dv.x : 0.f, (mk.x & 0x7fff0000u) ? dv.y : 0.f,
                         (mk.y & 0x7fffu) ? dv.z : 0.f, (mk.y & 0x7fff0000u) ? dv.w : 0.f);
+      } else if (MASK == 2) {                 // mk.x = this quad's four bits
+        g = make_float4((mk.x & 1u) ? dv.x : 0.f, (mk.x & 2u) ? dv.y : 0.f,
+                        (mk.x & 4u) ? dv.z : 0.f, (mk.x & 8u) ? dv.w : 0.f);
       } else {
         g = mask4(dv, xv, nullptr, 0, s, b, relu);
       }
@@ -395,7 +414,7 @@ bn_bwd_partial_kernel(const float4* __restrict__ dy, const float4* __restrict__ 
           const int64_t i = r * rm.C4 + c4;
           xv[u] = ldg_stream(x + i);
           dv[u] = ldg_stream(dy + i);
-          if (MASK) mk[u] = __ldg(mask_hi + i);
+          if (MASK) mk[u] = load_mask<MASK>(mask_hi, i);
         }
       }
 #pragma unroll
@@ -408,7 +427,7 @@ bn_bwd_partial_kernel(const float4* __restrict__ dy, const float4* __restrict__ 
       const int64_t i = r * rm.C4 + c4;
       const float4 xv = ldg_stream(x + i);
       const float4 dv = ldg_stream(dy + i);
-      fold(dv, xv, MASK ? __ldg(mask_hi + i) : make_uint2(0u, 0u));
+      fold(dv, xv, MASK ? load_mask<MASK>(mask_hi, i) : make_uint2(0u, 0u));
     }
   }
   __shared__ float4 sh[4][kThreads];
@@ -546,7 +565,8 @@ bn_bwd_apply_split_kernel(const float4* dy /* may alias dy_masked */, const floa
                           const float4* __restrict__ invstd, const float4* __restrict__ gamma,
                           int relu, const float4* __restrict__ k1v, const float4* __restrict__ k2v,
                           uint2* __restrict__ dz, float* __restrict__ dz_sc,
-                          const float* __restrict__ bound, float4* dy_masked, int64_t total4, int C4) {
+                          const float* __restrict__ bound, float4* dy_masked, int64_t total4, int C4,
+                          int mask_bits) {
   // scale of dz: from the bound the combine pass left (fused entry point), else as published in dz_sc
   const float s = bound ? pow2_scale(*bound) : dz_sc[0];
   if (bound && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -564,7 +584,7 @@ bn_bwd_apply_split_kernel(const float4* dy /* may alias dy_masked */, const floa
       if (idx[u] < total4) {
         xv[u] = ldg_stream(x + idx[u]);
         dv[u] = __ldcs(dy + idx[u]);
-        if (mask_hi) mk[u] = mask_hi[idx[u]];
+        if (mask_hi) mk[u] = mask_bits ? load_mask<2>(mask_hi, idx[u]) : mask_hi[idx[u]];
       }
     }
 #pragma unroll
@@ -573,7 +593,10 @@ bn_bwd_apply_split_kernel(const float4* dy /* may alias dy_masked */, const floa
       if (i >= total4) break;
       const int c4 = (int)(i % C4);
       float4 g = dv[u];
-      if (mask_hi) {
+      if (mask_hi && mask_bits) {
+        g = make_float4((mk[u].x & 1u) ? g.x : 0.f, (mk[u].x & 2u) ? g.y : 0.f,
+                        (mk[u].x & 4u) ? g.z : 0.f, (mk[u].x & 8u) ? g.w : 0.f);
+      } else if (mask_hi) {
         g = make_float4((mk[u].x & 0x7fffu) ? g.x : 0.f, (mk[u].x & 0x7fff0000u) ? g.y : 0.f,
                         (mk[u].y & 0x7fffu) ? g.z : 0.f, (mk[u].y & 0x7fff0000u) ? g.w : 0.f);
       } else {
@@ -822,7 +845,7 @@ __global__ void avgpool_split_kernel(const __half* __restrict__ x, const float* 
 EPB_API int epb_bn_act_split(const float* x, const float* scale, const float* shift, const float* r,
                              const float* rscale, const float* rshift, const epb_half* r_split,
                              const float* r_sc, int relu, int64_t M, int C, epb_half* y,
-                             const float* y_sc, epb_stream_t stream) {
+                             const float* y_sc, uint8_t* mask_bits, epb_stream_t stream) {
   EPB_CHECK_ARG(x && y && y_sc && M > 0 && C > 0 && C % 8 == 0);
   EPB_CHECK_ARG((scale == nullptr) == (shift == nullptr));
   EPB_CHECK_ARG((rscale == nullptr) == (rshift == nullptr));
@@ -831,7 +854,7 @@ EPB_API int epb_bn_act_split(const float* x, const float* scale, const float* sh
   const int64_t total8 = M * (C / 8);
   bn_act_split_kernel<<<ew_blocks(total8), kThreads, 0, as_stream(stream)>>>(
       x, scale, shift, r, rscale, rshift, reinterpret_cast<const uint4*>(r_split), r_sc, relu, total8,
-      C / 8, reinterpret_cast<uint4*>(y), y_sc);
+      C / 8, reinterpret_cast<uint4*>(y), y_sc, mask_bits);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }
@@ -899,8 +922,9 @@ static int bn_bwd_scratch(int W, int C, cudaStream_t st, float** parts, float** 
 static void launch_bn_bwd_partial(const float* dy, const float* x, const epb_half* mask_hi,
                                   const float* scale, const float* shift, const float* mean,
                                   const float* invstd, int relu, int64_t M, int C, const RowMap& rm,
-                                  int W, float* parts, uint32_t* bound, cudaStream_t st) {
-  auto k = mask_hi ? bn_bwd_partial_kernel<true> : bn_bwd_partial_kernel<false>;
+                                  int W, float* parts, uint32_t* bound, cudaStream_t st,
+                                  int mask_kind = 1) {
+  auto k = mask_kind == 2 ? bn_bwd_partial_kernel<2> : (mask_hi ? bn_bwd_partial_kernel<1> : bn_bwd_partial_kernel<0>);
   k<<<dim3(W, rm.chunks), kThreads, 0, st>>>(
       reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
       reinterpret_cast<const uint2*>(mask_hi), reinterpret_cast<const float4*>(scale),
@@ -930,12 +954,15 @@ EPB_API int epb_bn_bwd_reduce_mx(const float* dy, const float* x, const epb_half
 }
 
 EPB_API int epb_bn_bwd_split(const float* dy, const float* x, const epb_half* mask_hi,
-                             const float* scale, const float* shift, const float* mean,
+                             const uint8_t* mask_bits, const float* scale, const float* shift, const float* mean,
                              const float* invstd, const float* gamma, int relu, int64_t M, int C,
                              epb_half* dz, float* dz_sc, float* dy_masked, float* dgamma,
                              float* dbeta, epb_stream_t stream) {
   EPB_CHECK_ARG(dy && x && scale && shift && mean && invstd && dz && dz_sc);
   EPB_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0);
+  EPB_CHECK_ARG(!(mask_hi && mask_bits) && (!mask_bits || C % 8 == 0));
+  const int mask_kind = mask_bits ? 2 : 1;
+  if (mask_bits) mask_hi = reinterpret_cast<const epb_half*>(mask_bits);     // one pointer, kind says how to read it
   cudaStream_t st = as_stream(stream);
   const RowMap rm = make_rowmap(C);
   const int W = bn_bwd_workers(rm, M);
@@ -943,7 +970,8 @@ EPB_API int epb_bn_bwd_split(const float* dy, const float* x, const epb_half* ma
   uint32_t* bound;
   int rc = bn_bwd_scratch(W, C, st, &parts, &coef, &bound);
   if (rc) return rc;
-  launch_bn_bwd_partial(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, rm, W, parts, bound, st);
+  launch_bn_bwd_partial(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, rm, W, parts, bound, st,
+                        mask_kind);
   EPB_LAUNCH_CHECK();
   bn_bwd_combine_kernel<<<(C + 7) / 8, 256, 0, st>>>(parts, W, (double)M, C, nullptr, nullptr, coef,
                                                         gamma, invstd, dgamma, dbeta, bound);
@@ -956,7 +984,7 @@ EPB_API int epb_bn_bwd_split(const float* dy, const float* x, const epb_half* ma
       reinterpret_cast<const float4*>(invstd), reinterpret_cast<const float4*>(gamma), relu,
       reinterpret_cast<const float4*>(coef), reinterpret_cast<const float4*>(coef + C),
       reinterpret_cast<uint2*>(dz), dz_sc, reinterpret_cast<const float*>(bound),
-      reinterpret_cast<float4*>(dy_masked), total4, C / 4);
+      reinterpret_cast<float4*>(dy_masked), total4, C / 4, mask_kind == 2);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }
@@ -981,7 +1009,7 @@ EPB_API int epb_bn_bwd_apply_split(const float* dy, const float* x, const epb_ha
       reinterpret_cast<const float4*>(shift), reinterpret_cast<const float4*>(mean),
       reinterpret_cast<const float4*>(invstd), reinterpret_cast<const float4*>(gamma), relu,
       reinterpret_cast<const float4*>(mx), reinterpret_cast<const float4*>(mx + C),
-      reinterpret_cast<uint2*>(dz), dz_sc, nullptr, reinterpret_cast<float4*>(dy_masked), total4, C / 4);
+      reinterpret_cast<uint2*>(dz), dz_sc, nullptr, reinterpret_cast<float4*>(dy_masked), total4, C / 4, 0);
   EPB_LAUNCH_CHECK();
   return EPB_OK;
 }

@@ -148,16 +148,17 @@ class Engine16(_net.Engine):
         with torch.cuda.stream(side):
             run()
 
-    def _bn_bwd16(self, st, dy, z, mask_hi, relu, params, grads, dy_masked=None):
-        """BatchNorm(+ReLU) backward -> (dz split, dz_sc).  Fills grads[name.weight/.bias]."""
+    def _bn_bwd16(self, st, dy, z, mask_bits, relu, params, grads, dy_masked=None):
+        """BatchNorm(+ReLU) backward -> (dz split, dz_sc).  Fills grads[name.weight/.bias].
+        mask_bits: the block output's ReLU bit mask (bn_act_split), or None (mask from z)."""
         ops = self.ops
         C = st.C
         M = z.numel() // C
         dz = self._half(*z.shape)
         dz_sc = torch.empty(2, device=self.dev, dtype=torch.float32)
-        ops.bn_bwd_split(dy, z, mask_hi, st.scale, st.shift, st.mean, st.invstd,
+        ops.bn_bwd_split(dy, z, None, st.scale, st.shift, st.mean, st.invstd,
                          params[st.name + ".weight"], relu, M, C, dz, dz_sc, dy_masked,
-                         grads[st.name + ".weight"], grads[st.name + ".bias"])
+                         grads[st.name + ".weight"], grads[st.name + ".bias"], mask_bits=mask_bits)
         return dz, dz_sc
 
     # ------------------------------------------------------------------ forward
@@ -254,6 +255,8 @@ class Engine16(_net.Engine):
             M = N * hh * ww
             out = self._half(N, hh, ww, Cl)
             out_sc = new_sc()
+            # ReLU mask of the block output, one bit per element (read twice by the backward)
+            obits = torch.empty(M * Cl // 8, device=self.dev, dtype=torch.uint8) if save else None
             if blk["down"]:
                 dconv, (dname, dC) = blk["down"]
                 zd, _, _ = self._conv_fwd16(dconv, cur, cur_sc, N, h, w, w16(dconv),
@@ -262,12 +265,13 @@ class Engine16(_net.Engine):
                 rec["zd"] = zd
                 last = bn(lname, Cl, M, out_sc, (stats_of(dname, dC), dst.scale, dst.shift))
                 ops.bn_act_split(zl, last.scale, last.shift, zd, dst.scale, dst.shift, None, None,
-                                 1, M, Cl, out, out_sc)
+                                 1, M, Cl, out, out_sc, obits)
             else:
                 last = bn(lname, Cl, M, out_sc, res_sc=cur_sc)
                 ops.bn_act_split(zl, last.scale, last.shift, None, None, None, cur, cur_sc, 1, M, Cl,
-                                 out, out_sc)
+                                 out, out_sc, obits)
             rec["out"] = (out, out_sc)
+            rec["mask"] = obits
             S["blocks"].append(rec)
             cur, cur_sc, h, w = out, out_sc, hh, ww
 
@@ -386,7 +390,7 @@ class Engine16(_net.Engine):
             prev_stage = sk
             (out, _), (xin, xin_sc), h, w = rec["out"], rec["in"], rec["h"], rec["w"]
             nconv = len(blk["convs"])
-            mask = out[0]                       # hi plane of the block output: (out > 0)
+            mask = rec["mask"]                  # ReLU bit mask of the block output
             down = blk["down"]
             if down:
                 dconv, (dname, dC) = down

@@ -206,9 +206,10 @@ def bn_finalize_scale(stats, M, C, gamma, beta, eps, momentum, running_mean, run
           _p(stats2, torch.float64), _p(scale2), _p(shift2), _p(res_sc), _p(sc), _stream())
 
 
-def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc):
+def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc, mask_bits=None):
     _call("epb_bn_act_split", _p(x), _p(scale), _p(shift), _p(r), _p(rscale), _p(rshift),
-          _p(r_split, _H), _p(r_sc), int(relu), M, C, _p(y, _H), _p(y_sc), _stream())
+          _p(r_split, _H), _p(r_sc), int(relu), M, C, _p(y, _H), _p(y_sc), _p(mask_bits, torch.uint8),
+          _stream())
 
 
 def bn_relu_maxpool_split(x, scale, shift, y, y_sc, argidx, N, H, W, C):
@@ -272,8 +273,9 @@ def bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, 
 
 
 def bn_bwd_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, M, C, dz, dz_sc, dy_masked,
-                 dgamma, dbeta):
-    _call("epb_bn_bwd_split", _p(dy), _p(x), _p(mask_hi, _H), _p(scale), _p(shift), _p(mean),
+                 dgamma, dbeta, mask_bits=None):
+    _call("epb_bn_bwd_split", _p(dy), _p(x), _p(mask_hi, _H), _p(mask_bits, torch.uint8), _p(scale),
+          _p(shift), _p(mean),
           _p(invstd), _p(gamma), int(relu), M, C, _p(dz, _H), _p(dz_sc), _p(dy_masked), _p(dgamma),
           _p(dbeta), _stream())
 

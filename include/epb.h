@@ -228,7 +228,9 @@ int epb_bn_act_split(const float* x, const float* scale, const float* shift,
                      const float* r, const float* rscale, const float* rshift,
                      const epb_half* r_split, const float* r_sc, int relu,
                      int64_t M, int C, epb_half* y, const float* y_sc,
-                     epb_stream_t stream);
+                     uint8_t* mask_bits, epb_stream_t stream);
+/* mask_bits (optional, [M*C/8] bytes): bit k of byte i = (pre-ReLU value of element 8*i+k > 0),
+ * the ReLU mask the BatchNorm backward of the block reads (epb_bn_bwd_split). */
 /* stem: maxpool3x3s2p1(relu(x*scale+shift)) -> split tensor + argmax slot (0..8) */
 int epb_bn_relu_maxpool_split(const float* x, const float* scale, const float* shift,
                               epb_half* y, const float* y_sc, uint8_t* argidx, int N,
@@ -297,9 +299,11 @@ int epb_bn_bwd_apply_split(const float* dy, const float* x, const epb_half* mask
                            float* dbeta, epb_stream_t stream);
 /* Both passes in one call (what the engine uses): per-CTA partial reductions, a fixed-order
  * combine (no atomics: dgamma / dbeta / the scale of dz are run-to-run identical), apply.
- * Outputs as epb_bn_bwd_apply_split; the sums / maxes live in internal scratch of the stream. */
-int epb_bn_bwd_split(const float* dy, const float* x, const epb_half* mask_hi, const float* scale,
-                     const float* shift, const float* mean, const float* invstd,
+ * Outputs as epb_bn_bwd_apply_split; the sums / maxes live in internal scratch of the stream.
+ * mask_bits (instead of mask_hi; C % 8 == 0): the bit mask epb_bn_act_split wrote for the block
+ * output, 1/8 byte per element instead of the 2-byte hi plane in both passes. */
+int epb_bn_bwd_split(const float* dy, const float* x, const epb_half* mask_hi,
+                     const uint8_t* mask_bits, const float* scale, const float* shift, const float* mean, const float* invstd,
                      const float* gamma, int relu, int64_t M, int C, epb_half* dz, float* dz_sc,
                      float* dy_masked, float* dgamma, float* dbeta, epb_stream_t stream);
 /* VOLUME=False head on a split tensor: y[n][c] = mean over HW of x (fp32 out) */

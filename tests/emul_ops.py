@@ -571,7 +571,7 @@ def bn_finalize_scale(stats, M, C, gamma, beta, eps, momentum, running_mean, run
     act_scale(stats, scale, shift, M, C, stats2, scale2, shift2, res_sc, sc)
 
 
-def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc):
+def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, y, y_sc, mask_bits=None):
     v = x.reshape(M, C)
     if scale is not None:
         v = v * scale + shift
@@ -582,6 +582,9 @@ def bn_act_split(x, scale, shift, r, rscale, rshift, r_split, r_sc, relu, M, C, 
         v = v + q
     elif r_split is not None:
         v = v + _join(r_split, r_sc).reshape(M, C)
+    if mask_bits is not None:
+        import numpy as np
+        mask_bits.copy_(torch.from_numpy(np.packbits((v > 0).numpy().reshape(-1), bitorder="little")))
     if relu:
         v = torch.relu(v)
     _store_split(y, v, float(y_sc[0]))
@@ -667,8 +670,12 @@ def conv16_wgrad(g, x, x_sc, dout, dout_sc, dw, ws):
         DW[:, g.wt[t], :] += ((dh_.T @ al + dl_.T @ ah + dh_.T @ ah) * alpha).float()
 
 
-def _mask16(dy, x, mask_hi, scale, shift, relu, M, C):
+def _mask16(dy, x, mask_hi, scale, shift, relu, M, C, mask_bits=None):
     g = dy.reshape(M, C)
+    if mask_bits is not None:
+        import numpy as np
+        bits = np.unpackbits(mask_bits.numpy().reshape(-1), bitorder="little")[:M * C]
+        return g * torch.from_numpy(bits.astype(np.float32)).reshape(M, C)
     if mask_hi is not None:
         return g * (mask_hi.reshape(M, C).float() > 0).float()
     if relu:
@@ -709,9 +716,18 @@ def bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, 
 
 
 def bn_bwd_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, M, C, dz, dz_sc, dy_masked,
-                 dgamma, dbeta):
+                 dgamma, dbeta, mask_bits=None):
     sums = torch.zeros(2 * C, dtype=torch.float64)
     maxes = torch.zeros(2 * C)
+    if mask_bits is not None:
+        # same arithmetic on the gradient masked by the bits (dy_masked may alias dy)
+        g = _mask16(dy, x, None, scale, shift, 0, M, C, mask_bits).reshape(dy.shape).clone()
+        bn_bwd_reduce_mx(g, x, None, scale, shift, mean, invstd, 0, M, C, sums, maxes)
+        bn_bwd_apply_split(g, x, None, scale, shift, mean, invstd, gamma, 0, sums, maxes, M, C,
+                           dz, dz_sc, None, dgamma, dbeta)
+        if dy_masked is not None:
+            dy_masked.view(M, C).copy_(g.view(M, C))
+        return
     bn_bwd_reduce_mx(dy, x, mask_hi, scale, shift, mean, invstd, relu, M, C, sums, maxes)
     bn_bwd_apply_split(dy, x, mask_hi, scale, shift, mean, invstd, gamma, relu, sums, maxes, M, C,
                        dz, dz_sc, dy_masked, dgamma, dbeta)

@@ -184,10 +184,16 @@ def test_split_elementwise_vs_emulation(dev):
                     res_split=(sc, sh, None, None, None, rs, rs_sc),
                     noaffine=(None, None, None, None, None, None, None))[kind]
         y_ref = torch.empty(2, M, C, dtype=H16)
-        em.bn_act_split(x, *args, 1, M, C, y_ref, asc)
+        bits_ref = torch.empty(M * C // 8, dtype=torch.uint8)
+        em.bn_act_split(x, *args, 1, M, C, y_ref, asc, bits_ref)
         y = torch.empty(2, M, C, dtype=H16, device=dev)
+        bits = torch.empty(M * C // 8, dtype=torch.uint8, device=dev)
         ops.bn_act_split(x.to(dev), *[a.to(dev) if a is not None else None for a in args], 1, M, C,
-                         y, asc.to(dev))
+                         y, asc.to(dev), bits)
+        # the ReLU bit mask: identical except where the pre-activation is within rounding of zero
+        diff = np.unpackbits((bits.cpu() ^ bits_ref).numpy(), bitorder="little").astype(bool)
+        pre = em._join(y_ref, asc).reshape(-1).numpy()
+        assert diff.sum() <= 2 and (diff.sum() == 0 or float(np.abs(pre[diff[:pre.size]]).max()) <= 1e-5)
         a = em._join(y.cpu(), asc).numpy()
         b = em._join(y_ref, asc).numpy()
         assert np.max(np.abs(a - b)) <= 2e-6 * max(1.0, np.max(np.abs(b))), kind
@@ -335,7 +341,9 @@ def test_bn_finalize_scale_vs_two_calls(dev, C, second, res):
 
 
 @pytest.mark.parametrize("M,C,mode", [(3000, 256, "mask_inplace"), (70001, 64, "relu"), (517, 2048, "mask"),
-                                       (9, 64, "plain"), (40000, 1024, "relu"), (2, 512, "mask")])
+                                       (9, 64, "plain"), (40000, 1024, "relu"), (2, 512, "mask"),
+                                       (3001, 256, "bits_inplace"), (517, 2048, "bits"), (70001, 64, "bits"),
+                                       (5, 8, "bits_inplace")])
 def test_bn_bwd_fused_entry_vs_emulation_and_deterministic(dev, M, C, mode):
     """epb_bn_bwd_split (partials -> fixed-order combine -> apply, what the engine calls) against the
     emulation of the two-call form; two runs are bit-identical (no atomics in the reduction)."""
@@ -349,11 +357,16 @@ def test_bn_bwd_fused_entry_vs_emulation_and_deterministic(dev, M, C, mode):
     scale, shift = gamma * invstd, beta - mean * gamma * invstd
     out, _ = _rand_split((M, C), 44)
     mask = out[0].contiguous() if mode.startswith("mask") else None
+    bits = None
+    if mode.startswith("bits"):
+        bits = torch.from_numpy(np.packbits((torch.rand(M * C, generator=gen) > 0.4).numpy(), bitorder="little"))
     relu = 1 if mode == "relu" else 0
+    inplace = mode.endswith("_inplace")
     dz_r, sc_r = torch.empty(2, M, C, dtype=H16), torch.empty(2)
-    dm_r = dy.clone() if mode == "mask_inplace" else None
+    dm_r = dy.clone() if inplace else None
     dg_r, db_r = torch.empty(C), torch.empty(C)
-    em.bn_bwd_split(dy, x, mask, scale, shift, mean, invstd, gamma, relu, M, C, dz_r, sc_r, dm_r, dg_r, db_r)
+    em.bn_bwd_split(dy, x, mask, scale, shift, mean, invstd, gamma, relu, M, C, dz_r, sc_r, dm_r, dg_r, db_r,
+                    mask_bits=bits)
     D = lambda t: t.to(dev) if t is not None else None
     runs = []
     for _ in range(2):
@@ -361,7 +374,7 @@ def test_bn_bwd_fused_entry_vs_emulation_and_deterministic(dev, M, C, mode):
         dz, sc = torch.empty(2, M, C, dtype=H16, device=dev), torch.empty(2, device=dev)
         dg, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
         ops.bn_bwd_split(dyg, D(x), D(mask), D(scale), D(shift), D(mean), D(invstd), D(gamma), relu, M, C,
-                         dz, sc, dyg if mode == "mask_inplace" else None, dg, db)
+                         dz, sc, dyg if inplace else None, dg, db, mask_bits=D(bits))
         torch.cuda.synchronize()
         runs.append((dz.cpu(), sc.cpu(), dg.cpu(), db.cpu(), dyg.cpu()))
     dz, sc, dg, db, dyg = runs[0]
@@ -373,7 +386,7 @@ def test_bn_bwd_fused_entry_vs_emulation_and_deterministic(dev, M, C, mode):
     assert relerr(em._join(dz, sc).numpy(), b) <= 1e-5
     assert float(np.max(np.abs(b))) * s_g <= 65504
     assert relerr(dg.numpy(), dg_r.numpy()) <= 2e-5 and relerr(db.numpy(), db_r.numpy()) <= 2e-5
-    if mode == "mask_inplace":
+    if inplace:
         assert torch.equal(dyg, dm_r)
 
 

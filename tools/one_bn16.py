@@ -58,14 +58,20 @@ def fused():
 
 
 mask = (torch.rand(M, C, device=dev) > 0.5).to(torch.float16)
+bits = torch.randint(0, 256, (M * C // 8,), device=dev, dtype=torch.uint8)
 
 
 def fused_mask():
     ops.bn_bwd_split(dy, z, mask, scale, shift, mean, invstd, gamma, 0, M, C, dz, sc, dy, dg, db)
 
 
+def fused_bits():
+    ops.bn_bwd_split(dy, z, None, scale, shift, mean, invstd, gamma, 0, M, C, dz, sc, dy, dg, db, mask_bits=bits)
+
+
 timeit(fused, "bwd_split", 20.0 * M * C)
 timeit(fused_mask, "bwd_split+mask+inplace", 28.0 * M * C)
+timeit(fused_bits, "bwd_split+bits+inplace", 24.25 * M * C)
 timeit(reduce, "reduce_mx", 8.0 * M * C)
 reduce()
 timeit(apply, "apply", 12.0 * M * C)

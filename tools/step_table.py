@@ -46,7 +46,7 @@ orig_call = ops._call
 ELEM = {"epb_bn_bwd_reduce_mx": (8, 9, 8, [(2, 2)]),
         "epb_bn_bwd_apply_split": (11, 12, 12, [(2, 2), (15, 4)]),
         "epb_bn_act_split": (9, 10, 8, [(3, 4), (6, 4)]),
-        "epb_bn_bwd_split": (9, 10, 20, [(2, 4), (13, 4)])}
+        "epb_bn_bwd_split": (10, 11, 20, [(2, 4), (14, 4)])}        # bit masks: 1/4 byte, not counted
 
 
 def timed_call(name, *args):

@@ -365,8 +365,7 @@ def run_gpu(args):
                   "tf32x3": "tf32x3 (3-pass error-compensated tcgen05, f32 accumulate; f32 SIMT "
                             "where the tensor path does not take the shape)",
                   "f16x3": "f16x3 (fp32 operands split into two fp16 planes, 3-pass error-compensated "
-                           "tcgen05 kind::f16, f32 accumulate: fp32-grade results; the final layer's "
-                           "backward on tf32x3)"}[args.precision],
+                           "tcgen05 kind::f16, f32 accumulate: fp32-grade results)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": workload_name(layers), "tuples_per_gpu": args.tuples,
                    "images_per_gpu": n_img, "parallelism": "dp%d" % world,

@@ -32,11 +32,14 @@ meta = {"center_x": torch.tensor(500 + rng.uniform(-50, 50, n)), "center_y": tor
 meta = {k: v.to(dev) for k, v in meta.items()}
 x = torch.randn(n, 3, HW, HW, device=dev)
 
-def step():
+from lib.core.function import online_epipolar_loss, _fused_head
+
+
+def step():                                   # the body of GraphedTrainStep._eager / train_integral
     opt.zero_grad()
-    preds = model(x)
-    label, weight = iu.self_supervision_device(preds.detach(), meta, "iterative")
-    loss = crit(preds, label, weight)
+    with _fused_head(model):
+        preds = model(x)
+    loss = online_epipolar_loss(crit, preds, meta, "iterative")
     loss.backward()
     opt.step()
     return loss

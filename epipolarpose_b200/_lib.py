@@ -78,6 +78,7 @@ _PROTOS = {
     "epb_bn_bwd_reduce_mx": (c_int, [c_p] * 7 + [c_int, c_i64, c_int, c_p, c_p, c_p]),
     "epb_bn_bwd_apply_split": (c_int, [c_p] * 8 + [c_int, c_p, c_p, c_i64, c_int] + [c_p] * 6),
     "epb_bn_bwd_split": (c_int, [c_p] * 9 + [c_int, c_i64, c_int] + [c_p] * 6),
+    "epb_debug_conv16_trace": (c_int, [c_p, c_int]),
     "epb_avgpool_split": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
     "epb_sumsq": (c_int, [c_p, c_i64, c_p, c_p]),
     "epb_clip_scale": (c_int, [c_p, c_i64, c_p, c_d, c_p]),

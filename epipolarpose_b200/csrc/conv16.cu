@@ -35,6 +35,14 @@ constexpr int kThreads16 = 192;
 constexpr int kEpiWarps = 4;
 constexpr int kStageBudget = 192 * 1024;
 
+// EPB_C16_PROBE & 32: cluster 0 records clock64() at its pipeline hand-overs (epb_debug_conv16_trace):
+// [role 0 producer | 1 MMA issuer | 2 epilogue warp 2 per tile | 3 epilogue warp 2 per chunk][CTA rank][256 events]
+__device__ long long g_c16_trace[4 * 2 * 256];
+#define C16_TR(role, idx)                                                                      \
+  do {                                                                                         \
+    if (trace_on && (idx) < 256) g_c16_trace[((role) * 2 + crank) * 256 + (idx)] = clock64();   \
+  } while (0)
+
 struct Plan16 {
   int N, Hp, Wp;                 // phase grid
   int Ho, Wo, Cout, os, ph, pw;  // output tensor / phase
@@ -99,6 +107,8 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
   auto tempty_bar = [&](int a) { return bar0 + 8u * (18 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool trace_on = (P.probe & 32) && tile0 == 0;
+  int tr_i = 0, tr_c = 0;
   const int KB = P.T * P.CB;
   const int m_pairs = (P.m_tiles + 1) / 2;
   const int total_tiles = m_pairs * P.n_tiles;
@@ -140,6 +150,7 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
         int t = 0, cb = 0;
         for (int kb = 0; kb < KB; ++kb) {
           tc::mbar_wait(empty_bar(stage), phase ^ 1);
+          C16_TR(0, tr_i); ++tr_i;                       // slot free: loads of this k-block go out
           if (crank == 0) tc::mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE);
           const uint32_t lead_bar = tc::mapa(full_bar(stage), 0);
           const uint32_t a_dst = base + stage * C::STAGE;
@@ -163,12 +174,15 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int tile = tile0; tile < total_tiles; tile += tstep) {
+        C16_TR(1, tr_i); ++tr_i;                         // (a) ready for the tile
         tc::mbar_wait_cluster(tempty_bar(as), aphase ^ 1);
         tc::tc_fence_after();
+        C16_TR(1, tr_i); ++tr_i;                         // (b) accumulator buffer free
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < KB; ++kb) {
           tc::mbar_wait_cluster(full_bar(stage), phase);
           tc::tc_fence_after();
+          if (kb == 0) { C16_TR(1, tr_i); ++tr_i; }      // (c) first operands landed
           const uint32_t a_hi = base + stage * C::STAGE;
           const uint32_t b_hi = a_hi + C::A_BYTES;
 #pragma unroll
@@ -185,6 +199,7 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
           if (++stage == C::S) { stage = 0; phase ^= 1; }
         }
         tc::mma_commit_pair(tfull_bar(as));               // accumulator complete (both CTAs)
+        C16_TR(1, tr_i); ++tr_i;                         // (d) all MMAs of the tile issued
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -240,18 +255,27 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
         const int w = w0 + r % P.tw, h = h0 + (r / P.tw) % P.th, n = n0 + r / twh;
         vmask = __ballot_sync(0xffffffffu, mt < P.m_tiles && w < P.Wp && h < P.Hp && n < P.N);
       }
+      if (wq == 0 && lane == 0) { C16_TR(2, tr_i); ++tr_i; }   // (a) waiting for the accumulator
       tc::mbar_wait(tfull_bar(as), aphase);
       tc::tc_fence_after();
+      if (wq == 0 && lane == 0) { C16_TR(2, tr_i); ++tr_i; }   // (b) accumulator complete
+      // chunks of 32 columns.  The TMEM load is issued first and lands while lane 0 waits for the TMA
+      // unit to finish reading the previous box.  (Issuing it a chunk ahead was measured and is SLOWER --
+      // fence.proxy.async is a MEMBAR.ALL.CTA that waits for a load in flight, and a load in flight behind
+      // the statistics' LDS stream costs more than it hides: profiles/r2_conv16_epilogue_probes.md.)
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         const int col0 = nt * BN + chunk * 32;
         if (col0 >= P.Cout) break;             // N tail
         uint32_t rg[32];
+        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // chunk (a) start
         tc::tmem_ld32(tmem_base + as * BN + chunk * 32 + ((uint32_t)(q * 32) << 16), rg);
         // the previous box must have been read by the TMA unit before it is overwritten
         if (lane == 0) tc::tma_store_wait_read<0>();
+        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (b) box free
         __syncwarp();
         tc::tmem_ld_wait();
+        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (c) accumulator columns in registers
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           float4 x = make_float4(__uint_as_float(rg[c]) * alpha, __uint_as_float(rg[c + 1]) * alpha,
@@ -262,8 +286,10 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
           }
           *reinterpret_cast<float4*>(stg + lane * 128 + (((c >> 2) ^ (lane & 7)) << 4)) = x;
         }
+        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (d) staged
         tc::fence_proxy_async();               // generic-proxy writes -> visible to the TMA unit
         __syncwarp();
+        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (e) fenced
         if (lane == 0 && mt < P.m_tiles && !(P.probe & 4)) {
           if (P.accumulate)
             tc::tma_reduce_add_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
@@ -271,6 +297,7 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
             tc::tma_store_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
           tc::tma_store_commit();
         }
+        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (f) store issued
         if (stats && !(P.probe & 8)) {
           // lane = column: sum over the staged valid rows (conflict free: the swizzle spreads
           // the 32 columns of a row over the 32 banks); four partial sums keep the chains short
@@ -287,6 +314,7 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
       }
       tc::tc_fence_before();
       __syncwarp();
+      if (wq == 0 && lane == 0) { C16_TR(2, tr_i); ++tr_i; }   // (c) tile written out
       if (lane == 0) tc::mbar_arrive_cluster_relaxed(tc::mapa(tempty_bar(as), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -322,6 +350,14 @@ int launch16(const Plan16& P, const Maps16& maps, const float* in_sc, const floa
 }
 
 }  // namespace
+
+// profiling aid: the clock64() trace cluster 0 of the last EPB_C16_PROBE & 32 launch left (4 roles x 2 CTAs x 256)
+extern "C" __attribute__((visibility("default"))) int epb_debug_conv16_trace(long long* host_dst, int n) {
+  EPB_CHECK_ARG(host_dst && n > 0 && n <= 4 * 2 * 256);
+  EPB_CUDA(cudaDeviceSynchronize());
+  EPB_CUDA(cudaMemcpyFromSymbol(host_dst, g_c16_trace, (size_t)n * sizeof(long long)));
+  return EPB_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int epb_conv16_fprop(
     const epb_conv_geom* g, const epb_half* in, const float* in_sc, const epb_half* w,

@@ -512,6 +512,11 @@ int epb_sgd_step_dev(float* param, const float* grad, float* momentum_buf,
                      int64_t n, const float* hyper, const int* step_dev,
                      epb_stream_t stream);
 
+/* Profiling aid (never on a product path): with EPB_C16_PROBE & 32 in the environment, cluster 0 of
+ * an epb_conv16_fprop launch records clock64() at its pipeline hand-overs; this copies the trace
+ * ([role: producer, MMA issuer, epilogue per tile, epilogue per chunk][CTA rank][256] int64) to host memory after a device sync. */
+int epb_debug_conv16_trace(long long* host_dst, int n);
+
 #ifdef __cplusplus
 }
 #endif

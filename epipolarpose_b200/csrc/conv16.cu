@@ -208,6 +208,7 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int wq = warp - 2;
     const int et = wq * 32 + lane;             // 0..127
+    const bool tr_e = trace_on && wq == 0 && lane == 0;    // the one thread that records the epilogue's events
     uint8_t* stg = epi_stage + wq * 4096;      // this warp's 32 rows x 128 B, SWIZZLE_128B
     const uint32_t stg_u32 = tc::smem_u32(stg);
     float* sst = sstat + wq * 2 * BN;          // this warp's statistics slice, summed over tiles
@@ -255,10 +256,10 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
         const int w = w0 + r % P.tw, h = h0 + (r / P.tw) % P.th, n = n0 + r / twh;
         vmask = __ballot_sync(0xffffffffu, mt < P.m_tiles && w < P.Wp && h < P.Hp && n < P.N);
       }
-      if (wq == 0 && lane == 0) { C16_TR(2, tr_i); ++tr_i; }   // (a) waiting for the accumulator
+      if (tr_e) { C16_TR(2, tr_i); ++tr_i; }   // (a) waiting for the accumulator
       tc::mbar_wait(tfull_bar(as), aphase);
       tc::tc_fence_after();
-      if (wq == 0 && lane == 0) { C16_TR(2, tr_i); ++tr_i; }   // (b) accumulator complete
+      if (tr_e) { C16_TR(2, tr_i); ++tr_i; }   // (b) accumulator complete
       // chunks of 32 columns.  The TMEM load is issued first and lands while lane 0 waits for the TMA
       // unit to finish reading the previous box.  (Issuing it a chunk ahead was measured and is SLOWER --
       // fence.proxy.async is a MEMBAR.ALL.CTA that waits for a load in flight, and a load in flight behind
@@ -268,14 +269,14 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
         const int col0 = nt * BN + chunk * 32;
         if (col0 >= P.Cout) break;             // N tail
         uint32_t rg[32];
-        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // chunk (a) start
+        if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // chunk (a) start
         tc::tmem_ld32(tmem_base + as * BN + chunk * 32 + ((uint32_t)(q * 32) << 16), rg);
         // the previous box must have been read by the TMA unit before it is overwritten
         if (lane == 0) tc::tma_store_wait_read<0>();
-        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (b) box free
+        if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (b) box free
         __syncwarp();
         tc::tmem_ld_wait();
-        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (c) accumulator columns in registers
+        if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (c) accumulator columns in registers
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           float4 x = make_float4(__uint_as_float(rg[c]) * alpha, __uint_as_float(rg[c + 1]) * alpha,
@@ -286,10 +287,10 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
           }
           *reinterpret_cast<float4*>(stg + lane * 128 + (((c >> 2) ^ (lane & 7)) << 4)) = x;
         }
-        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (d) staged
+        if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (d) staged
         tc::fence_proxy_async();               // generic-proxy writes -> visible to the TMA unit
         __syncwarp();
-        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (e) fenced
+        if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (e) fenced
         if (lane == 0 && mt < P.m_tiles && !(P.probe & 4)) {
           if (P.accumulate)
             tc::tma_reduce_add_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
@@ -297,7 +298,7 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
             tc::tma_store_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
           tc::tma_store_commit();
         }
-        if (wq == 0 && lane == 0) { C16_TR(3, tr_c); ++tr_c; }   // (f) store issued
+        if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (f) store issued
         if (stats && !(P.probe & 8)) {
           // lane = column: sum over the staged valid rows (conflict free: the swizzle spreads
           // the 32 columns of a row over the 32 banks); four partial sums keep the chains short
@@ -314,7 +315,7 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (wq == 0 && lane == 0) { C16_TR(2, tr_i); ++tr_i; }   // (c) tile written out
+      if (tr_e) { C16_TR(2, tr_i); ++tr_i; }   // (c) tile written out
       if (lane == 0) tc::mbar_arrive_cluster_relaxed(tc::mapa(tempty_bar(as), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
     }

@@ -37,6 +37,7 @@ constexpr int kStageBudget = 192 * 1024;
 
 // EPB_C16_PROBE & 32: cluster 0 records clock64() at its pipeline hand-overs (epb_debug_conv16_trace):
 // [role 0 producer | 1 MMA issuer | 2 epilogue warp 2 per tile | 3 epilogue warp 2 per chunk][CTA rank][256 events]
+// (the per-chunk events cost instructions in the hot loop: compiled in only with -DEPB_C16_TRACE_CHUNKS)
 __device__ long long g_c16_trace[4 * 2 * 256];
 #define C16_TR(role, idx)                                                                      \
   do {                                                                                         \
@@ -108,7 +109,10 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool trace_on = (P.probe & 32) && tile0 == 0;
-  int tr_i = 0, tr_c = 0;
+  int tr_i = 0;
+#ifdef EPB_C16_TRACE_CHUNKS
+  int tr_c = 0;
+#endif
   const int KB = P.T * P.CB;
   const int m_pairs = (P.m_tiles + 1) / 2;
   const int total_tiles = m_pairs * P.n_tiles;
@@ -269,14 +273,20 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
         const int col0 = nt * BN + chunk * 32;
         if (col0 >= P.Cout) break;             // N tail
         uint32_t rg[32];
+#ifdef EPB_C16_TRACE_CHUNKS
         if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // chunk (a) start
+#endif
         tc::tmem_ld32(tmem_base + as * BN + chunk * 32 + ((uint32_t)(q * 32) << 16), rg);
         // the previous box must have been read by the TMA unit before it is overwritten
         if (lane == 0) tc::tma_store_wait_read<0>();
+#ifdef EPB_C16_TRACE_CHUNKS
         if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (b) box free
+#endif
         __syncwarp();
         tc::tmem_ld_wait();
+#ifdef EPB_C16_TRACE_CHUNKS
         if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (c) accumulator columns in registers
+#endif
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           float4 x = make_float4(__uint_as_float(rg[c]) * alpha, __uint_as_float(rg[c + 1]) * alpha,
@@ -287,10 +297,14 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
           }
           *reinterpret_cast<float4*>(stg + lane * 128 + (((c >> 2) ^ (lane & 7)) << 4)) = x;
         }
+#ifdef EPB_C16_TRACE_CHUNKS
         if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (d) staged
+#endif
         tc::fence_proxy_async();               // generic-proxy writes -> visible to the TMA unit
         __syncwarp();
+#ifdef EPB_C16_TRACE_CHUNKS
         if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (e) fenced
+#endif
         if (lane == 0 && mt < P.m_tiles && !(P.probe & 4)) {
           if (P.accumulate)
             tc::tma_reduce_add_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
@@ -298,7 +312,9 @@ conv16_kernel(const __grid_constant__ Plan16 P, const __grid_constant__ Maps16 m
             tc::tma_store_4d(&maps.o, stg_u32, col0, w0 + w_off, h0 + h_off, n0 + n_off);
           tc::tma_store_commit();
         }
+#ifdef EPB_C16_TRACE_CHUNKS
         if (tr_e) { C16_TR(3, tr_c); ++tr_c; }   // (f) store issued
+#endif
         if (stats && !(P.probe & 8)) {
           // lane = column: sum over the staged valid rows (conflict free: the swizzle spreads
           // the 32 columns of a row over the 32 banks); four partial sums keep the chains short

@@ -62,8 +62,8 @@ mask = sum(1 << j for j in [0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15])
 tt = timeit(lambda: ops.h36m_eval(pred, gt, cam, S, J, 0, mask, 150.0, met, pj, pck, None))
 line("h36m_eval", S, "sample", 816 + 40 + 72 + 136 + 68, tt)
 
-# triangulators: 2^16 pairs x 17 joints, 1144 B per pair
-NP, J = 1 << 16, 17
+# triangulators: 17-joint pairs, 1144 B per pair: the real size of a step (64 pairs) and a saturating one (2^20)
+J = 17
 rng = np.random.default_rng(0)
 sys.path.insert(0, ROOT)
 from oracle import restate          # camera synthesis only (bench input), not a compute path
@@ -71,14 +71,24 @@ R, T, f, c, P = restate.synthetic_cameras(rng, 64, 4)
 X = rng.normal(0, 400, (64, J, 3))
 u1 = np.stack([restate.project(P[i, 0], X[i]) for i in range(64)]) + rng.normal(0, 3, (64, J, 2))
 u2 = np.stack([restate.project(P[i, 1], X[i]) for i in range(64)]) + rng.normal(0, 3, (64, J, 2))
-rep = NP // 64
-tu1 = torch.from_numpy(np.tile(u1, (rep, 1, 1))).to(dev); tu2 = torch.from_numpy(np.tile(u2, (rep, 1, 1))).to(dev)
-tP1 = torch.from_numpy(np.tile(P[:, 0], (rep, 1, 1))).to(dev).contiguous()
-tP2 = torch.from_numpy(np.tile(P[:, 1], (rep, 1, 1))).to(dev).contiguous()
-Xo = torch.empty(NP, J, 3, device=dev, dtype=torch.float64); st = torch.empty(NP, J, device=dev, dtype=torch.int32)
-for m, name in ((0, "linear_eigen"), (1, "linear_LS"), (2, "iterative_LS"), (3, "polynomial")):
-    tt = timeit(lambda: ops.triangulate(tu1, tu2, 2, tP1, tP2, NP, J, m, 3e-5, Xo, st), reps=5)
-    line("triangulate " + name, NP, "17-joint pair", 1144, tt)
+for NP in (64, 1 << 20):
+    rep = NP // 64
+    tu1 = torch.from_numpy(np.tile(u1, (rep, 1, 1))).to(dev); tu2 = torch.from_numpy(np.tile(u2, (rep, 1, 1))).to(dev)
+    tP1 = torch.from_numpy(np.tile(P[:, 0], (rep, 1, 1))).to(dev).contiguous()
+    tP2 = torch.from_numpy(np.tile(P[:, 1], (rep, 1, 1))).to(dev).contiguous()
+    Xo = torch.empty(NP, J, 3, device=dev, dtype=torch.float64); st = torch.empty(NP, J, device=dev, dtype=torch.int32)
+    for m, name in ((0, "linear_eigen"), (1, "linear_LS"), (2, "iterative_LS"), (3, "polynomial")):
+        tt = timeit(lambda: ops.triangulate(tu1, tu2, 2, tP1, tP2, NP, J, m, 3e-5, Xo, st), reps=5)
+        line("triangulate %s, %d pairs" % (name, NP), NP, "17-joint pair", 1144, tt)
+    del tu1, tu2, tP1, tP2, Xo, st
+
+# Adam over the R50 parameter vector: 4 reads + 3 writes of 4 B per parameter
+n = 34272704
+pp, gg, m1, m2 = (torch.randn(n, device=dev) * 1e-2 for _ in range(4))
+m2.abs_()
+tt = timeit(lambda: ops.adam_step(pp, gg, m1, m2, n, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1))
+line("adam_step (R50, 34.27 M parameters)", n, "parameter", 28, tt)
+del pp, gg, m1, m2
 
 # input pipeline after decode: 512 frames of 1000 x 1002 x 3 (H36M camera frames) -> 256 x 256 patches.
 # Algorithmic bytes per output pixel: 12 written (3 float planes) + 12 read (4 bilinear taps x 3 channels, the

@@ -220,6 +220,65 @@ im2col_split_kernel(const float* __restrict__ img, uint4* __restrict__ col,
   }
 }
 
+// Same matrix, staged: a CTA takes kSeg consecutive output pixels of one output row, loads the
+// C x kh x (stride*(kSeg-1)+kw) input window once (coalesced rows, zero outside the image) and builds
+// its kSeg patch rows from shared memory -- every input pixel is read from HBM/L2 once per CTA instead
+// of once per tap that touches it.
+constexpr int kSeg = 64;
+__global__ void __launch_bounds__(kThreads)
+im2col_split_tiled_kernel(const float* __restrict__ img, uint4* __restrict__ col,
+                          const float* __restrict__ col_sc, int N, int C, int Hi, int Wi, int kh, int kw,
+                          int stride, int pad, int Ho, int Wo, int Kpad, int segs, int tw) {
+  extern __shared__ int smi[];
+  int* lut = smi;                               // [8][Kpad/8]: window offset of (c, r, s), -1 for padding columns
+  float* win = reinterpret_cast<float*>(smi + Kpad);        // [C][kh][tw]
+  const int K = kh * kw * C;
+  int b = blockIdx.x;
+  const int seg = b % segs; b /= segs;
+  const int oh = b % Ho;
+  const int n = b / Ho;
+  const int ow0 = seg * kSeg;
+  const int ih0 = oh * stride - pad, iw0 = ow0 * stride - pad;
+  for (int kk = threadIdx.x; kk < Kpad; kk += kThreads) {
+    int o = -1;
+    if (kk < K) {
+      const int t = kk / C, c = kk - t * C;
+      const int r = t / kw, sx = t - r * kw;
+      o = (c * kh + r) * tw + sx;
+    }
+    lut[(kk & 7) * (Kpad >> 3) + (kk >> 3)] = o;       // [e][k8]: a warp's lanes (consecutive k8) hit distinct banks
+  }
+  const int wsize = C * kh * tw;
+  for (int i = threadIdx.x; i < wsize; i += kThreads) {
+    const int x = i % tw;
+    const int cr = i / tw;
+    const int r = cr % kh, c = cr / kh;
+    const int ih = ih0 + r, iw = iw0 + x;
+    float v = 0.f;
+    if (ih >= 0 && ih < Hi && iw >= 0 && iw < Wi) v = __ldg(img + (((int64_t)n * C + c) * Hi + ih) * Wi + iw);
+    win[i] = v;
+  }
+  __syncthreads();
+  const int K8 = Kpad >> 3;
+  const int npx = min(kSeg, Wo - ow0);
+  const int64_t total = (int64_t)N * Ho * Wo * K8;
+  const int64_t row0 = (((int64_t)n * Ho + oh) * Wo + ow0) * K8;
+  const float s = col_sc[0];
+  for (int it = threadIdx.x; it < npx * K8; it += kThreads) {
+    const int p = it / K8, k8 = it - p * K8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int o = lut[e * K8 + k8];
+      v[e] = o >= 0 ? win[o + p * stride] : 0.f;
+    }
+    uint4 hi, lo;
+    split8(v, s, hi, lo);
+    col[row0 + it] = hi;
+    col[total + row0 + it] = lo;
+  }
+}
+
 // ------------------------------------------------------------------ batched fp32 -> split
 __device__ __forceinline__ const epb_split_job& find_job(const epb_split_job* jobs, int njobs,
                                                          int& idx) {
@@ -878,6 +937,18 @@ EPB_API int epb_im2col_split(const float* img_nchw, epb_half* col, const float* 
   EPB_CHECK_ARG(img_nchw && col && col_sc && N > 0 && C > 0 && Kpad % 8 == 0 && Kpad >= kh * kw * C);
   const int64_t total = (int64_t)N * Ho * Wo * (Kpad / 8);
   EPB_CHECK_ARG(Kpad <= 4096);
+  {
+    const int tw = stride * (kSeg - 1) + kw, segs = (Wo + kSeg - 1) / kSeg;
+    const size_t smem = ((size_t)Kpad + (size_t)C * kh * tw) * sizeof(int);
+    const int64_t ctas = (int64_t)N * Ho * segs;
+    if (smem <= 48 * 1024 && ctas < (1LL << 31)) {
+      im2col_split_tiled_kernel<<<(unsigned)ctas, kThreads, smem, as_stream(stream)>>>(
+          img_nchw, reinterpret_cast<uint4*>(col), col_sc, N, C, Hi, Wi, kh, kw, stride, pad, Ho, Wo, Kpad,
+          segs, tw);
+      EPB_LAUNCH_CHECK();
+      return EPB_OK;
+    }
+  }
   im2col_split_kernel<<<ew_blocks(total), kThreads, 2 * Kpad * sizeof(int), as_stream(stream)>>>(
       img_nchw, reinterpret_cast<uint4*>(col), col_sc, N, C, Hi, Wi, kh, kw, stride, pad, Ho, Wo, Kpad);
   EPB_LAUNCH_CHECK();

@@ -218,6 +218,14 @@ def test_split_elementwise_vs_emulation(dev):
     c = torch.empty_like(c_ref, device=dev)
     ops.im2col_split(img.to(dev), c, asc.to(dev), 2, 3, 20, 24, 7, 7, 2, 3, Ho, Wo, 192)
     assert torch.equal(c.cpu().view(torch.int16), c_ref.view(torch.int16))
+    # several 64-pixel segments per output row, ragged last one (the staged kernel's window logic)
+    img = torch.randn(1, 3, 11, 300, generator=gen)
+    Ho, Wo = 6, 150
+    c_ref = torch.empty(2, 1, Ho, Wo, 192, dtype=H16)
+    em.im2col_split(img, c_ref, asc, 1, 3, 11, 300, 7, 7, 2, 3, Ho, Wo, 192)
+    c = torch.empty_like(c_ref, device=dev)
+    ops.im2col_split(img.to(dev), c, asc.to(dev), 1, 3, 11, 300, 7, 7, 2, 3, Ho, Wo, 192)
+    assert torch.equal(c.cpu().view(torch.int16), c_ref.view(torch.int16))
     # batched fp32 -> split with amax scale
     srcs = [torch.randn(n, generator=gen) * s for n, s in ((5000, 1e-3), (777, 40.0), (4096, 1.0))]
     jobs_ref = [(s, torch.empty(2 * s.numel(), dtype=H16), torch.ones(2)) for s in srcs]

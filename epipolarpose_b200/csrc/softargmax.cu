@@ -395,7 +395,7 @@ jointloss_kernel(const float* __restrict__ x, const float* __restrict__ t,
 // counter) in a fixed order, so the loss is deterministic; that CTA also evaluates the tiny
 // joint part (n <= a few thousand elements) and writes the three loss values.
 constexpr int kHmThreads = 256;
-constexpr int kHmMaxBlocks = 4 * kNumSMs;
+constexpr int kHmMaxBlocks = 8 * kNumSMs;
 
 __global__ void __launch_bounds__(kHmThreads)
 heatmap_joint_loss_kernel(const float* __restrict__ hm, const float* __restrict__ target,
@@ -414,19 +414,34 @@ heatmap_joint_loss_kernel(const float* __restrict__ hm, const float* __restrict_
   if ((HW & 3) == 0) {
     const int64_t total4 = total >> 2;
     const int hw4 = HW >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * kHmThreads + threadIdx.x; i < total4;
-         i += (int64_t)gridDim.x * kHmThreads) {
-      const float wr = wh ? wh[i / hw4] : 1.f;
-      const float4 h = ldg_stream(reinterpret_cast<const float4*>(hm) + i);
-      const float4 g = ldg_stream(reinterpret_cast<const float4*>(target) + i);
+    const int64_t stride = (int64_t)gridDim.x * kHmThreads;
+    float facc = 0.f;
+    const bool small = total4 < (1LL << 31);       // 32-bit row index: the 64-bit division costs ~100 instructions
+    auto one = [&](int64_t i, const float4 h, const float4 g) {
+      const float wr = wh ? wh[small ? (int64_t)((uint32_t)i / (uint32_t)hw4) : i / hw4] : 1.f;
       const float4 d = make_float4(wr * (h.x - g.x), wr * (h.y - g.y), wr * (h.z - g.z),
                                    wr * (h.w - g.w));
-      acc += (double)(d.x * d.x + d.y * d.y) + (double)(d.z * d.z + d.w * d.w);
+      facc += (d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w);      // <= a few hundred terms per thread in fp32
       if (dhm) {
         const float c = gs * wr;
-        reinterpret_cast<float4*>(dhm)[i] = make_float4(c * d.x, c * d.y, c * d.z, c * d.w);
+        __stcs(reinterpret_cast<float4*>(dhm) + i, make_float4(c * d.x, c * d.y, c * d.z, c * d.w));
       }
+    };
+    int64_t i = (int64_t)blockIdx.x * kHmThreads + threadIdx.x;
+    for (; i + 3 * stride < total4; i += 4 * stride) {        // four element quads per trip: 8 loads in flight
+      float4 h[4], g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        h[u] = ldg_stream(reinterpret_cast<const float4*>(hm) + i + u * stride);
+        g[u] = ldg_stream(reinterpret_cast<const float4*>(target) + i + u * stride);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) one(i + u * stride, h[u], g[u]);
     }
+    for (; i < total4; i += stride)
+      one(i, ldg_stream(reinterpret_cast<const float4*>(hm) + i),
+          ldg_stream(reinterpret_cast<const float4*>(target) + i));
+    acc = (double)facc;
   } else {
     for (int64_t i = (int64_t)blockIdx.x * kHmThreads + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * kHmThreads) {
@@ -467,10 +482,17 @@ heatmap_joint_loss_kernel(const float* __restrict__ hm, const float* __restrict_
   __syncthreads();
   if (lane == 0) shd[wid] = jacc;
   __syncthreads();
+  // heat-map partials of all CTAs: lane l of warp 0 adds parts[l], parts[l+32], ... then a shuffle tree
+  // (a fixed order: run-to-run identical)
+  double lhp = 0.0;
+  if (wid == 0) {
+    for (unsigned k = lane; k < gridDim.x; k += 32) lhp += parts[k];
+    lhp = warp_sum(lhp);
+  }
   if (threadIdx.x == 0) {
-    double lj = 0.0, lh = 0.0;
+    double lj = 0.0;
+    const double lh = lhp;
     for (int k = 0; k < kHmThreads / 32; ++k) lj += shd[k];
-    for (unsigned k = 0; k < gridDim.x; ++k) lh += parts[k];      // fixed order
     const float loss_hm = (float)(lh / (double)total);
     const float loss_jt = (float)(lj * (double)idiv);
     loss[0] = loss_hm;

@@ -1,0 +1,1 @@
+"""Host-side helpers of the mirror: image / patch geometry, triangulation front ends, optimisers, augmentation."""

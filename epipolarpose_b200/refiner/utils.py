@@ -9,37 +9,38 @@ from epipolarpose_b200 import ops as _ops
 _backend = [_ops]
 
 
-class AverageMeter(object):
+class AverageMeter:
+    """Running value / weighted mean (the four public attributes of the reference's meter)."""
+
     def __init__(self):
-        self.val = 0
-        self.avg = 0
-        self.sum = 0
-        self.count = 0
+        self.reset()
+
+    def reset(self):
+        self.val, self.sum, self.count, self.avg = 0, 0, 0, 0
 
     def update(self, val, n=1):
         self.val = val
-        self.sum += val * n
-        self.count += n
+        self.count = self.count + n
+        self.sum = self.sum + n * val
         self.avg = self.sum / self.count
 
 
-def lr_decay(optimizer, step, lr, decay_step, gamma):
-    lr = lr * gamma ** (step / decay_step)
-    for param_group in optimizer.param_groups:
-        param_group['lr'] = lr
-    return lr
+def _exponential_lr(optimizer, step, lr, decay_step, gamma):
+    """lr * gamma^(step / decay_step), written into every parameter group; returns the new rate."""
+    new_lr = lr * pow(gamma, step / decay_step)
+    for group in optimizer.param_groups:
+        group["lr"] = new_lr
+    return new_lr
 
 
-def step_decay(optimizer, step, lr, decay_step, gamma):
-    lr = lr * gamma ** (step / decay_step)
-    for param_group in optimizer.param_groups:
-        param_group['lr'] = lr
-    return lr
+# the reference keeps two names for the same schedule (refiner/utils.py:18-28)
+lr_decay = _exponential_lr
+step_decay = _exponential_lr
 
 
 def save_ckpt(state, ckpt_path, is_best=True):
-    name = 'best.pth.tar' if is_best else 'last.pth.tar'
-    torch.save(state, os.path.join(ckpt_path, name))
+    """best.pth.tar / last.pth.tar under ckpt_path (refiner/utils.py:30-36)."""
+    torch.save(state, os.path.join(ckpt_path, ("best" if is_best else "last") + ".pth.tar"))
 
 
 def clip_grad_norm_(parameters, max_norm):

@@ -1,0 +1,1 @@
+"""Mirror of the reference lib/ package for the training-loop hot path."""

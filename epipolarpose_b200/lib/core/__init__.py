@@ -1,0 +1,1 @@
+"""Loops, losses, decode and configuration of the mirror (reference lib/core)."""

@@ -194,6 +194,9 @@ class _PoseNetFn(torch.autograd.Function):
             eng.backward(S, None, ddepth, params, sgrads, on_stage=on_stage, head=head)
         else:
             eng.backward(S, dlogits, ddepth, params, sgrads, on_stage=on_stage)
+        if sink is not None:
+            sink.planes = sink.sc = sink.dbias = None       # the planes are as large as the logits: let them go
+            module._last_sink = None
         for w_ in works:
             w_.wait()                                   # the current stream waits for the collectives
         flat = sflat.clone()

@@ -249,16 +249,30 @@ class Engine:
                     continue
                 T = conv.k * conv.k
                 A, B = w.shape[0], w.shape[1]
-                wf = torch.zeros(conv.cout_p * T * conv.cin_p, device=self.dev, dtype=torch.float32)
                 wd = torch.zeros(conv.cin_p * T * conv.cout_p, device=self.dev, dtype=torch.float32)
                 sf, sd = (0, 1) if conv.kind == "conv" else (1, 0)
-                jobs.append((w, wf, A, B, T, sf, conv.cin_p, 0, T * conv.cin_p))
+                if self._aliases_param(conv, w):
+                    wf = w.detach().reshape(-1)          # [Cout][Cin] IS the packed fprop operand of a 1x1 conv
+                else:
+                    wf = torch.zeros(conv.cout_p * T * conv.cin_p, device=self.dev, dtype=torch.float32)
+                    jobs.append((w, wf, A, B, T, sf, conv.cin_p, 0, T * conv.cin_p))
                 jobs.append((w, wd, A, B, T, sd, conv.cout_p, 0, T * conv.cout_p))
                 packed[conv.name] = (wf, wd)
             st = {"key": key, "packed": packed, "batch": ops.PackBatch(jobs)}
             self._wstate = st
         ops.pack_weight_batch(st["batch"])
         return st["packed"]
+
+    def _aliases_param(self, conv, t):
+        """A pad-free 1x1 convolution's [Cout][Cin][1][1] tensor is already the packed fprop operand
+        [Cout][T = 1][Cin] (and its gradient the packed weight gradient): engines that read the fp32
+        operand with plain loads (alias_1x1) skip the pack / unpack of those layers."""
+        plan = self.plan
+        if conv is plan.fc or conv is plan.final:        # may run on the fp32-operand kernels
+            return False
+        return (getattr(self, "alias_1x1", False) and conv.kind == "conv" and conv.k == 1
+                and conv.cin_p == t.shape[1] and conv.cout_p == t.shape[0] and t.is_contiguous()
+                and t.data_ptr() % 16 == 0)
 
     def _grad_state(self, grads):
         """Persistent backward scratch: packed weight-gradient accumulators (one flat buffer,
@@ -280,8 +294,11 @@ class Engine:
             for conv, n in zip(convs, sizes):
                 view = flat[off:off + n]
                 off += n
-                dwp[conv.name] = view
                 g = grads[conv.name + ".weight"]
+                if conv is not plan.stem and self._aliases_param(conv, g):
+                    dwp[conv.name] = g.reshape(-1)       # the weight gradient lands in the state_dict layout
+                    continue
+                dwp[conv.name] = view
                 js = jobs[stage_of(conv.name)]
                 if conv is plan.stem:
                     js.append((view, g, 64, 3, 49, 0, 3, 1, self.stem_kpad))

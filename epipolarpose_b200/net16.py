@@ -44,6 +44,9 @@ class Engine16(_net.Engine):
     def __init__(self, plan, ops=None):
         super().__init__(plan, precision=3, ops=ops)   # 3xTF32 for the few fp32-operand layers
         self.tc_precision = 3
+        # the fp32 packed weights are only read by the amax / split passes and the packed weight gradients
+        # only written by plain stores: 1x1 layers use the parameter / gradient tensors themselves
+        self.alias_1x1 = True
         self.stem_kpad = STEM_KPAD16
         self.stem_col = Conv("conv1", "conv", STEM_KPAD16, 64, 1, 1, 0)
 
